@@ -385,11 +385,14 @@ int gcmo_minmax_interpolate(int m, int n, double* src, double q, double* out) {
 	if (!(q >= 0)) { return 1; }               /* assert_ge(q, 0) */
 	const size_t k = (size_t) q;
 	if (k > (size_t) n - 1) { return 2; }       /* assert_le(k, src.size() - 1) */
-	if (k + 1 > (size_t) n - 1) { return 3; }   /* the reference would read src[k+1] out of bounds */
+	/* q == n-1 exactly (k == n-1) passes the reference's asserts but makes it read src[k+1] one past
+	 * the end of the std::vector (undefined behaviour; its own TestGridCharacteristicMethod.cpp:15-70
+	 * relies on the result being src[k]).  The only defined reading is a bracket made of src[k] alone. */
+	const size_t k1 = (k + 1 > (size_t) n - 1) ? k : k + 1;
 	double maximum[GCMO_MAX_M], minimum[GCMO_MAX_M];
 	for (int c = 0; c < m; c++) {
-		maximum[c] = fmax(src[k * m + c], src[(k + 1) * m + c]);
-		minimum[c] = fmin(src[k * m + c], src[(k + 1) * m + c]);
+		maximum[c] = fmax(src[k * m + c], src[k1 * m + c]);
+		minimum[c] = fmin(src[k * m + c], src[k1 * m + c]);
 	}
 	gcmo_interpolate(m, n, src, q, out);
 	for (int c = 0; c < m; c++) {

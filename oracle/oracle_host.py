@@ -536,6 +536,8 @@ def run_reference(task_text, workdir, matrices=False):
     with open(tf, "w") as f:
         f.write(task_text)
     prefix = os.path.join(workdir, "out")
+    for sub in ("zaxis", "detector"):  # SliceSnapshotter writes here (Snapshotter.hpp:53-68)
+        os.makedirs(os.path.join(workdir, "snapshots", sub), exist_ok=True)
     cmd = [exe, tf, prefix] + (["--matrices"] if matrices else [])
     subprocess.run(cmd, check=True, cwd=workdir)
     meta = {}
@@ -551,4 +553,8 @@ def run_reference(task_text, workdir, matrices=False):
             else:
                 meta[w[0]] = float(w[1])
     out["meta"] = meta
+    det = os.path.join(workdir, "snapshots", "detector")
+    files = sorted(os.listdir(det)) if os.path.isdir(det) else []
+    if files:  # the last file holds the whole history: columns time, value (float32 printed)
+        out["detector"] = np.loadtxt(os.path.join(det, files[-1]), ndmin=2)
     return out

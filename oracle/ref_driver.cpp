@@ -326,7 +326,7 @@ int main(int argc, char** argv) {
 			default: THROW_INVALID_ARG("bad dimensionality");
 		}
 	} catch (Exception& e) {
-		fprintf(stderr, "gcm::Exception: %s\n", e.what());
+		fprintf(stderr, "gcm::Exception: %s\n", e.what().c_str());
 		return 1;
 	}
 	MPI_Finalize();
