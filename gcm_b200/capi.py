@@ -1,0 +1,356 @@
+"""ctypes binding of the C ABI (include/gcm_b200.h) and of the host layer's C entry points.
+
+`Library()` loads gcm_b200/libgcm_b200.so + libgcm_b200_host.so and fails loudly when they are missing:
+there is no Python or CPU implementation behind these calls.  (The host-logic tests pass explicit paths
+to load their stepping harness instead; the product never does.)
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+c_ll_p = ctypes.POINTER(ctypes.c_longlong)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+vp = ctypes.c_void_p
+
+Q_PRESSURE_TRACE = -1
+
+# every symbol include/gcm_b200.h declares: name -> (restype, argtypes)
+C_ABI = {
+    "gcmb_last_error": (ctypes.c_char_p, []),
+    "gcmb_version": (ctypes.c_char_p, []),
+    "gcmb_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
+    "gcmb_destroy": (None, [vp]),
+    "gcmb_set_stream": (ctypes.c_int, [vp, vp]),
+    "gcmb_sync": (ctypes.c_int, [vp]),
+    "gcmb_timer_start": (ctypes.c_int, [vp]),
+    "gcmb_timer_stop": (ctypes.c_int, [vp, c_float_p]),
+    "gcmb_profile_enable": (ctypes.c_int, [vp, ctypes.c_int]),
+    "gcmb_profile_get": (ctypes.c_int, [vp, ctypes.c_int, c_double_p, c_ll_p]),
+    "gcmb_launch_count": (ctypes.c_longlong, [vp]),
+    "gcmb_device_bytes": (ctypes.c_size_t, [vp]),
+    "gcmb_cubic_body_create": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_int_p, c_int_p, c_double_p,
+                                              ctypes.c_int, ctypes.POINTER(vp)]),
+    "gcmb_cubic_body_destroy": (None, [vp]),
+    "gcmb_cubic_upload_state": (ctypes.c_int, [vp, vp, ctypes.c_int]),
+    "gcmb_cubic_download_state": (ctypes.c_int, [vp, vp, ctypes.c_int]),
+    "gcmb_cubic_set_materials": (ctypes.c_int, [vp, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_u8_p]),
+    "gcmb_cubic_assign_table_in_area": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_double_p]),
+    "gcmb_cubic_add_vector_in_area": (ctypes.c_int, [vp, c_double_p, ctypes.c_int, c_double_p]),
+    "gcmb_cubic_border_set": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_u8_p, c_u8_p, ctypes.c_int, c_int_p]),
+    "gcmb_cubic_border_set_area": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  c_double_p, ctypes.c_int, c_int_p]),
+    "gcmb_cubic_border_apply": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_double_p]),
+    "gcmb_cubic_contact_apply": (ctypes.c_int, [vp, vp, c_int_p, c_int_p, c_int_p]),
+    "gcmb_cubic_stage": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double]),
+    "gcmb_cubic_ode_maxwell": (ctypes.c_int, [vp, c_double_p]),
+    "gcmb_cubic_detector_set_area": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_double_p]),
+    "gcmb_cubic_detector_set_mask": (ctypes.c_int, [vp, ctypes.c_int, c_u8_p]),
+    "gcmb_cubic_seismo": (ctypes.c_int, [vp, c_double_p, c_ll_p, ctypes.c_int, c_double_p, ctypes.c_int]),
+    "gcmb_comm_unique_id": (ctypes.c_int, [vp]),
+    "gcmb_comm_init": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
+    "gcmb_cubic_halo_exchange": (ctypes.c_int, [vp]),
+    "gcmb_comm_allreduce_sum": (ctypes.c_int, [vp, c_double_p, ctypes.c_int]),
+    "gcmb_cubic_checksum": (ctypes.c_int, [vp, c_double_p]),
+    "gcmb_cubic_stage_kernel_name": (ctypes.c_char_p, [vp, ctypes.c_int]),
+}
+
+HOST_ABI = {
+    "gcmb_host_last_error": (ctypes.c_char_p, []),
+    "gcmb_host_engine_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                               ctypes.POINTER(vp)]),
+    "gcmb_host_engine_destroy": (None, [vp]),
+    "gcmb_host_engine_run": (ctypes.c_int, [vp]),
+    "gcmb_host_engine_info": (ctypes.c_int, [vp, c_int_p, c_double_p, c_double_p]),
+    "gcmb_host_engine_body_info": (ctypes.c_int, [vp, ctypes.c_size_t, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "gcmb_host_engine_body_pde": (ctypes.c_int, [vp, ctypes.c_size_t, c_double_p]),
+    "gcmb_host_engine_body_handle": (vp, [vp, ctypes.c_size_t]),
+    "gcmb_host_engine_context": (vp, [vp]),
+    "gcmb_host_engine_body_matrices": (ctypes.c_int, [vp, ctypes.c_size_t, c_int_p, c_double_p, c_double_p, c_double_p]),
+    "gcmb_host_engine_seismogram": (ctypes.c_int, [vp, c_double_p, c_float_p, ctypes.c_int]),
+    "gcmb_host_matrices": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
+                                          c_double_p, c_double_p]),
+}
+
+
+class GcmError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("gcm_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def dp(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def ip(a):
+    return None if a is None else a.ctypes.data_as(c_int_p)
+
+
+def bp(a):
+    return None if a is None else a.ctypes.data_as(c_u8_p)
+
+
+class Library:
+    def __init__(self, cuda_path=None, host_path=None):
+        cuda_path = cuda_path or os.path.join(HERE, "libgcm_b200.so")
+        host_path = host_path or os.path.join(HERE, "libgcm_b200_host.so")
+        for p in (cuda_path, host_path):
+            if not os.path.exists(p):
+                raise ImportError("%s is missing: build it with `python -m gcm_b200.build` "
+                                  "(gcm_b200 has no fallback implementation)" % p)
+        self.cuda_path, self.host_path = cuda_path, host_path
+        self.c = ctypes.CDLL(cuda_path, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in C_ABI.items():
+            f = getattr(self.c, name)
+            f.restype, f.argtypes = res, args
+        self.h = ctypes.CDLL(host_path, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in HOST_ABI.items():
+            f = getattr(self.h, name)
+            f.restype, f.argtypes = res, args
+
+    def check(self, rc):
+        if rc != 0:
+            raise GcmError(rc, self.c.gcmb_last_error().decode())
+
+    def hcheck(self, rc):
+        if rc != 0:
+            raise GcmError(rc, self.h.gcmb_host_last_error().decode())
+
+
+class Context:
+    def __init__(self, lib, device=0, real_bytes=8):
+        self.lib = lib
+        self.handle = vp()
+        lib.check(lib.c.gcmb_create(device, real_bytes, ctypes.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.lib.c.gcmb_destroy(self.handle)
+            self.handle = vp()
+
+    def sync(self):
+        self.lib.check(self.lib.c.gcmb_sync(self.handle))
+
+    def timer_start(self):
+        self.lib.check(self.lib.c.gcmb_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        self.lib.check(self.lib.c.gcmb_timer_stop(self.handle, ctypes.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self.lib.check(self.lib.c.gcmb_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_get(self):
+        ms = np.zeros(8)
+        n = np.zeros(8, dtype=np.int64)
+        self.lib.check(self.lib.c.gcmb_profile_get(self.handle, 8, dp(ms), n.ctypes.data_as(c_ll_p)))
+        return ms, n
+
+    def launch_count(self):
+        return int(self.lib.c.gcmb_launch_count(self.handle))
+
+    def device_bytes(self):
+        return int(self.lib.c.gcmb_device_bytes(self.handle))
+
+
+AREA_KINDS = {"infinite": 0, "box": 1, "sphere": 2, "cylinder": 3}
+
+
+def area_args(area):
+    """('box', lo, hi) / ('sphere', r, c) / ('cylinder', r, b, e) / ('infinite',) -> (kind, params array)"""
+    kind = AREA_KINDS[area[0]]
+    flat = []
+    for a in area[1:]:
+        flat.extend(a if isinstance(a, (list, tuple)) else [a])
+    return kind, np.array(flat + [0.0] * (10 - len(flat)), dtype=np.float64)
+
+
+class CubicBody:
+    """Thin wrapper over gcmb_cubic_* for one body."""
+
+    def __init__(self, ctx, D, M, sizes, start, h, border_size):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.D, self.M, self.bs = D, M, border_size
+        self.sizes = np.array(sizes, dtype=np.int32)
+        self.start = np.array(start, dtype=np.int32)
+        self.h = np.array(h, dtype=np.float64)
+        self.handle = vp()
+        self.lib.check(self.lib.c.gcmb_cubic_body_create(ctx.handle, D, M, ip(self.sizes), ip(self.start),
+                                                         dp(self.h), border_size, ctypes.byref(self.handle)))
+        self.border_nq = {}
+
+    def close(self):
+        if self.handle:
+            self.lib.c.gcmb_cubic_body_destroy(self.handle)
+            self.handle = vp()
+
+    def upload(self, array, with_ghosts):
+        a = np.ascontiguousarray(array, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_cubic_upload_state(self.handle, a.ctypes.data_as(vp), 1 if with_ghosts else 0))
+
+    def download(self, with_ghosts=False):
+        ext = self.sizes + (2 * self.bs if with_ghosts else 0)
+        out = np.empty(tuple(int(e) for e in ext) + (self.M,), dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_cubic_download_state(self.handle, out.ctypes.data_as(vp), 1 if with_ghosts else 0))
+        return out
+
+    def set_materials(self, U, U1, L, node_table=None):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        U1 = np.ascontiguousarray(U1, dtype=np.float64)
+        L = np.ascontiguousarray(L, dtype=np.float64)
+        nt = None if node_table is None else np.ascontiguousarray(node_table, dtype=np.uint8)
+        self.lib.check(self.lib.c.gcmb_cubic_set_materials(self.handle, U.shape[0], dp(U), dp(U1), dp(L), bp(nt)))
+
+    def assign_table_in_area(self, table, area):
+        kind, p = area_args(area)
+        self.lib.check(self.lib.c.gcmb_cubic_assign_table_in_area(self.handle, table, kind, dp(p)))
+
+    def add_vector_in_area(self, vec, area):
+        kind, p = area_args(area)
+        v = np.ascontiguousarray(vec, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_cubic_add_vector_in_area(self.handle, dp(v), kind, dp(p)))
+
+    def border_set(self, cond, direction, left_mask, right_mask, codes):
+        codes = np.array(codes, dtype=np.int32)
+        lm = None if left_mask is None else np.ascontiguousarray(left_mask, dtype=np.uint8)
+        rm = None if right_mask is None else np.ascontiguousarray(right_mask, dtype=np.uint8)
+        self.lib.check(self.lib.c.gcmb_cubic_border_set(self.handle, cond, direction, bp(lm), bp(rm), len(codes), ip(codes)))
+
+    def border_set_area(self, cond, direction, area, codes, sides=3):
+        kind, p = area_args(area)
+        codes = np.array(codes, dtype=np.int32)
+        self.lib.check(self.lib.c.gcmb_cubic_border_set_area(self.handle, cond, direction, sides, kind, dp(p),
+                                                             len(codes), ip(codes)))
+
+    def border_apply(self, direction, values):
+        v = np.array(values, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_cubic_border_apply(self.handle, direction, len(v), dp(v)))
+
+    def contact_apply(self, other, box_a, box_b, extent):
+        a, b, e = (np.array(x, dtype=np.int32) for x in (box_a, box_b, extent))
+        self.lib.check(self.lib.c.gcmb_cubic_contact_apply(self.handle, other.handle, ip(a), ip(b), ip(e)))
+
+    def stage(self, direction, tau):
+        self.lib.check(self.lib.c.gcmb_cubic_stage(self.handle, direction, tau))
+
+    def ode_maxwell(self, decay):
+        d = np.array(decay, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_cubic_ode_maxwell(self.handle, dp(d)))
+
+    def detector_set_area(self, code, area):
+        kind, p = area_args(area)
+        self.lib.check(self.lib.c.gcmb_cubic_detector_set_area(self.handle, code, kind, dp(p)))
+
+    def seismo(self, line_comp=None):
+        s = ctypes.c_double()
+        c = ctypes.c_longlong()
+        n = int(self.sizes[self.D - 1])
+        line = np.zeros(n) if line_comp is not None else None
+        self.lib.check(self.lib.c.gcmb_cubic_seismo(self.handle, ctypes.byref(s), ctypes.byref(c),
+                                                    0 if line_comp is None else line_comp, dp(line), n))
+        return s.value, c.value, line
+
+    def checksum(self):
+        out = ctypes.c_double()
+        self.lib.check(self.lib.c.gcmb_cubic_checksum(self.handle, ctypes.byref(out)))
+        return out.value
+
+    def halo_exchange(self):
+        self.lib.check(self.lib.c.gcmb_cubic_halo_exchange(self.handle))
+
+    def kernel_name(self, direction):
+        return self.lib.c.gcmb_cubic_stage_kernel_name(self.handle, direction).decode()
+
+
+class HostEngine:
+    """createEngine(task)->run() of the host layer, driven by a plain-text task (gcm_b200/host/task_file.cpp)."""
+
+    def __init__(self, lib, task_text, device=0, slab_rank=0, slab_count=1, nccl_id=None):
+        self.lib = lib
+        self.handle = vp()
+        idbuf = None
+        if nccl_id is not None:
+            idbuf = ctypes.create_string_buffer(bytes(nccl_id), 128)
+        self._idbuf = idbuf
+        lib.hcheck(lib.h.gcmb_host_engine_create(task_text.encode(), device, slab_rank, slab_count,
+                                                 ctypes.cast(idbuf, vp) if idbuf is not None else None,
+                                                 ctypes.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.lib.h.gcmb_host_engine_destroy(self.handle)
+            self.handle = vp()
+
+    def run(self):
+        self.lib.hcheck(self.lib.h.gcmb_host_engine_run(self.handle))
+        return self
+
+    def info(self):
+        steps = ctypes.c_int()
+        t = ctypes.c_double()
+        tau = ctypes.c_double()
+        self.lib.hcheck(self.lib.h.gcmb_host_engine_info(self.handle, ctypes.byref(steps), ctypes.byref(t), ctypes.byref(tau)))
+        return steps.value, t.value, tau.value
+
+    def body_info(self, bid):
+        D, M = ctypes.c_int(), ctypes.c_int()
+        sizes = np.zeros(3, dtype=np.int32)
+        start = np.zeros(3, dtype=np.int32)
+        self.lib.hcheck(self.lib.h.gcmb_host_engine_body_info(self.handle, bid, ctypes.byref(D), ctypes.byref(M), ip(sizes), ip(start)))
+        return D.value, M.value, sizes[:D.value].copy(), start[:D.value].copy()
+
+    def body_pde(self, bid):
+        D, M, sizes, _ = self.body_info(bid)
+        out = np.empty((int(np.prod(sizes)), M), dtype=np.float64)
+        self.lib.hcheck(self.lib.h.gcmb_host_engine_body_pde(self.handle, bid, dp(out)))
+        return out
+
+    def body_matrices(self, bid):
+        D, M, _, _ = self.body_info(bid)
+        n = ctypes.c_int()
+        self.lib.hcheck(self.lib.h.gcmb_host_engine_body_matrices(self.handle, bid, ctypes.byref(n), None, None, None))
+        U = np.zeros((n.value, D, M, M))
+        U1 = np.zeros((n.value, D, M, M))
+        L = np.zeros((n.value, D, M))
+        self.lib.hcheck(self.lib.h.gcmb_host_engine_body_matrices(self.handle, bid, ctypes.byref(n), dp(U), dp(U1), dp(L)))
+        return U, U1, L
+
+    def seismogram(self):
+        n = self.lib.h.gcmb_host_engine_seismogram(self.handle, None, None, 0)
+        t = np.zeros(n)
+        v = np.zeros(n, dtype=np.float32)
+        self.lib.h.gcmb_host_engine_seismogram(self.handle, dp(t), v.ctypes.data_as(c_float_p), n)
+        return t, v
+
+    def body_handle(self, bid):
+        return self.lib.h.gcmb_host_engine_body_handle(self.handle, bid)
+
+    def kernel_name(self, bid, direction):
+        return self.lib.c.gcmb_cubic_stage_kernel_name(self.body_handle(bid), direction).decode()
+
+    def context_handle(self):
+        return self.lib.h.gcmb_host_engine_context(self.handle)
+
+
+def host_matrices(lib, model, D, material):
+    """material: ('isotropic', rho, lambda, mu) or ('orthotropic', rho, c[9])"""
+    M = D + 1 if model == "acoustic" else D + D * (D + 1) // 2
+    U = np.zeros((D, M, M))
+    U1 = np.zeros((D, M, M))
+    L = np.zeros((D, M))
+    if material[0] == "isotropic":
+        p = np.array(material[1:4], dtype=np.float64)
+        kind = 0
+    else:
+        p = np.array([material[1]] + list(material[2]), dtype=np.float64)
+        kind = 1
+    lib.hcheck(lib.h.gcmb_host_matrices(1 if model == "acoustic" else 0, D, kind, dp(p), dp(U), dp(U1), dp(L)))
+    return U, U1, L

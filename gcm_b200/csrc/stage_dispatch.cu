@@ -1,0 +1,115 @@
+// Stage kernels of gcm_b200 and their registry: one specialised kernel per sparsity class of the
+// eigen-system (patterns.inc) x border size {1,2}, plus dense kernels for everything else.
+#include <cstdlib>
+
+#include "thread_fns.h"
+
+namespace gcmb {
+
+#define GCMB_L(...) {__VA_ARGS__}
+#define GCMB_PATTERN(NAME, MM, SGN, UM, U1M)                                                      \
+	struct Pat_##NAME {                                                                           \
+		static constexpr int M = MM;                                                              \
+		GCMB_HD static constexpr int sgn(int k) { constexpr int t[9] = SGN; return t[k]; }         \
+		GCMB_HD static constexpr unsigned um(int k) { constexpr unsigned t[9] = UM; return t[k]; } \
+		GCMB_HD static constexpr unsigned u1m(int k) { constexpr unsigned t[9] = U1M; return t[k]; } \
+	};
+#include "patterns.inc"
+#undef GCMB_PATTERN
+
+constexpr int ZT = 128;  // threads per block, all along the contiguous axis
+
+// block -> node mapping: blockIdx.x runs along the sweep axis when it is strided, so that blocks
+// scheduled together share their halo planes in L2
+GCMB_DEV bool block_node(const StageArgs& a, int& i0, int& i1, int& i2) {
+	int zc;
+	if (a.axis == 0) { i0 = blockIdx.x + a.x_begin; zc = blockIdx.y; i1 = blockIdx.z; }
+	else if (a.axis == 1) { i1 = blockIdx.x; zc = blockIdx.y; i0 = blockIdx.z + a.x_begin; }
+	else { zc = blockIdx.x; i1 = blockIdx.y; i0 = blockIdx.z + a.x_begin; }
+	i2 = zc * ZT + threadIdx.x;
+	return i2 < a.g.n[2];
+}
+
+static dim3 node_blocks(const StageArgs& a) {
+	const unsigned zc = (unsigned) ((a.g.n[2] + ZT - 1) / ZT);
+	const unsigned nx = (unsigned) (a.x_end - a.x_begin);
+	if (a.axis == 0) { return dim3(nx, zc, (unsigned) a.g.n[1]); }
+	if (a.axis == 1) { return dim3((unsigned) a.g.n[1], zc, nx); }
+	return dim3(zc, (unsigned) a.g.n[1], nx);
+}
+
+template<class P, int BS>
+GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_direct(const StageArgs a) {
+	int i0, i1, i2;
+	if (block_node(a, i0, i1, i2)) { stage_thread_sparse<P, BS>(a, i0, i1, i2); }
+}
+
+template<int M>
+GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_dense(const StageArgs a) {
+	int i0, i1, i2;
+	if (block_node(a, i0, i1, i2)) { stage_thread_dense<M>(a, i0, i1, i2); }
+}
+
+// marching kernel: grid = (segments along the sweep axis, z chunks, perpendicular axis)
+template<class P, int BS>
+GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_march(const StageArgs a, int seg) {
+	const int i2 = blockIdx.y * ZT + threadIdx.x;
+	if (i2 >= a.g.n[2]) { return; }
+	const int lo = a.axis == 0 ? a.x_begin : 0;
+	const int hi = a.axis == 0 ? a.x_end : a.g.n[1];
+	const int s_begin = lo + blockIdx.x * seg;
+	const int s_end = min(hi, s_begin + seg);
+	const int perp = a.axis == 0 ? (int) blockIdx.z : (int) blockIdx.z + a.x_begin;
+	stage_thread_march<P, BS>(a, perp, i2, s_begin, s_end);
+}
+
+static int env_int(const char* name, int dflt) {
+	const char* v = getenv(name);
+	return v ? atoi(v) : dflt;
+}
+
+template<class P, int BS>
+static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
+	static const int impl = env_int("GCMB_STAGE_IMPL", 1);   // 0 = direct, 1 = march on strided axes
+	static const int seg_env = env_int("GCMB_MARCH_SEG", 256);
+	if (impl == 1 && a.axis != 2) {
+		const int len = a.axis == 0 ? a.x_end - a.x_begin : a.g.n[1];
+		const int seg = seg_env < 1 ? len : seg_env;
+		const int perp = a.axis == 0 ? a.g.n[1] : a.x_end - a.x_begin;
+		const dim3 grid((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZT - 1) / ZT), (unsigned) perp);
+		auto kernel = k_stage_march<P, BS>;
+		GCMB_LAUNCH(kernel, grid, ZT, stream, a, seg);
+	} else {
+		auto kernel = k_stage_direct<P, BS>;
+		GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a);
+	}
+}
+
+template<int M>
+static void launch_dense(const StageArgs& a, cudaStream_t stream) {
+	auto kernel = k_stage_dense<M>;
+	GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a);
+}
+
+#define GCMB_PATTERN(NAME, MM, SGN, UM, U1M) \
+	{#NAME, MM, SGN, UM, U1M, &launch_sparse<Pat_##NAME, 1>, &launch_sparse<Pat_##NAME, 2>},
+static const PatternInfo g_patterns[] = {
+#include "patterns.inc"
+};
+#undef GCMB_PATTERN
+
+int pattern_count() { return (int) (sizeof(g_patterns) / sizeof(g_patterns[0])); }
+const PatternInfo& pattern(int i) { return g_patterns[i]; }
+
+StageLauncher dense_launcher(int M) {
+	switch (M) {
+		case 2: return &launch_dense<2>;
+		case 3: return &launch_dense<3>;
+		case 4: return &launch_dense<4>;
+		case 5: return &launch_dense<5>;
+		case 9: return &launch_dense<9>;
+		default: return nullptr;
+	}
+}
+
+}  // namespace gcmb

@@ -1,0 +1,372 @@
+// gcm_b200 host layer: the reference's Task / Engine entry points on top of the C ABI.
+//
+// Mirrors the public interface of libgcm for the cubic hot path so that a user of the reference can
+// switch by changing the namespace:  gcm::Task -> gcmb::Task  (reference util/task/Task.hpp:24-234),
+// gcm::createEngine -> gcmb::createEngine (engine/EngineFactory.hpp:11-36), AbstractEngine::run()
+// (engine/AbstractEngine.cpp:30-46), cubic::Engine<D>::getMesh(id)->pde(it) (engine/cubic/Engine.hpp:34-36,
+// engine/cubic/DefaultMesh.hpp:70-81).  All grid data lives on the GPU; the host keeps only the task
+// description, the per-material eigen-systems and lazily downloaded copies for accessors/snapshots.
+#pragma once
+#include <array>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gcm_b200.h"
+
+namespace gcmb {
+
+typedef double real;
+typedef std::array<real, 3> Real3;
+typedef size_t GridId;
+
+/// thrown for every failure; code() follows gcm::Exception codes (Exception.hpp:94-126)
+class Exception : public std::runtime_error {
+public:
+	Exception(int code, const std::string& what) : std::runtime_error(what), code_(code) { }
+	int code() const { return code_; }
+private:
+	int code_;
+};
+
+// ---- enumerations: same names and order as reference util/Enum.hpp ---------------------------
+struct PhysicalQuantities {
+	enum class T { VELOCITY, FORCE, Vx, Vy, Vz, Sxx, Sxy, Sxz, Syy, Syz, Szz, RHO, PRESSURE, DAMAGE_MEASURE };
+};
+struct Waves { enum class T { P_FORWARD, P_BACKWARD, S1_FORWARD, S1_BACKWARD, S2_FORWARD, S2_BACKWARD }; };
+struct ContactConditions { enum class T { ADHESION, SLIDE }; };
+struct Materials { enum class T { ISOTROPIC, ORTHOTROPIC }; };
+struct Grids { enum class T { CUBIC, SIMPLEX }; };
+struct Models { enum class T { ELASTIC, ACOUSTIC, MAXWELL_ACOUSTIC }; };
+struct Snapshotters { enum class T { VTK, DETECTOR, SLICESNAP }; };
+struct Odes { enum class T { MAXWELL_VISCOSITY, CONTINUAL_DAMAGE, IDEAL_PLASTIC_FLOW }; };
+
+// ---- areas (reference util/math/Area.hpp) ------------------------------------------------------
+struct Area {
+	virtual ~Area() { }
+	virtual bool contains(const Real3& coords) const = 0;
+	virtual void move(const Real3& shift) = 0;
+	/// description for the device-side evaluation: kind + parameters (see gcm_b200.h)
+	virtual int deviceKind() const = 0;
+	virtual std::vector<double> deviceParams() const = 0;
+};
+struct InfiniteArea : Area {
+	bool contains(const Real3&) const override { return true; }
+	void move(const Real3&) override { }
+	int deviceKind() const override { return 0; }
+	std::vector<double> deviceParams() const override { return {}; }
+};
+struct AxisAlignedBoxArea : Area {
+	AxisAlignedBoxArea(const Real3& min_, const Real3& max_);
+	bool contains(const Real3& c) const override;
+	void move(const Real3& shift) override;
+	int deviceKind() const override { return 1; }
+	std::vector<double> deviceParams() const override;
+	Real3 getMin() const { return min; }
+	Real3 getMax() const { return max; }
+private:
+	Real3 min, max;
+};
+struct SphereArea : Area {
+	SphereArea(const real& radius_, const Real3& center_);
+	bool contains(const Real3& c) const override;
+	void move(const Real3& shift) override;
+	int deviceKind() const override { return 2; }
+	std::vector<double> deviceParams() const override;
+private:
+	real radius;
+	Real3 center;
+};
+struct StraightBoundedCylinderArea : Area {
+	StraightBoundedCylinderArea(const real& radius_, const Real3& begin_, const Real3& end_);
+	bool contains(const Real3& c) const override;
+	void move(const Real3& shift) override;
+	int deviceKind() const override { return 3; }
+	std::vector<double> deviceParams() const override;
+private:
+	real radius;
+	Real3 begin, end, axis;
+};
+
+// ---- materials (reference rheology/materials/*.hpp) --------------------------------------------
+struct AbstractMaterial {
+	virtual ~AbstractMaterial() { }
+	int materialNumber = 0;
+};
+struct IsotropicMaterial : AbstractMaterial {
+	static const Materials::T Type = Materials::T::ISOTROPIC;
+	real rho = 0, lambda = 0, mu = 0, yieldStrength = 0, continualDamageParameter = 0, tau0 = 0;
+	IsotropicMaterial(real rho_ = 0, real lambda_ = 0, real mu_ = 0, real yieldStrength_ = 0,
+	                  real continualDamageParameter_ = 0, int materialNumber_ = 0, real tau0_ = 0);
+};
+struct OrthotropicMaterial : AbstractMaterial {
+	static const Materials::T Type = Materials::T::ORTHOTROPIC;
+	real rho = 0;
+	/// c11, c12, c13, c22, c23, c33, c44, c55, c66
+	real c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	real yieldStrength = 0, continualDamageParameter = 0, tau0 = 0;
+	Real3 anglesOfRotation = {{0, 0, 0}};
+	OrthotropicMaterial(real rho_ = 0, std::initializer_list<real> c_ = {0, 0, 0, 0, 0, 0, 0, 0, 0},
+	                    real yieldStrength_ = 0, real continualDamageParameter_ = 0,
+	                    Real3 phi = {{0, 0, 0}}, real tau0_ = 0);
+	explicit OrthotropicMaterial(const IsotropicMaterial& isotropic);
+};
+
+// ---- eigen-systems (reference util/math/GridCharacteristicMethod.hpp:33-111) -------------------
+/// U, U1 row-major [D][M*M]; L [D][M] -- directly the layout gcmb_cubic_set_materials takes
+struct GcmMatrices {
+	int D = 0, M = 0;
+	std::vector<real> U, U1, L;
+	real getMaximalEigenvalue() const;
+	const real* u(int s) const { return U.data() + (size_t) s * M * M; }
+	const real* u1(int s) const { return U1.data() + (size_t) s * M * M; }
+	const real* l(int s) const { return L.data() + (size_t) s * M; }
+	/// U*U1 == I etc. within eps; throws Exception like checkDecomposition
+	void checkDecomposition(real eps) const;
+};
+int pdeSize(Models::T model, int D);
+/// position of sigma_ij in the elastic PDE vector (velocities first, then the packed upper triangle)
+int sigmaComponent(int D, int i, int j);
+/// Model::constructGcmMatrices in the global basis (reference ElasticModel.hpp:56-65,
+/// ElasticModel3D.cpp:432-448, ElasticModel2D.cpp:79-91, AcousticModel.hpp:57-65)
+GcmMatrices constructGcmMatrices(Models::T model, int D, const AbstractMaterial& material);
+/// column of U1 holding the given wave (reference rheology/models/Model.cpp:6-63)
+int waveColumn(Models::T model, Materials::T material, int D, Waves::T wave);
+/// component index, or GCMB_Q_PRESSURE_TRACE; throws if the model has no such quantity
+int quantityCode(Models::T model, int D, PhysicalQuantities::T q);
+
+// ---- Task: field-for-field the reference's (util/task/Task.hpp:24-234) --------------------------
+struct Task {
+	typedef std::function<real(real)> TimeDependency;
+
+	struct Body {
+		Materials::T materialId;
+		Models::T modelId;
+		std::vector<Odes::T> odes;
+	};
+	std::map<size_t, Body> bodies;
+
+	struct GlobalSettings {
+		int dimensionality = 0;
+		Grids::T gridId = Grids::T::CUBIC;
+		bool forceSequence = false;
+		std::vector<Snapshotters::T> snapshottersId;
+		std::string outputDirectory = "";
+		real CourantNumber = 0;
+		int numberOfSnaps = 0;
+		int stepsPerSnap = 1;
+		real requiredTime = 0;
+		bool verboseTimeSteps = true;
+	} globalSettings;
+
+	struct CubicGrid {
+		struct Cube {
+			std::vector<int> sizes;
+			std::vector<int> start;
+		};
+		std::vector<real> h;
+		int borderSize = 0;
+		std::map<size_t, Cube> cubics;
+	} cubicGrid;
+
+	struct MaterialCondition {
+		typedef std::shared_ptr<AbstractMaterial> Material;
+		enum class Type { BY_AREAS, BY_BODIES } type = Type::BY_AREAS;
+		struct ByAreas {
+			Material defaultMaterial;
+			struct Inhomogenity {
+				std::shared_ptr<Area> area;
+				Material material;
+			};
+			std::vector<Inhomogenity> materials;
+		} byAreas;
+		struct ByBodies {
+			typedef size_t BodyId;
+			std::map<BodyId, Material> bodyMaterialMap;
+		} byBodies;
+	} materialConditions;
+
+	struct InitialCondition {
+		struct Vector {
+			std::shared_ptr<Area> area;
+			std::vector<real> list;
+		};
+		std::vector<Vector> vectors;
+		struct Wave {
+			std::shared_ptr<Area> area;
+			Waves::T waveType;
+			int direction;
+			PhysicalQuantities::T quantity;
+			real quantityValue;
+		};
+		std::vector<Wave> waves;
+		struct Quantity {
+			std::shared_ptr<Area> area;
+			PhysicalQuantities::T physicalQuantity;
+			real value;
+		};
+		std::vector<Quantity> quantities;
+	} initialCondition;
+
+	struct CubicBorderCondition {
+		int direction;
+		std::shared_ptr<Area> area;
+		typedef std::map<PhysicalQuantities::T, TimeDependency> Values;
+		Values values;
+	};
+	std::map<size_t, std::vector<CubicBorderCondition>> cubicBorderConditions;
+
+	struct ContactCondition {
+		ContactConditions::T defaultCondition = ContactConditions::T::ADHESION;
+	} contactCondition;
+
+	struct VtkSnapshotter {
+		std::vector<PhysicalQuantities::T> quantitiesToSnap;
+	} vtkSnapshotter;
+
+	struct Detector {
+		std::vector<PhysicalQuantities::T> quantities;
+		std::shared_ptr<Area> area;
+		size_t gridId = 0;
+	} detector;
+
+	/// gcm_b200 extension: CUDA device to run on (default 0) and slab decomposition along x
+	struct Device {
+		int device = 0;
+		int slabRank = 0, slabCount = 1;   ///< this process owns slab slabRank of slabCount
+		const void* ncclUniqueId = nullptr; ///< 128 bytes shared by all slabs when slabCount > 1
+	} device;
+};
+
+// ---- engine ---------------------------------------------------------------------------------
+/// time and step of the running engine (reference engine/GlobalVariables.hpp:16-40)
+struct Clock {
+	static real Time() { return time; }
+	static real TimeStep() { return timeStep; }
+private:
+	static real time, timeStep;
+	static void setZero() { time = timeStep = 0; }
+	static void tickTack() { time += timeStep; }
+	friend class AbstractEngine;
+};
+
+class AbstractEngine {
+public:
+	AbstractEngine(const Task& task);
+	virtual ~AbstractEngine() { }
+	AbstractEngine(const AbstractEngine&) = delete;
+	AbstractEngine& operator=(const AbstractEngine&) = delete;
+	/// perform all calculations (reference engine/AbstractEngine.cpp:30-46)
+	void run();
+	/// steps performed by run() so far
+	int stepsDone() const { return step; }
+protected:
+	const real CourantNumber = 0;
+	real requiredTime = 0;
+	bool verboseTimeSteps = true;
+	int step = 0;
+	void afterConstruction(const Task& task);
+	virtual void nextTimeStep() = 0;
+	virtual real estimateTimeStep() = 0;
+	virtual void writeSnapshots(const int step) = 0;
+};
+
+namespace cubic {
+
+/// host view of one body (reference cubic/AbstractMesh.hpp + DefaultMesh.hpp accessors)
+class Mesh {
+public:
+	typedef std::array<int, 3> Iterator;  ///< only the first D entries are used
+	GridId id = 0;
+	int D = 0, M = 0, borderSize = 0;
+	std::array<int, 3> sizes = {{1, 1, 1}}, start = {{0, 0, 0}};
+	std::array<real, 3> h = {{1, 1, 1}};
+	Models::T modelType = Models::T::ELASTIC;
+	Materials::T materialType = Materials::T::ISOTROPIC;
+
+	~Mesh();
+	/// PDE vector (M values) of a real node; downloads the current layer on first use after a step
+	const real* pde(const Iterator& it) const;
+	/// all real nodes, x slowest, M per node
+	const std::vector<real>& pdeRealNodes() const;
+	Real3 coords(const Iterator& it) const;
+	size_t sizeOfRealNodes() const;
+	real getMaximalEigenvalue() const { return maximalEigenvalue; }
+	real getMinimalSpatialStep() const;
+	gcmb_body* handle() const { return body; }
+	const std::vector<std::shared_ptr<AbstractMaterial>>& tableMaterials() const { return materials; }
+	const std::vector<GcmMatrices>& tableMatrices() const { return matrices; }
+	void invalidateHostCopy() const { hostValid = false; }
+
+	// filled by the engine
+	gcmb_body* body = nullptr;
+	real maximalEigenvalue = 0;
+	std::vector<std::shared_ptr<AbstractMaterial>> materials;  ///< one per table id
+	std::vector<GcmMatrices> matrices;
+private:
+	mutable std::vector<real> host;
+	mutable bool hostValid = false;
+};
+
+class EngineBase : public AbstractEngine {
+public:
+	EngineBase(const Task& task, int dimensionality);
+	virtual ~EngineBase();
+	std::shared_ptr<const Mesh> getMesh(const GridId gridId) const;
+	/// detector history written so far: (time, value) as the SliceSnapshotter records them
+	const std::vector<std::pair<real, float>>& seismogram() const { return seismo; }
+	gcmb_ctx* context() const { return ctx; }
+protected:
+	void nextTimeStep() override;
+	real estimateTimeStep() override;
+	void writeSnapshots(const int step) override;
+private:
+	struct Contact {
+		GridId neighborId;
+		int direction;
+		int boxA[3], boxB[3], extent[3];
+	};
+	struct Border {
+		int direction;
+		std::vector<Task::TimeDependency> values;  ///< std::map order
+	};
+	struct Body {
+		std::shared_ptr<Mesh> mesh;
+		std::vector<Contact> contacts;
+		std::vector<Border> borders;
+		std::vector<Odes::T> odes;
+	};
+	int D;
+	gcmb_ctx* ctx = nullptr;
+	std::vector<Body> bodies;
+	Task taskCopy;
+	std::vector<std::pair<real, float>> seismo;
+	int slabRank = 0, slabCount = 1;
+
+	Body& getBody(const GridId id);
+	const Body& getBody(const GridId id) const;
+	void createGridsAndContacts(const Task& task);
+	void setUpPde(const Task& task, Body& body);
+	void setUpBorders(const Task& task, Body& body);
+	void sliceSnapshot(const int step);
+};
+
+template<int Dimensionality>
+class Engine : public EngineBase {
+public:
+	static const int DIMENSIONALITY = Dimensionality;
+	Engine(const Task& task) : EngineBase(task, Dimensionality) { }
+};
+
+}  // namespace cubic
+
+/// reference engine/EngineFactory.hpp:11-36 (cubic grids only: the simplex engine is separate)
+std::shared_ptr<AbstractEngine> createEngine(const Task& task);
+
+/// plain-text task files (DESIGN.md "task files")
+Task parseTaskText(const std::string& text);
+
+}  // namespace gcmb

@@ -1,0 +1,192 @@
+// Plain-text task files -> gcmb::Task.  One statement per line, '#' starts a comment:
+//   dimensionality D | courant C | border_size B | h h0 [h1 [h2]] | steps N | required_time T
+//   body ID (elastic|acoustic) (isotropic|orthotropic) sizes n.. start s.. [ode maxwell]
+//   material default MATERIAL | material area AREA MATERIAL | material body ID MATERIAL
+//   initial quantity Q value AREA | initial wave W direction Q value AREA
+//   border ID direction AREA {Q (const c | sin amp omega)}...
+//   detector ID Q AREA [output-directory]
+//   AREA = infinite | box x0 y0 z0 x1 y1 z1 | sphere r cx cy cz | cylinder r bx by bz ex ey ez
+//   MATERIAL = isotropic rho lambda mu [tau0 t] | orthotropic rho c11 c12 c13 c22 c23 c33 c44 c55 c66 [tau0 t]
+// The test suite feeds the same files to the unmodified reference.
+#include <cmath>
+#include <sstream>
+
+#include "gcmb_host.hpp"
+
+namespace gcmb {
+namespace {
+
+struct Words {
+	std::vector<std::string> w;
+	size_t pos = 0;
+	bool done() const { return pos >= w.size(); }
+	const std::string& next() {
+		if (done()) { throw Exception(GCMB_E_INVALID_ARG, "task text: unexpected end of line"); }
+		return w[pos++];
+	}
+	std::string peek() const { return done() ? std::string() : w[pos]; }
+	real num() { return std::stod(next()); }
+	int inum() { return std::stoi(next()); }
+	Real3 vec() { Real3 v; for (int i = 0; i < 3; i++) { v[(size_t) i] = num(); } return v; }
+};
+
+std::shared_ptr<Area> area(Words& t) {
+	const std::string kind = t.next();
+	if (kind == "infinite") { return std::make_shared<InfiniteArea>(); }
+	if (kind == "box") { const Real3 a = t.vec(), b = t.vec(); return std::make_shared<AxisAlignedBoxArea>(a, b); }
+	if (kind == "sphere") { const real r = t.num(); return std::make_shared<SphereArea>(r, t.vec()); }
+	if (kind == "cylinder") {
+		const real r = t.num();
+		const Real3 a = t.vec(), b = t.vec();
+		return std::make_shared<StraightBoundedCylinderArea>(r, a, b);
+	}
+	throw Exception(GCMB_E_INVALID_ARG, "task text: unknown area " + kind);
+}
+
+Task::MaterialCondition::Material material(Words& t) {
+	const std::string kind = t.next();
+	Task::MaterialCondition::Material ans;
+	if (kind == "isotropic") {
+		const real rho = t.num(), la = t.num(), mu = t.num();
+		real tau0 = 0;
+		if (t.peek() == "tau0") { t.next(); tau0 = t.num(); }
+		ans = std::make_shared<IsotropicMaterial>(rho, la, mu, 0, 0, 0, tau0);
+	} else if (kind == "orthotropic") {
+		const real rho = t.num();
+		real c[9];
+		for (real& x : c) { x = t.num(); }
+		real tau0 = 0;
+		if (t.peek() == "tau0") { t.next(); tau0 = t.num(); }
+		ans = std::make_shared<OrthotropicMaterial>(rho,
+				std::initializer_list<real>{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]},
+				0, 0, Real3{{0, 0, 0}}, tau0);
+	} else {
+		throw Exception(GCMB_E_INVALID_ARG, "task text: unknown material " + kind);
+	}
+	return ans;
+}
+
+PhysicalQuantities::T quantity(const std::string& s) {
+	typedef PhysicalQuantities::T Q;
+	static const std::map<std::string, Q> names = {
+			{"Vx", Q::Vx}, {"Vy", Q::Vy}, {"Vz", Q::Vz}, {"Sxx", Q::Sxx}, {"Sxy", Q::Sxy}, {"Sxz", Q::Sxz},
+			{"Syy", Q::Syy}, {"Syz", Q::Syz}, {"Szz", Q::Szz}, {"PRESSURE", Q::PRESSURE}};
+	const auto it = names.find(s);
+	if (it == names.end()) { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown quantity " + s); }
+	return it->second;
+}
+
+Waves::T wave(const std::string& s) {
+	typedef Waves::T W;
+	static const std::map<std::string, W> names = {
+			{"P_FORWARD", W::P_FORWARD}, {"P_BACKWARD", W::P_BACKWARD}, {"S1_FORWARD", W::S1_FORWARD},
+			{"S1_BACKWARD", W::S1_BACKWARD}, {"S2_FORWARD", W::S2_FORWARD}, {"S2_BACKWARD", W::S2_BACKWARD}};
+	const auto it = names.find(s);
+	if (it == names.end()) { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown wave " + s); }
+	return it->second;
+}
+
+Task::TimeDependency timeDependency(Words& t) {
+	const std::string kind = t.next();
+	if (kind == "const") { const real c = t.num(); return [c](real) { return c; }; }
+	if (kind == "sin") {
+		const real amp = t.num(), omega = t.num();
+		return [amp, omega](real time) { return amp * std::sin(omega * time); };
+	}
+	throw Exception(GCMB_E_INVALID_ARG, "task text: unknown time dependency " + kind);
+}
+
+}  // namespace
+
+Task parseTaskText(const std::string& text) {
+	Task task;
+	task.globalSettings.gridId = Grids::T::CUBIC;
+	task.globalSettings.verboseTimeSteps = false;
+	task.globalSettings.stepsPerSnap = 1;
+	std::istringstream in(text);
+	std::string line;
+	while (std::getline(in, line)) {
+		const size_t hash = line.find('#');
+		if (hash != std::string::npos) { line.resize(hash); }
+		std::istringstream ls(line);
+		Words t;
+		for (std::string w; ls >> w;) { t.w.push_back(w); }
+		if (t.done()) { continue; }
+		const std::string key = t.next();
+		const int D = task.globalSettings.dimensionality;
+		if (key == "dimensionality") { task.globalSettings.dimensionality = t.inum(); }
+		else if (key == "courant") { task.globalSettings.CourantNumber = t.num(); }
+		else if (key == "border_size") { task.cubicGrid.borderSize = t.inum(); }
+		else if (key == "h") { task.cubicGrid.h.clear(); while (!t.done()) { task.cubicGrid.h.push_back(t.num()); } }
+		else if (key == "steps") { task.globalSettings.numberOfSnaps = t.inum(); }
+		else if (key == "required_time") { task.globalSettings.numberOfSnaps = 0; task.globalSettings.requiredTime = t.num(); }
+		else if (key == "body") {
+			const size_t id = (size_t) t.inum();
+			const std::string model = t.next(), mat = t.next();
+			Task::Body body;
+			body.modelId = model == "acoustic" ? Models::T::ACOUSTIC : Models::T::ELASTIC;
+			body.materialId = mat == "orthotropic" ? Materials::T::ORTHOTROPIC : Materials::T::ISOTROPIC;
+			Task::CubicGrid::Cube cube;
+			while (!t.done()) {
+				const std::string sub = t.next();
+				if (sub == "sizes") { for (int i = 0; i < D; i++) { cube.sizes.push_back(t.inum()); } }
+				else if (sub == "start") { for (int i = 0; i < D; i++) { cube.start.push_back(t.inum()); } }
+				else if (sub == "ode") { t.next(); body.odes.push_back(Odes::T::MAXWELL_VISCOSITY); }
+				else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown body option " + sub); }
+			}
+			task.bodies[id] = body;
+			task.cubicGrid.cubics[id] = cube;
+		} else if (key == "material") {
+			const std::string how = t.next();
+			if (how == "default") { task.materialConditions.byAreas.defaultMaterial = material(t); }
+			else if (how == "area") {
+				Task::MaterialCondition::ByAreas::Inhomogenity inh;
+				inh.area = area(t);
+				inh.material = material(t);
+				task.materialConditions.byAreas.materials.push_back(inh);
+			} else if (how == "body") {
+				task.materialConditions.type = Task::MaterialCondition::Type::BY_BODIES;
+				const size_t id = (size_t) t.inum();
+				task.materialConditions.byBodies.bodyMaterialMap[id] = material(t);
+			} else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown material clause " + how); }
+		} else if (key == "initial") {
+			const std::string what = t.next();
+			if (what == "quantity") {
+				Task::InitialCondition::Quantity q;
+				q.physicalQuantity = quantity(t.next());
+				q.value = t.num();
+				q.area = area(t);
+				task.initialCondition.quantities.push_back(q);
+			} else if (what == "wave") {
+				Task::InitialCondition::Wave w;
+				w.waveType = wave(t.next());
+				w.direction = t.inum();
+				w.quantity = quantity(t.next());
+				w.quantityValue = t.num();
+				w.area = area(t);
+				task.initialCondition.waves.push_back(w);
+			} else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown initial clause " + what); }
+		} else if (key == "border") {
+			const size_t id = (size_t) t.inum();
+			Task::CubicBorderCondition bc;
+			bc.direction = t.inum();
+			bc.area = area(t);
+			while (!t.done()) {
+				const PhysicalQuantities::T q = quantity(t.next());
+				bc.values[q] = timeDependency(t);
+			}
+			task.cubicBorderConditions[id].push_back(bc);
+		} else if (key == "detector") {
+			task.detector.gridId = (size_t) t.inum();
+			task.detector.quantities = {quantity(t.next())};
+			task.detector.area = area(t);
+			task.globalSettings.snapshottersId.push_back(Snapshotters::T::SLICESNAP);
+			task.globalSettings.outputDirectory = t.done() ? "" : t.next();
+		} else {
+			throw Exception(GCMB_E_INVALID_ARG, "task text: unknown key " + key);
+		}
+	}
+	return task;
+}
+
+}  // namespace gcmb

@@ -1,0 +1,164 @@
+/*
+ * gcm_b200 — C ABI of the B200-native grid-characteristic time-stepping engine.
+ *
+ * This is the drop-in boundary for the hot path of AlexanderKazakov/gcm (libgcm): everything
+ * cubic::Engine<D>::nextTimeStep (reference src/libgcm/engine/cubic/Engine.cpp:92-121) calls through its
+ * per-body virtual interfaces is available here as a plain-C entry point working on device-resident
+ * state.  No torch / C++ types cross this boundary: opaque handles, plain pointers and sizes.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a GCMB_E_* code; gcmb_last_error() gives the message
+ *     (codes follow gcm::Exception, reference util/infrastructure/Exception.hpp:94-126);
+ *   - one host thread per context; all device work is enqueued on the context's CUDA stream and is
+ *     asynchronous unless the comment says "sync";
+ *   - host-side array layout is the reference's: nodes x-slowest / last axis fastest, `border_size`
+ *     ghost nodes on both sides of every axis, M reals per node (array of structures)
+ *     (reference grid/cubic/CubicGrid.hpp:141-147,204-226);
+ *   - there is NO CPU fallback: without a CUDA device gcmb_create fails with GCMB_E_NO_DEVICE.
+ */
+#ifndef GCM_B200_H
+#define GCM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCMB_MAX_M 9       /* largest PDE vector: 3-D velocity + symmetric stress */
+#define GCMB_MAX_BORDER 8  /* largest border size (= interpolation order) */
+#define GCMB_MAX_TABLES 255
+
+enum {
+	GCMB_OK = 0,
+	GCMB_E_INVALID_ARG = 1,  /* gcm::Exception::INVALID_ARG */
+	GCMB_E_INVALID_OP = 3,   /* gcm::Exception::INVALID_OP */
+	GCMB_E_BAD_MESH = 4,     /* gcm::Exception::BAD_MESH */
+	GCMB_E_UNSUPPORTED = -1, /* gcm::Exception::UNSUPPORTED */
+	GCMB_E_CUDA = 100,
+	GCMB_E_NO_DEVICE = 101,
+	GCMB_E_NCCL = 102,
+};
+
+/* quantity codes (border conditions, detectors): 0..M-1 selects a PDE component;
+ * GCMB_Q_PRESSURE_TRACE is VelocitySigmaVariables::Get/SetPressure
+ * (reference rheology/variables/VelocitySigmaVariables.hpp:100-111: set clears the vector first). */
+#define GCMB_Q_PRESSURE_TRACE (-1)
+
+typedef struct gcmb_ctx gcmb_ctx;
+typedef struct gcmb_body gcmb_body;
+
+const char* gcmb_last_error(void);
+const char* gcmb_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* real_bytes: 8 (fp64, the reference's `real`, util/infrastructure/Types.hpp:8-14).  4 is reserved. */
+int gcmb_create(int device, int real_bytes, gcmb_ctx** out);
+void gcmb_destroy(gcmb_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the own stream */
+int gcmb_set_stream(gcmb_ctx* ctx, void* cuda_stream);
+int gcmb_sync(gcmb_ctx* ctx); /* sync */
+/* device-side timing of everything enqueued between start and stop (CUDA events on the context's
+ * stream); stop is sync and returns milliseconds */
+int gcmb_timer_start(gcmb_ctx* ctx);
+int gcmb_timer_stop(gcmb_ctx* ctx, float* ms);
+/* per-kernel-class accumulated device time (CUDA events around every launch when enabled):
+ * classes: 0..2 stage along internal axis 0,1,2 (2 = contiguous axis); 3 border; 4 contact; 5 ode;
+ * 6 halo pack/unpack; 7 seismo.  get is sync. */
+int gcmb_profile_enable(gcmb_ctx* ctx, int on);
+int gcmb_profile_get(gcmb_ctx* ctx, int n_classes, double* ms, long long* launches);
+/* number of kernels of this library launched on the context since creation */
+long long gcmb_launch_count(gcmb_ctx* ctx);
+/* bytes of device memory currently held by the context's bodies */
+size_t gcmb_device_bytes(gcmb_ctx* ctx);
+
+/* ---- cubic body = one CubicGrid + DefaultMesh storage (engine/cubic/DefaultMesh.hpp:142-167) -- */
+/* D in 1..3, M <= GCMB_MAX_M, sizes/start/h have D entries, 1 <= border_size <= GCMB_MAX_BORDER,
+ * sizes[i] >= border_size (CubicGrid.hpp:186-199).  Both time layers start zeroed. */
+int gcmb_cubic_body_create(gcmb_ctx* ctx, int D, int M, const int* sizes, const int* start,
+                           const double* h, int border_size, gcmb_body** out);
+void gcmb_cubic_body_destroy(gcmb_body* body);
+
+/* current time layer <-> host array in the reference layout.  with_ghosts=1: all
+ * prod(sizes+2*border) nodes; 0: real nodes only (prod(sizes)).  Both sync. */
+int gcmb_cubic_upload_state(gcmb_body* body, const void* aos_pde, int with_ghosts);
+int gcmb_cubic_download_state(gcmb_body* body, void* aos_pde, int with_ghosts);
+
+/* Eigen-system tables of the materials present in the body (GcmMatrices, reference
+ * util/math/GridCharacteristicMethod.hpp:33-111): U, U1 are [n_tables][D][M][M] row-major,
+ * L is [n_tables][D][M].  node_table_id: one byte per REAL node (x slowest), NULL = all nodes use
+ * table 0 (MaterialsCondition.hpp:23-36).  The library analyses the sparsity of the tables and picks
+ * the specialised stage kernels (or the dense one).  sync. */
+int gcmb_cubic_set_materials(gcmb_body* body, int n_tables, const double* U, const double* U1,
+                             const double* L, const uint8_t* node_table_id);
+
+/* Device-side evaluation of Area-based setup (util/math/Area.hpp), so that large grids never exist
+ * on the host.  area_kind: 0 infinite, 1 axis-aligned box {min[3],max[3]}, 2 sphere {r, c[3]},
+ * 3 straight bounded cylinder {r, begin[3], end[3]}; params as listed. */
+int gcmb_cubic_assign_table_in_area(gcmb_body* body, int table_id, int area_kind, const double* params);
+/* pde(node) += vector for real nodes inside the area (InitialCondition.hpp:28-35) */
+int gcmb_cubic_add_vector_in_area(gcmb_body* body, const double* vector_M, int area_kind,
+                                  const double* params);
+
+/* ---- border conditions = ghost mirroring (engine/cubic/BorderConditions.hpp:46-114) ----------- */
+/* Registers condition number `cond` (conditions are applied in increasing `cond`, later ones
+ * overwrite): direction, masks over the left/right face nodes (slice(dir,0) / slice(dir,size-1) in
+ * x-slowest order, 1 = node inside the condition's area; NULL = no node), the quantity codes in the
+ * reference's std::map order.  sync. */
+int gcmb_cubic_border_set(gcmb_body* body, int cond, int dir, const uint8_t* left_mask,
+                          const uint8_t* right_mask, int n_q, const int* q_codes);
+/* same, the masks evaluated on the device from an Area.  sides: bit 0 = left face, bit 1 = right face
+ * (3 = both, the reference's behaviour; slabs of a decomposed grid switch off their inner x faces) */
+int gcmb_cubic_border_set_area(gcmb_body* body, int cond, int dir, int sides, int area_kind,
+                               const double* params, int n_q, const int* q_codes);
+/* apply all registered conditions of direction `dir`; values: for every registered condition of that
+ * direction in order, its n_q border values b_q(t_n) evaluated by the caller (time dependencies are
+ * host functors in the reference); n_values = total count, checked. */
+int gcmb_cubic_border_apply(gcmb_body* body, int dir, int n_values, const double* values);
+
+/* ---- contact = ghost copy from the neighbour body (engine/cubic/ContactConditions.hpp:56-68) --- */
+/* boxes in LOCAL node indices of each body (ghosts are negative / >= size), `extent` nodes per axis */
+int gcmb_cubic_contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_min,
+                             const int* boxB_min, const int* extent);
+
+/* ---- one stage of the dimensional splitting (engine/cubic/GridCharacteristicMethod.hpp:42-87) -- */
+/* computes the next time layer of all real nodes along reference direction `dir` and swaps the two
+ * layers, like cubic/Engine.cpp:110-111 */
+int gcmb_cubic_stage(gcmb_body* body, int dir, double tau);
+
+/* ---- Maxwell viscosity (rheology/ode/Ode.hpp:28-38): sigma *= decay[table of the node];
+ * decay = exp(-tau/tau0) is evaluated by the caller with the host libm, like the reference ------- */
+int gcmb_cubic_ode_maxwell(gcmb_body* body, const double* decay_per_table);
+
+/* ---- seismogram taps (util/snapshot/SliceSnapshotter.hpp:44-82) ------------------------------- */
+/* register the detector: nodes of the right border of the last axis inside the area */
+int gcmb_cubic_detector_set_area(gcmb_body* body, int q_code, int area_kind, const double* params);
+int gcmb_cubic_detector_set_mask(gcmb_body* body, int q_code, const uint8_t* face_mask);
+/* sum of the quantity over the detector nodes and their number (the reference writes sum/count);
+ * n_line values of component `line_comp` along the last axis through the centre node (sizes/2)
+ * -> line (may be NULL).  sync. */
+int gcmb_cubic_seismo(gcmb_body* body, double* sum, long long* count, int line_comp, double* line,
+                      int n_line);
+
+/* ---- multi-GPU: slab decomposition along x (the slowest axis), one process per GPU ------------- */
+/* NCCL communicator shared by all slabs: rank 0 makes the id (128 bytes), the launcher distributes it */
+int gcmb_comm_unique_id(void* id128);
+int gcmb_comm_init(gcmb_ctx* ctx, int n_ranks, int rank, const void* id128);
+/* exchange `border_size` x-planes with the slab neighbours (rank-1 on the left, rank+1 on the right,
+ * none at the ends): my ghost planes <- neighbour's outermost real planes.  Equivalent to two
+ * ContactCopiers between neighbouring slabs; call before the direction-0 stage. */
+int gcmb_cubic_halo_exchange(gcmb_body* body);
+/* in-place sum over all ranks of n doubles held on the host (detector sums of decomposed grids). sync */
+int gcmb_comm_allreduce_sum(gcmb_ctx* ctx, double* host_values, int n);
+
+/* ---- checksum of the current layer over real nodes: sum_nodes sum_i (i+1)*u_i (sync) ---------- */
+int gcmb_cubic_checksum(gcmb_body* body, double* out);
+
+/* description of the stage kernel chosen for a direction (for logs/tests), e.g. "sparse:elastic3d_iso_x/bs2" */
+const char* gcmb_cubic_stage_kernel_name(gcmb_body* body, int dir);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCM_B200_H */

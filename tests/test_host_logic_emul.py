@@ -1,0 +1,104 @@
+"""Host logic + kernel index math on the build machine (no GPU).
+
+Runs the product's host engine (gcm_b200/host) against tests/emul's stepping harness — the product's own
+CUDA sources executed thread by thread on the CPU — and requires bit-for-bit agreement with the outputs of
+the unmodified reference (tests/golden).  This is NOT the parity claim for the CUDA path (that is
+tests/test_gpu_parity.py, marked gpu); it proves the host layer, the table builder, the sparsity-pattern
+selection and the per-thread index arithmetic before GPU time is spent."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import compare_with_golden, emul_library, golden, run_engine
+from scenarios import SCENARIOS
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emul_library()
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_engine_matches_reference_bitwise(lib, name):
+    eng, _ = compare_with_golden(lib, name, SCENARIOS[name])
+    eng.close()
+
+
+EXPECTED_KERNELS = {
+    "elastic3d_iso": ["sparse:elastic3d_iso_x/bs2", "sparse:elastic3d_iso_y/bs2", "sparse:elastic3d_iso_z/bs2"],
+    "elastic3d_iso_bs1": ["sparse:elastic3d_iso_x/bs1", "sparse:elastic3d_iso_y/bs1", "sparse:elastic3d_iso_z/bs1"],
+    "elastic3d_layers": ["sparse:elastic3d_iso_x/bs2", "sparse:elastic3d_iso_y/bs2", "sparse:elastic3d_iso_z/bs2"],
+    "elastic3d_ortho": ["sparse:elastic3d_ortho_x/bs2", "sparse:elastic3d_ortho_y/bs2", "sparse:elastic3d_ortho_z/bs2"],
+    "acoustic3d_free": ["sparse:acoustic3d_x/bs2", "sparse:acoustic3d_y/bs2", "sparse:acoustic3d_z/bs2"],
+    "elastic2d_pwave": ["sparse:elastic2d_iso_x/bs2", "sparse:elastic2d_iso_y/bs2"],
+    "elastic2d_courant45": ["dense:M5", "dense:M5"],  # border size 5: no specialised kernel
+    "elastic1d": ["sparse:elastic1d_iso_x/bs2"],
+}
+
+
+@pytest.mark.parametrize("name", sorted(EXPECTED_KERNELS))
+def test_sparsity_pattern_selection(lib, name):
+    from gcm_b200 import capi
+    eng = capi.HostEngine(lib, SCENARIOS[name])
+    try:
+        D = eng.body_info(0)[0]
+        assert [eng.kernel_name(0, d) for d in range(D)] == EXPECTED_KERNELS[name]
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_MARCH_SEG": "7"}])
+@pytest.mark.parametrize("name", ["elastic3d_layers", "ortho3d_contact", "acoustic2d_border1", "elastic2d_ortho"])
+def test_kernel_variants_agree(name, env):
+    """dense kernel, direct kernel and short marching segments give the same bits (fresh process: the
+    variant is read from the environment once)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from helpers import compare_with_golden, emul_library\n"
+            "from scenarios import SCENARIOS\n"
+            "compare_with_golden(emul_library(), %r, SCENARIOS[%r])\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+               os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"), name, name))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_adhesion_contact_equals_single_body(lib):
+    """test/sequence/TestEngine.cpp:27-87 through our engine: two glued bodies == one body, bitwise."""
+    two = run_engine(lib, SCENARIOS["adhesion2d_two"])
+    one = run_engine(lib, SCENARIOS["adhesion2d_one"])
+    full = one.body_pde(0).reshape(11, 26, 5)
+    assert np.array_equal(full[:, :13], two.body_pde(0).reshape(11, 13, 5))
+    assert np.array_equal(full[:, 13:], two.body_pde(1).reshape(11, 13, 5))
+    two.close()
+    one.close()
+
+
+def test_upload_download_roundtrip(lib):
+    from gcm_b200 import capi
+    ctx = capi.Context(lib)
+    rng = np.random.default_rng(0)
+    for D, sizes, M, bs in ((3, (5, 4, 7), 9, 2), (2, (6, 9), 5, 3), (1, (11,), 2, 1)):
+        body = capi.CubicBody(ctx, D, M, sizes, [0] * D, [0.1] * D, bs)
+        full = rng.normal(size=tuple(s + 2 * bs for s in sizes) + (M,))
+        body.upload(full, with_ghosts=True)
+        assert np.array_equal(body.download(with_ghosts=True), full)
+        real = tuple(slice(bs, bs + s) for s in sizes)
+        assert np.array_equal(body.download(with_ghosts=False), full[real])
+        chk = body.checksum()
+        want = (full[real] * np.arange(1, M + 1)).sum()
+        assert abs(chk - want) <= 1e-12 * np.abs(full).sum()
+        body.close()
+    ctx.close()
+
+
+def test_courant_above_border_size_is_rejected(lib):
+    """EqualDistanceLineInterpolator.hpp:22 asserts k <= size-1: the reference throws, so do we."""
+    from gcm_b200 import capi
+    bad = SCENARIOS["elastic2d_pwave"].replace("courant 0.9", "courant 3.5")
+    eng = capi.HostEngine(lib, bad)
+    with pytest.raises(capi.GcmError):
+        eng.run()
+    eng.close()
