@@ -61,8 +61,8 @@ def build(force=False, verbose=False):
     host_src = [os.path.join(HERE, s) for s in HOST_SOURCES]
     host_dep = host_src + [os.path.join(HERE, h) for h in HOST_HEADERS]
     if force or _newer(host, host_dep):
-        # gcmb_* symbols stay undefined here: libgcm_b200.so is loaded/linked alongside
-        _run(["g++"] + CXX_FLAGS + ["-shared", "-o", host] + host_src)
+        _run(["g++"] + CXX_FLAGS + ["-shared", "-o", host] + host_src +
+             ["-L" + HERE, "-lgcm_b200", "-Wl,-rpath,$ORIGIN"])
     return lib, host
 
 

@@ -105,11 +105,13 @@ class Library:
                 raise ImportError("%s is missing: build it with `python -m gcm_b200.build` "
                                   "(gcm_b200 has no fallback implementation)" % p)
         self.cuda_path, self.host_path = cuda_path, host_path
-        self.c = ctypes.CDLL(cuda_path, mode=ctypes.RTLD_GLOBAL)
+        # local + deep binding: each library resolves its references within itself and its own dependencies
+        mode = ctypes.RTLD_LOCAL | os.RTLD_DEEPBIND
+        self.c = ctypes.CDLL(cuda_path, mode=mode)
         for name, (res, args) in C_ABI.items():
             f = getattr(self.c, name)
             f.restype, f.argtypes = res, args
-        self.h = ctypes.CDLL(host_path, mode=ctypes.RTLD_GLOBAL)
+        self.h = ctypes.CDLL(host_path, mode=mode)
         for name, (res, args) in HOST_ABI.items():
             f = getattr(self.h, name)
             f.restype, f.argtypes = res, args

@@ -13,6 +13,20 @@ def build_emul():
                     ("gcmb_capi.cu", "stage_dispatch.cu", "thread_fns.h", "internal.cuh", "patterns.inc")]
     if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out
+
+
+def build_host_emul():
+    """The product's host layer (gcm_b200/host/*.cpp, unchanged) linked against the stepping harness."""
+    emul = build_emul()
+    out = os.path.join(HERE, "libgcm_b200_host_emul.so")
+    hdir = os.path.join(ROOT, "gcm_b200", "host")
+    srcs = [os.path.join(hdir, f) for f in ("models.cpp", "engine.cpp", "task_file.cpp", "host_capi.cpp")]
+    deps = srcs + [os.path.join(hdir, "gcmb_host.hpp"), emul]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out] + srcs +
+                   ["-L" + HERE, "-lgcm_b200_emul", "-Wl,-rpath,$ORIGIN"], check=True)
+    return out
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
                     "-Wl,-Bsymbolic",

@@ -18,9 +18,7 @@ def emul_library():
     spec = importlib.util.spec_from_file_location("build_emul", os.path.join(ROOT, "tests", "emul", "build_emul.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    from gcm_b200 import build as product_build
-    _, host = product_build.build()
-    return capi.Library(cuda_path=mod.build_emul(), host_path=host)
+    return capi.Library(cuda_path=mod.build_emul(), host_path=mod.build_host_emul())
 
 
 def run_engine(lib, task_text, **kw):
