@@ -66,6 +66,7 @@ HOST_ABI = {
                                                ctypes.POINTER(vp)]),
     "gcmb_host_engine_destroy": (None, [vp]),
     "gcmb_host_engine_run": (ctypes.c_int, [vp]),
+    "gcmb_host_engine_advance": (ctypes.c_int, [vp, ctypes.c_int]),
     "gcmb_host_engine_info": (ctypes.c_int, [vp, c_int_p, c_double_p, c_double_p]),
     "gcmb_host_engine_body_info": (ctypes.c_int, [vp, ctypes.c_size_t, c_int_p, c_int_p, c_int_p, c_int_p]),
     "gcmb_host_engine_body_pde": (ctypes.c_int, [vp, ctypes.c_size_t, c_double_p]),
@@ -293,6 +294,10 @@ class HostEngine:
 
     def run(self):
         self.lib.hcheck(self.lib.h.gcmb_host_engine_run(self.handle))
+        return self
+
+    def advance(self, n):
+        self.lib.hcheck(self.lib.h.gcmb_host_engine_advance(self.handle, n))
         return self
 
     def info(self):

@@ -261,6 +261,8 @@ public:
 	AbstractEngine& operator=(const AbstractEngine&) = delete;
 	/// perform all calculations (reference engine/AbstractEngine.cpp:30-46)
 	void run();
+	/// gcm_b200 extension: perform exactly n more time steps (the body of run()'s loop), for benchmarks
+	void advance(int n);
 	/// steps performed by run() so far
 	int stepsDone() const { return step; }
 protected:

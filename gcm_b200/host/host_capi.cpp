@@ -44,6 +44,10 @@ int gcmb_host_engine_run(void* handle) {
 	return guarded([&] { static_cast<Handle*>(handle)->engine->run(); });
 }
 
+int gcmb_host_engine_advance(void* handle, int n) {
+	return guarded([&] { static_cast<Handle*>(handle)->engine->advance(n); });
+}
+
 int gcmb_host_engine_info(void* handle, int* steps_done, double* time, double* tau) {
 	return guarded([&] {
 		*steps_done = static_cast<Handle*>(handle)->engine->stepsDone();
