@@ -492,7 +492,7 @@ int gcmb_cubic_body_create(gcmb_ctx* ctx, int D, int M, const int* sizes, const 
 		}
 		GCMB_CUDA(cudaMemsetAsync(b->buf[i], 0, bytes, ctx->stream));
 	}
-	GCMB_CUDA(cudaMalloc(&b->node_table, (size_t) g.comp));
+	GCMB_CUDA(cudaMalloc(&b->node_table, (size_t) g.comp + 64));  // slack: 4-byte id copies of the z-tile kernel
 	GCMB_CUDA(cudaMemsetAsync(b->node_table, 0, (size_t) g.comp, ctx->stream));
 	GCMB_CUDA(cudaMalloc(&b->decay_dev, 256 * sizeof(double)));
 	ctx->bytes += 2 * bytes + (size_t) g.comp;

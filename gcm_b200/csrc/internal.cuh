@@ -16,6 +16,12 @@
 #define GCMB_DEV __device__ __forceinline__
 #define GCMB_BOUNDS(n) __launch_bounds__(n)
 #define GCMB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+// kernels with block barriers: written as phases over GCMB_BLOCK_THREADS (a single pass on the device)
+#define GCMB_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define GCMB_BLOCK_THREADS(tid) for (int tid = threadIdx.x, gcmb_once_ = 1; gcmb_once_; gcmb_once_ = 0)
+#define GCMB_DYN_SMEM(type, name)                                  \
+	extern __shared__ __align__(16) unsigned char gcmb_dyn_smem_[]; \
+	type& name = *reinterpret_cast<type*>(gcmb_dyn_smem_)
 #endif
 #ifdef __CUDACC__
 #define GCMB_HD __host__ __device__ __forceinline__

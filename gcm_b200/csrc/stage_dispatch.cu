@@ -2,7 +2,7 @@
 // eigen-system (patterns.inc) x border size {1,2}, plus dense kernels for everything else.
 #include <cstdlib>
 
-#include "thread_fns.h"
+#include "ztile.h"
 
 namespace gcmb {
 
@@ -63,6 +63,43 @@ GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_march(const StageArgs a, int seg) {
 	stage_thread_march<P, BS>(a, perp, i2, s_begin, s_end);
 }
 
+// marching kernel fed by the cp.async ring (march_async.h)
+template<class P, int BS>
+GCMB_GLOBAL void GCMB_BOUNDS(MARCH_ZT) k_stage_march_async(const StageArgs a, int seg) {
+	__shared__ double ring[MARCH_RING][P::M][MARCH_ZT];
+	const int i2 = blockIdx.y * MARCH_ZT + threadIdx.x;
+	if (i2 >= a.g.n[2]) { return; }
+	const int lo = a.axis == 0 ? a.x_begin : 0;
+	const int hi = a.axis == 0 ? a.x_end : a.g.n[1];
+	const int s_begin = lo + blockIdx.x * seg;
+	const int s_end = min(hi, s_begin + seg);
+	const int perp = a.axis == 0 ? (int) blockIdx.z : (int) blockIdx.z + a.x_begin;
+	stage_thread_march_async<P, BS>(a, ring, threadIdx.x, perp, i2, s_begin, s_end);
+}
+
+// contiguous-axis kernel: row tiles staged in shared memory by cp.async (ztile.h)
+template<class P, int BS>
+GCMB_GLOBAL void GCMB_BOUNDS(ZTILE) k_stage_ztile(const StageArgs a, int rows) {
+	GCMB_DYN_SMEM(ZTileSmem<P::M>, sm);
+	const int z0 = blockIdx.x * ZTILE;
+	const int r0 = blockIdx.y * rows;
+	const int r1 = min(a.g.n[1], r0 + rows);
+	const int i0 = blockIdx.z + a.x_begin;
+	for (int d = 0; d < ZLEAD; d++) {
+		GCMB_BLOCK_THREADS(tid) { ztile_issue<P, BS>(a, sm, d % ZRING, tid, i0, r0 + d, z0, r1); }
+	}
+	for (int r = r0; r < r1; r++) {
+		const int it = r - r0;
+		// tile it+ZLEAD goes into the slot read one iteration ago (protected by the barrier below)
+		GCMB_BLOCK_THREADS(tid) { ztile_issue<P, BS>(a, sm, (it + ZLEAD) % ZRING, tid, i0, r + ZLEAD, z0, r1); }
+		cp_async_wait<ZLEAD>();
+		__syncthreads();
+		GCMB_BLOCK_THREADS(tid) { ztile_compute<P, BS>(a, sm, it % ZRING, tid, i0, r, z0); }
+		__syncthreads();
+	}
+	cp_async_wait<0>();
+}
+
 static int env_int(const char* name, int dflt) {
 	const char* v = getenv(name);
 	return v ? atoi(v) : dflt;
@@ -70,15 +107,30 @@ static int env_int(const char* name, int dflt) {
 
 template<class P, int BS>
 static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
-	static const int impl = env_int("GCMB_STAGE_IMPL", 1);   // 0 = direct, 1 = march on strided axes
+	// 0 = one thread per node; 1 = marching, register prefetch; 2 = marching, cp.async ring (default)
+	static const int impl = env_int("GCMB_STAGE_IMPL", 2);
 	static const int seg_env = env_int("GCMB_MARCH_SEG", 256);
-	if (impl == 1 && a.axis != 2) {
+	if (impl >= 1 && a.axis != 2) {
 		const int len = a.axis == 0 ? a.x_end - a.x_begin : a.g.n[1];
 		const int seg = seg_env < 1 ? len : seg_env;
 		const int perp = a.axis == 0 ? a.g.n[1] : a.x_end - a.x_begin;
 		const dim3 grid((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZT - 1) / ZT), (unsigned) perp);
-		auto kernel = k_stage_march<P, BS>;
-		GCMB_LAUNCH(kernel, grid, ZT, stream, a, seg);
+		if (impl == 2) {
+			auto kernel = k_stage_march_async<P, BS>;
+			GCMB_LAUNCH(kernel, grid, MARCH_ZT, stream, a, seg);
+		} else {
+			auto kernel = k_stage_march<P, BS>;
+			GCMB_LAUNCH(kernel, grid, ZT, stream, a, seg);
+		}
+	} else if (impl == 2 && a.axis == 2) {
+		static const int rows = env_int("GCMB_ZTILE_ROWS", 32);
+		auto kernel = k_stage_ztile<P, BS>;
+		static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                                     (int) sizeof(ZTileSmem<P::M>));
+		(void) attr;
+		const dim3 grid((unsigned) ((a.g.n[2] + ZTILE - 1) / ZTILE), (unsigned) ((a.g.n[1] + rows - 1) / rows),
+		                (unsigned) (a.x_end - a.x_begin));
+		GCMB_LAUNCH_COOP(kernel, grid, ZTILE, sizeof(ZTileSmem<P::M>), stream, a, rows);
 	} else {
 		auto kernel = k_stage_direct<P, BS>;
 		GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a);

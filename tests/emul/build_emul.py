@@ -1,18 +1,27 @@
-"""Builds tests/emul/libgcm_b200_emul.so (see README.md: test infrastructure, not a product path)."""
+"""Builds tests/emul/libgcm_b200_emul.so and libgcm_b200_host_emul.so (see README.md: test infrastructure,
+not a product path)."""
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "gcm_b200", "csrc")
+
+
+def _fresh(out, deps):
+    return os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps)
 
 
 def build_emul():
+    """The product's CUDA sources compiled for the host; kernels are stepped thread by thread."""
     out = os.path.join(HERE, "libgcm_b200_emul.so")
     src = os.path.join(HERE, "emul_all.cpp")
-    deps = [src] + [os.path.join(ROOT, "gcm_b200", "csrc", f) for f in
-                    ("gcmb_capi.cu", "stage_dispatch.cu", "thread_fns.h", "internal.cuh", "patterns.inc")]
-    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
-        return out
+    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc"))]
+    if not _fresh(out, deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
+                        "-Wl,-Bsymbolic", "-I" + cuda_inc, src, "-o", out, "-ldl"], check=True)
+    return out
 
 
 def build_host_emul():
@@ -22,13 +31,7 @@ def build_host_emul():
     hdir = os.path.join(ROOT, "gcm_b200", "host")
     srcs = [os.path.join(hdir, f) for f in ("models.cpp", "engine.cpp", "task_file.cpp", "host_capi.cpp")]
     deps = srcs + [os.path.join(hdir, "gcmb_host.hpp"), emul]
-    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
-        return out
-    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out] + srcs +
-                   ["-L" + HERE, "-lgcm_b200_emul", "-Wl,-rpath,$ORIGIN"], check=True)
-    return out
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
-                    "-Wl,-Bsymbolic",
-                    "-I" + cuda_inc, src, "-o", out, "-ldl"], check=True)
+    if not _fresh(out, deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out] + srcs +
+                       ["-L" + HERE, "-lgcm_b200_emul", "-Wl,-rpath,$ORIGIN"], check=True)
     return out

@@ -30,6 +30,18 @@ void launch(dim3 grid, dim3 block, F body) {
 	}
 }
 
+// kernels written as barrier-separated phases: one call per block, the kernel loops over its threads
+template<typename F>
+void launch_blocks(dim3 grid, dim3 block, F body) {
+	t_gridDim = grid;
+	t_blockDim = block;
+	t_threadIdx = {0, 0, 0};
+	for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
+		t_blockIdx = {bx, by, bz};
+		body();
+	}
+}
+
 inline cudaError_t e_malloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t e_free(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t e_memcpy(void* d, const void* s, size_t n) { std::memcpy(d, s, n); return cudaSuccess; }
@@ -78,6 +90,13 @@ using std::max;
 #define GCMB_BOUNDS(n)
 #define GCMB_LAUNCH(kernel, grid, block, stream, ...) \
 	gcmb_emul::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); })
+#define GCMB_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
+	gcmb_emul::launch_blocks(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); })
+#define GCMB_BLOCK_THREADS(tid) for (int tid = 0; tid < (int) gcmb_emul::t_blockDim.x; tid++)
+#define GCMB_DYN_SMEM(type, name)            \
+	static thread_local type name##_storage_; \
+	type& name = name##_storage_
+#define cudaFuncSetAttribute(k, a, v) cudaSuccess
 #define GCMB_EMUL_BLOCK_SUM(v, c) \
 	do { gcmb_emul::acc_v += (v); gcmb_emul::acc_c += (c); (v) = gcmb_emul::acc_v; (c) = gcmb_emul::acc_c; } while (0)
 

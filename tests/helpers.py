@@ -62,3 +62,40 @@ def compare_with_golden(lib, name, task_text, exact=True):
     except Exception:
         eng.close()
         raise
+
+
+def random_stage_check(lib, cases, seed=7):
+    """C-ABI level: random state with ghosts, random material map, every direction, bitwise vs gcmo_stage."""
+    import oracle_host as oh
+    L = oh.lib()
+    rng = np.random.default_rng(seed)
+    ctx = capi.Context(lib)
+    for (D, sizes, model, bs) in cases:
+        mats = [{"kind": "isotropic", "rho": rng.uniform(1, 5), "lambda": rng.uniform(1, 5), "mu": rng.uniform(0.5, 3)}
+                for _ in range(3)]
+        ms = [oh.matrices_for(model, D, m) for m in mats]
+        U = np.ascontiguousarray(np.stack([m[0] for m in ms]))
+        U1 = np.ascontiguousarray(np.stack([m[1] for m in ms]))
+        Lm = np.ascontiguousarray(np.stack([m[2] for m in ms]))
+        M = U.shape[-1]
+        h = rng.uniform(0.5, 1.5, D)
+        full = tuple(s + 2 * bs for s in sizes)
+        state = rng.normal(size=full + (M,))
+        table_full = rng.integers(0, 3, size=full).astype(np.uint8)
+        real = tuple(slice(bs, bs + s) for s in sizes)
+        body = capi.CubicBody(ctx, D, M, sizes, [0] * D, h, bs)
+        body.set_materials(U, U1, Lm, np.ascontiguousarray(table_full[real]))
+        tau = 0.4 * h.min() / np.abs(Lm).max()
+        sz = np.array(sizes, dtype=np.int32)
+        for s in range(D):
+            body.upload(state, with_ghosts=True)
+            body.stage(s, tau)
+            got = body.download(with_ghosts=False)
+            nxt = np.zeros_like(state)
+            rc = L.gcmo_stage(D, M, oh._ip(sz), bs, oh._dp(h), s, tau, 3, oh._dp(U), oh._dp(U1), oh._dp(Lm),
+                              oh._bp(table_full), oh._dp(state), oh._dp(nxt))
+            assert rc == 0
+            assert np.array_equal(nxt[real], got), (D, sizes, model, bs, s, body.kernel_name(s),
+                                                    np.abs(nxt[real] - got).max())
+        body.close()
+    ctx.close()

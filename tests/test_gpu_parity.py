@@ -36,7 +36,7 @@ def test_cuda_engine_matches_reference_bitwise(lib, name):
     eng.close()
 
 
-@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_MARCH_SEG": "5"},
+@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "5"},
                                  {"GCMB_MARCH_SEG": "0"}])
 def test_kernel_variants_match_reference(env):
     """dense / direct / marching-with-odd-segments kernels: every variant reproduces the reference bits."""
@@ -72,39 +72,11 @@ def test_cuda_engine_matches_oracle_at_medium_size(lib, maker, kw):
 
 def test_random_state_single_stages_match_oracle(lib):
     """C-ABI level: random state with ghosts, random material map, each direction, vs gcmo_stage."""
-    import oracle_host as oh
-    L = oh.lib()
-    rng = np.random.default_rng(7)
-    ctx = capi.Context(lib)
-    for (D, sizes, model, bs) in ((3, (19, 13, 37), "elastic", 2), (3, (9, 17, 150), "acoustic", 2),
-                                  (2, (23, 131), "elastic", 2), (2, (33, 40), "elastic", 1), (1, (300,), "elastic", 2)):
-        mats = [{"kind": "isotropic", "rho": rng.uniform(1, 5), "lambda": rng.uniform(1, 5), "mu": rng.uniform(0.5, 3)}
-                for _ in range(3)]
-        ms = [oh.matrices_for(model, D, m) for m in mats]
-        U = np.ascontiguousarray(np.stack([m[0] for m in ms]))
-        U1 = np.ascontiguousarray(np.stack([m[1] for m in ms]))
-        Lm = np.ascontiguousarray(np.stack([m[2] for m in ms]))
-        M = U.shape[-1]
-        h = rng.uniform(0.5, 1.5, D)
-        full = tuple(s + 2 * bs for s in sizes)
-        state = rng.normal(size=full + (M,))
-        table_full = rng.integers(0, 3, size=full).astype(np.uint8)
-        real = tuple(slice(bs, bs + s) for s in sizes)
-        body = capi.CubicBody(ctx, D, M, sizes, [0] * D, h, bs)
-        body.set_materials(U, U1, Lm, np.ascontiguousarray(table_full[real]))
-        tau = 0.4 * h.min() / np.abs(Lm).max()
-        sz = np.array(sizes, dtype=np.int32)
-        for s in range(D):
-            body.upload(state, with_ghosts=True)
-            body.stage(s, tau)
-            got = body.download(with_ghosts=False)
-            nxt = np.zeros_like(state)
-            rc = L.gcmo_stage(D, M, oh._ip(sz), bs, oh._dp(h), s, tau, 3, oh._dp(U), oh._dp(U1), oh._dp(Lm),
-                              oh._bp(table_full), oh._dp(state), oh._dp(nxt))
-            assert rc == 0
-            assert np.array_equal(nxt[real], got), (D, sizes, model, s, np.abs(nxt[real] - got).max())
-        body.close()
-    ctx.close()
+    from helpers import random_stage_check
+    random_stage_check(lib, ((3, (19, 13, 37), "elastic", 2), (3, (9, 17, 150), "acoustic", 2),
+                             (3, (5, 40, 700), "elastic", 2), (3, (300, 3, 33), "elastic", 1),
+                             (2, (23, 131), "elastic", 2), (2, (33, 40), "elastic", 1), (2, (70, 515), "acoustic", 1),
+                             (1, (300,), "elastic", 2), (1, (1000,), "acoustic", 2)))
 
 
 def test_ghost_layers_roundtrip_and_checksum(lib):

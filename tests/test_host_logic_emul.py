@@ -48,7 +48,7 @@ def test_sparsity_pattern_selection(lib, name):
         eng.close()
 
 
-@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_MARCH_SEG": "7"}])
+@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "7"}])
 @pytest.mark.parametrize("name", ["elastic3d_layers", "ortho3d_contact", "acoustic2d_border1", "elastic2d_ortho"])
 def test_kernel_variants_agree(name, env):
     """dense kernel, direct kernel and short marching segments give the same bits (fresh process: the
@@ -102,3 +102,10 @@ def test_courant_above_border_size_is_rejected(lib):
     with pytest.raises(capi.GcmError):
         eng.run()
     eng.close()
+
+
+def test_random_state_single_stages_match_oracle(lib):
+    """multi-chunk rows, ragged sizes, first-order border: stepping harness vs gcmo_stage, bitwise"""
+    from helpers import random_stage_check
+    random_stage_check(lib, ((3, (7, 6, 37), "elastic", 2), (3, (3, 35, 300), "elastic", 2), (3, (260, 2, 9), "acoustic", 1),
+                             (2, (9, 515), "elastic", 1), (2, (300, 8), "acoustic", 2), (1, (600,), "elastic", 2)))
