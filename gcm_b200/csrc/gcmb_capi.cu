@@ -222,6 +222,7 @@ struct gcmb_body {
 	double tables_tau = NAN;
 	bool any_k0 = false;                  // some characteristic foot beyond the first cell (Courant > 1)
 	int pattern_of_dir[3] = {-1, -1, -1};
+	double* packed[3] = {nullptr, nullptr, nullptr};  // device: packed non-zero coefficients per direction
 	std::string kernel_name[3];
 	std::map<int, BorderCond> borders;    // ordered by condition number
 	uint8_t* detector_mask = nullptr;
@@ -323,6 +324,24 @@ int build_tables(gcmb_body* b, double tau) {
 		}
 	}
 	GCMB_CUDA(cudaMemcpyAsync(b->tables, host.data(), host.size() * sizeof(StageTable), cudaMemcpyHostToDevice, b->ctx->stream));
+	// packed copies of the structurally non-zero coefficients for the specialised kernels
+	std::vector<double> pk;
+	for (int s = 0; s < D; s++) {
+		cudaFree(b->packed[s]);
+		b->packed[s] = nullptr;
+		if (b->pattern_of_dir[s] < 0) { continue; }
+		const PatternInfo& P = pattern(b->pattern_of_dir[s]);
+		pk.assign((size_t) b->n_tables * (MAXM * MAXM * 2 + MAXM * MAXBS), 0.0);
+		int size = 0;
+		for (int t = 0; t < b->n_tables; t++) {
+			double one[MAXM * MAXM * 2 + MAXM * MAXBS];
+			size = pack_table(P, g.bs, host[(size_t) t * D + s], one);
+			std::memcpy(pk.data() + (size_t) t * size, one, (size_t) size * sizeof(double));
+		}
+		GCMB_CUDA(cudaMalloc(&b->packed[s], (size_t) b->n_tables * size * sizeof(double)));
+		GCMB_CUDA(cudaMemcpyAsync(b->packed[s], pk.data(), (size_t) b->n_tables * size * sizeof(double), cudaMemcpyHostToDevice, b->ctx->stream));
+		GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+	}
 	GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));
 	b->tables_tau = tau;
 	return GCMB_OK;
@@ -511,6 +530,7 @@ void gcmb_cubic_body_destroy(gcmb_body* b) {
 	cudaFree(b->buf[1]);
 	cudaFree(b->node_table);
 	cudaFree(b->tables);
+	for (int s = 0; s < 3; s++) { cudaFree(b->packed[s]); }
 	cudaFree(b->decay_dev);
 	cudaFree(b->detector_mask);
 	for (auto& kv : b->borders) { cudaFree(kv.second.mask[0]); cudaFree(kv.second.mask[1]); }
@@ -763,6 +783,8 @@ int gcmb_cubic_stage(gcmb_body* b, int dir, double tau) {
 	a.nxt = b->buf[1 - b->cur];
 	a.node_table = b->node_table;
 	a.tables = b->tables;
+	a.packed = b->packed[dir];
+	a.n_tables = b->n_tables;
 	a.g = b->g;
 	a.axis = dir + b->g.shift;
 	a.dir = dir;

@@ -73,6 +73,8 @@ struct StageArgs {
 	double* nxt;
 	const uint8_t* node_table;
 	const StageTable* tables; // indexed [table * D + dir]
+	const double* packed;     // this direction's packed coefficient tables [table][Packed::SIZE] or null
+	int n_tables;
 	Geom g;
 	int axis;                 // internal axis of the sweep
 	int dir;                  // reference direction
@@ -90,6 +92,21 @@ struct PatternInfo {
 	StageLauncher launch_bs1;
 	StageLauncher launch_bs2;
 };
+
+// host side of thread_fns.h Packed<P,BS>: the non-zero coefficients of one table in kernel order
+inline int pack_table(const PatternInfo& p, int bs, const StageTable& T, double* out) {
+	int n = 0;
+	for (int k = 0; k < p.M; k++) {
+		if (p.sgn[k] != 0) { for (int i = 0; i < bs; i++) { out[n++] = T.F[k * MAXBS + i]; } }
+	}
+	for (int k = 0; k < p.M; k++) {
+		for (int j = 0; j < p.M; j++) { if ((p.um[k] >> j) & 1u) { out[n++] = T.U[k * p.M + j]; } }
+	}
+	for (int i = 0; i < p.M; i++) {
+		for (int k = 0; k < p.M; k++) { if ((p.u1m[i] >> k) & 1u) { out[n++] = T.U1[i * p.M + k]; } }
+	}
+	return n;
+}
 
 // stage_dispatch.cu
 int pattern_count();

@@ -31,12 +31,19 @@ inline void cp_async_wait() { }
 constexpr int MARCH_ZT = 128;  // threads per block = z extent of a block
 constexpr int MARCH_LEAD = 3;  // planes in flight ahead of the one being consumed
 constexpr int MARCH_RING = MARCH_LEAD + 1;
+constexpr int SMEM_TABLES = 16; // material tables kept in shared memory by the pipelined kernels
+
+// phase 0 of the pipelined kernels, one thread: copy the packed coefficient tables to shared memory
+GCMB_HD void copy_tables(const StageArgs& a, double* tab, int table_size, int tid, int n_threads) {
+	const int n = a.n_tables * table_size;
+	for (int i = tid; i < n; i += n_threads) { tab[i] = a.packed[i]; }
+}
 
 // ring[slot][component][thread]; slot of iteration s' holds: interpolated components at plane s'+BS,
 // centre-only components at plane s'
 template<class P, int BS>
-GCMB_HD void stage_thread_march_async(const StageArgs& a, double (*ring)[P::M][MARCH_ZT], int tid,
-                                      int perp, int i2, int s_begin, int s_end) {
+GCMB_HD void stage_thread_march_async(const StageArgs& a, double (*ring)[P::M][MARCH_ZT], const double* tab,
+                                      int tid, int perp, int i2, int s_begin, int s_end) {
 	constexpr int M = P::M;
 	constexpr int W = 2 * BS + 1;
 	constexpr unsigned IC = PatternSets<P>::interp();
@@ -91,10 +98,9 @@ GCMB_HD void stage_thread_march_async(const StageArgs& a, double (*ring)[P::M][M
 		}
 		// refill: iteration s+LEAD goes into the slot consumed one iteration ago (RING = LEAD + 1)
 		issue(s + MARCH_LEAD);
-		const StageTable* T = a.tables + (t * g.D + a.dir);
 		auto load = [&](int j, int o) -> double { return ((IC >> j) & 1u) ? w[j][BS + o] : cv[j]; };
 		double out[M];
-		gcm_node_sparse<P, BS>(T, load, out);
+		gcm_node_sparse<P, BS>(PackedCoef<P, BS>{tab + t * Packed<P, BS>::SIZE}, load, out);
 #pragma unroll
 		for (int c = 0; c < M; c++) { a.nxt[c * g.comp + idx] = out[c]; }
 	}

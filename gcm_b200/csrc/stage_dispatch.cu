@@ -67,20 +67,26 @@ GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_march(const StageArgs a, int seg) {
 template<class P, int BS>
 GCMB_GLOBAL void GCMB_BOUNDS(MARCH_ZT) k_stage_march_async(const StageArgs a, int seg) {
 	__shared__ double ring[MARCH_RING][P::M][MARCH_ZT];
-	const int i2 = blockIdx.y * MARCH_ZT + threadIdx.x;
-	if (i2 >= a.g.n[2]) { return; }
+	__shared__ double tab[SMEM_TABLES * Packed<P, BS>::SIZE];
+	GCMB_BLOCK_THREADS(tid) { copy_tables(a, tab, Packed<P, BS>::SIZE, tid, MARCH_ZT); }
+	__syncthreads();
 	const int lo = a.axis == 0 ? a.x_begin : 0;
 	const int hi = a.axis == 0 ? a.x_end : a.g.n[1];
 	const int s_begin = lo + blockIdx.x * seg;
 	const int s_end = min(hi, s_begin + seg);
 	const int perp = a.axis == 0 ? (int) blockIdx.z : (int) blockIdx.z + a.x_begin;
-	stage_thread_march_async<P, BS>(a, ring, threadIdx.x, perp, i2, s_begin, s_end);
+	GCMB_BLOCK_THREADS(tid) {
+		const int i2 = blockIdx.y * MARCH_ZT + tid;
+		if (i2 < a.g.n[2]) { stage_thread_march_async<P, BS>(a, ring, tab, tid, perp, i2, s_begin, s_end); }
+	}
 }
 
 // contiguous-axis kernel: row tiles staged in shared memory by cp.async (ztile.h)
 template<class P, int BS>
 GCMB_GLOBAL void GCMB_BOUNDS(ZTILE) k_stage_ztile(const StageArgs a, int rows) {
-	GCMB_DYN_SMEM(ZTileSmem<P::M>, sm);
+	typedef ZTileSmem<P::M, Packed<P, BS>::SIZE> Smem;
+	GCMB_DYN_SMEM(Smem, sm);
+	GCMB_BLOCK_THREADS(tid) { copy_tables(a, sm.tab, Packed<P, BS>::SIZE, tid, ZTILE); }
 	const int z0 = blockIdx.x * ZTILE;
 	const int r0 = blockIdx.y * rows;
 	const int r1 = min(a.g.n[1], r0 + rows);
@@ -110,27 +116,29 @@ static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
 	// 0 = one thread per node; 1 = marching, register prefetch; 2 = marching, cp.async ring (default)
 	static const int impl = env_int("GCMB_STAGE_IMPL", 2);
 	static const int seg_env = env_int("GCMB_MARCH_SEG", 256);
-	if (impl >= 1 && a.axis != 2) {
+	const bool tables_fit = a.packed && a.n_tables <= SMEM_TABLES;
+	if (impl >= 1 && a.axis != 2 && (impl == 1 || tables_fit)) {
 		const int len = a.axis == 0 ? a.x_end - a.x_begin : a.g.n[1];
 		const int seg = seg_env < 1 ? len : seg_env;
 		const int perp = a.axis == 0 ? a.g.n[1] : a.x_end - a.x_begin;
 		const dim3 grid((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZT - 1) / ZT), (unsigned) perp);
 		if (impl == 2) {
 			auto kernel = k_stage_march_async<P, BS>;
-			GCMB_LAUNCH(kernel, grid, MARCH_ZT, stream, a, seg);
+			GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
 		} else {
 			auto kernel = k_stage_march<P, BS>;
 			GCMB_LAUNCH(kernel, grid, ZT, stream, a, seg);
 		}
-	} else if (impl == 2 && a.axis == 2) {
+	} else if (impl == 2 && a.axis == 2 && tables_fit) {
 		static const int rows = env_int("GCMB_ZTILE_ROWS", 32);
 		auto kernel = k_stage_ztile<P, BS>;
+		typedef ZTileSmem<P::M, Packed<P, BS>::SIZE> Smem;
 		static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                                                     (int) sizeof(ZTileSmem<P::M>));
+		                                                     (int) sizeof(Smem));
 		(void) attr;
 		const dim3 grid((unsigned) ((a.g.n[2] + ZTILE - 1) / ZTILE), (unsigned) ((a.g.n[1] + rows - 1) / rows),
 		                (unsigned) (a.x_end - a.x_begin));
-		GCMB_LAUNCH_COOP(kernel, grid, ZTILE, sizeof(ZTileSmem<P::M>), stream, a, rows);
+		GCMB_LAUNCH_COOP(kernel, grid, ZTILE, sizeof(Smem), stream, a, rows);
 	} else {
 		auto kernel = k_stage_direct<P, BS>;
 		GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a);

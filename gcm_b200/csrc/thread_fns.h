@@ -69,8 +69,57 @@ GCMB_HD double limited_newton(double (&s)[BS + 1], const double* __restrict__ F,
 // products are formed, in the reference's index order: the dropped terms are exact zeros.
 // LOAD(j, o) returns component j at offset o (in nodes) along the sweep axis.
 // ---------------------------------------------------------------------------------------------
-template<class P, int BS, class LOAD>
-GCMB_HD void gcm_node_sparse(const StageTable* __restrict__ T, LOAD load, double (&out)[P::M]) {
+// Coefficient sources for gcm_node_sparse.
+// (1) the full StageTable in global memory (one-thread-per-node kernels)
+template<int M>
+struct TableCoef {
+	const StageTable* __restrict__ T;
+	GCMB_HD double u(int k, int j) const { return GCMB_LDG(&T->U[k * M + j]); }
+	GCMB_HD double u1(int i, int k) const { return GCMB_LDG(&T->U1[i * M + k]); }
+	GCMB_HD const double* f(int k) const { return T->F + k * MAXBS; }
+};
+
+// (2) the structurally non-zero coefficients only, packed in the order the kernel consumes them:
+//     [Newton factors of the interpolated rows][non-zeros of U, row by row][non-zeros of U1, row by row].
+//     All positions are compile-time constants of the pattern, so every coefficient is one LDS with an
+//     immediate offset from the node's table base in shared memory.
+GCMB_HD constexpr int popcount_u(unsigned m) { int n = 0; for (; m; m &= m - 1) { n++; } return n; }
+template<class P, int BS>
+GCMB_HD constexpr int packed_fpos(int k) {
+	int n = 0;
+	for (int r = 0; r < k; r++) { if (P::sgn(r) != 0) { n += BS; } }
+	return n;
+}
+template<class P, int BS>
+GCMB_HD constexpr int packed_upos(int k, int j) {
+	int n = packed_fpos<P, BS>(P::M);
+	for (int r = 0; r < k; r++) { n += popcount_u(P::um(r)); }
+	return k < P::M ? n + popcount_u(P::um(k) & ((1u << j) - 1u)) : n;
+}
+template<class P, int BS>
+GCMB_HD constexpr int packed_u1pos(int i, int k) {
+	int n = packed_upos<P, BS>(P::M, 0);
+	for (int r = 0; r < i; r++) { n += popcount_u(P::u1m(r)); }
+	return i < P::M ? n + popcount_u(P::u1m(i) & ((1u << k) - 1u)) : n;
+}
+template<class P, int BS>
+struct Packed {
+	GCMB_HD static constexpr int fpos(int k) { return packed_fpos<P, BS>(k); }
+	GCMB_HD static constexpr int upos(int k, int j) { return packed_upos<P, BS>(k, j); }
+	GCMB_HD static constexpr int u1pos(int i, int k) { return packed_u1pos<P, BS>(i, k); }
+	static constexpr int SIZE = packed_u1pos<P, BS>(P::M, 0);
+};
+
+template<class P, int BS>
+struct PackedCoef {
+	const double* __restrict__ t;  // packed table of the node's material (shared memory)
+	GCMB_HD double u(int k, int j) const { return t[Packed<P, BS>::upos(k, j)]; }
+	GCMB_HD double u1(int i, int k) const { return t[Packed<P, BS>::u1pos(i, k)]; }
+	GCMB_HD const double* f(int k) const { return t + Packed<P, BS>::fpos(k); }
+};
+
+template<class P, int BS, class COEF, class LOAD>
+GCMB_HD void gcm_node_sparse(const COEF coef, LOAD load, double (&out)[P::M]) {
 	constexpr int M = P::M;
 	double r[M];
 #pragma unroll
@@ -89,9 +138,9 @@ GCMB_HD void gcm_node_sparse(const StageTable* __restrict__ T, LOAD load, double
 					double s[BS + 1];
 #pragma unroll
 					for (int i = 0; i <= BS; i++) { s[i] = load(j, sg * i); }
-					v = limited_newton<BS, false>(s, T->F + k * MAXBS, 0);
+					v = limited_newton<BS, false>(s, coef.f(k), 0);
 				}
-				const double t = GCMB_LDG(&T->U[k * M + j]) * v;
+				const double t = coef.u(k, j) * v;
 				if (first) { acc = t; first = false; } else { acc += t; }
 			}
 		}
@@ -105,7 +154,7 @@ GCMB_HD void gcm_node_sparse(const StageTable* __restrict__ T, LOAD load, double
 #pragma unroll
 		for (int k = 0; k < M; k++) {
 			if ((mask >> k) & 1u) {
-				const double t = GCMB_LDG(&T->U1[i * M + k]) * r[k];
+				const double t = coef.u1(i, k) * r[k];
 				if (first) { acc = t; first = false; } else { acc += t; }
 			}
 		}
@@ -161,7 +210,7 @@ GCMB_HD void stage_thread_sparse(const StageArgs& a, int i0, int i1, int i2) {
 	const StageTable* T = a.tables + ((int) a.node_table[idx] * a.g.D + a.dir);
 	SoaLoad ld{a.cur + idx, a.g.comp, a.g.stride(a.axis)};
 	double out[P::M];
-	gcm_node_sparse<P, BS>(T, ld, out);
+	gcm_node_sparse<P, BS>(TableCoef<P::M>{T}, ld, out);
 #pragma unroll
 	for (int c = 0; c < P::M; c++) { a.nxt[c * a.g.comp + idx] = out[c]; }
 }
@@ -417,7 +466,7 @@ GCMB_HD void stage_thread_march(const StageArgs& a, int perp, int i2, int s_begi
 		const StageTable* T = a.tables + (t * g.D + a.dir);
 		auto load = [&](int j, int o) -> double { return ((IC >> j) & 1u) ? w[j][BS + o] : cv[j]; };
 		double out[M];
-		gcm_node_sparse<P, BS>(T, load, out);
+		gcm_node_sparse<P, BS>(TableCoef<M>{T}, load, out);
 #pragma unroll
 		for (int c = 0; c < M; c++) { a.nxt[c * g.comp + idx] = out[c]; }
 	}

@@ -30,15 +30,16 @@ constexpr int ZRING = ZLEAD + 1;
 constexpr int ZHALO = 2;               // largest border size served by this kernel
 constexpr int ZROW = ZTILE + 2 * ZHALO;
 
-template<int M>
+template<int M, int TABLE_SIZE>
 struct ZTileSmem {
 	double v[ZRING][M][ZROW];
+	double tab[SMEM_TABLES * TABLE_SIZE];
 	uint8_t id[ZRING][ZTILE];
 };
 
 // phase A, one thread: start the copies of row `i1` (tile slot `slot`); rows past the end copy nothing
 template<class P, int BS>
-GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M>& sm, int slot, int tid, int i0, int i1, int z0, int i1_end) {
+GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M, Packed<P, BS>::SIZE>& sm, int slot, int tid, int i0, int i1, int z0, int i1_end) {
 	constexpr int M = P::M;
 	constexpr unsigned IC = PatternSets<P>::interp();
 	constexpr unsigned CC = PatternSets<P>::center();
@@ -70,17 +71,17 @@ GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M>& sm, int slot, int 
 
 // phase B, one thread: one node of the tile from shared memory
 template<class P, int BS>
-GCMB_HD void ztile_compute(const StageArgs& a, const ZTileSmem<P::M>& sm, int slot, int tid, int i0, int i1, int z0) {
+GCMB_HD void ztile_compute(const StageArgs& a, const ZTileSmem<P::M, Packed<P, BS>::SIZE>& sm, int slot, int tid, int i0, int i1, int z0) {
 	constexpr int M = P::M;
 	const Geom& g = a.g;
 	const int z = z0 + tid;
 	if (z >= g.n[2]) { return; }
 	const long long idx = g.index(i0, i1, z);
-	const StageTable* T = a.tables + ((int) sm.id[slot][tid] * g.D + a.dir);
+	const double* tab = sm.tab + (int) sm.id[slot][tid] * Packed<P, BS>::SIZE;
 	const double (*v)[ZROW] = sm.v[slot];
 	auto load = [&](int j, int o) -> double { return v[j][tid + ZHALO + o]; };
 	double out[M];
-	gcm_node_sparse<P, BS>(T, load, out);
+	gcm_node_sparse<P, BS>(PackedCoef<P, BS>{tab}, load, out);
 #pragma unroll
 	for (int c = 0; c < M; c++) { a.nxt[c * g.comp + idx] = out[c]; }
 }
