@@ -333,11 +333,14 @@ int build_tables(gcmb_body* b, double tau) {
 		const PatternInfo& P = pattern(b->pattern_of_dir[s]);
 		pk.assign((size_t) b->n_tables * (MAXM * MAXM * 2 + MAXM * MAXBS), 0.0);
 		int size = 0;
+		bool shares = true;
 		for (int t = 0; t < b->n_tables; t++) {
 			double one[MAXM * MAXM * 2 + MAXM * MAXBS];
 			size = pack_table(P, g.bs, host[(size_t) t * D + s], one);
 			std::memcpy(pk.data() + (size_t) t * size, one, (size_t) size * sizeof(double));
+			shares = shares && table_shares_as_pattern(P, g.bs, host[(size_t) t * D + s]);
 		}
+		if (!shares) { continue; }  // no packed table: the stage falls back to the full-table kernels
 		GCMB_CUDA(cudaMalloc(&b->packed[s], (size_t) b->n_tables * size * sizeof(double)));
 		GCMB_CUDA(cudaMemcpyAsync(b->packed[s], pk.data(), (size_t) b->n_tables * size * sizeof(double), cudaMemcpyHostToDevice, b->ctx->stream));
 		GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));

@@ -15,6 +15,7 @@
 #define GCMB_GLOBAL __global__
 #define GCMB_DEV __device__ __forceinline__
 #define GCMB_BOUNDS(n) __launch_bounds__(n)
+#define GCMB_BOUNDS2(n, b) __launch_bounds__(n, b)
 #define GCMB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 // kernels with block barriers: written as phases over GCMB_BLOCK_THREADS (a single pass on the device)
 #define GCMB_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
@@ -89,23 +90,44 @@ struct PatternInfo {
 	int sgn[MAXM];
 	unsigned um[MAXM];
 	unsigned u1m[MAXM];
+	int base[MAXM];        // row/column whose coefficients row/column k shares (k itself when none)
+	unsigned uneg[MAXM];   // bit j: U(k,j) == -U(base,j)
+	unsigned u1neg[MAXM];  // bit i: U1(i,k) == -U1(i,base)
 	StageLauncher launch_bs1;
 	StageLauncher launch_bs2;
 };
 
-// host side of thread_fns.h Packed<P,BS>: the non-zero coefficients of one table in kernel order
+// host side of thread_fns.h Packed<P,BS>: the non-zero coefficients of one table in kernel order, the
+// rows/columns that share their coefficients with a base row stored once
 inline int pack_table(const PatternInfo& p, int bs, const StageTable& T, double* out) {
 	int n = 0;
 	for (int k = 0; k < p.M; k++) {
-		if (p.sgn[k] != 0) { for (int i = 0; i < bs; i++) { out[n++] = T.F[k * MAXBS + i]; } }
+		if (p.sgn[k] != 0 && p.base[k] == k) { for (int i = 0; i < bs; i++) { out[n++] = T.F[k * MAXBS + i]; } }
 	}
 	for (int k = 0; k < p.M; k++) {
+		if (p.base[k] != k) { continue; }
 		for (int j = 0; j < p.M; j++) { if ((p.um[k] >> j) & 1u) { out[n++] = T.U[k * p.M + j]; } }
 	}
 	for (int i = 0; i < p.M; i++) {
-		for (int k = 0; k < p.M; k++) { if ((p.u1m[i] >> k) & 1u) { out[n++] = T.U1[i * p.M + k]; } }
+		for (int k = 0; k < p.M; k++) { if (((p.u1m[i] >> k) & 1u) && p.base[k] == k) { out[n++] = T.U1[i * p.M + k]; } }
 	}
 	return n;
+}
+
+// true when the table really has the sharing structure the pattern assumes (checked bit for bit)
+inline bool table_shares_as_pattern(const PatternInfo& p, int bs, const StageTable& T) {
+	for (int k = 0; k < p.M; k++) {
+		const int b = p.base[k];
+		if (b == k) { continue; }
+		for (int i = 0; i < bs; i++) { if (T.F[k * MAXBS + i] != T.F[b * MAXBS + i]) { return false; } }
+		for (int j = 0; j < p.M; j++) {
+			const double want = ((p.uneg[k] >> j) & 1u) ? -T.U[b * p.M + j] : T.U[b * p.M + j];
+			if (T.U[k * p.M + j] != want) { return false; }
+			const double want1 = ((p.u1neg[k] >> j) & 1u) ? -T.U1[j * p.M + b] : T.U1[j * p.M + b];
+			if (T.U1[j * p.M + k] != want1) { return false; }
+		}
+	}
+	return true;
 }
 
 // stage_dispatch.cu

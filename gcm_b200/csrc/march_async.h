@@ -29,8 +29,7 @@ inline void cp_async_wait() { }
 #endif
 
 constexpr int MARCH_ZT = 128;  // threads per block = z extent of a block
-constexpr int MARCH_LEAD = 3;  // planes in flight ahead of the one being consumed
-constexpr int MARCH_RING = MARCH_LEAD + 1;
+constexpr int MARCH_LEAD = 3;  // default number of planes in flight ahead of the one being consumed
 constexpr int SMEM_TABLES = 16; // material tables kept in shared memory by the pipelined kernels
 
 // phase 0 of the pipelined kernels, one thread: copy the packed coefficient tables to shared memory
@@ -41,7 +40,7 @@ GCMB_HD void copy_tables(const StageArgs& a, double* tab, int table_size, int ti
 
 // ring[slot][component][thread]; slot of iteration s' holds: interpolated components at plane s'+BS,
 // centre-only components at plane s'
-template<class P, int BS>
+template<class P, int BS, int LEAD>
 GCMB_HD void stage_thread_march_async(const StageArgs& a, double (*ring)[P::M][MARCH_ZT], const double* tab,
                                       int tid, int perp, int i2, int s_begin, int s_end) {
 	constexpr int M = P::M;
@@ -52,6 +51,8 @@ GCMB_HD void stage_thread_march_async(const StageArgs& a, double (*ring)[P::M][M
 	const long long sstride = g.stride(a.axis);
 	const long long idx0 = a.axis == 0 ? g.index(s_begin, perp, i2) : g.index(perp, s_begin, i2);
 	const double* __restrict__ cur = a.cur;
+	constexpr int MARCH_LEAD = LEAD;
+	constexpr int MARCH_RING = LEAD + 1;
 
 	auto issue = [&](int s) {  // all copies of iteration s (s may run past the segment: then nothing)
 		if (s < s_end) {

@@ -7,12 +7,15 @@
 namespace gcmb {
 
 #define GCMB_L(...) {__VA_ARGS__}
-#define GCMB_PATTERN(NAME, MM, SGN, UM, U1M)                                                      \
+#define GCMB_PATTERN(NAME, MM, SGN, UM, U1M, BASE, UNEG, U1NEG)                                    \
 	struct Pat_##NAME {                                                                           \
 		static constexpr int M = MM;                                                              \
 		GCMB_HD static constexpr int sgn(int k) { constexpr int t[9] = SGN; return t[k]; }         \
 		GCMB_HD static constexpr unsigned um(int k) { constexpr unsigned t[9] = UM; return t[k]; } \
 		GCMB_HD static constexpr unsigned u1m(int k) { constexpr unsigned t[9] = U1M; return t[k]; } \
+		GCMB_HD static constexpr int base(int k) { constexpr int t[9] = BASE; return t[k]; }       \
+		GCMB_HD static constexpr unsigned uneg(int k) { constexpr unsigned t[9] = UNEG; return t[k]; } \
+		GCMB_HD static constexpr unsigned u1neg(int k) { constexpr unsigned t[9] = U1NEG; return t[k]; } \
 	};
 #include "patterns.inc"
 #undef GCMB_PATTERN
@@ -64,9 +67,9 @@ GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_march(const StageArgs a, int seg) {
 }
 
 // marching kernel fed by the cp.async ring (march_async.h)
-template<class P, int BS>
-GCMB_GLOBAL void GCMB_BOUNDS(MARCH_ZT) k_stage_march_async(const StageArgs a, int seg) {
-	__shared__ double ring[MARCH_RING][P::M][MARCH_ZT];
+template<class P, int BS, int LEAD, int MINB>
+GCMB_GLOBAL void GCMB_BOUNDS2(MARCH_ZT, MINB) k_stage_march_async(const StageArgs a, int seg) {
+	__shared__ double ring[LEAD + 1][P::M][MARCH_ZT];
 	__shared__ double tab[SMEM_TABLES * Packed<P, BS>::SIZE];
 	GCMB_BLOCK_THREADS(tid) { copy_tables(a, tab, Packed<P, BS>::SIZE, tid, MARCH_ZT); }
 	__syncthreads();
@@ -77,7 +80,7 @@ GCMB_GLOBAL void GCMB_BOUNDS(MARCH_ZT) k_stage_march_async(const StageArgs a, in
 	const int perp = a.axis == 0 ? (int) blockIdx.z : (int) blockIdx.z + a.x_begin;
 	GCMB_BLOCK_THREADS(tid) {
 		const int i2 = blockIdx.y * MARCH_ZT + tid;
-		if (i2 < a.g.n[2]) { stage_thread_march_async<P, BS>(a, ring, tab, tid, perp, i2, s_begin, s_end); }
+		if (i2 < a.g.n[2]) { stage_thread_march_async<P, BS, LEAD>(a, ring, tab, tid, perp, i2, s_begin, s_end); }
 	}
 }
 
@@ -123,8 +126,17 @@ static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
 		const int perp = a.axis == 0 ? a.g.n[1] : a.x_end - a.x_begin;
 		const dim3 grid((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZT - 1) / ZT), (unsigned) perp);
 		if (impl == 2) {
-			auto kernel = k_stage_march_async<P, BS>;
-			GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
+			static const int variant = env_int("GCMB_MARCH_VARIANT", 0);
+			if (variant == 1) {  // fewer planes in flight, registers capped for 6 blocks per SM
+				auto kernel = k_stage_march_async<P, BS, 2, 6>;
+				GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
+			} else if (variant == 2) {  // registers uncapped (3 blocks per SM), one more plane in flight
+				auto kernel = k_stage_march_async<P, BS, 4, 1>;
+				GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
+			} else {
+				auto kernel = k_stage_march_async<P, BS, MARCH_LEAD, 5>;
+				GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
+			}
 		} else {
 			auto kernel = k_stage_march<P, BS>;
 			GCMB_LAUNCH(kernel, grid, ZT, stream, a, seg);
@@ -151,8 +163,8 @@ static void launch_dense(const StageArgs& a, cudaStream_t stream) {
 	GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a);
 }
 
-#define GCMB_PATTERN(NAME, MM, SGN, UM, U1M) \
-	{#NAME, MM, SGN, UM, U1M, &launch_sparse<Pat_##NAME, 1>, &launch_sparse<Pat_##NAME, 2>},
+#define GCMB_PATTERN(NAME, MM, SGN, UM, U1M, BASE, UNEG, U1NEG) \
+	{#NAME, MM, SGN, UM, U1M, BASE, UNEG, U1NEG, &launch_sparse<Pat_##NAME, 1>, &launch_sparse<Pat_##NAME, 2>},
 static const PatternInfo g_patterns[] = {
 #include "patterns.inc"
 };

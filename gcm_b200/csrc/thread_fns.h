@@ -84,38 +84,51 @@ struct TableCoef {
 //     All positions are compile-time constants of the pattern, so every coefficient is one LDS with an
 //     immediate offset from the node's table base in shared memory.
 GCMB_HD constexpr int popcount_u(unsigned m) { int n = 0; for (; m; m &= m - 1) { n++; } return n; }
+// mask of the rows/columns that store their own coefficients
+template<class P>
+GCMB_HD constexpr unsigned packed_base_mask() {
+	unsigned m = 0;
+	for (int k = 0; k < P::M; k++) { if (P::base(k) == k) { m |= 1u << k; } }
+	return m;
+}
 template<class P, int BS>
-GCMB_HD constexpr int packed_fpos(int k) {
+GCMB_HD constexpr int packed_fpos(int k) {  // k must be a base row (or P::M for the total)
 	int n = 0;
-	for (int r = 0; r < k; r++) { if (P::sgn(r) != 0) { n += BS; } }
+	for (int r = 0; r < k; r++) { if (P::sgn(r) != 0 && P::base(r) == r) { n += BS; } }
 	return n;
 }
 template<class P, int BS>
 GCMB_HD constexpr int packed_upos(int k, int j) {
 	int n = packed_fpos<P, BS>(P::M);
-	for (int r = 0; r < k; r++) { n += popcount_u(P::um(r)); }
+	for (int r = 0; r < k; r++) { if (P::base(r) == r) { n += popcount_u(P::um(r)); } }
 	return k < P::M ? n + popcount_u(P::um(k) & ((1u << j) - 1u)) : n;
 }
 template<class P, int BS>
 GCMB_HD constexpr int packed_u1pos(int i, int k) {
+	constexpr unsigned B = packed_base_mask<P>();
 	int n = packed_upos<P, BS>(P::M, 0);
-	for (int r = 0; r < i; r++) { n += popcount_u(P::u1m(r)); }
-	return i < P::M ? n + popcount_u(P::u1m(i) & ((1u << k) - 1u)) : n;
+	for (int r = 0; r < i; r++) { n += popcount_u(P::u1m(r) & B); }
+	return i < P::M ? n + popcount_u(P::u1m(i) & B & ((1u << k) - 1u)) : n;
 }
 template<class P, int BS>
 struct Packed {
-	GCMB_HD static constexpr int fpos(int k) { return packed_fpos<P, BS>(k); }
-	GCMB_HD static constexpr int upos(int k, int j) { return packed_upos<P, BS>(k, j); }
-	GCMB_HD static constexpr int u1pos(int i, int k) { return packed_u1pos<P, BS>(i, k); }
 	static constexpr int SIZE = packed_u1pos<P, BS>(P::M, 0);
 };
 
 template<class P, int BS>
 struct PackedCoef {
 	const double* __restrict__ t;  // packed table of the node's material (shared memory)
-	GCMB_HD double u(int k, int j) const { return t[Packed<P, BS>::upos(k, j)]; }
-	GCMB_HD double u1(int i, int k) const { return t[Packed<P, BS>::u1pos(i, k)]; }
-	GCMB_HD const double* f(int k) const { return t + Packed<P, BS>::fpos(k); }
+	// a row/column that shares reads its base's entry (the compiler merges the two loads) and flips the
+	// sign where the pattern says so: (-c) * v == -(c * v) exactly
+	GCMB_HD double u(int k, int j) const {
+		const double c = t[packed_upos<P, BS>(P::base(k), j)];
+		return ((P::uneg(k) >> j) & 1u) ? -c : c;
+	}
+	GCMB_HD double u1(int i, int k) const {
+		const double c = t[packed_u1pos<P, BS>(i, P::base(k))];
+		return ((P::u1neg(k) >> i) & 1u) ? -c : c;
+	}
+	GCMB_HD const double* f(int k) const { return t + packed_fpos<P, BS>(P::base(k)); }
 };
 
 template<class P, int BS, class COEF, class LOAD>

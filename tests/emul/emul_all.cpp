@@ -88,6 +88,7 @@ using std::max;
 #define GCMB_GLOBAL static
 #define GCMB_DEV static inline
 #define GCMB_BOUNDS(n)
+#define GCMB_BOUNDS2(n, b)
 #define GCMB_LAUNCH(kernel, grid, block, stream, ...) \
 	gcmb_emul::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); })
 #define GCMB_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
