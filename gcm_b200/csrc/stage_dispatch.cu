@@ -130,8 +130,8 @@ static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
 			if (variant == 1) {  // fewer planes in flight, registers capped for 6 blocks per SM
 				auto kernel = k_stage_march_async<P, BS, 2, 6>;
 				GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
-			} else if (variant == 2) {  // registers uncapped (3 blocks per SM), one more plane in flight
-				auto kernel = k_stage_march_async<P, BS, 4, 1>;
+			} else if (variant == 2) {  // registers uncapped (3 blocks per SM)
+				auto kernel = k_stage_march_async<P, BS, MARCH_LEAD, 1>;
 				GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
 			} else {
 				auto kernel = k_stage_march_async<P, BS, MARCH_LEAD, 5>;
