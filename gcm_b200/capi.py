@@ -55,6 +55,9 @@ C_ABI = {
     "gcmb_comm_unique_id": (ctypes.c_int, [vp]),
     "gcmb_comm_init": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
     "gcmb_cubic_halo_exchange": (ctypes.c_int, [vp]),
+    "gcmb_cubic_halo_bytes": (ctypes.c_size_t, [vp]),
+    "gcmb_cubic_halo_get": (ctypes.c_int, [vp, ctypes.c_int, vp]),
+    "gcmb_cubic_halo_put": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "gcmb_comm_allreduce_sum": (ctypes.c_int, [vp, c_double_p, ctypes.c_int]),
     "gcmb_cubic_checksum": (ctypes.c_int, [vp, c_double_p]),
     "gcmb_cubic_stage_kernel_name": (ctypes.c_char_p, [vp, ctypes.c_int]),
@@ -271,6 +274,16 @@ class CubicBody:
 
     def kernel_name(self, direction):
         return self.lib.c.gcmb_cubic_stage_kernel_name(self.handle, direction).decode()
+
+    def halo_get(self, side):
+        buf = np.empty(self.lib.c.gcmb_cubic_halo_bytes(self.handle) // 8, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_cubic_halo_get(self.handle, side, buf.ctypes.data_as(vp)))
+        return buf
+
+    def halo_put(self, side, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.float64)
+        assert buf.nbytes == self.lib.c.gcmb_cubic_halo_bytes(self.handle)
+        self.lib.check(self.lib.c.gcmb_cubic_halo_put(self.handle, side, buf.ctypes.data_as(vp)))
 
 
 class HostEngine:

@@ -974,6 +974,34 @@ int gcmb_cubic_halo_exchange(gcmb_body* b) {
 	return GCMB_OK;
 }
 
+size_t gcmb_cubic_halo_bytes(gcmb_body* b) {
+	return b ? (size_t) b->g.M * (size_t) b->g.g[0] * (size_t) b->g.plane * sizeof(double) : 0;
+}
+
+static int halo_host(gcmb_body* b, int side, void* host, bool get) {
+	if (!b || !host) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	if (side != 0 && side != 1) { GCMB_FAIL(GCMB_E_INVALID_ARG, "side must be 0 or 1"); }
+	const Geom& g = b->g;
+	if (g.g[0] == 0) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "slab decomposition needs the x axis to be the slowest internal axis (3-D grids)"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	const size_t count = (size_t) g.g[0] * (size_t) g.plane;
+	// real planes next to the face: [bs, 2bs) left, [n0, n0+bs) right; ghost planes: [0, bs) / [n0+bs, n0+2bs)
+	const long long first = get ? (side == 0 ? g.g[0] : g.n[0]) : (side == 0 ? 0 : g.n[0] + g.g[0]);
+	for (int c = 0; c < g.M; c++) {
+		double* dev = b->buf[b->cur] + (long long) c * g.comp + first * g.plane;
+		double* h = static_cast<double*>(host) + (size_t) c * count;
+		if (get) { GCMB_CUDA(cudaMemcpyAsync(h, dev, count * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream)); }
+		else { GCMB_CUDA(cudaMemcpyAsync(dev, h, count * sizeof(double), cudaMemcpyHostToDevice, b->ctx->stream)); }
+	}
+	GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+	return GCMB_OK;
+}
+
+int gcmb_cubic_halo_get(gcmb_body* b, int side, void* host_buffer) { return halo_host(b, side, host_buffer, true); }
+int gcmb_cubic_halo_put(gcmb_body* b, int side, const void* host_buffer) {
+	return halo_host(b, side, const_cast<void*>(host_buffer), false);
+}
+
 int gcmb_comm_allreduce_sum(gcmb_ctx* ctx, double* host_values, int n) {
 	if (!ctx || !host_values || n < 1 || n > 2048) { GCMB_FAIL(GCMB_E_INVALID_ARG, "bad argument"); }
 	if (!ctx->comm || ctx->n_ranks == 1) { return GCMB_OK; }

@@ -29,7 +29,7 @@ inline void cp_async_wait() { }
 #endif
 
 constexpr int MARCH_ZT = 128;  // threads per block = z extent of a block
-constexpr int MARCH_LEAD = 3;  // default number of planes in flight ahead of the one being consumed
+constexpr int MARCH_LEAD = 2;  // planes in flight ahead of the one being consumed
 constexpr int SMEM_TABLES = 16; // material tables kept in shared memory by the pipelined kernels
 
 // phase 0 of the pipelined kernels, one thread: copy the packed coefficient tables to shared memory

@@ -85,9 +85,10 @@ GCMB_GLOBAL void GCMB_BOUNDS2(MARCH_ZT, MINB) k_stage_march_async(const StageArg
 }
 
 // contiguous-axis kernel: row tiles staged in shared memory by cp.async (ztile.h)
-template<class P, int BS>
+template<class P, int BS, int ZLEAD>
 GCMB_GLOBAL void GCMB_BOUNDS(ZTILE) k_stage_ztile(const StageArgs a, int rows) {
-	typedef ZTileSmem<P::M, Packed<P, BS>::SIZE> Smem;
+	constexpr int ZRING = ZLEAD + 1;
+	typedef ZTileSmem<P::M, Packed<P, BS>::SIZE, ZLEAD> Smem;
 	GCMB_DYN_SMEM(Smem, sm);
 	GCMB_BLOCK_THREADS(tid) { copy_tables(a, sm.tab, Packed<P, BS>::SIZE, tid, ZTILE); }
 	const int z0 = blockIdx.x * ZTILE;
@@ -95,15 +96,15 @@ GCMB_GLOBAL void GCMB_BOUNDS(ZTILE) k_stage_ztile(const StageArgs a, int rows) {
 	const int r1 = min(a.g.n[1], r0 + rows);
 	const int i0 = blockIdx.z + a.x_begin;
 	for (int d = 0; d < ZLEAD; d++) {
-		GCMB_BLOCK_THREADS(tid) { ztile_issue<P, BS>(a, sm, d % ZRING, tid, i0, r0 + d, z0, r1); }
+		GCMB_BLOCK_THREADS(tid) { ztile_issue<P, BS, ZLEAD>(a, sm, d % ZRING, tid, i0, r0 + d, z0, r1); }
 	}
 	for (int r = r0; r < r1; r++) {
 		const int it = r - r0;
 		// tile it+ZLEAD goes into the slot read one iteration ago (protected by the barrier below)
-		GCMB_BLOCK_THREADS(tid) { ztile_issue<P, BS>(a, sm, (it + ZLEAD) % ZRING, tid, i0, r + ZLEAD, z0, r1); }
+		GCMB_BLOCK_THREADS(tid) { ztile_issue<P, BS, ZLEAD>(a, sm, (it + ZLEAD) % ZRING, tid, i0, r + ZLEAD, z0, r1); }
 		cp_async_wait<ZLEAD>();
 		__syncthreads();
-		GCMB_BLOCK_THREADS(tid) { ztile_compute<P, BS>(a, sm, it % ZRING, tid, i0, r, z0); }
+		GCMB_BLOCK_THREADS(tid) { ztile_compute<P, BS, ZLEAD>(a, sm, it % ZRING, tid, i0, r, z0); }
 		__syncthreads();
 	}
 	cp_async_wait<0>();
@@ -126,30 +127,22 @@ static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
 		const int perp = a.axis == 0 ? a.g.n[1] : a.x_end - a.x_begin;
 		const dim3 grid((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZT - 1) / ZT), (unsigned) perp);
 		if (impl == 2) {
-			static const int variant = env_int("GCMB_MARCH_VARIANT", 0);
-			if (variant == 1) {  // fewer planes in flight, registers capped for 6 blocks per SM
-				auto kernel = k_stage_march_async<P, BS, 2, 6>;
-				GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
-			} else if (variant == 2) {  // registers uncapped (3 blocks per SM)
-				auto kernel = k_stage_march_async<P, BS, MARCH_LEAD, 1>;
-				GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
-			} else {
-				auto kernel = k_stage_march_async<P, BS, MARCH_LEAD, 5>;
-				GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
-			}
+			// 2 planes in flight per thread, registers capped for 6 blocks = 24 warps per SM: the best of the
+			// variants measured on B200 (profiles/r1_variants.md)
+			auto kernel = k_stage_march_async<P, BS, MARCH_LEAD, 6>;
+			GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
 		} else {
 			auto kernel = k_stage_march<P, BS>;
 			GCMB_LAUNCH(kernel, grid, ZT, stream, a, seg);
 		}
 	} else if (impl == 2 && a.axis == 2 && tables_fit) {
 		static const int rows = env_int("GCMB_ZTILE_ROWS", 32);
-		auto kernel = k_stage_ztile<P, BS>;
-		typedef ZTileSmem<P::M, Packed<P, BS>::SIZE> Smem;
-		static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                                                     (int) sizeof(Smem));
-		(void) attr;
 		const dim3 grid((unsigned) ((a.g.n[2] + ZTILE - 1) / ZTILE), (unsigned) ((a.g.n[1] + rows - 1) / rows),
 		                (unsigned) (a.x_end - a.x_begin));
+		typedef ZTileSmem<P::M, Packed<P, BS>::SIZE, ZLEAD> Smem;
+		auto kernel = k_stage_ztile<P, BS, ZLEAD>;
+		static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem));
+		(void) attr;
 		GCMB_LAUNCH_COOP(kernel, grid, ZTILE, sizeof(Smem), stream, a, rows);
 	} else {
 		auto kernel = k_stage_direct<P, BS>;

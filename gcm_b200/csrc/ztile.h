@@ -25,21 +25,20 @@ inline void cp_async_b32(void* smem_dst, const void* gmem_src) { memcpy(smem_dst
 #endif
 
 constexpr int ZTILE = 256;             // threads per block = nodes per tile
-constexpr int ZLEAD = 2;               // tiles in flight ahead of the one being computed
-constexpr int ZRING = ZLEAD + 1;
+constexpr int ZLEAD = 1;               // tiles in flight ahead of the one being computed
 constexpr int ZHALO = 2;               // largest border size served by this kernel
 constexpr int ZROW = ZTILE + 2 * ZHALO;
 
-template<int M, int TABLE_SIZE>
+template<int M, int TABLE_SIZE, int LEAD>
 struct ZTileSmem {
-	double v[ZRING][M][ZROW];
+	double v[LEAD + 1][M][ZROW];
 	double tab[SMEM_TABLES * TABLE_SIZE];
-	uint8_t id[ZRING][ZTILE];
+	uint8_t id[LEAD + 1][ZTILE];
 };
 
 // phase A, one thread: start the copies of row `i1` (tile slot `slot`); rows past the end copy nothing
-template<class P, int BS>
-GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M, Packed<P, BS>::SIZE>& sm, int slot, int tid, int i0, int i1, int z0, int i1_end) {
+template<class P, int BS, int LEAD>
+GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M, Packed<P, BS>::SIZE, LEAD>& sm, int slot, int tid, int i0, int i1, int z0, int i1_end) {
 	constexpr int M = P::M;
 	constexpr unsigned IC = PatternSets<P>::interp();
 	constexpr unsigned CC = PatternSets<P>::center();
@@ -70,8 +69,8 @@ GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M, Packed<P, BS>::SIZE
 }
 
 // phase B, one thread: one node of the tile from shared memory
-template<class P, int BS>
-GCMB_HD void ztile_compute(const StageArgs& a, const ZTileSmem<P::M, Packed<P, BS>::SIZE>& sm, int slot, int tid, int i0, int i1, int z0) {
+template<class P, int BS, int LEAD>
+GCMB_HD void ztile_compute(const StageArgs& a, const ZTileSmem<P::M, Packed<P, BS>::SIZE, LEAD>& sm, int slot, int tid, int i0, int i1, int z0) {
 	constexpr int M = P::M;
 	const Geom& g = a.g;
 	const int z = z0 + tid;

@@ -149,6 +149,14 @@ int gcmb_comm_init(gcmb_ctx* ctx, int n_ranks, int rank, const void* id128);
  * none at the ends): my ghost planes <- neighbour's outermost real planes.  Equivalent to two
  * ContactCopiers between neighbouring slabs; call before the direction-0 stage. */
 int gcmb_cubic_halo_exchange(gcmb_body* body);
+/* Host-staged variant for transports that are not GPU-aware (the reference's own MPI_Sendrecv of raw
+ * PdeVector bytes, src/test/TestMPI.cpp:31-51): get copies the outermost `border_size` REAL x-planes of
+ * side (0 left, 1 right) into a host buffer of gcmb_cubic_halo_bytes(body) bytes, put writes such a buffer
+ * into the GHOST planes of that side.  The buffer layout is opaque but identical for slabs of equal y/z
+ * extent.  Both sync. */
+size_t gcmb_cubic_halo_bytes(gcmb_body* body);
+int gcmb_cubic_halo_get(gcmb_body* body, int side, void* host_buffer);
+int gcmb_cubic_halo_put(gcmb_body* body, int side, const void* host_buffer);
 /* in-place sum over all ranks of n doubles held on the host (detector sums of decomposed grids). sync */
 int gcmb_comm_allreduce_sum(gcmb_ctx* ctx, double* host_values, int n);
 
