@@ -430,9 +430,9 @@ void EngineBase::sliceSnapshot(const int step_) {
 			sum = both[0];
 			count = (long long) both[1];
 		}
-		if (slabRank != slabCount / 2) { continue; }
+		const bool writer = slabRank == slabCount / 2;  // every slab records the seismogram, one writes files
 		const std::string name = "mesh" + std::to_string(m.id) + "core" + padded(slabRank, 2) + "snap" + padded(step_, 4) + ".txt";
-		{
+		if (writer) {
 			std::ofstream f(dir + "/zaxis/" + name);
 			Mesh::Iterator it = {{m.sizes[0] / 2, m.sizes[1] / 2, m.sizes[2] / 2}};
 			for (int k = 0; k < m.sizes[last]; k++) {
@@ -444,6 +444,7 @@ void EngineBase::sliceSnapshot(const int step_) {
 		if (count < 1) { throw Exception(GCMB_E_INVALID_ARG, "the detector area holds no node"); }
 		const real value = sum / (real) count;
 		seismo.push_back({Clock::Time(), (float) value});
+		if (!writer) { continue; }
 		std::ofstream f(dir + "/detector/" + name);
 		for (const auto& s : seismo) { f << s.first << "\t" << (real) s.second << "\t" << std::endl; }
 	}

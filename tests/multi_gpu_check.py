@@ -23,7 +23,19 @@ from helpers import golden
 from scenarios import SCENARIOS, elastic3d_layers, ortho3d_contact
 
 
-def run_slabs(lib, text, rank, world, local, nccl_id):
+def new_nccl_id(lib, rank):
+    """a fresh NCCL id for every engine (an id initialises exactly one communicator)"""
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        raw = (capi.ctypes.c_ubyte * 128)()
+        lib.check(lib.c.gcmb_comm_unique_id(capi.ctypes.cast(raw, capi.vp)))
+        buf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().tolist())
+
+
+def run_slabs(lib, text, rank, world, local, nccl_id=None):
+    nccl_id = new_nccl_id(lib, rank)
     eng = capi.HostEngine(lib, text, device=local, slab_rank=rank, slab_count=world, nccl_id=nccl_id)
     eng.run()
     out = {}
@@ -56,13 +68,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     lib = gcm_b200.library()
-    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        raw = (capi.ctypes.c_ubyte * 128)()
-        lib.check(lib.c.gcmb_comm_unique_id(capi.ctypes.cast(raw, capi.vp)))
-        buf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
-    dist.broadcast(buf, 0)
-    nccl_id = bytes(buf.cpu().tolist())
+    nccl_id = None
     os.chdir("/tmp")
 
     # (1) against the reference fixtures
