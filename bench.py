@@ -287,7 +287,11 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("bytes_per_launch")
+            t = json.load(open(traffic_file))
+            # dram__bytes_read+write of one launch from the ncu --set full capture (taken at 512^3), scaled
+            # to this run's launch by the node count
+            roofline["traffic"] = t["ratio_to_algorithmic"] * bytes_per_launch
+            roofline["traffic_source"] = t["source"]
         except Exception:
             pass
 
