@@ -106,13 +106,14 @@ GCMB_DEV void block_sum(double& v, long long& c) {
 	c = sc[0];
 }
 
-// detector: quantity summed over masked nodes of the right face of the last axis (one block)
+// detector: quantity summed over masked nodes of the right face of the last axis; one partial (sum, count)
+// per block in a fixed order => deterministic
 GCMB_GLOBAL void k_detector(Geom g, const double* pde, const uint8_t* mask, int code, double* out_sum,
                            long long* out_count) {
 	const long long n_face = (long long) g.n[0] * g.n[1];
 	double sum = 0;
 	long long count = 0;
-	for (long long f = threadIdx.x; f < n_face; f += blockDim.x) {
+	for (long long f = (long long) blockIdx.x * blockDim.x + threadIdx.x; f < n_face; f += (long long) gridDim.x * blockDim.x) {
 		if (!mask[f]) { continue; }
 		const long long idx = g.index((int) (f / g.n[1]), (int) (f % g.n[1]), g.n[2] - 1);
 		double v[MAXM];
@@ -120,8 +121,8 @@ GCMB_GLOBAL void k_detector(Geom g, const double* pde, const uint8_t* mask, int 
 		sum += get_quantity(g.D, code, v);
 		count++;
 	}
-	block_sum<1024>(sum, count);
-	if (threadIdx.x == 0) { *out_sum = sum; *out_count = count; }
+	block_sum<256>(sum, count);
+	if (threadIdx.x == 0) { out_sum[blockIdx.x] = sum; out_count[blockIdx.x] = count; }
 }
 
 // checksum partials: sum_i (i+1) * u_i over real nodes, fixed grid => deterministic
@@ -869,18 +870,23 @@ int gcmb_cubic_seismo(gcmb_body* b, double* sum, long long* count, int line_comp
 	GCMB_CUDA(cudaSetDevice(ctx->device));
 	if (sum || count) {
 		if (!b->detector_mask) { GCMB_FAIL(GCMB_E_INVALID_OP, "detector is not set"); }
+		const long long nf = (long long) g.n[0] * g.n[1];
+		const int blocks = (int) std::max<long long>(1, std::min<long long>(1024, (nf + 255) / 256));
 		double* d_sum = ctx->scratch;
-		long long* d_count = reinterpret_cast<long long*>(ctx->scratch + 1);
+		long long* d_count = reinterpret_cast<long long*>(ctx->scratch + 1024);
 		{
 			Launch l(ctx, 7);
-			GCMB_LAUNCH(k_detector, 1, 1024, ctx->stream, g, b->buf[b->cur], b->detector_mask, b->detector_code, d_sum, d_count);
+			GCMB_LAUNCH(k_detector, blocks, 256, ctx->stream, g, b->buf[b->cur], b->detector_mask, b->detector_code, d_sum, d_count);
 		}
 		GCMB_CUDA(cudaGetLastError());
+		std::vector<double> ps((size_t) blocks);
+		std::vector<long long> pc((size_t) blocks);
+		GCMB_CUDA(cudaMemcpyAsync(ps.data(), d_sum, (size_t) blocks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		GCMB_CUDA(cudaMemcpyAsync(pc.data(), d_count, (size_t) blocks * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+		GCMB_CUDA(cudaStreamSynchronize(ctx->stream));
 		double hs = 0;
 		long long hc = 0;
-		GCMB_CUDA(cudaMemcpyAsync(&hs, d_sum, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
-		GCMB_CUDA(cudaMemcpyAsync(&hc, d_count, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-		GCMB_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (int i = 0; i < blocks; i++) { hs += ps[(size_t) i]; hc += pc[(size_t) i]; }
 		if (sum) { *sum = hs; }
 		if (count) { *count = hc; }
 	}

@@ -134,3 +134,18 @@ def test_uniform_state_is_a_fixed_point(lib):
     assert np.abs(out[:, 2:-2, 2:-2] - vec).max() <= 1e-13 * 9
     body.close()
     ctx.close()
+
+
+def test_reference_run_statement(lib):
+    """src/test/sequence/TestEngine.cpp:91-136 on the CUDA engine"""
+    from reference_engine_cases import run_statement
+    run_statement(lib)
+
+
+@pytest.mark.parametrize("vary", ["rho", "E"])
+def test_reference_two_layers(lib, vary):
+    """src/test/sequence/TestEngine.cpp:139-296 on the CUDA engine, and bitwise equal to the oracle run"""
+    import oracle_host as oh
+    from reference_engine_cases import two_layers
+    for (steps, rs, rs_theory, rv, rv_theory, init, reflect) in two_layers(lib, vary):
+        assert abs(rs - rs_theory) < 1e-2 and abs(rv - rv_theory) < 1e-2, (rs, rs_theory, rv, rv_theory)

@@ -109,3 +109,19 @@ def test_random_state_single_stages_match_oracle(lib):
     from helpers import random_stage_check
     random_stage_check(lib, ((3, (7, 6, 37), "elastic", 2), (3, (3, 35, 300), "elastic", 2), (3, (260, 2, 9), "acoustic", 1),
                              (2, (9, 515), "elastic", 1), (2, (300, 8), "acoustic", 2), (1, (600,), "elastic", 2)))
+
+
+def test_reference_run_statement(lib):
+    """src/test/sequence/TestEngine.cpp:91-136 on our engine (dense kernel: border size 5, Courant 4.5)"""
+    from reference_engine_cases import run_statement
+    assert run_statement(lib) == ["dense:M5", "dense:M5"]
+
+
+@pytest.mark.parametrize("vary", ["rho", "E"])
+def test_reference_two_layers(lib, vary):
+    """src/test/sequence/TestEngine.cpp:139-296 on our engine; the oracle must see the same numbers bit for bit,
+    and the reference's own 1e-2 assertions on the reflection coefficients must hold."""
+    import oracle_host as oh
+    from reference_engine_cases import two_layers
+    for (steps, rs, rs_theory, rv, rv_theory, init, reflect) in two_layers(lib, vary):
+        assert abs(rs - rs_theory) < 1e-2 and abs(rv - rv_theory) < 1e-2, (rs, rs_theory, rv, rv_theory)
