@@ -20,8 +20,9 @@ NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-line
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall"]
 
 CUDA_SOURCES = ["csrc/gcmb_capi.cu", "csrc/stage_dispatch.cu"]
-CUDA_HEADERS = ["csrc/internal.cuh", "csrc/thread_fns.h", "csrc/patterns.inc", "../include/gcm_b200.h"]
-HOST_SOURCES = ["host/models.cpp", "host/engine.cpp", "host/task_file.cpp", "host/host_capi.cpp"]
+CUDA_HEADERS = ["csrc/internal.cuh", "csrc/thread_fns.h", "csrc/march_async.h", "csrc/ztile.h", "csrc/patterns.inc",
+                "csrc/simplex_fns.h", "csrc/simplex_capi.inc", "../include/gcm_b200.h"]
+HOST_SOURCES = ["host/models.cpp", "host/engine.cpp", "host/task_file.cpp", "host/host_capi.cpp", "host/simplex_mesh.cpp"]
 HOST_HEADERS = ["host/gcmb_host.hpp", "../include/gcm_b200.h"]
 
 

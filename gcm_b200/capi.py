@@ -60,6 +60,20 @@ C_ABI = {
     "gcmb_cubic_halo_put": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "gcmb_comm_allreduce_sum": (ctypes.c_int, [vp, c_double_p, ctypes.c_int]),
     "gcmb_cubic_checksum": (ctypes.c_int, [vp, c_double_p]),
+    "gcmb_simplex_body_create": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_int_p, c_int_p,
+                                                c_int_p, c_int_p, c_int_p, ctypes.c_int, ctypes.POINTER(vp)]),
+    "gcmb_simplex_body_destroy": (None, [vp]),
+    "gcmb_simplex_info": (ctypes.c_int, [vp, c_int_p, c_int_p, c_int_p]),
+    "gcmb_simplex_vertices": (ctypes.c_int, [vp, c_int_p, c_u8_p, c_double_p, c_double_p]),
+    "gcmb_simplex_locate": (ctypes.c_int, [vp, ctypes.c_int, c_int_p, c_double_p, c_int_p]),
+    "gcmb_simplex_errors": (ctypes.c_int, [vp, c_int_p]),
+    "gcmb_simplex_set_material": (ctypes.c_int, [vp, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "gcmb_simplex_upload_state": (ctypes.c_int, [vp, c_double_p]),
+    "gcmb_simplex_download_state": (ctypes.c_int, [vp, c_double_p]),
+    "gcmb_simplex_border_set": (ctypes.c_int, [vp, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_int_p]),
+    "gcmb_simplex_plain_border": (ctypes.c_int, [vp, c_double_p]),
+    "gcmb_simplex_stage": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double, c_double_p]),
+    "gcmb_simplex_gradient": (ctypes.c_int, [vp, c_double_p, c_double_p]),
     "gcmb_cubic_stage_kernel_name": (ctypes.c_char_p, [vp, ctypes.c_int]),
 }
 

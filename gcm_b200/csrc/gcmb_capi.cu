@@ -1021,3 +1021,5 @@ int gcmb_comm_allreduce_sum(gcmb_ctx* ctx, double* host_values, int n) {
 }
 
 }  // extern "C"
+
+#include "simplex_capi.inc"

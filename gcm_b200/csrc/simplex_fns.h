@@ -1,0 +1,673 @@
+// Per-thread work functions of the simplex (tetrahedral) path: characteristic-foot cell location by line
+// walk, least-squares gradients, hybrid quadratic interpolation, space-time interpolation at border facets and
+// the outer-wave border correction.  Like thread_fns.h these are __host__ __device__ so that the host-logic
+// tests can step through them; the arithmetic follows the reference expression by expression (fp64, no FMA):
+// the integer results of the cell location must equal the reference's bit for bit.
+//
+// Reference (relative to src/libgcm): grid/simplex/SimplexGrid.cpp:61-164, grid/simplex/cgal/LineWalker.hpp:26-89,
+// grid/simplex/cgal/Cgal3DTriangulation.hpp:160-292, linal/geometry.hpp, linal/linearSystems.hpp:46-158,
+// util/math/Differentiation.hpp:33-63, util/math/interpolation/TetrahedronInterpolator.hpp:15-155,
+// engine/simplex/GridCharacteristicMethodInRiemannInvariants.hpp:44-198, engine/simplex/common.hpp:48-260,
+// engine/simplex/BorderCorrector.hpp:122-286, rheology/models/ElasticModel.hpp:111-232, AcousticModel.hpp:95-147.
+#pragma once
+#include "internal.cuh"
+
+namespace gcmb {
+namespace sx {
+
+constexpr double TOL = 1e-9;       // EQUALITY_TOLERANCE (util/infrastructure/Types.hpp:10)
+constexpr int MAX_NEIGHBORS = 20;  // Cgal3DTriangulation.hpp:53
+constexpr int EMPTY = -1;          // CellInfo::EmptySpaceFlag
+
+struct V3 {
+	double x, y, z;
+	GCMB_HD double operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+GCMB_HD V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+GCMB_HD V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+GCMB_HD V3 operator*(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+GCMB_HD V3 operator/(V3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+GCMB_HD double dot(V3 a, V3 b) { double r = a.x * b.x; r += a.y * b.y; r += a.z * b.z; return r; }
+GCMB_HD double length(V3 a) { return sqrt(dot(a, a)); }
+GCMB_HD V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+GCMB_HD double det2(double a, double b, double c, double d) { return a * d - b * c; }
+GCMB_HD double det3(double a11, double a12, double a13, double a21, double a22, double a23,
+                    double a31, double a32, double a33) {
+	return a11 * (a22 * a33 - a23 * a32) - a12 * (a21 * a33 - a23 * a31) + a13 * (a21 * a32 - a22 * a31);
+}
+
+// Cramer's rule; false when the reference throws "SLE determinant is zero"
+GCMB_HD bool solve3(const double (&A)[3][3], const double (&b)[3], double (&x)[3]) {
+	const double det = det3(A[0][0], A[0][1], A[0][2], A[1][0], A[1][1], A[1][2], A[2][0], A[2][1], A[2][2]);
+	if (det == 0) { return false; }
+	x[0] = det3(b[0], A[0][1], A[0][2], b[1], A[1][1], A[1][2], b[2], A[2][1], A[2][2]) / det;
+	x[1] = det3(A[0][0], b[0], A[0][2], A[1][0], b[1], A[1][2], A[2][0], b[2], A[2][2]) / det;
+	x[2] = det3(A[0][0], A[0][1], b[0], A[1][0], A[1][1], b[1], A[2][0], A[2][1], b[2]) / det;
+	return true;
+}
+
+// least squares with unit weights: 3x2 system (columns p, q) and 3x1 system (column p)
+GCMB_HD bool leastSquares2(V3 p, V3 q, V3 rhs, double (&x)[2]) {
+	const V3 c[2] = {p, q};
+	double N[2][2], b[2];
+	for (int i = 0; i < 2; i++) {
+		for (int j = 0; j < 2; j++) {
+			double r = c[i].x * (1.0 * c[j].x); r += c[i].y * (1.0 * c[j].y); r += c[i].z * (1.0 * c[j].z);
+			N[i][j] = r;
+		}
+		double r = c[i].x * (1.0 * rhs.x); r += c[i].y * (1.0 * rhs.y); r += c[i].z * (1.0 * rhs.z);
+		b[i] = r;
+	}
+	const double det = det2(N[0][0], N[0][1], N[1][0], N[1][1]);
+	if (det == 0) { return false; }
+	x[0] = det2(b[0], N[0][1], b[1], N[1][1]) / det;
+	x[1] = det2(N[0][0], b[0], N[1][0], b[1]) / det;
+	return true;
+}
+GCMB_HD bool leastSquares1(V3 p, V3 rhs, double& x) {
+	double a = p.x * (1.0 * p.x); a += p.y * (1.0 * p.y); a += p.z * (1.0 * p.z);
+	double b = p.x * (1.0 * rhs.x); b += p.y * (1.0 * rhs.y); b += p.z * (1.0 * rhs.z);
+	if (a == 0) { return false; }
+	x = b / a;
+	return true;
+}
+
+GCMB_HD double orientedVolume(V3 a, V3 b, V3 c, V3 d) {
+	const V3 ba = b - a, ca = c - a, da = d - a;
+	return det3(ba.x, ba.y, ba.z, ca.x, ca.y, ca.z, da.x, da.y, da.z) / 6;
+}
+GCMB_HD bool barycentric(V3 a, V3 b, V3 c, V3 d, V3 q, double (&l)[4]) {
+	const double T[3][3] = {{a.x - d.x, b.x - d.x, c.x - d.x}, {a.y - d.y, b.y - d.y, c.y - d.y}, {a.z - d.z, b.z - d.z, c.z - d.z}};
+	const double rhs[3] = {q.x - d.x, q.y - d.y, q.z - d.z};
+	double x[3];
+	if (!solve3(T, rhs, x)) { return false; }
+	l[0] = x[0]; l[1] = x[1]; l[2] = x[2]; l[3] = 1 - x[0] - x[1] - x[2];
+	return true;
+}
+GCMB_HD double area(V3 a, V3 b, V3 c) { return length(cross(b - a, c - a)) / 2; }
+GCMB_HD double volume(V3 a, V3 b, V3 c, V3 d) { return fabs(orientedVolume(a, b, c, d)); }
+GCMB_HD bool degenerateTetra(V3 a, V3 b, V3 c, V3 d, double eps) {
+	const double V = volume(a, b, c, d);
+	const double A = area(b, c, d), B = area(c, d, a), C = area(d, a, b), D = area(a, b, c);
+	const double h = 3 * V / fmax(A, fmax(B, fmax(C, D)));
+	const double l = (length(a - b) + length(a - c) + length(a - d) + length(d - b) + length(d - c) + length(b - c)) / 6;
+	return h <= eps * l;
+}
+GCMB_HD bool degenerateTriangle(V3 a, V3 b, V3 c, double eps) {
+	const double S = area(a, b, c);
+	const double ab = length(a - b), ac = length(a - c), bc = length(b - c);
+	const double h = 2 * S / fmax(ab, fmax(ac, bc));
+	const double l = (length(a - b) + length(a - c) + length(b - c)) / 3;
+	return h <= eps * l;
+}
+GCMB_HD bool segmentContains(V3 a, V3 b, V3 q, double eps, double degEps, int& err) {
+	if (!degenerateTriangle(a, b, q, degEps)) { return false; }
+	double x;
+	if (!leastSquares1(a - b, q - b, x)) { err = 1; return false; }
+	return x >= -eps && 1 - x >= -eps;
+}
+GCMB_HD bool triangleContains(V3 a, V3 b, V3 c, V3 q, double eps, double degEps, int& err) {
+	if (!degenerateTetra(a, b, c, q, degEps)) { return false; }
+	double x[2];
+	if (!leastSquares2(a - c, b - c, q - c, x)) { err = 1; return false; }
+	return x[0] >= -eps && x[1] >= -eps && 1 - x[0] - x[1] >= -eps;
+}
+GCMB_HD bool tetrahedronContains(V3 a, V3 b, V3 c, V3 d, V3 q, double eps, int& err) {
+	double l[4];
+	if (!barycentric(a, b, c, d, q, l)) { err = 1; return false; }
+	return l[0] >= -eps && l[1] >= -eps && l[2] >= -eps && l[3] >= -eps;
+}
+GCMB_HD bool solidAngleContains(V3 a, V3 b, V3 c, V3 d, V3 q, double eps, int& err) {
+	double l[4];
+	if (!barycentric(a, b, c, d, q, l)) { err = 1; return false; }
+	return l[0] <= 1 + eps && l[1] >= -eps && l[2] >= -eps && l[3] >= -eps;
+}
+GCMB_HD bool lineFlatIntersection(V3 f1, V3 f2, V3 f3, V3 l1, V3 l2, V3& out) {
+	const V3 tau = l2 - l1, p = f2 - f1, q = f3 - f1;
+	const double A[3][3] = {{tau.x, -p.x, -q.x}, {tau.y, -p.y, -q.y}, {tau.z, -p.z, -q.z}};
+	const double b[3] = {f1.x - l1.x, f1.y - l1.y, f1.z - l1.z};
+	double x[3];
+	if (!solve3(A, b, x)) { return false; }
+	out = l1 + tau * x[0];
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the body's view of the flat triangulation (all arrays in device memory)
+// ---------------------------------------------------------------------------------------------
+struct Tri {
+	int nV, nC, nLocal, gridId;
+	const double* xyz;      // [nV][3]
+	const int* cellV;       // [nC][4] global vertex ids
+	const int* cellN;       // [nC][4]
+	const int* cellGrid;    // [nC]
+	const int* incOff;      // [nV+1]
+	const int* incCell;
+	const int* localOf;     // [nV]
+	const int* globalOf;    // [nLocal]
+	const int* nbOff;       // [nLocal+1] neighbour vertices (ascending local id, at most MAX_NEIGHBORS)
+	const int* nbIdx;
+	const uint8_t* state;   // [nLocal] 0 inner, 1 border, 2 contact, 3 multicontact
+
+	GCMB_HD V3 point(int g) const { return {xyz[3 * (long long) g], xyz[3 * (long long) g + 1], xyz[3 * (long long) g + 2]}; }
+	GCMB_HD V3 localPoint(int l) const { return point(globalOf[l]); }
+	GCMB_HD bool isLocal(int cell) const { return cell >= 0 && cellGrid[cell] == gridId; }
+	GCMB_HD int otherVertexIndex(int cell, int a, int b, int c) const {
+		for (int i = 0; i < 4; i++) {
+			const int d = cellV[4 * (long long) cell + i];
+			if (d != a && d != b && d != c) { return i; }
+		}
+		return 0;
+	}
+	GCMB_HD int otherVertex(int cell, int a, int b, int c) const { return cellV[4 * (long long) cell + otherVertexIndex(cell, a, b, c)]; }
+};
+
+struct Found { int n; int p[4]; };
+GCMB_HD Found nothing() { return {0, {-1, -1, -1, -1}}; }
+GCMB_HD Found wholeCell(const Tri& t, int cell) {
+	Found f;
+	f.n = 4;
+	for (int i = 0; i < 4; i++) { f.p[i] = t.localOf[t.cellV[4 * (long long) cell + i]]; }
+	return f;
+}
+
+// the reference keeps the list of crossed cells; only its size, the last two cells and the facet the walk
+// left the previous cell through are ever used
+struct Walked { int count, last, prev, exitSlot; };
+
+GCMB_HD int crossedIncidentCell(const Tri& t, int gv, V3 query, double eps, int& err) {
+	for (int i = t.incOff[gv]; i < t.incOff[gv + 1]; i++) {
+		const int cand = t.incCell[i];
+		if (!t.isLocal(cand)) { continue; }
+		const int a = t.otherVertex(cand, gv, gv, gv);
+		const int b = t.otherVertex(cand, gv, gv, a);
+		const int c = t.otherVertex(cand, gv, a, b);
+		if (solidAngleContains(t.point(gv), t.point(a), t.point(b), t.point(c), query, eps, err)) { return cand; }
+	}
+	return -2;
+}
+
+GCMB_HD Walked collectCells(const Tri& t, V3 q, V3 p, int cell, int u, int v, int w) {
+	Walked ans = {1, cell, -2, -1};
+	for (int guard = 0; guard < 100000; guard++) {
+		if (!(orientedVolume(t.point(u), t.point(v), t.point(w), p) < 0)) { break; }
+		ans.exitSlot = t.otherVertexIndex(cell, u, v, w);
+		cell = t.cellN[4 * (long long) cell + ans.exitSlot];
+		ans.prev = ans.last; ans.last = cell; ans.count++;
+		if (!t.isLocal(cell)) { break; }
+		const int s = t.otherVertex(cell, u, v, w);
+		const V3 ps = t.point(s);
+		if (orientedVolume(t.point(u), ps, q, p) > 0) {
+			if (orientedVolume(t.point(v), ps, q, p) > 0) { u = s; } else { w = s; }
+		} else {
+			if (orientedVolume(t.point(w), ps, q, p) > 0) { v = s; } else { u = s; }
+		}
+	}
+	return ans;
+}
+
+GCMB_HD Walked walkFromVertex(const Tri& t, int gv, V3 p, int& err) {
+	const int cell = crossedIncidentCell(t, gv, p, 0, err);
+	if (cell == -2) { return {0, -2, -2, -1}; }
+	int u = t.otherVertex(cell, gv, gv, gv);
+	int v = t.otherVertex(cell, gv, gv, u);
+	const int w = t.otherVertex(cell, gv, u, v);
+	if (orientedVolume(t.point(u), t.point(v), t.point(w), t.point(gv)) < 0) { const int x = u; u = v; v = x; }
+	return collectCells(t, t.point(gv), p, cell, u, v, w);
+}
+
+GCMB_HD Walked walkFromCell(const Tri& t, int cell, V3 q, V3 p, int& err) {
+	int u = -1, v = -1, w = -1;
+	for (int attempt = 0; attempt < 2 && u < 0; attempt++) {
+		const double eps = attempt == 0 ? 0.0 : TOL;
+		for (int i = 0; i < 4; i++) {
+			const int a1 = t.cellV[4 * (long long) cell + (i + 1) % 4];
+			const int b1 = t.cellV[4 * (long long) cell + (i + 2) % 4];
+			const int c1 = t.cellV[4 * (long long) cell + (i + 3) % 4];
+			if (solidAngleContains(q, t.point(a1), t.point(b1), t.point(c1), p, eps, err)) { u = a1; v = b1; w = c1; break; }
+		}
+	}
+	if (u < 0) { return {0, -2, -2, -1}; }
+	if (orientedVolume(t.point(u), t.point(v), t.point(w), q) < 0) { const int x = u; u = v; v = x; }
+	return collectCells(t, q, p, cell, u, v, w);
+}
+
+GCMB_HD bool cellContains(const Tri& t, int cell, V3 q, int& err) {
+	const int* v = t.cellV + 4 * (long long) cell;
+	return tetrahedronContains(t.point(v[0]), t.point(v[1]), t.point(v[2]), t.point(v[3]), q, TOL, err);
+}
+
+GCMB_HD Found borderFacet(const Tri& t, int prev, int exitSlot, V3 start, V3 query, int& err) {
+	int face[3], n = 0;
+	for (int i = 0; i < 4; i++) { if (i != exitSlot) { face[n++] = t.cellV[4 * (long long) prev + i]; } }
+	Found f = nothing();
+	const V3 p[3] = {t.point(face[0]), t.point(face[1]), t.point(face[2])};
+	V3 x;
+	if (!lineFlatIntersection(p[0], p[1], p[2], start, query, x)) { err = 1; return f; }
+	if (triangleContains(p[0], p[1], p[2], x, TOL, TOL, err)) {
+		f.n = 3;
+		for (int i = 0; i < 3; i++) { f.p[i] = t.localOf[face[i]]; }
+		return f;
+	}
+	for (int i = 0; i < 3; i++) for (int j = i + 1; j < 3; j++) {
+		if (segmentContains(p[i], p[j], x, TOL, TOL, err)) { f.n = 2; f.p[0] = t.localOf[face[i]]; f.p[1] = t.localOf[face[j]]; return f; }
+	}
+	for (int i = 0; i < 3; i++) {
+		if (segmentContains(start, query, p[i], TOL, TOL, err)) { f.n = 1; f.p[0] = t.localOf[face[i]]; return f; }
+	}
+	return f;
+}
+
+GCMB_HD Found checkWalk(const Tri& t, bool inner, Walked w, V3 start, V3 query, int& err) {
+	if (w.count == 0) { return nothing(); }
+	if (t.isLocal(w.last) && cellContains(t, w.last, query, err)) { return wholeCell(t, w.last); }
+	if (w.count == 1) { if (inner) { err = 1; } return nothing(); }
+	if (cellContains(t, w.prev, query, err)) { return wholeCell(t, w.prev); }
+	if (!inner) { return nothing(); }
+	if (!t.isLocal(w.last)) { return borderFacet(t, w.prev, w.exitSlot, start, query, err); }
+	return nothing();
+}
+
+// SimplexGrid::findCellCrossedByTheRay
+GCMB_HD Found locate(const Tri& t, int lv, V3 shift, int& err) {
+	const int gv = t.globalOf[lv];
+	const bool inner = t.state[lv] == 0;
+	const V3 start = t.point(gv);
+	const V3 query = start + shift;
+	Found f = checkWalk(t, inner, walkFromVertex(t, gv, query, err), start, query, err);
+	if (f.n > 0) { return f; }
+	int startCell = crossedIncidentCell(t, gv, query, 0, err);
+	if (startCell == -2) { startCell = crossedIncidentCell(t, gv, query, TOL, err); }
+	if (startCell == -2) {
+		for (int i = t.incOff[gv]; i < t.incOff[gv + 1]; i++) { if (t.isLocal(t.incCell[i])) { startCell = t.incCell[i]; break; } }
+	}
+	const int* cv = t.cellV + 4 * (long long) startCell;
+	const V3 center = (t.point(cv[0]) + t.point(cv[1]) + t.point(cv[2]) + t.point(cv[3])) / 4;
+	const double w = 1e-3;
+	const V3 startPoint = center * w + start * (1 - w);
+	f = checkWalk(t, inner, walkFromCell(t, startCell, startPoint, query, err), start, query, err);
+	if (f.n > 0) { return f; }
+	if (inner) { err = 1; }
+	return nothing();
+}
+
+// border state and normals of a local vertex (SimplexGrid.hpp:385-444); which: 0 border, 1 common
+GCMB_HD int borderState(const Tri& t, int lv) {
+	const int g = t.globalOf[lv];
+	bool empty = false, other = false, multi = false;
+	int otherId = 0;
+	for (int i = t.incOff[g]; i < t.incOff[g + 1]; i++) {
+		const int c = t.incCell[i];
+		for (int k = 0; k < 4; k++) { if (t.cellN[4 * (long long) c + k] < 0 && t.cellV[4 * (long long) c + k] != g) { empty = true; } }
+		const int id = t.cellGrid[c];
+		if (id == t.gridId) { continue; }
+		if (id == EMPTY) { empty = true; continue; }
+		if (!other) { other = true; otherId = id; } else if (id != otherId) { multi = true; }
+	}
+	if (!empty && !other) { return 0; }
+	if (multi || (empty && other)) { return 3; }
+	return empty ? 1 : 2;
+}
+GCMB_HD bool vertexNormal(const Tri& t, int lv, int which, V3& out) {
+	const int g = t.globalOf[lv];
+	V3 sum = {0, 0, 0};
+	int count = 0;
+	for (int i = t.incOff[g]; i < t.incOff[g + 1]; i++) {
+		const int cell = t.incCell[i];
+		if (!t.isLocal(cell)) { continue; }
+		for (int k = 0; k < 4; k++) {
+			const int oc = t.cellN[4 * (long long) cell + k];
+			const int og = oc < 0 ? EMPTY : t.cellGrid[oc];
+			if (og == t.gridId || (which == 0 && og != EMPTY)) { continue; }
+			if (t.cellV[4 * (long long) cell + k] == g) { continue; }
+			const V3 opposite = t.point(t.cellV[4 * (long long) cell + k]);
+			const V3 a = t.point(t.cellV[4 * (long long) cell + (k + 1) % 4]);
+			const V3 b = t.point(t.cellV[4 * (long long) cell + (k + 2) % 4]);
+			const V3 c = t.point(t.cellV[4 * (long long) cell + (k + 3) % 4]);
+			V3 n = cross(a - b, c - b);
+			n = n / length(n);
+			if (!(dot(n, a - opposite) > 0)) { n = n * -1.0; }
+			sum = sum + n;
+			count++;
+		}
+	}
+	if (!count) { out = {0, 0, 0}; return false; }
+	out = sum / length(sum);
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage pieces
+// ---------------------------------------------------------------------------------------------
+template<int M>
+GCMB_HD void matVec(const double* A, const double* x, double* y) {
+	for (int i = 0; i < M; i++) {
+		double r = A[i * M] * x[0];
+		for (int n = 1; n < M; n++) { r += A[i * M + n] * x[n]; }
+		y[i] = r;
+	}
+}
+
+// Differentiation::estimateGradient for one vertex: values [nLocal][M] -> grad [3][M] of that vertex
+template<int M>
+GCMB_HD void gradientThread(const Tri& t, const double* values, int it, double* grad, int& err) {
+	const int n = t.nbOff[it + 1] - t.nbOff[it];
+	const int* nb = t.nbIdx + t.nbOff[it];
+	const V3 x0 = t.localPoint(it);
+	double A[MAX_NEIGHBORS][3], W[MAX_NEIGHBORS];
+	for (int i = 0; i < n; i++) {
+		const V3 d = t.localPoint(nb[i]) - x0;
+		A[i][0] = d.x; A[i][1] = d.y; A[i][2] = d.z;
+		W[i] = 1.0 / length(d);
+	}
+	double N[3][3];
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+		double r = 0;
+		for (int k = 0; k < n; k++) { const double term = A[k][i] * (W[k] * A[k][j]); r = k == 0 ? term : r + term; }
+		N[i][j] = r;
+	}
+	const double det = det3(N[0][0], N[0][1], N[0][2], N[1][0], N[1][1], N[1][2], N[2][0], N[2][1], N[2][2]);
+	for (int c = 0; c < M; c++) {
+		double b[3];
+		for (int i = 0; i < 3; i++) {
+			double r = 0;
+			for (int k = 0; k < n; k++) {
+				const double bk = values[(long long) nb[k] * M + c] - values[(long long) it * M + c];
+				const double term = (bk * W[k]) * A[k][i];
+				r = k == 0 ? term : r + term;
+			}
+			b[i] = r;
+		}
+		double g[3] = {0, 0, 0};
+		if (det == 0) { err = 1; }
+		else {
+			g[0] = det3(b[0], N[0][1], N[0][2], b[1], N[1][1], N[1][2], b[2], N[2][1], N[2][2]) / det;
+			g[1] = det3(N[0][0], b[0], N[0][2], N[1][0], b[1], N[1][2], N[2][0], b[2], N[2][2]) / det;
+			g[2] = det3(N[0][0], N[0][1], b[0], N[1][0], N[1][1], b[1], N[2][0], N[2][1], b[2]) / det;
+		}
+		for (int d = 0; d < 3; d++) { grad[d * M + c] = g[d]; }
+	}
+}
+
+GCMB_HD bool isInterpolation(const double (&l)[4]) { return l[0] > -TOL && l[1] > -TOL && l[2] > -TOL && l[3] > -TOL; }
+
+// TetrahedronInterpolator::hybridInterpolate of component k; grad is [nLocal][3][M]
+template<int M>
+GCMB_HD double hybridInterpolate(const Tri& t, const double* values, const double* grad, const int (&cell)[4], int k, V3 q, int& err) {
+	V3 c[4], g[4];
+	double v[4], l[4];
+	for (int i = 0; i < 4; i++) {
+		c[i] = t.localPoint(cell[i]);
+		v[i] = values[(long long) cell[i] * M + k];
+		const double* gi = grad + (long long) cell[i] * 3 * M;
+		g[i] = {gi[0 * M + k], gi[1 * M + k], gi[2 * M + k]};
+	}
+	if (!barycentric(c[0], c[1], c[2], c[3], q, l) || !isInterpolation(l)) { err = 1; }
+	double quadratic = l[0] * (v[0] + dot(g[0], q - c[0]) / 2.0);
+	for (int i = 1; i < 4; i++) { quadratic = quadratic + l[i] * (v[i] + dot(g[i], q - c[i]) / 2.0); }
+	const double lo = fmin(fmin(v[0], v[1]), fmin(v[2], v[3]));
+	const double hi = fmax(fmax(v[0], v[1]), fmax(v[2], v[3]));
+	const double limited = fmin(fmax(quadratic, lo), hi);
+	if (quadratic == limited) { return quadratic; }
+	return l[0] * v[0] + l[1] * v[1] + l[2] * v[2] + l[3] * v[3];
+}
+
+GCMB_HD double interpolateInOwner(const V3 (&c)[6], const double (&v)[6], V3 q, int& err) {
+	const int T[15][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 2, 5}, {0, 1, 3, 4}, {0, 1, 3, 5}, {0, 1, 4, 5}, {0, 2, 3, 4},
+			{0, 2, 3, 5}, {0, 2, 4, 5}, {0, 3, 4, 5}, {1, 2, 3, 4}, {1, 2, 3, 5}, {1, 2, 4, 5}, {1, 3, 4, 5}, {2, 3, 4, 5}};
+	for (int i = 0; i < 15; i++) {
+		const int* p = T[i];
+		if (volume(c[p[0]], c[p[1]], c[p[2]], c[p[3]]) != 0) {
+			double l[4];
+			if (!barycentric(c[p[0]], c[p[1]], c[p[2]], c[p[3]], q, l)) { err = 1; continue; }
+			if (isInterpolation(l)) { return l[0] * v[p[0]] + l[1] * v[p[1]] + l[2] * v[p[2]] + l[3] * v[p[3]]; }
+		}
+	}
+	err = 1;
+	return 0;
+}
+
+GCMB_HD double interpolateSpaceTime(V3 shift, V3 r0, const V3 (&r)[3], const double (&vc)[3], const double (&vn)[3], int& err) {
+	V3 rc;
+	if (!lineFlatIntersection(r[0], r[1], r[2], r0, r0 + shift, rc)) { err = 1; return 0; }
+	double w[2];
+	if (!leastSquares2(r[1] - r[0], r[2] - r[0], rc - r[0], w)) { err = 1; return 0; }
+	const V3 c[6] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}};
+	const double v[6] = {vc[0], vc[1], vc[2], vn[0], vn[1], vn[2]};
+	const V3 q = {w[0], w[1], 1 - length(rc - r0) / length(shift)};
+	return interpolateInOwner(c, v, q, err);
+}
+
+// arguments of the stage kernels
+struct StageS {
+	Tri t;
+	int model;              // 0 elastic (M = 9, 3 outer waves), 1 acoustic (M = 4, 1 outer wave)
+	int s;                  // stage
+	double tau;
+	const double* U;        // [M*M] of this stage
+	const double* U1;
+	const double* L;        // [M]
+	double dir[3];          // calculation direction = column s of the basis
+	const double* cur;      // PDE vectors [nLocal][M]
+	double* riem;           // Riemann invariants of the current layer
+	double* grad;           // [nLocal][3][M]
+	double* next;           // next layer (invariants until the last kernel)
+	unsigned* waves;        // outer invariants of border vertices (bit k)
+	int* errors;            // counter of "the reference would have thrown"
+};
+
+// interpolateValuesAround for one vertex (…InRiemannInvariants.hpp:146-198 + :59-96 for border vertices)
+template<int M>
+GCMB_HD void nodeThread(const StageS& a, int it, bool borderPass) {
+	const Tri& t = a.t;
+	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
+	const V3 direction = {a.dir[0], a.dir[1], a.dir[2]};
+	const V3 x0 = t.localPoint(it);
+	unsigned outers = 0;
+	int err = 0;
+	double ans[M];
+	for (int k = 0; k < M; k++) {
+		const double dx = -a.tau * a.L[k];
+		if (dx == 0) { ans[k] = a.riem[(long long) it * M + k]; continue; }
+		const V3 shift = direction * dx;
+		const Found f = locate(t, it, shift, err);
+		double u = 0;
+		if (f.n == 4) {
+			const int cell[4] = {f.p[0], f.p[1], f.p[2], f.p[3]};
+			u = hybridInterpolate<M>(t, a.riem, a.grad, cell, k, x0 + shift, err);
+		} else if (f.n == 0) {
+			outers |= 1u << k;
+		} else if (f.n == 3) {
+			if (!borderPass) {
+				V3 r[3];
+				double vc[3], vn[3];
+				for (int i = 0; i < 3; i++) {
+					r[i] = t.localPoint(f.p[i]);
+					vc[i] = a.riem[(long long) f.p[i] * M + k];
+					vn[i] = a.next[(long long) f.p[i] * M + k];
+				}
+				u = interpolateSpaceTime(shift, x0, r, vc, vn, err);
+			} else { outers |= 1u << k; }
+		} else if (f.n == 2) {
+			if (!borderPass) { err = 1; } else { outers |= 1u << k; }
+		}
+		ans[k] = u;
+	}
+	if (borderPass) {
+		if (outers != RIGHT && outers != LEFT && outers != (LEFT | RIGHT) && outers != 0) {
+			if (outers & RIGHT) { outers |= RIGHT; }
+			if (outers & LEFT) { outers |= LEFT; }
+			for (int k = 0; k < M; k++) { if ((outers >> k) & 1u) { ans[k] = 0; } }
+		}
+		a.waves[it] = outers;
+	}
+	for (int k = 0; k < M; k++) { a.next[(long long) it * M + k] = ans[k]; }
+	if (err) {
+#ifdef __CUDA_ARCH__
+		atomicAdd(a.errors, 1);
+#else
+		(*a.errors)++;
+#endif
+	}
+}
+
+// ---- border conditions -----------------------------------------------------------------------
+GCMB_HD int symIndex3(int i, int j) { if (i > j) { const int x = i; i = j; j = x; } return i * 3 - ((i - 1) * i) / 2 + j - i; }
+
+GCMB_HD void localBasis(V3 n, double (&S)[3][3]) {
+	V3 a = {n.y, -n.x, 0};
+	if (n.x == 0 && n.y == 0) { a = {n.z, 0, 0}; }
+	const V3 t1 = (a * length(n)) / length(a);
+	const V3 t2 = cross(n, t1);
+	S[0][0] = t1.x; S[1][0] = t1.y; S[2][0] = t1.z;
+	S[0][1] = t2.x; S[1][1] = t2.y; S[2][1] = t2.z;
+	S[0][2] = n.x; S[1][2] = n.y; S[2][2] = n.z;
+}
+
+template<int M>
+GCMB_HD void borderMatrix(int model, int type, V3 p, double* B) {
+	const int outer = model == 0 ? 3 : 1;
+	for (int i = 0; i < outer * M; i++) { B[i] = 0; }
+	if (model == 1) {
+		if (type == 0) { B[3] = 1; } else { B[0] = p.x; B[1] = p.y; B[2] = p.z; }
+		return;
+	}
+	double S[3][3];
+	localBasis(p, S);
+	for (int k = 0; k < 3; k++) {
+		if (type == 0) {
+			double G[6] = {0, 0, 0, 0, 0, 0};
+			for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { G[symIndex3(i, j)] += S[i][k] * p[j]; }
+			for (int i = 0; i < 6; i++) { B[k * M + 3 + i] = G[i]; }
+		} else {
+			for (int i = 0; i < 3; i++) { B[k * M + i] = S[i][k]; }
+		}
+	}
+}
+
+GCMB_HD void mul33(const double (&A)[3][3], const double (&B)[3][3], double (&C)[3][3]) {
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+		double r = A[i][0] * B[0][j]; r += A[i][1] * B[1][j]; r += A[i][2] * B[2][j];
+		C[i][j] = r;
+	}
+}
+
+GCMB_HD void plainBorder(int model, int type, V3 normal, const double* value, double* u) {
+	double S[3][3], St[3][3];
+	localBasis(normal, S);
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { St[i][j] = S[j][i]; }
+	if (model == 1) {
+		if (type == 0) { u[3] = value[0]; return; }
+		double vl[3], vg[3];
+		for (int i = 0; i < 3; i++) { double r = St[i][0] * u[0]; r += St[i][1] * u[1]; r += St[i][2] * u[2]; vl[i] = r; }
+		vl[2] = value[0];
+		for (int i = 0; i < 3; i++) { double r = St[0][i] * vl[0]; r += St[1][i] * vl[1]; r += St[2][i] * vl[2]; vg[i] = r; }
+		for (int i = 0; i < 3; i++) { u[i] = vg[i]; }
+		return;
+	}
+	if (type == 1) {
+		for (int i = 0; i < 3; i++) { double r = S[i][0] * value[0]; r += S[i][1] * value[1]; r += S[i][2] * value[2]; u[i] = r; }
+		return;
+	}
+	double sg[3][3], t1[3][3], sl[3][3], t2[3][3];
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { sg[i][j] = u[3 + symIndex3(i, j)]; }
+	mul33(St, sg, t1);
+	mul33(t1, S, sl);
+	for (int i = 0; i < 3; i++) { sl[i][2] = value[i]; }
+	for (int j = 0; j < 3; j++) { sl[2][j] = value[j]; }
+	mul33(S, sl, t2);
+	mul33(t2, St, sg);
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { u[3 + symIndex3(i, j)] = sg[i][j]; }
+}
+
+// calculateOuterWaveCorrection (common.hpp:187-207); Omega [M][outer], B [outer][M]
+template<int M>
+GCMB_HD bool outerWaveCorrection(int outer, const double* u, const double* Omega, const double* B, const double* b,
+                                 double minDet, double* value, double& detFabs) {
+	double X[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+	for (int i = 0; i < outer; i++) for (int j = 0; j < outer; j++) {
+		double r = B[i * M] * Omega[j];
+		for (int n = 1; n < M; n++) { r += B[i * M + n] * Omega[n * outer + j]; }
+		X[i][j] = r;
+	}
+	const double det = outer == 1 ? X[0][0] : det3(X[0][0], X[0][1], X[0][2], X[1][0], X[1][1], X[1][2], X[2][0], X[2][1], X[2][2]);
+	detFabs = fabs(det);
+	for (int i = 0; i < M; i++) { value[i] = 0; }
+	if (!(detFabs > minDet)) { return false; }
+	double rhs[3] = {0, 0, 0}, alpha[3] = {0, 0, 0};
+	for (int i = 0; i < outer; i++) {
+		double r = B[i * M] * u[0];
+		for (int n = 1; n < M; n++) { r += B[i * M + n] * u[n]; }
+		rhs[i] = b[i] - r;
+	}
+	if (outer == 1) { if (X[0][0] == 0) { return false; } alpha[0] = rhs[0] / X[0][0]; }
+	else if (!solve3(X, rhs, alpha)) { return false; }
+	for (int i = 0; i < M; i++) {
+		double r = Omega[i * outer] * alpha[0];
+		for (int n = 1; n < outer; n++) { r += Omega[i * outer + n] * alpha[n]; }
+		value[i] = r;
+	}
+	return true;
+}
+
+template<int M>
+GCMB_HD void outerColumns(int outer, const double* U1, unsigned mask, double* Omega) {
+	int c = 0;
+	for (int i = 0; i < M * outer; i++) { Omega[i] = 0; }
+	for (int k = 0; k < M; k++) {
+		if (!((mask >> k) & 1u)) { continue; }
+		if (c < outer) { for (int i = 0; i < M; i++) { Omega[i * outer + c] = U1[i * M + k]; } }
+		c++;
+	}
+}
+
+struct BorderS {
+	int model, type;        // condition type 0 FIXED_FORCE, 1 FIXED_VELOCITY
+	const double* U;        // this stage
+	const double* U1;
+	double dir[3];          // calculation direction (the aligned case of getMaximalPossibleDeterminant)
+	double b[3];            // border values at t + tau
+	int n;                  // nodes of this condition
+	const int* node;        // local vertex ids
+	const double* normal;   // [n][3]
+	const unsigned* waves;
+	double* next;           // invariants of the next layer
+};
+
+// BorderCorrectorInRiemannInvariants::applyInGlobalBasis for one border node
+template<int M>
+GCMB_HD void borderCorrectThread(const BorderS& a, int i) {
+	const int outer = a.model == 0 ? 3 : 1;
+	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
+	double Omega[M * 3], B[3 * M], zero[M], value[M], det;
+	outerColumns<M>(outer, a.U1, RIGHT, Omega);
+	borderMatrix<M>(a.model, a.type, V3{a.dir[0], a.dir[1], a.dir[2]}, B);
+	for (int k = 0; k < M; k++) { zero[k] = 0; }
+	outerWaveCorrection<M>(outer, zero, Omega, B, a.b, 0, value, det);
+	const double minDet = 1e-3 * det;
+	const int node = a.node[i];
+	const V3 normal = {a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2]};
+	double u[M], w[M];
+	matVec<M>(a.U1, a.next + (long long) node * M, u);
+	borderMatrix<M>(a.model, a.type, normal, B);
+	const unsigned outers = a.waves[node];
+	if (outers == RIGHT || outers == LEFT) {
+		outerColumns<M>(outer, a.U1, outers, Omega);
+		if (outerWaveCorrection<M>(outer, u, Omega, B, a.b, minDet, value, det)) { for (int k = 0; k < M; k++) { u[k] += value[k]; } }
+		else { plainBorder(a.model, a.type, normal, a.b, u); }
+	} else {
+		double vr[M], vl[M], d2;
+		outerColumns<M>(outer, a.U1, RIGHT, Omega);
+		const bool okr = outerWaveCorrection<M>(outer, u, Omega, B, a.b, minDet, vr, det);
+		outerColumns<M>(outer, a.U1, LEFT, Omega);
+		const bool okl = outerWaveCorrection<M>(outer, u, Omega, B, a.b, minDet, vl, d2);
+		if (okr && okl) { for (int k = 0; k < M; k++) { u[k] += (vr[k] + vl[k]) / 2; } }
+		else { plainBorder(a.model, a.type, normal, a.b, u); }
+	}
+	matVec<M>(a.U, u, w);
+	for (int k = 0; k < M; k++) { a.next[(long long) node * M + k] = w[k]; }
+}
+
+}  // namespace sx
+}  // namespace gcmb

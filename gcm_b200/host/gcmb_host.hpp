@@ -365,6 +365,24 @@ public:
 
 }  // namespace cubic
 
+namespace simplex {
+
+/// CGAL-free triangulation consumed by the simplex path (see host/simplex_mesh.cpp)
+struct FlatTriangulation {
+	int nV = 0, nC = 0;
+	std::vector<double> xyz;     ///< [nV][3]
+	std::vector<int> cellV;      ///< [nC][4]
+	std::vector<int> cellN;      ///< [nC][4] neighbour opposite vertex i, -1 outside the hull
+	std::vector<int> cellGrid;   ///< [nC] body id, -1 = empty space
+	std::vector<int> incOff;     ///< [nV+1]
+	std::vector<int> incCell;    ///< incident cells, ascending id
+	void buildTopology();        ///< orientation, neighbours, incidence from xyz + cellV (+ cellGrid)
+};
+FlatTriangulation makeBoxMesh(int nx, int ny, int nz, const Real3& origin, real h, real jitter, unsigned seed,
+		const Real3* voidMin, const Real3* voidMax, int gridId);
+
+}  // namespace simplex
+
 /// reference engine/EngineFactory.hpp:11-36 (cubic grids only: the simplex engine is separate)
 std::shared_ptr<AbstractEngine> createEngine(const Task& task);
 

@@ -160,6 +160,44 @@ int gcmb_cubic_halo_put(gcmb_body* body, int side, const void* host_buffer);
 /* in-place sum over all ranks of n doubles held on the host (detector sums of decomposed grids). sync */
 int gcmb_comm_allreduce_sum(gcmb_ctx* ctx, double* host_values, int n);
 
+/* ---- simplex (tetrahedral) path: engine/simplex/*, grid/simplex/* of the reference ------------------------
+ * The triangulation is passed as flat arrays (what the reference's CGAL structure holds for the hot path):
+ * xyz[nV][3]; cell_v[nC][4]; cell_n[nC][4] (neighbour i opposite vertex i, -1 outside the hull);
+ * cell_grid[nC] (body id, -1 = empty space); the incident cells of every vertex (inc_off[nV+1], inc_cell,
+ * ascending cell id).  A body is the set of cells with grid_id; its vertices get local indices in ascending
+ * global id.  model: 0 elastic (M = 9), 1 acoustic (M = 4); isotropic materials (BorderCorrector.hpp:299-302). */
+typedef struct gcmb_sbody gcmb_sbody;
+int gcmb_simplex_body_create(gcmb_ctx* ctx, int model, int nV, int nC, const double* xyz, const int* cell_v,
+                             const int* cell_n, const int* cell_grid, const int* inc_off, const int* inc_cell,
+                             int grid_id, gcmb_sbody** out);
+void gcmb_simplex_body_destroy(gcmb_sbody* body);
+int gcmb_simplex_info(gcmb_sbody* body, int* n_local, int* M, int* n_border_vertices);
+/* per local vertex (any output may be NULL): global id, border state (0 inner, 1 border, 2 contact,
+ * 3 multicontact: SimplexGrid.hpp:385-393), border and common unit normals (SimplexGrid.hpp:141-160,427-444). sync */
+int gcmb_simplex_vertices(gcmb_sbody* body, int* global_of, uint8_t* state, double* border_normal, double* common_normal);
+/* SimplexGrid::findCellCrossedByTheRay (SimplexGrid.cpp:61-164) for nq (vertex, shift) pairs on the GPU:
+ * out5[q] = {n, p0..p3}: n = 4 cell, 3/2/1 border facet/edge/vertex, 0 none; local vertex ids, -1 padded. sync */
+int gcmb_simplex_locate(gcmb_sbody* body, int nq, const int* vertex, const double* shift, int* out5);
+/* number of node computations in which the reference would have thrown (degenerate systems, failed asserts). sync */
+int gcmb_simplex_errors(gcmb_sbody* body, int* count);
+/* eigen-system in the calculation basis: U, U1 [3][M][M], L [3][M], basis row-major 3x3 (stage s runs along
+ * column s; Task::calculationBasis) */
+int gcmb_simplex_set_material(gcmb_sbody* body, const double* U, const double* U1, const double* L, const double* basis);
+int gcmb_simplex_upload_state(gcmb_sbody* body, const double* pde /* [n_local][M] */);  /* sync */
+int gcmb_simplex_download_state(gcmb_sbody* body, double* pde);                          /* sync */
+/* border nodes as Engine::addBorderNode collects them (engine/simplex/Engine.cpp:288-309): condition types
+ * (0 FIXED_FORCE, 1 FIXED_VELOCITY), and for every border node its local id, normal and condition */
+int gcmb_simplex_border_set(gcmb_sbody* body, int n_cond, const int* types, int n_border, const int* node,
+                            const double* normal, const int* cond_of_node);
+/* Engine::applyPlainBorderContactCorrection (Engine.cpp:197-214); values [n_cond][outer] at the given time */
+int gcmb_simplex_plain_border(gcmb_sbody* body, const double* values);
+/* Engine::gcmStage (Engine.cpp:121-141), Riemann-invariant GCM, GLOBAL_BASIS, PRODUCT splitting: invariants,
+ * gradients, border vertices, border correction with values [n_cond][outer] at t+tau, inner vertices, back to
+ * PDE variables, swap */
+int gcmb_simplex_stage(gcmb_sbody* body, int s, double tau, const double* values);
+/* Differentiation::estimateGradient of a host field [n_local][M] -> [n_local][3][M] (test hook). sync */
+int gcmb_simplex_gradient(gcmb_sbody* body, const double* values, double* grad);
+
 /* ---- checksum of the current layer over real nodes: sum_nodes sum_i (i+1)*u_i (sync) ---------- */
 int gcmb_cubic_checksum(gcmb_body* body, double* out);
 

@@ -1,0 +1,91 @@
+/*
+ * TEST INFRASTRUCTURE ONLY — plain-C CPU restatement of the reference's simplex (tetrahedral) GCM path.
+ * Nothing under gcm_b200/ may include, link or call this.
+ *
+ * Parity status: **parity unpinned**.  The reference's simplex engine needs CGAL (absent from this image and
+ * not vendored: `find_package(CGAL 4.8)`, /root/reference/CMakeLists.txt:41-43), so it cannot be compiled here,
+ * and none of its tests pins a cell index or a non-trivial field value.  This file restates the
+ * published algorithm line by line from the reference sources cited at every function and is anchored on the
+ * reference tests' PROPERTIES (tests/test_simplex_*.py): containment of the query in the returned cell for
+ * every vertex x 16x16 directions x 9 lengths (src/test/sequence/TestLineWalkSearch3D.cpp:120-154), interpolator
+ * exactness on linear/quadratic fields (TestInterpolator.cpp:129-252), zero stays zero (TestSimplexGcm.cpp:29-67).
+ *
+ * Topology is a flat triangulation (our own, CGAL-free): points, 4 vertex ids and 4 neighbour ids per cell
+ * (neighbour i is opposite vertex i, -1 outside the hull), a grid id per cell (EMPTY = no body), and the
+ * incident cells of every vertex in ascending cell id (the reference's order is unspecified,
+ * grid/simplex/cgal/Cgal3DTriangulation.hpp:88-101; both sides freeze this one).
+ */
+#ifndef GCM_SIMPLEX_ORACLE_H
+#define GCM_SIMPLEX_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCMO_EMPTY_SPACE (-1)
+#define GCMO_MAX_NEIGHBORS 20 /* Cgal3DTriangulation.hpp:53 */
+
+typedef struct {
+	int nV, nC;
+	const double* xyz;       /* [nV][3] */
+	const int* cell_v;       /* [nC][4] global vertex ids */
+	const int* cell_n;       /* [nC][4] neighbour cell ids, -1 = outside the convex hull */
+	const int* cell_grid;    /* [nC] */
+	const int* inc_off;      /* [nV+1] */
+	const int* inc_cell;     /* incident cells of every vertex, ascending cell id */
+	int grid_id;             /* the body this view works on */
+	const int* local_of;     /* [nV] local index of a global vertex in this body, -1 if not in the body */
+	const int* global_of;    /* [nLocal] */
+	int n_local;
+} gcmo_tri;
+
+/* border state of a local vertex: 0 inner, 1 border, 2 contact, 3 multicontact (SimplexGrid.hpp:385-393) */
+int gcmo_simplex_border_state(const gcmo_tri* t, int local_vertex);
+
+/* border (which=0) or common (which=1) unit normal of a local vertex; returns 0 when there is none */
+int gcmo_simplex_normal(const gcmo_tri* t, int local_vertex, int which, double out[3]);
+
+/* SimplexGrid::findCellCrossedByTheRay (grid/simplex/SimplexGrid.cpp:61-164).  out[0] = n (4 cell, 3/2/1
+ * border facet/edge/vertex, 0 none), out[1..n] = local vertex ids, rest -1.  Returns 0, or 1 when the reference
+ * would have thrown (degenerate linear system / failed assertion). */
+int gcmo_simplex_locate(const gcmo_tri* t, int local_vertex, const double shift[3], int out[5]);
+
+/* neighbours of a local vertex: ascending local id, itself excluded (SimplexGrid.hpp:226-236); returns count */
+int gcmo_simplex_neighbors(const gcmo_tri* t, int local_vertex, int* out, int capacity);
+
+/* Differentiation::estimateGradient (util/math/Differentiation.hpp:33-63): values [nLocal][M] ->
+ * grad [nLocal][3][M] */
+int gcmo_simplex_gradient(const gcmo_tri* t, int M, const double* values, double* grad);
+
+/* TetrahedronInterpolator::hybridInterpolate of component k in a located cell (…Interpolator.hpp:93-104) */
+double gcmo_simplex_hybrid_interpolate(const gcmo_tri* t, int M, const double* values, const double* grad,
+                                       const int cell[4], int k, const double q[3], int* err);
+
+/* geometry helpers exported for the known-answer tests (linal/geometry.hpp) */
+double gcmo_oriented_volume(const double a[3], const double b[3], const double c[3], const double d[3]);
+int gcmo_barycentric4(const double a[3], const double b[3], const double c[3], const double d[3],
+                      const double q[3], double lambda[4]);
+
+/* One stage of the simplex GCM in Riemann invariants with border correction, single body, GLOBAL_BASIS,
+ * PRODUCT splitting (engine/simplex/Engine.cpp:121-141 and everything it calls).
+ *   U, U1 [3][M][M], L [3][M] in the calculation basis `basis` (row-major 3x3, stage s runs along column s)
+ *   border nodes: n_border, node ids (local), normals [n][3], condition id per node;
+ *   conditions: type (0 FIXED_FORCE, 1 FIXED_VELOCITY), b values at t+tau [n_cond][outer_number]
+ *   model: 0 elastic (M=9, outer 3), 1 acoustic (M=4, outer 1)
+ * cur [nLocal][M] -> next [nLocal][M].  Returns 0 or an error count. */
+int gcmo_simplex_stage(const gcmo_tri* t, int model, int M, int s, double tau,
+                       const double* U, const double* U1, const double* L, const double* basis,
+                       int n_border, const int* border_node, const double* border_normal, const int* border_cond,
+                       int n_cond, const int* cond_type, const double* cond_b,
+                       const double* cur, double* next);
+
+/* Engine::applyPlainBorderContactCorrection for border nodes (Engine.cpp:197-214) */
+void gcmo_simplex_plain_border(int model, int M, int n_border, const int* border_node, const double* border_normal,
+                               const int* border_cond, const int* cond_type, const double* cond_b, double* pde);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -83,6 +83,7 @@ using std::max;
 #define cudaMemsetAsync(d, v, n, s) gcmb_emul::e_memset(d, v, n)
 #define cudaMemcpyAsync(d, s, n, k, st) gcmb_emul::e_memcpy(d, s, n)
 #define cudaMemcpy(d, s, n, k) gcmb_emul::e_memcpy(d, s, n)
+#define cudaMemset(d, v, n) gcmb_emul::e_memset(d, v, n)
 #define cudaGetErrorString(e) "emulated CUDA error"
 
 #define GCMB_GLOBAL static

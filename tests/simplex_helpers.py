@@ -1,0 +1,186 @@
+"""Helpers of the simplex-path tests: box meshes from the product's mesher, the oracle's view of a body."""
+import ctypes
+import os
+
+import numpy as np
+
+import oracle_host as oh
+
+ip = ctypes.POINTER(ctypes.c_int)
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+class GcmoTri(ctypes.Structure):
+    _fields_ = [("nV", ctypes.c_int), ("nC", ctypes.c_int), ("xyz", dp), ("cell_v", ip), ("cell_n", ip),
+                ("cell_grid", ip), ("inc_off", ip), ("inc_cell", ip), ("grid_id", ctypes.c_int),
+                ("local_of", ip), ("global_of", ip), ("n_local", ctypes.c_int)]
+
+
+def _i(a):
+    return a.ctypes.data_as(ip)
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+class Mesh:
+    """flat triangulation arrays (see gcm_b200/host/simplex_mesh.cpp)"""
+
+    def __init__(self, host_lib, nx, ny, nz, origin=(0.0, 0.0, 0.0), h=1.0, jitter=0.0, seed=1, void_box=None, grid_id=0):
+        f = host_lib.gcmb_host_simplex_box_mesh
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int] * 3 + [dp, ctypes.c_double, ctypes.c_double, ctypes.c_uint, dp, ctypes.c_int, ip,
+                                           dp, ip, ip, ip, ip, ip]
+        o = np.array(origin, dtype=np.float64)
+        vb = None if void_box is None else np.array(void_box, dtype=np.float64)
+        sizes = np.zeros(3, dtype=np.int32)
+        f(nx, ny, nz, _d(o), h, jitter, seed, None if vb is None else _d(vb), grid_id, _i(sizes), None, None, None, None, None, None)
+        self.nV, self.nC, ninc = (int(s) for s in sizes)
+        self.xyz = np.zeros((self.nV, 3))
+        self.cell_v = np.zeros((self.nC, 4), dtype=np.int32)
+        self.cell_n = np.zeros((self.nC, 4), dtype=np.int32)
+        self.cell_grid = np.zeros(self.nC, dtype=np.int32)
+        self.inc_off = np.zeros(self.nV + 1, dtype=np.int32)
+        self.inc_cell = np.zeros(ninc, dtype=np.int32)
+        f(nx, ny, nz, _d(o), h, jitter, seed, None if vb is None else _d(vb), grid_id, _i(sizes), _d(self.xyz),
+          _i(self.cell_v), _i(self.cell_n), _i(self.cell_grid), _i(self.inc_off), _i(self.inc_cell))
+        self.grid_id = grid_id
+        used = np.zeros(self.nV, dtype=bool)
+        used[self.cell_v[self.cell_grid == grid_id].ravel()] = True
+        self.global_of = np.nonzero(used)[0].astype(np.int32)
+        self.local_of = np.full(self.nV, -1, dtype=np.int32)
+        self.local_of[self.global_of] = np.arange(len(self.global_of), dtype=np.int32)
+        self.n_local = len(self.global_of)
+
+    def oracle_view(self):
+        t = GcmoTri(self.nV, self.nC, _d(self.xyz), _i(self.cell_v), _i(self.cell_n), _i(self.cell_grid),
+                    _i(self.inc_off), _i(self.inc_cell), self.grid_id, _i(self.local_of), _i(self.global_of), self.n_local)
+        return t
+
+    def local_xyz(self):
+        return self.xyz[self.global_of]
+
+
+def oracle():
+    L = oh.lib()
+    tp = ctypes.POINTER(GcmoTri)
+    L.gcmo_simplex_locate.argtypes = [tp, ctypes.c_int, dp, ip]
+    L.gcmo_simplex_border_state.argtypes = [tp, ctypes.c_int]
+    L.gcmo_simplex_normal.argtypes = [tp, ctypes.c_int, ctypes.c_int, dp]
+    L.gcmo_simplex_neighbors.argtypes = [tp, ctypes.c_int, ip, ctypes.c_int]
+    L.gcmo_simplex_gradient.argtypes = [tp, ctypes.c_int, dp, dp]
+    L.gcmo_simplex_hybrid_interpolate.argtypes = [tp, ctypes.c_int, dp, dp, ip, ctypes.c_int, dp, ip]
+    L.gcmo_simplex_hybrid_interpolate.restype = ctypes.c_double
+    L.gcmo_barycentric4.argtypes = [dp] * 6
+    L.gcmo_oriented_volume.argtypes = [dp] * 4
+    L.gcmo_oriented_volume.restype = ctypes.c_double
+    L.gcmo_simplex_stage.argtypes = [tp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp,
+                                     ctypes.c_int, ip, dp, ip, ctypes.c_int, ip, dp, dp, dp]
+    L.gcmo_simplex_plain_border.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, dp, ip, ip, dp, dp]
+    return L
+
+
+def directions(n=16):
+    """the 16 x 16 directions x 9 lengths protocol of src/test/sequence/TestLineWalkSearch3D.cpp:120-154"""
+    out = []
+    for a in range(n):
+        for b in range(n):
+            phi, teta = 2 * np.pi * a / n, np.pi * (b + 0.5) / n
+            out.append((np.sin(teta) * np.cos(phi), np.sin(teta) * np.sin(phi), np.cos(teta)))
+    return np.array(out)
+
+
+def oracle_locate_all(L, mesh, vertices, shifts):
+    t = mesh.oracle_view()
+    out = np.zeros((len(vertices), 5), dtype=np.int32)
+    errs = 0
+    for i, (v, s) in enumerate(zip(vertices, shifts)):
+        sv = np.ascontiguousarray(s, dtype=np.float64)
+        errs += L.gcmo_simplex_locate(ctypes.byref(t), int(v), _d(sv), _i(out[i]))
+    return out, errs
+
+
+class SimplexBody:
+    """gcmb_simplex_* through ctypes"""
+
+    def __init__(self, lib, ctx, mesh, model):
+        from gcm_b200 import capi
+        self.lib, self.mesh, self.model = lib, mesh, model
+        self.handle = capi.vp()
+        lib.check(lib.c.gcmb_simplex_body_create(ctx.handle, model, mesh.nV, mesh.nC, _d(mesh.xyz), _i(mesh.cell_v),
+                                                 _i(mesh.cell_n), _i(mesh.cell_grid), _i(mesh.inc_off), _i(mesh.inc_cell),
+                                                 mesh.grid_id, ctypes.byref(self.handle)))
+        n, M, nb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib.check(lib.c.gcmb_simplex_info(self.handle, ctypes.byref(n), ctypes.byref(M), ctypes.byref(nb)))
+        self.n, self.M, self.n_border_vertices = n.value, M.value, nb.value
+
+    def close(self):
+        if self.handle:
+            self.lib.c.gcmb_simplex_body_destroy(self.handle)
+            self.handle = None
+
+    def vertices(self):
+        g = np.zeros(self.n, dtype=np.int32)
+        st = np.zeros(self.n, dtype=np.uint8)
+        bn = np.zeros((self.n, 3))
+        cn = np.zeros((self.n, 3))
+        self.lib.check(self.lib.c.gcmb_simplex_vertices(self.handle, _i(g), st.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _d(bn), _d(cn)))
+        return g, st, bn, cn
+
+    def locate(self, vertices, shifts):
+        v = np.ascontiguousarray(vertices, dtype=np.int32)
+        s = np.ascontiguousarray(shifts, dtype=np.float64)
+        out = np.zeros((len(v), 5), dtype=np.int32)
+        self.lib.check(self.lib.c.gcmb_simplex_locate(self.handle, len(v), _i(v), _d(s), _i(out)))
+        return out
+
+    def errors(self):
+        c = ctypes.c_int()
+        self.lib.check(self.lib.c.gcmb_simplex_errors(self.handle, ctypes.byref(c)))
+        return c.value
+
+    def set_material(self, U, U1, L, basis):
+        U, U1, L, basis = (np.ascontiguousarray(a, dtype=np.float64) for a in (U, U1, L, basis))
+        self.lib.check(self.lib.c.gcmb_simplex_set_material(self.handle, _d(U), _d(U1), _d(L), _d(basis)))
+
+    def upload(self, pde):
+        p = np.ascontiguousarray(pde, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_simplex_upload_state(self.handle, _d(p)))
+
+    def download(self):
+        out = np.zeros((self.n, self.M))
+        self.lib.check(self.lib.c.gcmb_simplex_download_state(self.handle, _d(out)))
+        return out
+
+    def border_set(self, types, nodes, normals, cond_of_node):
+        t = np.ascontiguousarray(types, dtype=np.int32)
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        nr = np.ascontiguousarray(normals, dtype=np.float64)
+        cd = np.ascontiguousarray(cond_of_node, dtype=np.int32)
+        self.lib.check(self.lib.c.gcmb_simplex_border_set(self.handle, len(t), _i(t), len(nd), _i(nd), _d(nr), _i(cd)))
+
+    def plain_border(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_simplex_plain_border(self.handle, _d(v)))
+
+    def stage(self, s, tau, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_simplex_stage(self.handle, s, tau, _d(v)))
+
+    def gradient(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        g = np.zeros((self.n, 3, self.M))
+        self.lib.check(self.lib.c.gcmb_simplex_gradient(self.handle, _d(v), _d(g)))
+        return g
+
+
+def protocol_queries(mesh, n_dirs=16, lengths=9, scale=1.0, vertices=None):
+    """every vertex x n_dirs^2 directions x `lengths` lengths (TestLineWalkSearch3D.cpp:120-154)"""
+    dirs = directions(n_dirs)
+    lens = scale * (0.15 + 0.35 * np.arange(lengths))
+    vs = np.arange(mesh.n_local) if vertices is None else np.asarray(vertices)
+    v = np.repeat(vs, len(dirs) * len(lens)).astype(np.int32)
+    sh = (dirs[None, :, None, :] * lens[None, None, :, None]).reshape(1, -1, 3)
+    sh = np.broadcast_to(sh, (len(vs), sh.shape[1], 3)).reshape(-1, 3).copy()
+    return v, sh

@@ -149,3 +149,45 @@ def test_reference_two_layers(lib, vary):
     from reference_engine_cases import two_layers
     for (steps, rs, rs_theory, rv, rv_theory, init, reflect) in two_layers(lib, vary):
         assert abs(rs - rs_theory) < 1e-2 and abs(rv - rv_theory) < 1e-2, (rs, rs_theory, rv, rv_theory)
+
+
+# ---- simplex path on the device; oracle: oracle/simplex_oracle.c (parity unpinned) --------
+def test_simplex_vertex_info_gpu(lib):
+    import simplex_cases
+    simplex_cases.check_vertex_info(lib)
+    simplex_cases.check_vertex_info(lib, "regular")
+
+
+def test_simplex_cell_location_protocol_gpu(lib):
+    """the full TestLineWalkSearch3D.cpp:120-154 protocol: every vertex x 16x16 directions x 9 lengths"""
+    import simplex_cases
+    hist = simplex_cases.check_locate_protocol(lib, "jitter_void", n_dirs=16, lengths=9)
+    assert hist[3] > 0 and hist[0] > 0
+    simplex_cases.check_locate_protocol(lib, "regular", n_dirs=16, lengths=9)
+
+
+def test_simplex_cell_location_big_mesh_gpu(lib):
+    import numpy as np
+    import simplex_cases
+    rng = np.random.default_rng(0)
+    m = simplex_cases.make_mesh(lib, "big")
+    vs = np.sort(rng.choice(m.n_local, 600, replace=False))
+    simplex_cases.check_locate_protocol(lib, "big", n_dirs=8, lengths=6, vertices=vs)
+
+
+def test_simplex_gradient_gpu(lib):
+    import simplex_cases
+    simplex_cases.check_gradient(lib)
+    simplex_cases.check_gradient(lib, "regular")
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_simplex_time_steps_gpu(lib, model):
+    import simplex_cases
+    simplex_cases.check_stage(lib, model, steps=4)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_simplex_zero_stays_zero_gpu(lib, model):
+    import simplex_cases
+    simplex_cases.check_stage(lib, model, kind="regular", steps=3, zero=True)

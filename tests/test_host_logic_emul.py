@@ -125,3 +125,35 @@ def test_reference_two_layers(lib, vary):
     from reference_engine_cases import two_layers
     for (steps, rs, rs_theory, rv, rv_theory, init, reflect) in two_layers(lib, vary):
         assert abs(rs - rs_theory) < 1e-2 and abs(rv - rv_theory) < 1e-2, (rs, rs_theory, rv, rv_theory)
+
+
+# ---- simplex path on the stepping harness (oracle: oracle/simplex_oracle.c, parity unpinned) -----------------
+def test_simplex_vertex_info(lib):
+    import simplex_cases
+    simplex_cases.check_vertex_info(lib)
+    simplex_cases.check_vertex_info(lib, "regular")
+
+
+def test_simplex_cell_location_protocol(lib):
+    """src/test/sequence/TestLineWalkSearch3D.cpp:120-154 protocol, integer-exact vs the restatement"""
+    import simplex_cases
+    simplex_cases.check_locate_protocol(lib, "jitter_void", n_dirs=8, lengths=5)
+    simplex_cases.check_locate_protocol(lib, "regular", n_dirs=8, lengths=5)
+
+
+def test_simplex_gradient(lib):
+    import simplex_cases
+    simplex_cases.check_gradient(lib)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_simplex_time_steps(lib, model):
+    import simplex_cases
+    simplex_cases.check_stage(lib, model, steps=2)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_simplex_zero_stays_zero(lib, model):
+    """src/test/sequence/TestSimplexGcm.cpp:29-67"""
+    import simplex_cases
+    simplex_cases.check_stage(lib, model, kind="regular", steps=2, zero=True)
