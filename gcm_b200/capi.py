@@ -74,6 +74,16 @@ C_ABI = {
     "gcmb_simplex_plain_border": (ctypes.c_int, [vp, c_double_p]),
     "gcmb_simplex_stage": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double, c_double_p]),
     "gcmb_simplex_gradient": (ctypes.c_int, [vp, c_double_p, c_double_p]),
+    "gcmb_simplex_before_stage": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double]),
+    "gcmb_simplex_border_contact_stage": (ctypes.c_int, [vp]),
+    "gcmb_simplex_border_correct": (ctypes.c_int, [vp, c_double_p]),
+    "gcmb_simplex_inner_stage": (ctypes.c_int, [vp]),
+    "gcmb_simplex_after_stage": (ctypes.c_int, [vp]),
+    "gcmb_simplex_contact_normals": (ctypes.c_int, [vp, ctypes.c_int, c_double_p]),
+    "gcmb_simplex_contact_create": (ctypes.c_int, [vp, vp, ctypes.c_int, c_int_p, c_int_p, c_double_p, ctypes.POINTER(vp)]),
+    "gcmb_simplex_contact_destroy": (None, [vp]),
+    "gcmb_simplex_contact_plain": (ctypes.c_int, [vp]),
+    "gcmb_simplex_contact_correct": (ctypes.c_int, [vp]),
     "gcmb_cubic_stage_kernel_name": (ctypes.c_char_p, [vp, ctypes.c_int]),
 }
 

@@ -309,7 +309,8 @@ GCMB_HD int borderState(const Tri& t, int lv) {
 	if (multi || (empty && other)) { return 3; }
 	return empty ? 1 : 2;
 }
-GCMB_HD bool vertexNormal(const Tri& t, int lv, int which, V3& out) {
+// which: 0 faces towards empty space, 1 towards anything that is not this body, 2 towards the body `neighbor`
+GCMB_HD bool vertexNormal(const Tri& t, int lv, int which, V3& out, int neighbor = 0) {
 	const int g = t.globalOf[lv];
 	V3 sum = {0, 0, 0};
 	int count = 0;
@@ -319,7 +320,7 @@ GCMB_HD bool vertexNormal(const Tri& t, int lv, int which, V3& out) {
 		for (int k = 0; k < 4; k++) {
 			const int oc = t.cellN[4 * (long long) cell + k];
 			const int og = oc < 0 ? EMPTY : t.cellGrid[oc];
-			if (og == t.gridId || (which == 0 && og != EMPTY)) { continue; }
+			if (og == t.gridId || (which == 0 && og != EMPTY) || (which == 2 && og != neighbor)) { continue; }
 			if (t.cellV[4 * (long long) cell + k] == g) { continue; }
 			const V3 opposite = t.point(t.cellV[4 * (long long) cell + k]);
 			const V3 a = t.point(t.cellV[4 * (long long) cell + (k + 1) % 4]);
@@ -667,6 +668,314 @@ GCMB_HD void borderCorrectThread(const BorderS& a, int i) {
 	}
 	matVec<M>(a.U, u, w);
 	for (int k = 0; k < M; k++) { a.next[(long long) node * M + k] = w[k]; }
+}
+
+// ---- contact of two bodies --------------------------------------------------------------------
+// C[R][C] = A[R][N] * B[N][C] in the reference's accumulation order (linal/operators.hpp:109-123)
+template<int R, int N, int C>
+GCMB_HD void matMul(const double* A, const double* B, double* Cm) {
+	for (int i = 0; i < R; i++) for (int j = 0; j < C; j++) {
+		double x = A[i * N] * B[j];
+		for (int k = 1; k < N; k++) { x += A[i * N + k] * B[k * C + j]; }
+		Cm[i * C + j] = x;
+	}
+}
+
+// LU with partial pivoting (the reference calls GSL for N > 3: util/math/GslUtils.hpp:70-150)
+template<int N>
+GCMB_HD double luDecompose(double* a, int* perm) {
+	double sign = 1;
+	for (int i = 0; i < N; i++) { perm[i] = i; }
+	for (int j = 0; j < N - 1; j++) {
+		double best = fabs(a[j * N + j]);
+		int piv = j;
+		for (int i = j + 1; i < N; i++) { if (fabs(a[i * N + j]) > best) { best = fabs(a[i * N + j]); piv = i; } }
+		if (piv != j) {
+			for (int k = 0; k < N; k++) { const double x = a[j * N + k]; a[j * N + k] = a[piv * N + k]; a[piv * N + k] = x; }
+			const int x = perm[j]; perm[j] = perm[piv]; perm[piv] = x;
+			sign = -sign;
+		}
+		const double ajj = a[j * N + j];
+		if (ajj != 0) {
+			for (int i = j + 1; i < N; i++) {
+				const double aij = a[i * N + j] / ajj;
+				a[i * N + j] = aij;
+				for (int k = j + 1; k < N; k++) { a[i * N + k] = a[i * N + k] - aij * a[j * N + k]; }
+			}
+		}
+	}
+	double det = sign;
+	for (int i = 0; i < N; i++) { det = det * a[i * N + i]; }
+	return det;
+}
+
+template<int N>
+GCMB_HD double detN(const double* m) {
+	if constexpr (N == 1) { return m[0]; }
+	else if constexpr (N == 2) { return m[0] * m[3] - m[1] * m[2]; }
+	else if constexpr (N == 3) { return det3(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]); }
+	else {
+		double a[N * N];
+		int perm[N];
+		for (int i = 0; i < N * N; i++) { a[i] = m[i]; }
+		return luDecompose<N>(a, perm);
+	}
+}
+
+// linal::solveLinearSystem for N = 1, 2, 3 (Cramer) and N > 3 (LU); false when the reference would throw
+template<int N>
+GCMB_HD bool solveN(const double* m, const double* b, double* x) {
+	if constexpr (N == 1) { if (m[0] == 0) { return false; } x[0] = b[0] / m[0]; return true; }
+	else if constexpr (N == 2) {
+		const double det = m[0] * m[3] - m[1] * m[2];
+		if (det == 0) { return false; }
+		const double d1 = b[0] * m[3] - m[1] * b[1];
+		const double d2 = m[0] * b[1] - b[0] * m[2];
+		x[0] = d1 / det; x[1] = d2 / det;
+		return true;
+	}
+	else if constexpr (N == 3) {
+		const double det = det3(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
+		if (det == 0) { return false; }
+		x[0] = det3(b[0], m[1], m[2], b[1], m[4], m[5], b[2], m[7], m[8]) / det;
+		x[1] = det3(m[0], b[0], m[2], m[3], b[1], m[5], m[6], b[2], m[8]) / det;
+		x[2] = det3(m[0], m[1], b[0], m[3], m[4], b[1], m[6], m[7], b[2]) / det;
+		return true;
+	}
+	else {
+		double a[N * N];
+		int perm[N];
+		for (int i = 0; i < N * N; i++) { a[i] = m[i]; }
+		luDecompose<N>(a, perm);
+		for (int i = 0; i < N; i++) { x[i] = b[perm[i]]; }
+		for (int i = 0; i < N; i++) { double t = x[i]; for (int j = 0; j < i; j++) { t -= a[i * N + j] * x[j]; } x[i] = t; }
+		for (int i = N - 1; i >= 0; i--) { double t = x[i]; for (int j = i + 1; j < N; j++) { t -= a[i * N + j] * x[j]; } x[i] = t / a[i * N + i]; }
+		return true;
+	}
+}
+
+// border form of calculateOuterWaveCorrection with N outer waves (common.hpp:187-207)
+template<int M, int N>
+GCMB_HD bool outerWaveCorrectionN(const double* u, const double* Omega, const double* B, const double* b, double minDet,
+                                  double* value, int& err) {
+	double X[N * N], rhs[N], alpha[N], Bu[N];
+	matMul<N, M, N>(B, Omega, X);
+	const double detFabs = fabs(detN<N>(X));
+	for (int i = 0; i < M; i++) { value[i] = 0; }
+	if (!(detFabs > minDet)) { return false; }
+	matMul<N, M, 1>(B, u, Bu);
+	for (int i = 0; i < N; i++) { rhs[i] = b[i] - Bu[i]; }
+	if (!solveN<N>(X, rhs, alpha)) { err = 1; return false; }
+	matMul<M, N, 1>(Omega, alpha, value);
+	return true;
+}
+
+// linal::invert for 1x1 and 3x3 (linal/functions.hpp:101-134)
+template<int N>
+GCMB_HD void invertN(const double* m, double* r) {
+	if constexpr (N == 1) { r[0] = 1.0 / m[0]; }
+	else {
+		const double det = det3(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
+		const double adj[9] = {
+			m[4] * m[8] - m[5] * m[7], m[2] * m[7] - m[1] * m[8], m[1] * m[5] - m[4] * m[2],
+			m[5] * m[6] - m[3] * m[8], m[0] * m[8] - m[2] * m[6], m[2] * m[3] - m[0] * m[5],
+			m[3] * m[7] - m[4] * m[6], m[1] * m[6] - m[0] * m[7], m[0] * m[4] - m[1] * m[3]};
+		for (int i = 0; i < 9; i++) { r[i] = adj[i] / det; }
+	}
+}
+
+// contact form of calculateOuterWaveCorrection (common.hpp:209-260); O outer waves per body
+template<int M, int O>
+GCMB_HD bool contactWaveCorrection(const double* uA, const double* OmA, const double* B1A, const double* B2A,
+                                   const double* uB, const double* OmB, const double* B1B, const double* B2B,
+                                   double min1, double min2, double* valueA, double* valueB, double& det1, double& det2, int& err) {
+	double R1[O * O], R[O * O], t1[O], t2[O], d[O], p[O], BO[O * O], Q[O * O], B2Bo[O * O], B2Ao[O * O], BQ[O * O], A[O * O],
+			f[O], Bp[O], alphaB[O], alphaA[O], Qa[O];
+	det1 = det2 = 0;
+	for (int i = 0; i < M; i++) { valueA[i] = 0; valueB[i] = 0; }
+	matMul<O, M, O>(B1A, OmA, R1);
+	det1 = fabs(detN<O>(R1));
+	if (!(det1 > min1)) { return false; }
+	invertN<O>(R1, R);
+	matMul<O, M, 1>(B1B, uB, t1);
+	matMul<O, M, 1>(B1A, uA, t2);
+	for (int i = 0; i < O; i++) { d[i] = t1[i] - t2[i]; }
+	matMul<O, O, 1>(R, d, p);
+	matMul<O, M, O>(B1B, OmB, BO);
+	matMul<O, O, O>(R, BO, Q);
+	matMul<O, M, O>(B2B, OmB, B2Bo);
+	matMul<O, M, O>(B2A, OmA, B2Ao);
+	matMul<O, O, O>(B2Ao, Q, BQ);
+	for (int i = 0; i < O * O; i++) { A[i] = B2Bo[i] - BQ[i]; }
+	matMul<O, O, 1>(B2Ao, p, Bp);
+	matMul<O, M, 1>(B2A, uA, t1);
+	matMul<O, M, 1>(B2B, uB, t2);
+	for (int i = 0; i < O; i++) { f[i] = (Bp[i] + t1[i]) - t2[i]; }
+	det2 = fabs(detN<O>(A));
+	if (!(det2 > min2)) { return false; }
+	if (!solveN<O>(A, f, alphaB)) { err = 1; return false; }
+	matMul<O, O, 1>(Q, alphaB, Qa);
+	for (int i = 0; i < O; i++) { alphaA[i] = p[i] + Qa[i]; }
+	matMul<M, O, 1>(OmA, alphaA, valueA);
+	matMul<M, O, 1>(OmB, alphaB, valueB);
+	return true;
+}
+
+// contact matrices B1 (which = 1) and B2 (which = 2): elastic ADHESION in the global basis
+// (ElasticModel.hpp:156-189), acoustic SLIDE (AcousticModel.hpp:95-117); ContactCorrector.hpp:443-481
+template<int M>
+GCMB_HD void contactMatrix(int model, int which, V3 n, double* B) {
+	const int outer = model == 0 ? 3 : 1;
+	for (int i = 0; i < outer * M; i++) { B[i] = 0; }
+	if (model == 1) {
+		if (which == 1) { B[0] = n.x; B[1] = n.y; B[2] = n.z; } else { B[3] = 1; }
+		return;
+	}
+	for (int i = 0; i < 3; i++) {
+		if (which == 1) { B[i * M + i] = 1; }
+		else { for (int j = 0; j < 3; j++) { B[i * M + 3 + symIndex3(i, j)] = n[j]; } }
+	}
+}
+
+// Model::applyPlainContactCorrectionAsAverage (average) / applyPlainContactCorrection (A takes B's values)
+// (ElasticModel.hpp:243-298, AcousticModel.hpp:158-210)
+GCMB_HD void plainContact(int model, bool average, V3 normal, double* uA, double* uB) {
+	double S[3][3], St[3][3];
+	localBasis(normal, S);
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { St[i][j] = S[j][i]; }
+	if (model == 1) {
+		if (average) { const double p = (uA[3] + uB[3]) / 2; uA[3] = p; uB[3] = p; } else { uA[3] = uB[3]; }
+		double la[3], lb[3], g[3];
+		for (int i = 0; i < 3; i++) { double r = St[i][0] * uA[0]; r += St[i][1] * uA[1]; r += St[i][2] * uA[2]; la[i] = r; }
+		for (int i = 0; i < 3; i++) { double r = St[i][0] * uB[0]; r += St[i][1] * uB[1]; r += St[i][2] * uB[2]; lb[i] = r; }
+		if (average) { const double vn = (la[2] + lb[2]) / 2; la[2] = vn; lb[2] = vn; } else { la[2] = lb[2]; }
+		for (int i = 0; i < 3; i++) { double r = St[0][i] * la[0]; r += St[1][i] * la[1]; r += St[2][i] * la[2]; g[i] = r; }
+		for (int i = 0; i < 3; i++) { uA[i] = g[i]; }
+		if (average) {
+			for (int i = 0; i < 3; i++) { double r = St[0][i] * lb[0]; r += St[1][i] * lb[1]; r += St[2][i] * lb[2]; g[i] = r; }
+			for (int i = 0; i < 3; i++) { uB[i] = g[i]; }
+		}
+		return;
+	}
+	if (average) { for (int i = 0; i < 3; i++) { const double v = (uA[i] + uB[i]) / 2; uA[i] = v; uB[i] = v; } }
+	else { for (int i = 0; i < 3; i++) { uA[i] = uB[i]; } }
+	double ga[3][3], gb[3][3], t[3][3], la[3][3], lb[3][3], sn[3];
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { ga[i][j] = uA[3 + symIndex3(i, j)]; gb[i][j] = uB[3 + symIndex3(i, j)]; }
+	mul33(St, ga, t); mul33(t, S, la);
+	mul33(St, gb, t); mul33(t, S, lb);
+	for (int i = 0; i < 3; i++) { sn[i] = average ? (la[i][2] + lb[i][2]) / 2 : lb[i][2]; }
+	for (int i = 0; i < 3; i++) { la[i][2] = sn[i]; }
+	for (int j = 0; j < 3; j++) { la[2][j] = sn[j]; }
+	mul33(S, la, t); mul33(t, St, ga);
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { uA[3 + symIndex3(i, j)] = ga[i][j]; }
+	if (average) {
+		for (int i = 0; i < 3; i++) { lb[i][2] = sn[i]; }
+		for (int j = 0; j < 3; j++) { lb[2][j] = sn[j]; }
+		mul33(S, lb, t); mul33(t, St, gb);
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { uB[3 + symIndex3(i, j)] = gb[i][j]; }
+	}
+}
+
+// [M][2*O]: RIGHT columns then LEFT columns of U1 (ContactCorrector.hpp:186-190)
+template<int M, int O>
+GCMB_HD void outerColumnsBoth(const double* U1, unsigned RIGHT, unsigned LEFT, double* Omega) {
+	double part[M * O];
+	outerColumns<M>(O, U1, RIGHT, part);
+	for (int i = 0; i < M; i++) for (int c = 0; c < O; c++) { Omega[i * 2 * O + c] = part[i * O + c]; }
+	outerColumns<M>(O, U1, LEFT, part);
+	for (int i = 0; i < M; i++) for (int c = 0; c < O; c++) { Omega[i * 2 * O + O + c] = part[i * O + c]; }
+}
+
+GCMB_HD int popcountU(unsigned x) { int c = 0; while (x) { c += (int) (x & 1u); x >>= 1; } return c; }
+
+struct ContactS {
+	int model, n;
+	const double *UA, *U1A, *UB, *U1B;   // this stage, body A and body B
+	double dir[3];
+	const int *nodeA, *nodeB;            // local vertex ids of the pairs
+	const double* normal;                // [n][3], from A to B
+	unsigned *wavesA, *wavesB;
+	double *nextA, *nextB;               // invariants of the next layers
+	int* errors;
+};
+
+// ContactCorrectorInRiemannInvariants::applyInGlobalBasis for one pair of nodes (ContactCorrector.hpp:334-410
+// around :133-253)
+template<int M, int O>
+GCMB_HD void contactCorrectThread(const ContactS& a, int i) {
+	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
+	int err = 0;
+	double OmA[M * 2 * O], OmB[M * O], B1A[O * M], B1B[O * M], B2A[O * M], B2B[O * M], zero[M], vA[M], vB[M], det1, det2;
+	const V3 direction = {a.dir[0], a.dir[1], a.dir[2]};
+	// getMaximalPossibleDeterminants (:273-300)
+	for (int k = 0; k < M; k++) { zero[k] = 0; }
+	outerColumns<M>(O, a.U1A, LEFT, OmA);
+	outerColumns<M>(O, a.U1B, RIGHT, OmB);
+	contactMatrix<M>(a.model, 1, direction, B1A); contactMatrix<M>(a.model, 1, direction, B1B);
+	contactMatrix<M>(a.model, 2, direction, B2A); contactMatrix<M>(a.model, 2, direction, B2B);
+	if (!contactWaveCorrection<M, O>(zero, OmA, B1A, B2A, zero, OmB, B1B, B2B, 0, 0, vA, vB, det1, det2, err)) { err = 1; }
+	const double min1 = 1e-3 * det1, min2 = 1e-3 * det2;
+	double* ra = a.nextA + (long long) a.nodeA[i] * M;
+	double* rb = a.nextB + (long long) a.nodeB[i] * M;
+	unsigned wa = a.wavesA[a.nodeA[i]], wb = a.wavesB[a.nodeB[i]];
+	// matchInnersAndOuters (:381-410)
+	const int N = (popcountU(wa) + popcountU(wb)) / O;
+	if (N % 2 != 0) {
+		if (N == 3) { wa = wb = LEFT | RIGHT; }
+		else if (wa == 0) { if (wb == LEFT) { wa = RIGHT; } else { if (wb != RIGHT) { err = 1; } wa = LEFT; } }
+		else { if (wb != 0) { err = 1; } if (wa == LEFT) { wb = RIGHT; } else { if (wa != RIGHT) { err = 1; } wb = LEFT; } }
+		for (int k = 0; k < M; k++) { if ((wa >> k) & 1u) { ra[k] = 0; } if ((wb >> k) & 1u) { rb[k] = 0; } }
+	}
+	a.wavesA[a.nodeA[i]] = wa; a.wavesB[a.nodeB[i]] = wb;
+	double uA[M], uB[M], w[M];
+	matVec<M>(a.U1A, ra, uA);
+	matVec<M>(a.U1B, rb, uB);
+	const V3 normal = {a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2]};
+	contactMatrix<M>(a.model, 1, normal, B1A); contactMatrix<M>(a.model, 1, normal, B1B);
+	contactMatrix<M>(a.model, 2, normal, B2A); contactMatrix<M>(a.model, 2, normal, B2B);
+	const int na = popcountU(wa), nb = popcountU(wb);
+	if (na == O && nb == O) {
+		outerColumns<M>(O, a.U1A, wa, OmA);
+		outerColumns<M>(O, a.U1B, wb, OmB);
+		if (contactWaveCorrection<M, O>(uA, OmA, B1A, B2A, uB, OmB, B1B, B2B, min1, min2, vA, vB, det1, det2, err)) {
+			for (int k = 0; k < M; k++) { uA[k] += vA[k]; uB[k] += vB[k]; }
+		} else { plainContact(a.model, true, normal, uA, uB); }
+	} else if ((na == 2 * O && nb == 0) || (nb == 2 * O && na == 0)) {
+		// the node with both families outer is a border with two conditions taken from the other node
+		const bool first = na == 2 * O;
+		double* uX = first ? uA : uB;
+		double* uY = first ? uB : uA;
+		const double* U1X = first ? a.U1A : a.U1B;
+		const double *B1X = first ? B1A : B1B, *B2X = first ? B2A : B2B, *B1Y = first ? B1B : B1A, *B2Y = first ? B2B : B2A;
+		double Bc[2 * O * M], b12[2 * O], value[M];
+		for (int k = 0; k < O * M; k++) { Bc[k] = B1X[k]; Bc[O * M + k] = B2X[k]; }
+		matMul<O, M, 1>(B1Y, uY, b12);
+		matMul<O, M, 1>(B2Y, uY, b12 + O);
+		outerColumnsBoth<M, O>(U1X, RIGHT, LEFT, OmA);
+		if (outerWaveCorrectionN<M, 2 * O>(uX, OmA, Bc, b12, min1, value, err)) { for (int k = 0; k < M; k++) { uX[k] += value[k]; } }
+		else { plainContact(a.model, false, normal, uX, uY); }
+	} else {
+		double vA2[M], vB2[M], d1, d2;
+		outerColumns<M>(O, a.U1A, RIGHT, OmA);
+		outerColumns<M>(O, a.U1B, LEFT, OmB);
+		const bool ok1 = contactWaveCorrection<M, O>(uA, OmA, B1A, B2A, uB, OmB, B1B, B2B, min1, min2, vA, vB, d1, d2, err);
+		outerColumns<M>(O, a.U1A, LEFT, OmA);
+		outerColumns<M>(O, a.U1B, RIGHT, OmB);
+		const bool ok2 = contactWaveCorrection<M, O>(uA, OmA, B1A, B2A, uB, OmB, B1B, B2B, min1, min2, vA2, vB2, d1, d2, err);
+		if (ok1 && ok2) { for (int k = 0; k < M; k++) { uA[k] += (vA[k] + vA2[k]) / 2; uB[k] += (vB[k] + vB2[k]) / 2; } }
+		else { plainContact(a.model, true, normal, uA, uB); }
+	}
+	matVec<M>(a.UA, uA, w);
+	for (int k = 0; k < M; k++) { ra[k] = w[k]; }
+	matVec<M>(a.UB, uB, w);
+	for (int k = 0; k < M; k++) { rb[k] = w[k]; }
+	if (err) {
+#ifdef __CUDA_ARCH__
+		atomicAdd(a.errors, 1);
+#else
+		(*a.errors)++;
+#endif
+	}
 }
 
 }  // namespace sx

@@ -195,6 +195,30 @@ int gcmb_simplex_plain_border(gcmb_sbody* body, const double* values);
  * gradients, border vertices, border correction with values [n_cond][outer] at t+tau, inner vertices, back to
  * PDE variables, swap */
 int gcmb_simplex_stage(gcmb_sbody* body, int s, double tau, const double* values);
+/* The same stage as the four calls simplex::Engine::gcmStage makes over ALL bodies
+ * (engine/simplex/Engine.cpp:118-141; simplex::GridCharacteristicMethodBase, engine/simplex/common.hpp:16-41), so
+ * that contacts between bodies are corrected in the reference's order:
+ *   before_stage (every body) -> border_contact_stage (every body) -> contact_correct (every contact)
+ *   -> border_correct (every body) -> inner_stage (every body) -> after_stage (every body; swaps the layers) */
+int gcmb_simplex_before_stage(gcmb_sbody* body, int s, double tau);
+int gcmb_simplex_border_contact_stage(gcmb_sbody* body);
+int gcmb_simplex_border_correct(gcmb_sbody* body, const double* values /* [n_cond][outer] at t+tau */);
+int gcmb_simplex_inner_stage(gcmb_sbody* body);
+int gcmb_simplex_after_stage(gcmb_sbody* body);
+/* SimplexGrid::contactNormal(it, neighborId) of every local vertex (grid/simplex/SimplexGrid.hpp:141-144):
+ * unit normal over the faces shared with body `neighbor_grid_id`, zero where there is none. sync */
+int gcmb_simplex_contact_normals(gcmb_sbody* body, int neighbor_grid_id, double* normals /* [n_local][3] */);
+/* A contact of two bodies as Engine::addContactNode collects it (Engine.cpp:273-285): pairs of local vertex ids
+ * and the normal from a to b.  Elastic bodies are glued (ADHESION), acoustic bodies slide (SLIDE) — the two
+ * combinations the reference's ContactCorrectorFactory offers (ContactCorrector.hpp:484-560). */
+typedef struct gcmb_scontact gcmb_scontact;
+int gcmb_simplex_contact_create(gcmb_sbody* a, gcmb_sbody* b, int n, const int* node_a, const int* node_b,
+                                const double* normals, gcmb_scontact** out);
+void gcmb_simplex_contact_destroy(gcmb_scontact* contact);
+/* AbstractContactCorrector::applyPlainCorrection on the current layers (ContactCorrector.hpp:256-269) */
+int gcmb_simplex_contact_plain(gcmb_scontact* contact);
+/* ContactCorrectorInRiemannInvariants::applyInGlobalBasis on the stage in flight (ContactCorrector.hpp:334-356) */
+int gcmb_simplex_contact_correct(gcmb_scontact* contact);
 /* Differentiation::estimateGradient of a host field [n_local][M] -> [n_local][3][M] (test hook). sync */
 int gcmb_simplex_gradient(gcmb_sbody* body, const double* values, double* grad);
 

@@ -394,7 +394,7 @@ int gcmo_simplex_locate(const gcmo_tri* t, int lv, const double shift[3], int ou
 /* SimplexGrid.hpp:427-444 + Cgal3DTriangulation.hpp:103-113 + geometry.hpp:423-427.
  * which: 0 = border normal (faces towards empty space only), 1 = common normal (faces towards anything that is
  * not this grid).  Returns 0 and a zero vector when there is no such face. */
-int gcmo_simplex_normal(const gcmo_tri* t, int lv, int which, double out[3]) {
+static int normal_impl(const gcmo_tri* t, int lv, int which, int neighbor, double out[3]) {
 	const int g = t->global_of[lv];
 	R3 sum = {{0, 0, 0}};
 	int count = 0;
@@ -406,6 +406,7 @@ int gcmo_simplex_normal(const gcmo_tri* t, int lv, int which, double out[3]) {
 			const int outer_grid = outerc < 0 ? GCMO_EMPTY_SPACE : t->cell_grid[outerc];
 			if (outer_grid == t->grid_id) { continue; }
 			if (which == 0 && outer_grid != GCMO_EMPTY_SPACE) { continue; }
+			if (which == 2 && outer_grid != neighbor) { continue; }
 			if (t->cell_v[4 * cell + k] == g) { continue; }  /* the shared facet must contain the vertex */
 			const R3 opposite = point(t, t->cell_v[4 * cell + k]);
 			const R3 a = point(t, t->cell_v[4 * cell + (k + 1) % 4]);
@@ -423,6 +424,11 @@ int gcmo_simplex_normal(const gcmo_tri* t, int lv, int which, double out[3]) {
 	out[0] = sum.v[0]; out[1] = sum.v[1]; out[2] = sum.v[2];
 	return 1;
 }
+
+int gcmo_simplex_normal(const gcmo_tri* t, int lv, int which, double out[3]) { return normal_impl(t, lv, which, 0, out); }
+
+/* SimplexGrid.hpp:141-144: faces towards the body `neighbor` only */
+int gcmo_simplex_contact_normal(const gcmo_tri* t, int lv, int neighbor, double out[3]) { return normal_impl(t, lv, 2, neighbor, out); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* neighbours, gradient, interpolation                                                         */
@@ -683,128 +689,500 @@ static void columns(int M, int outer, const double* U1, unsigned mask, double* O
 	}
 }
 
+
+/* [M][2*outer] = RIGHT columns then LEFT columns (ContactCorrector.hpp:186-190) */
+static void columns_right_left(int M, int outer, const double* U1, unsigned RIGHT, unsigned LEFT, double* Omega) {
+	double part[9 * 3];
+	columns(M, outer, U1, RIGHT, part);
+	for (int i = 0; i < M; i++) for (int c = 0; c < outer; c++) { Omega[i * 2 * outer + c] = part[i * outer + c]; }
+	columns(M, outer, U1, LEFT, part);
+	for (int i = 0; i < M; i++) for (int c = 0; c < outer; c++) { Omega[i * 2 * outer + outer + c] = part[i * outer + c]; }
+}
+
+/* C[r][c] = A[r][n] * B[n][c], first product assigned, the rest added (linal/operators.hpp:109-123) */
+static void mat_mul(int r, int n, int c, const double* A, const double* B, double* C) {
+	for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) {
+		double x = A[i * n] * B[j];
+		for (int k = 1; k < n; k++) { x += A[i * n + k] * B[k * c + j]; }
+		C[i * c + j] = x;
+	}
+}
+
+/* LU with partial pivoting standing in for GSL (util/math/GslUtils.hpp:70-150: gsl_linalg_LU_decomp/_det/_solve);
+ * the reference reaches it for N > 3 only (linal/linearSystems.hpp:25-32, determinants.hpp:62-70) */
+static double lu_decompose(int n, double* a, int* perm) {
+	double sign = 1;
+	for (int i = 0; i < n; i++) { perm[i] = i; }
+	for (int j = 0; j < n - 1; j++) {
+		double best = fabs(a[j * n + j]);
+		int piv = j;
+		for (int i = j + 1; i < n; i++) { if (fabs(a[i * n + j]) > best) { best = fabs(a[i * n + j]); piv = i; } }
+		if (piv != j) {
+			for (int k = 0; k < n; k++) { const double x = a[j * n + k]; a[j * n + k] = a[piv * n + k]; a[piv * n + k] = x; }
+			const int x = perm[j]; perm[j] = perm[piv]; perm[piv] = x;
+			sign = -sign;
+		}
+		const double ajj = a[j * n + j];
+		if (ajj != 0) {
+			for (int i = j + 1; i < n; i++) {
+				const double aij = a[i * n + j] / ajj;
+				a[i * n + j] = aij;
+				for (int k = j + 1; k < n; k++) { a[i * n + k] = a[i * n + k] - aij * a[j * n + k]; }
+			}
+		}
+	}
+	double det = sign;
+	for (int i = 0; i < n; i++) { det = det * a[i * n + i]; }
+	return det;
+}
+static void lu_solve(int n, const double* lu, const int* perm, const double* b, double* x) {
+	for (int i = 0; i < n; i++) { x[i] = b[perm[i]]; }
+	for (int i = 0; i < n; i++) { double t = x[i]; for (int j = 0; j < i; j++) { t -= lu[i * n + j] * x[j]; } x[i] = t; }
+	for (int i = n - 1; i >= 0; i--) { double t = x[i]; for (int j = i + 1; j < n; j++) { t -= lu[i * n + j] * x[j]; } x[i] = t / lu[i * n + i]; }
+}
+
+/* determinant of an n x n matrix the way linal dispatches it (determinants.hpp) */
+static double det_n(int n, const double* m) {
+	if (n == 1) { return m[0]; }
+	if (n == 2) { return m[0] * m[3] - m[1] * m[2]; }
+	if (n == 3) { return det3(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]); }
+	double a[36];
+	int perm[6];
+	memcpy(a, m, (size_t) (n * n) * sizeof(double));
+	return lu_decompose(n, a, perm);
+}
+/* linal::solveLinearSystem (linearSystems.hpp:35-129); returns 1 when the reference would throw */
+static int solve_n(int n, const double* m, const double* b, double* x) {
+	if (n == 1) { if (m[0] == 0) { return 1; } x[0] = b[0] / m[0]; return 0; }
+	if (n == 2) {
+		const double det = m[0] * m[3] - m[1] * m[2];
+		if (det == 0) { return 1; }
+		const double d1 = b[0] * m[3] - m[1] * b[1];
+		const double d2 = m[0] * b[1] - b[0] * m[2];
+		x[0] = d1 / det; x[1] = d2 / det;
+		return 0;
+	}
+	if (n == 3) {
+		double A[3][3];
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { A[i][j] = m[i * 3 + j]; }
+		return solve3(A, b, x);
+	}
+	double a[36];
+	int perm[6];
+	memcpy(a, m, (size_t) (n * n) * sizeof(double));
+	lu_decompose(n, a, perm);
+	lu_solve(n, a, perm, b, x);
+	return 0;
+}
+
+/* border form of calculateOuterWaveCorrection for any outer count n <= 6 (common.hpp:187-207) */
+static int outer_wave_correction_n(int M, int n, const double* u, const double* Omega /*[M][n]*/,
+		const double* B /*[n][M]*/, const double* b, double min_det, double* value, double* det_fabs, int* err) {
+	double Mx[36], rhs[6], alpha[6], Bu[6];
+	mat_mul(n, M, n, B, Omega, Mx);
+	*det_fabs = fabs(det_n(n, Mx));
+	for (int i = 0; i < M; i++) { value[i] = 0; }
+	if (!(*det_fabs > min_det)) { return 0; }
+	mat_mul(n, M, 1, B, u, Bu);
+	for (int i = 0; i < n; i++) { rhs[i] = b[i] - Bu[i]; }
+	if (solve_n(n, Mx, rhs, alpha)) { *err += 1; return 0; }
+	mat_mul(M, n, 1, Omega, alpha, value);
+	return 1;
+}
+
+/* linal::invert for 1x1 and 3x3 (linal/functions.hpp:101-134) */
+static void invert_n(int n, const double* m, double* r) {
+	if (n == 1) { r[0] = 1.0 / m[0]; return; }
+	const double det = det3(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
+	const double adj[9] = {
+		m[4] * m[8] - m[5] * m[7], m[2] * m[7] - m[1] * m[8], m[1] * m[5] - m[4] * m[2],
+		m[5] * m[6] - m[3] * m[8], m[0] * m[8] - m[2] * m[6], m[2] * m[3] - m[0] * m[5],
+		m[3] * m[7] - m[4] * m[6], m[1] * m[6] - m[0] * m[7], m[0] * m[4] - m[1] * m[3]};
+	for (int i = 0; i < 9; i++) { r[i] = adj[i] / det; }
+}
+
+/* contact form of calculateOuterWaveCorrection (common.hpp:209-260) */
+static int contact_wave_correction(int M, int o, const double* uA, const double* OmA, const double* B1A, const double* B2A,
+		const double* uB, const double* OmB, const double* B1B, const double* B2B, double min1, double min2,
+		double* valueA, double* valueB, double* det1, double* det2, int* err) {
+	double R1[9], R[9], t1[3], t2[3], d[3], p[3], BO[9], Q[9], B2Bo[9], B2Ao[9], BQ[9], A[9], f[3], Bp[3], alphaB[3], alphaA[3], Qa[3];
+	*det1 = *det2 = 0;
+	for (int i = 0; i < M; i++) { valueA[i] = 0; valueB[i] = 0; }
+	mat_mul(o, M, o, B1A, OmA, R1);
+	*det1 = fabs(det_n(o, R1));
+	if (!(*det1 > min1)) { return 0; }
+	invert_n(o, R1, R);
+	mat_mul(o, M, 1, B1B, uB, t1);
+	mat_mul(o, M, 1, B1A, uA, t2);
+	for (int i = 0; i < o; i++) { d[i] = t1[i] - t2[i]; }
+	mat_mul(o, o, 1, R, d, p);
+	mat_mul(o, M, o, B1B, OmB, BO);
+	mat_mul(o, o, o, R, BO, Q);
+	mat_mul(o, M, o, B2B, OmB, B2Bo);
+	mat_mul(o, M, o, B2A, OmA, B2Ao);
+	mat_mul(o, o, o, B2Ao, Q, BQ);
+	for (int i = 0; i < o * o; i++) { A[i] = B2Bo[i] - BQ[i]; }
+	mat_mul(o, o, 1, B2Ao, p, Bp);
+	mat_mul(o, M, 1, B2A, uA, t1);
+	mat_mul(o, M, 1, B2B, uB, t2);
+	for (int i = 0; i < o; i++) { f[i] = (Bp[i] + t1[i]) - t2[i]; }
+	*det2 = fabs(det_n(o, A));
+	if (!(*det2 > min2)) { return 0; }
+	if (solve_n(o, A, f, alphaB)) { *err += 1; return 0; }
+	mat_mul(o, o, 1, Q, alphaB, Qa);
+	for (int i = 0; i < o; i++) { alphaA[i] = p[i] + Qa[i]; }
+	mat_mul(M, o, 1, OmA, alphaA, valueA);
+	mat_mul(M, o, 1, OmB, alphaB, valueB);
+	return 1;
+}
+
+/* contact matrices: elastic ADHESION = fixed velocity / fixed force in the GLOBAL basis (ElasticModel.hpp:156-189,
+ * ContactCorrector.hpp:443-462); acoustic SLIDE = normal velocity / pressure (AcousticModel.hpp:95-117,
+ * ContactCorrector.hpp:463-481).  which: 1 -> B1, 2 -> B2 */
+static void contact_matrix(int model, int M, int which, R3 normal, double* B) {
+	const int outer = model == 0 ? 3 : 1;
+	memset(B, 0, (size_t) (outer * M) * sizeof(double));
+	if (model == 1) {
+		if (which == 1) { for (int i = 0; i < 3; i++) { B[i] = normal.v[i]; } } else { B[3] = 1; }
+		return;
+	}
+	for (int i = 0; i < 3; i++) {
+		if (which == 1) { B[i * M + i] = 1; }
+		else { for (int j = 0; j < 3; j++) { B[i * M + 3 + sym_index3(i, j)] = normal.v[j]; } }
+	}
+}
+
+#define MM33(A, B, C) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double r = A[i][0] * B[0][j]; r += A[i][1] * B[1][j]; r += A[i][2] * B[2][j]; C[i][j] = r; }
+/* Model::applyPlainContactCorrectionAsAverage (average != 0) / applyPlainContactCorrection (A takes B's values)
+ * (ElasticModel.hpp:243-298, AcousticModel.hpp:158-210) */
+static void plain_contact(int model, int average, R3 normal, double* uA, double* uB) {
+	double S[3][3], St[3][3];
+	local_basis3(normal, S);
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { St[i][j] = S[j][i]; }
+	if (model == 1) {
+		if (average) { const double p = (uA[3] + uB[3]) / 2; uA[3] = p; uB[3] = p; } else { uA[3] = uB[3]; }
+		double la[3], lb[3], g[3];
+		for (int i = 0; i < 3; i++) { double r = St[i][0] * uA[0]; r += St[i][1] * uA[1]; r += St[i][2] * uA[2]; la[i] = r; }
+		for (int i = 0; i < 3; i++) { double r = St[i][0] * uB[0]; r += St[i][1] * uB[1]; r += St[i][2] * uB[2]; lb[i] = r; }
+		if (average) { const double vn = (la[2] + lb[2]) / 2; la[2] = vn; lb[2] = vn; } else { la[2] = lb[2]; }
+		for (int i = 0; i < 3; i++) { double r = St[0][i] * la[0]; r += St[1][i] * la[1]; r += St[2][i] * la[2]; g[i] = r; }
+		for (int i = 0; i < 3; i++) { uA[i] = g[i]; }
+		if (average) {
+			for (int i = 0; i < 3; i++) { double r = St[0][i] * lb[0]; r += St[1][i] * lb[1]; r += St[2][i] * lb[2]; g[i] = r; }
+			for (int i = 0; i < 3; i++) { uB[i] = g[i]; }
+		}
+		return;
+	}
+	if (average) { for (int i = 0; i < 3; i++) { const double v = (uA[i] + uB[i]) / 2; uA[i] = v; uB[i] = v; } }
+	else { for (int i = 0; i < 3; i++) { uA[i] = uB[i]; } }
+	double ga[3][3], gb[3][3], t[3][3], la[3][3], lb[3][3], sn[3];
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { ga[i][j] = uA[3 + sym_index3(i, j)]; gb[i][j] = uB[3 + sym_index3(i, j)]; }
+	MM33(St, ga, t)
+	MM33(t, S, la)
+	MM33(St, gb, t)
+	MM33(t, S, lb)
+	for (int i = 0; i < 3; i++) { sn[i] = average ? (la[i][2] + lb[i][2]) / 2 : lb[i][2]; }
+	for (int i = 0; i < 3; i++) { la[i][2] = sn[i]; }
+	for (int j = 0; j < 3; j++) { la[2][j] = sn[j]; }
+	MM33(S, la, t)
+	MM33(t, St, ga)
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { uA[3 + sym_index3(i, j)] = ga[i][j]; }
+	if (average) {
+		for (int i = 0; i < 3; i++) { lb[i][2] = sn[i]; }
+		for (int j = 0; j < 3; j++) { lb[2][j] = sn[j]; }
+		MM33(S, lb, t)
+		MM33(t, St, gb)
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { uB[3 + sym_index3(i, j)] = gb[i][j]; }
+	}
+}
+#undef MM33
+
+/* AbstractContactCorrector::applyPlainCorrection over a list of node pairs (ContactCorrector.hpp:256-269) */
+void gcmo_simplex_plain_contact(int model, int M, int n, const int* node_a, const int* node_b, const double* normal,
+		double* pde_a, double* pde_b) {
+	for (int i = 0; i < n; i++) {
+		plain_contact(model, 1, r3(normal + 3 * i), pde_a + (size_t) node_a[i] * M, pde_b + (size_t) node_b[i] * M);
+	}
+}
+
 /* ------------------------------------------------------------------------------------------ */
-/* stage                                                                                       */
+/* stage, in the four phases simplex::Engine::gcmStage calls (Engine.cpp:118-141)             */
 /* ------------------------------------------------------------------------------------------ */
+struct gcmo_sstage {
+	const gcmo_tri* t;
+	int model, M, s, outer;
+	unsigned LEFT, RIGHT;   /* Model.cpp:65-82 */
+	double tau;
+	const double *U, *U1, *L;
+	R3 direction;
+	double *riem, *grad, *next;
+	unsigned* waves;
+	int errors;
+};
+
+/* beforeStage (…InRiemannInvariants.hpp:44-56) */
+gcmo_sstage* gcmo_sx_begin(const gcmo_tri* t, int model, int M, int s, double tau, const double* U_, const double* U1_,
+		const double* L_, const double* basis, const double* cur, double* next) {
+	gcmo_sstage* h = (gcmo_sstage*) calloc(1, sizeof(gcmo_sstage));
+	const int n = t->n_local;
+	h->t = t; h->model = model; h->M = M; h->s = s; h->tau = tau;
+	h->outer = model == 0 ? 3 : 1;
+	h->LEFT = model == 0 ? 0x15u : 0x1u;
+	h->RIGHT = model == 0 ? 0x2au : 0x2u;
+	h->U = U_ + (size_t) s * M * M; h->U1 = U1_ + (size_t) s * M * M; h->L = L_ + (size_t) s * M;
+	h->riem = (double*) malloc((size_t) n * M * sizeof(double));
+	h->grad = (double*) malloc((size_t) n * 3 * M * sizeof(double));
+	h->waves = (unsigned*) calloc((size_t) n, sizeof(unsigned));
+	h->next = next;
+	for (int v = 0; v < n; v++) { mat_vec(M, h->U, cur + (size_t) v * M, h->riem + (size_t) v * M); }
+	h->errors += gcmo_simplex_gradient(t, M, h->riem, h->grad);
+	const R3 direction = {{basis[0 * 3 + s], basis[1 * 3 + s], basis[2 * 3 + s]}};
+	h->direction = direction;
+	return h;
+}
+
+/* pass 0: contactAndBorderStage (…InRiemannInvariants.hpp:59-96), pass 1: innerStage (:99-113); both through
+ * interpolateValuesAround (:146-198) */
+void gcmo_sx_nodes(gcmo_sstage* h, int pass) {
+	const gcmo_tri* t = h->t;
+	const int M = h->M;
+	for (int it = 0; it < t->n_local; it++) {
+		const int state = gcmo_simplex_border_state(t, it);
+		if ((pass == 0) != (state != 0)) { continue; }
+		const int can_st = pass == 1;
+		unsigned outers = 0;
+		double* ans = h->next + (size_t) it * M;
+		const R3 x0 = point(t, t->global_of[it]);
+		for (int k = 0; k < M; k++) {
+			const double dx = -h->tau * h->L[k];
+			if (dx == 0) { ans[k] = h->riem[(size_t) it * M + k]; continue; }
+			const R3 shift = scale(h->direction, dx);
+			int cell[5];
+			h->errors += gcmo_simplex_locate(t, it, shift.v, cell);
+			double u = 0;
+			if (cell[0] == 4) {
+				const R3 q = add(x0, shift);
+				int e = 0;
+				u = gcmo_simplex_hybrid_interpolate(t, M, h->riem, h->grad, cell + 1, k, q.v, &e);
+				h->errors += e;
+			} else if (cell[0] == 0) {
+				outers |= 1u << k;
+			} else if (cell[0] == 3) {
+				if (can_st) {
+					R3 r[3];
+					double vc[3], vn[3];
+					for (int i = 0; i < 3; i++) {
+						r[i] = point(t, t->global_of[cell[1 + i]]);
+						vc[i] = h->riem[(size_t) cell[1 + i] * M + k];
+						vn[i] = h->next[(size_t) cell[1 + i] * M + k];
+					}
+					int e = 0;
+					u = interpolate_space_time(shift, x0, r, vc, vn, &e);
+					h->errors += e;
+				} else { outers |= 1u << k; }
+			} else if (cell[0] == 2) {
+				if (can_st) { h->errors++; /* THROW_UNSUPPORTED in 3-D */ } else { outers |= 1u << k; }
+			}
+			ans[k] = u;
+		}
+		if (pass == 0) {
+			/* …InRiemannInvariants.hpp:73-85 */
+			if (outers != h->RIGHT && outers != h->LEFT && outers != (h->LEFT | h->RIGHT) && outers != 0) {
+				if (outers & h->RIGHT) { outers |= h->RIGHT; }
+				if (outers & h->LEFT) { outers |= h->LEFT; }
+				for (int k = 0; k < M; k++) { if ((outers >> k) & 1u) { ans[k] = 0; } }
+			}
+			h->waves[it] = outers;
+		}
+	}
+}
+
+/* BorderCorrectorInRiemannInvariants::applyInGlobalBasis for every condition in order
+ * (Engine.cpp:158-167; BorderCorrector.hpp:122-174,241-286) */
+void gcmo_sx_border_correct(gcmo_sstage* h, int n_border, const int* border_node, const double* border_normal,
+		const int* border_cond, int n_cond, const int* cond_type, const double* cond_b) {
+	const int M = h->M, outer = h->outer, model = h->model;
+	const double *U = h->U, *U1 = h->U1;
+	double* next = h->next;
+	for (int c = 0; c < n_cond; c++) {
+		int first = -1;
+		for (int i = 0; i < n_border; i++) { if (border_cond[i] == c) { first = i; break; } }
+		if (first < 0) { continue; }
+		const double* b = cond_b + (size_t) c * outer;
+		double Omega[9 * 3], B[3 * 9], tmp[9], value[9], det;
+		/* getMaximalPossibleDeterminant: aligned case, right invariants */
+		columns(M, outer, U1, h->RIGHT, Omega);
+		border_matrix(model, M, cond_type[c], h->direction, B);
+		memset(tmp, 0, sizeof tmp);
+		outer_wave_correction(M, outer, tmp, Omega, B, b, 0, value, &det);
+		const double min_det = 1e-3 * det;
+		for (int i = 0; i < n_border; i++) {
+			if (border_cond[i] != c) { continue; }
+			const int node = border_node[i];
+			const R3 normal = r3(border_normal + 3 * i);
+			double u[9], w[9];
+			mat_vec(M, U1, next + (size_t) node * M, u);          /* to PDE variables */
+			border_matrix(model, M, cond_type[c], normal, B);
+			const unsigned outers = h->waves[node];
+			if (outers == h->RIGHT || outers == h->LEFT) {
+				columns(M, outer, U1, outers, Omega);
+				if (outer_wave_correction(M, outer, u, Omega, B, b, min_det, value, &det)) {
+					for (int k = 0; k < M; k++) { u[k] += value[k]; }
+				} else { plain_border(model, M, cond_type[c], normal, b, u); }
+			} else {
+				double vr[9], vl[9], d2;
+				columns(M, outer, U1, h->RIGHT, Omega);
+				const int okr = outer_wave_correction(M, outer, u, Omega, B, b, min_det, vr, &det);
+				columns(M, outer, U1, h->LEFT, Omega);
+				const int okl = outer_wave_correction(M, outer, u, Omega, B, b, min_det, vl, &d2);
+				if (okr && okl) { for (int k = 0; k < M; k++) { u[k] += (vr[k] + vl[k]) / 2; } }
+				else { plain_border(model, M, cond_type[c], normal, b, u); }
+			}
+			mat_vec(M, U, u, w);                                   /* back to invariants */
+			memcpy(next + (size_t) node * M, w, (size_t) M * sizeof(double));
+		}
+	}
+}
+
+static int popcount_u(unsigned x) { int c = 0; while (x) { c += (int) (x & 1u); x >>= 1; } return c; }
+
+/* ContactCorrectorInRiemannInvariants::applyInGlobalBasis (ContactCorrector.hpp:334-356, 381-410) around
+ * ContactCorrectorInPdeVectors::applyInGlobalBasis (:133-253).  Both bodies carry the same model (the factory
+ * offers elastic-elastic ADHESION and acoustic-acoustic SLIDE only, :484-560). */
+void gcmo_sx_contact_correct(gcmo_sstage* a, gcmo_sstage* b, int n, const int* node_a, const int* node_b, const double* normals) {
+	if (n == 0) { return; }
+	const int M = a->M, o = a->outer, model = a->model;
+	const unsigned LEFT = a->LEFT, RIGHT = a->RIGHT;
+	double OmA[9 * 6], OmB[9 * 6], B1A[27], B1B[27], B2A[27], B2B[27], zero[9], vA[9], vB[9], det1, det2;
+	/* getMaximalPossibleDeterminants (:273-300): calculation direction as the normal */
+	memset(zero, 0, sizeof zero);
+	columns(M, o, a->U1, LEFT, OmA);
+	columns(M, o, b->U1, RIGHT, OmB);
+	contact_matrix(model, M, 1, a->direction, B1A); contact_matrix(model, M, 1, a->direction, B1B);
+	contact_matrix(model, M, 2, a->direction, B2A); contact_matrix(model, M, 2, a->direction, B2B);
+	if (!contact_wave_correction(M, o, zero, OmA, B1A, B2A, zero, OmB, B1B, B2B, 0, 0, vA, vB, &det1, &det2, &a->errors)) { a->errors++; }
+	const double min1 = 1e-3 * det1, min2 = 1e-3 * det2;
+	for (int i = 0; i < n; i++) {
+		double* ra = a->next + (size_t) node_a[i] * M;
+		double* rb = b->next + (size_t) node_b[i] * M;
+		unsigned wa = a->waves[node_a[i]], wb = b->waves[node_b[i]];
+		/* matchInnersAndOuters */
+		const int N = (popcount_u(wa) + popcount_u(wb)) / o;
+		if (N % 2 != 0) {
+			if (N == 3) { wa = wb = LEFT | RIGHT; }
+			else if (wa == 0) { if (wb == LEFT) { wa = RIGHT; } else { if (wb != RIGHT) { a->errors++; } wa = LEFT; } }
+			else { if (wb != 0) { a->errors++; } if (wa == LEFT) { wb = RIGHT; } else { if (wa != RIGHT) { a->errors++; } wb = LEFT; } }
+			for (int k = 0; k < M; k++) { if ((wa >> k) & 1u) { ra[k] = 0; } if ((wb >> k) & 1u) { rb[k] = 0; } }
+		}
+		a->waves[node_a[i]] = wa; b->waves[node_b[i]] = wb;
+		double uA[9], uB[9], w[9];
+		mat_vec(M, a->U1, ra, uA);
+		mat_vec(M, b->U1, rb, uB);
+		const R3 normal = r3(normals + 3 * i);
+		contact_matrix(model, M, 1, normal, B1A); contact_matrix(model, M, 1, normal, B1B);
+		contact_matrix(model, M, 2, normal, B2A); contact_matrix(model, M, 2, normal, B2B);
+		const int na = popcount_u(wa), nb = popcount_u(wb);
+		if (na == o && nb == o) {
+			columns(M, o, a->U1, wa, OmA);
+			columns(M, o, b->U1, wb, OmB);
+			if (contact_wave_correction(M, o, uA, OmA, B1A, B2A, uB, OmB, B1B, B2B, min1, min2, vA, vB, &det1, &det2, &a->errors)) {
+				for (int k = 0; k < M; k++) { uA[k] += vA[k]; uB[k] += vB[k]; }
+			} else { plain_contact(model, 1, normal, uA, uB); }
+		} else if ((na == 2 * o && nb == 0) || (nb == 2 * o && na == 0)) {
+			/* the node with both families outer is a border with two conditions taken from the other node */
+			const int first = na == 2 * o;
+			double* uX = first ? uA : uB;
+			double* uY = first ? uB : uA;
+			const double* U1X = first ? a->U1 : b->U1;
+			const double *B1X = first ? B1A : B1B, *B2X = first ? B2A : B2B, *B1Y = first ? B1B : B1A, *B2Y = first ? B2B : B2A;
+			double Bc[6 * 9], b12[6], value[9], det;
+			memcpy(Bc, B1X, (size_t) (o * M) * sizeof(double));
+			memcpy(Bc + o * M, B2X, (size_t) (o * M) * sizeof(double));
+			mat_mul(o, M, 1, B1Y, uY, b12);
+			mat_mul(o, M, 1, B2Y, uY, b12 + o);
+			columns_right_left(M, o, U1X, RIGHT, LEFT, OmA);
+			if (outer_wave_correction_n(M, 2 * o, uX, OmA, Bc, b12, min1, value, &det, &a->errors)) {
+				for (int k = 0; k < M; k++) { uX[k] += value[k]; }
+			} else { plain_contact(model, 0, normal, uX, uY); }
+		} else {
+			double vA2[9], vB2[9], d1, d2;
+			columns(M, o, a->U1, RIGHT, OmA);
+			columns(M, o, b->U1, LEFT, OmB);
+			const int ok1 = contact_wave_correction(M, o, uA, OmA, B1A, B2A, uB, OmB, B1B, B2B, min1, min2, vA, vB, &d1, &d2, &a->errors);
+			columns(M, o, a->U1, LEFT, OmA);
+			columns(M, o, b->U1, RIGHT, OmB);
+			const int ok2 = contact_wave_correction(M, o, uA, OmA, B1A, B2A, uB, OmB, B1B, B2B, min1, min2, vA2, vB2, &d1, &d2, &a->errors);
+			if (ok1 && ok2) { for (int k = 0; k < M; k++) { uA[k] += (vA[k] + vA2[k]) / 2; uB[k] += (vB[k] + vB2[k]) / 2; } }
+			else { plain_contact(model, 1, normal, uA, uB); }
+		}
+		mat_vec(M, a->U, uA, w); memcpy(ra, w, (size_t) M * sizeof(double));
+		mat_vec(M, b->U, uB, w); memcpy(rb, w, (size_t) M * sizeof(double));
+	}
+}
+
+/* afterStage (…InRiemannInvariants.hpp:116-127); frees the handle and returns its error count */
+int gcmo_sx_end(gcmo_sstage* h) {
+	const int M = h->M;
+	for (int v = 0; v < h->t->n_local; v++) {
+		double w[9];
+		mat_vec(M, h->U1, h->next + (size_t) v * M, w);
+		memcpy(h->next + (size_t) v * M, w, (size_t) M * sizeof(double));
+	}
+	const int errors = h->errors;
+	free(h->riem); free(h->grad); free(h->waves); free(h);
+	return errors;
+}
+
 int gcmo_simplex_stage(const gcmo_tri* t, int model, int M, int s, double tau,
 		const double* U_, const double* U1_, const double* L_, const double* basis,
 		int n_border, const int* border_node, const double* border_normal, const int* border_cond,
 		int n_cond, const int* cond_type, const double* cond_b,
 		const double* cur, double* next) {
-	const int n = t->n_local;
-	const int outer = model == 0 ? 3 : 1;
-	const unsigned LEFT = model == 0 ? 0x15u : 0x1u;   /* Model.cpp:65-82 */
-	const unsigned RIGHT = model == 0 ? 0x2au : 0x2u;
-	const double* U = U_ + (size_t) s * M * M;
-	const double* U1 = U1_ + (size_t) s * M * M;
-	const double* L = L_ + (size_t) s * M;
-	int errors = 0;
-	double* riem = (double*) malloc((size_t) n * M * sizeof(double));
-	double* grad = (double*) malloc((size_t) n * 3 * M * sizeof(double));
-	unsigned* waves = (unsigned*) calloc((size_t) n, sizeof(unsigned));
-	/* beforeStage (…InRiemannInvariants.hpp:44-56) */
-	for (int v = 0; v < n; v++) { mat_vec(M, U, cur + (size_t) v * M, riem + (size_t) v * M); }
-	errors += gcmo_simplex_gradient(t, M, riem, grad);
-	const R3 direction = {{basis[0 * 3 + s], basis[1 * 3 + s], basis[2 * 3 + s]}};
+	gcmo_sstage* h = gcmo_sx_begin(t, model, M, s, tau, U_, U1_, L_, basis, cur, next);
+	gcmo_sx_nodes(h, 0);
+	gcmo_sx_border_correct(h, n_border, border_node, border_normal, border_cond, n_cond, cond_type, cond_b);
+	gcmo_sx_nodes(h, 1);
+	return gcmo_sx_end(h);
+}
 
-	/* two passes: border/contact vertices (no space-time interpolation), correction, then inner vertices */
-	for (int pass = 0; pass < 2; pass++) {
-		for (int it = 0; it < n; it++) {
-			const int state = gcmo_simplex_border_state(t, it);
-			if ((pass == 0) != (state != 0)) { continue; }
-			const int can_st = pass == 1;
-			unsigned outers = 0;
-			double* ans = next + (size_t) it * M;
-			const R3 x0 = point(t, t->global_of[it]);
-			for (int k = 0; k < M; k++) {
-				const double dx = -tau * L[k];
-				if (dx == 0) { ans[k] = riem[(size_t) it * M + k]; continue; }
-				const R3 shift = scale(direction, dx);
-				int cell[5];
-				errors += gcmo_simplex_locate(t, it, shift.v, cell);
-				double u = 0;
-				if (cell[0] == 4) {
-					const R3 q = add(x0, shift);
-					int e = 0;
-					u = gcmo_simplex_hybrid_interpolate(t, M, riem, grad, cell + 1, k, q.v, &e);
-					errors += e;
-				} else if (cell[0] == 0) {
-					outers |= 1u << k;
-				} else if (cell[0] == 3) {
-					if (can_st) {
-						R3 r[3];
-						double vc[3], vn[3];
-						for (int i = 0; i < 3; i++) {
-							r[i] = point(t, t->global_of[cell[1 + i]]);
-							vc[i] = riem[(size_t) cell[1 + i] * M + k];
-							vn[i] = next[(size_t) cell[1 + i] * M + k];
-						}
-						int e = 0;
-						u = interpolate_space_time(shift, x0, r, vc, vn, &e);
-						errors += e;
-					} else { outers |= 1u << k; }
-				} else if (cell[0] == 2) {
-					if (can_st) { errors++; /* THROW_UNSUPPORTED in 3-D */ } else { outers |= 1u << k; }
-				}
-				ans[k] = u;
-			}
-			if (pass == 0) {
-				/* …InRiemannInvariants.hpp:73-85 */
-				if (outers != RIGHT && outers != LEFT && outers != (LEFT | RIGHT) && outers != 0) {
-					if (outers & RIGHT) { outers |= RIGHT; }
-					if (outers & LEFT) { outers |= LEFT; }
-					for (int k = 0; k < M; k++) { if ((outers >> k) & 1u) { ans[k] = 0; } }
-				}
-				waves[it] = outers;
-			}
-		}
-		if (pass == 1) { break; }
-		/* correctContactsAndBorders, GLOBAL_BASIS (Engine.cpp:147-168; BorderCorrector.hpp:122-174,241-286) */
-		for (int c = 0; c < n_cond; c++) {
-			int first = -1;
-			for (int i = 0; i < n_border; i++) { if (border_cond[i] == c) { first = i; break; } }
-			if (first < 0) { continue; }
-			const double* b = cond_b + (size_t) c * outer;
-			double Omega[9 * 3], B[3 * 9], tmp[9], value[9], det;
-			/* getMaximalPossibleDeterminant: aligned case, right invariants */
-			columns(M, outer, U1, RIGHT, Omega);
-			border_matrix(model, M, cond_type[c], direction, B);
-			memset(tmp, 0, sizeof tmp);
-			outer_wave_correction(M, outer, tmp, Omega, B, b, 0, value, &det);
-			const double min_det = 1e-3 * det;
-			for (int i = 0; i < n_border; i++) {
-				if (border_cond[i] != c) { continue; }
-				const int node = border_node[i];
-				const R3 normal = r3(border_normal + 3 * i);
-				double u[9], w[9];
-				mat_vec(M, U1, next + (size_t) node * M, u);          /* to PDE variables */
-				border_matrix(model, M, cond_type[c], normal, B);
-				const unsigned outers = waves[node];
-				if (outers == RIGHT || outers == LEFT) {
-					columns(M, outer, U1, outers, Omega);
-					if (outer_wave_correction(M, outer, u, Omega, B, b, min_det, value, &det)) {
-						for (int k = 0; k < M; k++) { u[k] += value[k]; }
-					} else { plain_border(model, M, cond_type[c], normal, b, u); }
-				} else {
-					double vr[9], vl[9], d2;
-					columns(M, outer, U1, RIGHT, Omega);
-					const int okr = outer_wave_correction(M, outer, u, Omega, B, b, min_det, vr, &det);
-					columns(M, outer, U1, LEFT, Omega);
-					const int okl = outer_wave_correction(M, outer, u, Omega, B, b, min_det, vl, &d2);
-					if (okr && okl) { for (int k = 0; k < M; k++) { u[k] += (vr[k] + vl[k]) / 2; } }
-					else { plain_border(model, M, cond_type[c], normal, b, u); }
-				}
-				mat_vec(M, U, u, w);                                   /* back to invariants */
-				memcpy(next + (size_t) node * M, w, (size_t) M * sizeof(double));
-			}
-		}
+/* linal/geometry.hpp:275-284 */
+static double minimal_height4(R3 a, R3 b, R3 c, R3 d) {
+	const double V = volume(a, b, c, d);
+	const double A = area3(b, c, d), B = area3(c, d, a), C = area3(d, a, b), D = area3(a, b, c);
+	return 3 * V / fmax(A, fmax(B, fmax(C, D)));
+}
+
+/* SimplexGrid::getAverageHeight: the MEAN OF A 100-BIN HISTOGRAM of the cells' minimal heights
+ * (SimplexGrid.cpp:183-194,266-274; util/math/Histogram.hpp:14-58), which Engine::estimateTimeStep uses
+ * (engine/simplex/Engine.hpp:77-92).  out[0] = average, out[1] = minimum */
+void gcmo_simplex_heights(const gcmo_tri* t, double out[2]) {
+	const size_t bins_n = 100;
+	double* h = (double*) malloc((size_t) t->nC * sizeof(double));
+	size_t n = 0;
+	for (int c = 0; c < t->nC; c++) {
+		if (!is_local(t, c)) { continue; }
+		const int* v = t->cell_v + 4 * c;
+		h[n++] = minimal_height4(point(t, v[0]), point(t, v[1]), point(t, v[2]), point(t, v[3]));
 	}
-	/* afterStage (…InRiemannInvariants.hpp:116-127) */
-	for (int v = 0; v < n; v++) {
-		double w[9];
-		mat_vec(M, U1, next + (size_t) v * M, w);
-		memcpy(next + (size_t) v * M, w, (size_t) M * sizeof(double));
+	double lo = h[0], hi = h[0];
+	for (size_t i = 1; i < n; i++) { if (h[i] < lo) { lo = h[i]; } if (hi < h[i]) { hi = h[i]; } }
+	size_t bins[101];
+	memset(bins, 0, sizeof bins);
+	size_t used = bins_n;
+	if (hi == lo) { bins[0] = n; }
+	else {
+		const double size = (hi - lo) / (double) bins_n;
+		for (size_t i = 0; i < n; i++) { bins[(size_t) ((h[i] - lo) / size)]++; }
+		bins[bins_n - 1] += bins[bins_n];
 	}
-	free(riem); free(grad); free(waves);
-	return errors;
+	const double bin_size = (hi - lo) / (double) used;
+	double dot_sum = 0, count = 0;
+	for (size_t i = 0; i < used; i++) {
+		const double center = lo + ((double) i + 0.5) * bin_size;
+		dot_sum = dot_sum + (double) bins[i] * center;
+		count = count + (double) bins[i];
+	}
+	out[0] = dot_sum / count;
+	out[1] = lo;
+	free(h);
 }

@@ -81,6 +81,31 @@ int gcmo_simplex_stage(const gcmo_tri* t, int model, int M, int s, double tau,
                        int n_cond, const int* cond_type, const double* cond_b,
                        const double* cur, double* next);
 
+/* the same stage in the four phases simplex::Engine::gcmStage runs over ALL bodies (Engine.cpp:118-141), so that
+ * several bodies with contacts can be driven in the reference's order:
+ *   begin (all bodies) -> nodes(pass 0) (all) -> contact_correct (every contact) -> border_correct (all)
+ *   -> nodes(pass 1) (all) -> end (all) */
+typedef struct gcmo_sstage gcmo_sstage;
+gcmo_sstage* gcmo_sx_begin(const gcmo_tri* t, int model, int M, int s, double tau, const double* U, const double* U1,
+                           const double* L, const double* basis, const double* cur, double* next);
+void gcmo_sx_nodes(gcmo_sstage* h, int pass);
+void gcmo_sx_border_correct(gcmo_sstage* h, int n_border, const int* border_node, const double* border_normal,
+                            const int* border_cond, int n_cond, const int* cond_type, const double* cond_b);
+/* contact of body a with body b (ContactCorrector.hpp:133-253,334-410): node pairs (local ids), normals a -> b.
+ * Elastic bodies: ADHESION; acoustic bodies: SLIDE (the only combinations the reference's factory offers). */
+void gcmo_sx_contact_correct(gcmo_sstage* a, gcmo_sstage* b, int n, const int* node_a, const int* node_b, const double* normals);
+int gcmo_sx_end(gcmo_sstage* h);
+
+/* normal of a local vertex towards the body `neighbor` only (SimplexGrid.hpp:141-144) */
+int gcmo_simplex_contact_normal(const gcmo_tri* t, int local_vertex, int neighbor, double out[3]);
+
+/* AbstractContactCorrector::applyPlainCorrection: averages of the two nodes' values (ContactCorrector.hpp:256-269) */
+void gcmo_simplex_plain_contact(int model, int M, int n, const int* node_a, const int* node_b, const double* normal,
+                                double* pde_a, double* pde_b);
+
+/* out[0] = SimplexGrid::getAverageHeight (mean of a 100-bin histogram of minimal cell heights), out[1] = minimal */
+void gcmo_simplex_heights(const gcmo_tri* t, double out[2]);
+
 /* Engine::applyPlainBorderContactCorrection for border nodes (Engine.cpp:197-214) */
 void gcmo_simplex_plain_border(int model, int M, int n_border, const int* border_node, const double* border_normal,
                                const int* border_cond, const int* cond_type, const double* cond_b, double* pde);

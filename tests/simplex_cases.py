@@ -6,7 +6,7 @@ import ctypes
 import numpy as np
 
 from gcm_b200 import capi
-from simplex_helpers import Mesh, SimplexBody, _d, _i, directions, oracle, oracle_locate_all, protocol_queries
+from simplex_helpers import Mesh, SimplexBody, SimplexContact, _d, _i, directions, oracle, oracle_locate_all, protocol_queries
 
 
 def make_mesh(lib, kind):
@@ -178,3 +178,151 @@ def check_stage(lib, model, kind="jitter_void", steps=2, zero=False):
         assert np.isfinite(cur).all() and np.abs(cur).max() < 10 and np.abs(cur - pde).max() > 1e-3
     body.close(); ctx.close()
     return cur
+
+
+def check_two_bodies(lib, model, steps=2, kind="layers"):
+    """two bodies glued (elastic, ADHESION) or sliding (acoustic, SLIDE) along a jittered interface, different
+    materials, free/forced outer borders: whole time steps in the order of simplex::Engine::nextTimeStep
+    (engine/simplex/Engine.cpp:97-141) == the oracle driven in the same order, bit for bit"""
+    import oracle_host as oh
+    L = oracle()
+    base = Mesh(lib.h, 5, 4, 6, origin=(0.0, 0.0, 0.0), h=0.5, jitter=0.3, seed=11,
+                void_box=(0.9, 0.6, 2.2, 1.6, 1.4, 2.8) if kind == "layers_void" else None)
+    zcut = 1.5
+    base.retag(lambda c: 0 if c[2] < zcut else 1)
+    meshes = [base.view(0), base.view(1)]
+    M = 9 if model == 0 else 4
+    outer = 3 if model == 0 else 1
+    name = "elastic" if model == 0 else "acoustic"
+    mats = [("isotropic", 2.0, 3.0, 1.2 if model == 0 else 0.0), ("isotropic", 1.0, 2.0, 0.7 if model == 0 else 0.0)]
+    mat3 = [capi.host_matrices(lib, name, 3, m) for m in mats]
+    basis = np.eye(3)
+    ctx = capi.Context(lib)
+    bodies = [SimplexBody(lib, ctx, m, model) for m in meshes]
+    for b, (U, U1, Lm) in zip(bodies, mat3):
+        b.set_material(U, U1, Lm, basis)
+
+    # Engine::addBorderOrContact (Engine.cpp:250-309)
+    inc = base.incident_grids()
+    views = [m.oracle_view() for m in meshes]
+    zmax = base.xyz[:, 2].max()
+    areas = [lambda p: True, lambda p: p[2] > zmax - 1e-9]
+    types = np.array([0, 1], dtype=np.int32)
+    border = [([], [], []) for _ in meshes]
+    pair_a, pair_b, pair_n = [], [], []
+    cn_lib = bodies[0].contact_normals(1)
+    for g in range(base.nV):
+        grids = set(inc[g])
+        if len(grids) == 1:
+            continue
+        if -1 in grids:
+            targets = sorted(grids - {-1})
+        elif len(grids) == 2:
+            la, lb = meshes[0].local_of[g], meshes[1].local_of[g]
+            n = np.zeros(3)
+            L.gcmo_simplex_contact_normal(ctypes.byref(views[0]), int(la), 1, _d(n))
+            assert np.array_equal(n, cn_lib[la])          # device normals == oracle normals
+            if n.any():
+                pair_a.append(la); pair_b.append(lb); pair_n.append(n)
+            continue
+        else:
+            targets = sorted(grids)
+        for gid in targets:
+            m = meshes[gid]
+            lv = int(m.local_of[g])
+            bn = np.zeros(3)
+            multicontact = L.gcmo_simplex_normal(ctypes.byref(views[gid]), lv, 0, _d(bn)) == 0
+            chosen = -1
+            for c, contains in enumerate(areas):
+                if contains(base.xyz[g]) and not multicontact:   # useForMulticontactNodes = false
+                    chosen = c
+            if chosen < 0:
+                continue
+            n = np.zeros(3)
+            assert L.gcmo_simplex_normal(ctypes.byref(views[gid]), lv, 1, _d(n)) == 1
+            border[gid][0].append(lv); border[gid][1].append(n); border[gid][2].append(chosen)
+    pair_a = np.array(pair_a, dtype=np.int32); pair_b = np.array(pair_b, dtype=np.int32)
+    pair_n = np.array(pair_n).reshape(-1, 3)
+    assert len(pair_a) > 10
+    border = [(np.array(n_, dtype=np.int32), np.array(r_).reshape(-1, 3), np.array(c_, dtype=np.int32)) for n_, r_, c_ in border]
+    for b, (nodes, normals, conds) in zip(bodies, border):
+        b.border_set(types, nodes, normals, conds)
+    contact = SimplexContact(lib, bodies[0], bodies[1], pair_a, pair_b, pair_n)
+
+    def values(time):
+        amp = 0.3 * np.sin(9 * time)
+        return np.array([[0.0] * outer, [0.0] * (outer - 1) + [amp]])
+
+    state = []
+    for m in meshes:
+        X = m.local_xyz()
+        r = np.linalg.norm(X - np.array([1.2, 1.0, 1.1]), axis=1)
+        amp = np.exp(-(r / 0.7) ** 2)
+        pde = np.zeros((m.n_local, M))
+        if model == 0:
+            for i in (3, 6, 8):
+                pde[:, i] = -amp
+            pde[:, 1] = 0.2 * amp
+        else:
+            pde[:, 3] = amp
+        state.append(pde)
+    for b, pde in zip(bodies, state):
+        b.upload(pde)
+    lam = max(np.abs(m3[2]).max() for m3 in mat3)
+    tau = 0.3 * 0.5 / lam
+    time = 0.0
+    # the constructor's plain correction at t = 0 (Engine.cpp:45), then the steps
+    def plain(at):
+        b_at = values(at)
+        contact.plain()
+        L.gcmo_simplex_plain_contact(model, M, len(pair_a), _i(pair_a), _i(pair_b), _d(pair_n), _d(state[0]), _d(state[1]))
+        for b, (nodes, normals, conds), pde in zip(bodies, border, state):
+            b.plain_border(b_at)
+            L.gcmo_simplex_plain_border(model, M, len(nodes), _i(nodes), _d(normals), _i(conds), _i(types), _d(b_at), _d(pde))
+    plain(0.0)
+    for step in range(steps):
+        plain(time + tau)
+        b_next = values(time + tau)
+        for s in range(3):
+            for b in bodies:
+                b.before_stage(s, tau)
+            for b in bodies:
+                b.border_contact_stage()
+            contact.correct()
+            for b in bodies:
+                b.border_correct(b_next)
+            for b in bodies:
+                b.inner_stage()
+            for b in bodies:
+                b.after_stage()
+            nxt = [np.zeros_like(p) for p in state]
+            hs = [L.gcmo_sx_begin(ctypes.byref(v), model, M, s, tau, _d(m3[0]), _d(m3[1]), _d(m3[2]), _d(basis), _d(cur), _d(nx))
+                  for v, m3, cur, nx in zip(views, mat3, state, nxt)]
+            for h in hs:
+                L.gcmo_sx_nodes(h, 0)
+            L.gcmo_sx_contact_correct(hs[0], hs[1], len(pair_a), _i(pair_a), _i(pair_b), _d(pair_n))
+            for h, (nodes, normals, conds) in zip(hs, border):
+                L.gcmo_sx_border_correct(h, len(nodes), _i(nodes), _d(normals), _i(conds), 2, _i(types), _d(b_next))
+            for h in hs:
+                L.gcmo_sx_nodes(h, 1)
+            for h in hs:
+                assert L.gcmo_sx_end(h) == 0, (step, s)
+            state = nxt
+        time += tau
+        for b, pde in zip(bodies, state):
+            got = b.download()
+            assert np.array_equal(got, pde), (step, np.abs(got - pde).max())
+    for b in bodies:
+        assert b.errors() == 0
+    # the contact condition holds at the interface: equal velocity (elastic) / equal pressure (acoustic)
+    a, b = state[0][pair_a], state[1][pair_b]
+    if model == 0:
+        assert np.abs(a[:, :3] - b[:, :3]).max() < 1e-9
+    else:
+        assert np.abs(a[:, 3] - b[:, 3]).max() < 1e-9
+    assert all(np.isfinite(p).all() and np.abs(p).max() < 10 for p in state)
+    contact.close()
+    for b in bodies:
+        b.close()
+    ctx.close()
+    return state

@@ -46,12 +46,43 @@ class Mesh:
         f(nx, ny, nz, _d(o), h, jitter, seed, None if vb is None else _d(vb), grid_id, _i(sizes), _d(self.xyz),
           _i(self.cell_v), _i(self.cell_n), _i(self.cell_grid), _i(self.inc_off), _i(self.inc_cell))
         self.grid_id = grid_id
+        self._index_body()
+
+    def _index_body(self):
         used = np.zeros(self.nV, dtype=bool)
-        used[self.cell_v[self.cell_grid == grid_id].ravel()] = True
+        used[self.cell_v[self.cell_grid == self.grid_id].ravel()] = True
         self.global_of = np.nonzero(used)[0].astype(np.int32)
         self.local_of = np.full(self.nV, -1, dtype=np.int32)
         self.local_of[self.global_of] = np.arange(len(self.global_of), dtype=np.int32)
         self.n_local = len(self.global_of)
+
+    def retag(self, grid_of_centroid):
+        """give every non-empty cell the body id grid_of_centroid(centroid) (topology does not depend on it)"""
+        cent = self.xyz[self.cell_v].mean(axis=1)
+        for c in range(self.nC):
+            if self.cell_grid[c] >= 0:
+                self.cell_grid[c] = grid_of_centroid(cent[c])
+        self._index_body()
+
+    def view(self, grid_id):
+        """the same triangulation seen by another body"""
+        import copy
+        m = copy.copy(self)
+        m.grid_id = grid_id
+        m._index_body()
+        return m
+
+    def incident_grids(self):
+        """Triangulation::incidentGridsIds of every global vertex; hull vertices see EmptySpace (-1)"""
+        out = [set() for _ in range(self.nV)]
+        for c in range(self.nC):
+            for k in range(4):
+                out[self.cell_v[c, k]].add(int(self.cell_grid[c]))
+                if self.cell_n[c, k] < 0:
+                    for j in range(4):
+                        if j != k:
+                            out[self.cell_v[c, j]].add(-1)
+        return out
 
     def oracle_view(self):
         t = GcmoTri(self.nV, self.nC, _d(self.xyz), _i(self.cell_v), _i(self.cell_n), _i(self.cell_grid),
@@ -78,6 +109,20 @@ def oracle():
     L.gcmo_simplex_stage.argtypes = [tp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp,
                                      ctypes.c_int, ip, dp, ip, ctypes.c_int, ip, dp, dp, dp]
     L.gcmo_simplex_plain_border.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, dp, ip, ip, dp, dp]
+    L.gcmo_sx_begin.argtypes = [tp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp, dp, dp]
+    L.gcmo_sx_begin.restype = ctypes.c_void_p
+    L.gcmo_sx_nodes.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.gcmo_sx_nodes.restype = None
+    L.gcmo_sx_border_correct.argtypes = [ctypes.c_void_p, ctypes.c_int, ip, dp, ip, ctypes.c_int, ip, dp]
+    L.gcmo_sx_border_correct.restype = None
+    L.gcmo_sx_contact_correct.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ip, ip, dp]
+    L.gcmo_sx_contact_correct.restype = None
+    L.gcmo_sx_end.argtypes = [ctypes.c_void_p]
+    L.gcmo_simplex_contact_normal.argtypes = [tp, ctypes.c_int, ctypes.c_int, dp]
+    L.gcmo_simplex_plain_contact.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ip, dp, dp, dp]
+    L.gcmo_simplex_plain_contact.restype = None
+    L.gcmo_simplex_heights.argtypes = [tp, dp]
+    L.gcmo_simplex_heights.restype = None
     return L
 
 
@@ -168,11 +213,54 @@ class SimplexBody:
         v = np.ascontiguousarray(values, dtype=np.float64)
         self.lib.check(self.lib.c.gcmb_simplex_stage(self.handle, s, tau, _d(v)))
 
+    def before_stage(self, s, tau):
+        self.lib.check(self.lib.c.gcmb_simplex_before_stage(self.handle, s, tau))
+
+    def border_contact_stage(self):
+        self.lib.check(self.lib.c.gcmb_simplex_border_contact_stage(self.handle))
+
+    def border_correct(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self.lib.check(self.lib.c.gcmb_simplex_border_correct(self.handle, _d(v)))
+
+    def inner_stage(self):
+        self.lib.check(self.lib.c.gcmb_simplex_inner_stage(self.handle))
+
+    def after_stage(self):
+        self.lib.check(self.lib.c.gcmb_simplex_after_stage(self.handle))
+
+    def contact_normals(self, neighbor):
+        out = np.zeros((self.n, 3))
+        self.lib.check(self.lib.c.gcmb_simplex_contact_normals(self.handle, neighbor, _d(out)))
+        return out
+
     def gradient(self, values):
         v = np.ascontiguousarray(values, dtype=np.float64)
         g = np.zeros((self.n, 3, self.M))
         self.lib.check(self.lib.c.gcmb_simplex_gradient(self.handle, _d(v), _d(g)))
         return g
+
+
+class SimplexContact:
+    def __init__(self, lib, a, b, node_a, node_b, normals):
+        from gcm_b200 import capi
+        self.lib = lib
+        self.handle = capi.vp()
+        na = np.ascontiguousarray(node_a, dtype=np.int32)
+        nb = np.ascontiguousarray(node_b, dtype=np.int32)
+        nr = np.ascontiguousarray(normals, dtype=np.float64)
+        lib.check(lib.c.gcmb_simplex_contact_create(a.handle, b.handle, len(na), _i(na), _i(nb), _d(nr), ctypes.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.lib.c.gcmb_simplex_contact_destroy(self.handle)
+            self.handle = None
+
+    def plain(self):
+        self.lib.check(self.lib.c.gcmb_simplex_contact_plain(self.handle))
+
+    def correct(self):
+        self.lib.check(self.lib.c.gcmb_simplex_contact_correct(self.handle))
 
 
 def protocol_queries(mesh, n_dirs=16, lengths=9, scale=1.0, vertices=None):

@@ -191,3 +191,10 @@ def test_simplex_time_steps_gpu(lib, model):
 def test_simplex_zero_stays_zero_gpu(lib, model):
     import simplex_cases
     simplex_cases.check_stage(lib, model, kind="regular", steps=3, zero=True)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+@pytest.mark.parametrize("kind", ["layers", "layers_void"])
+def test_simplex_two_bodies_in_contact_gpu(lib, model, kind):
+    import simplex_cases
+    simplex_cases.check_two_bodies(lib, model, steps=3, kind=kind)

@@ -157,3 +157,9 @@ def test_simplex_zero_stays_zero(lib, model):
     """src/test/sequence/TestSimplexGcm.cpp:29-67"""
     import simplex_cases
     simplex_cases.check_stage(lib, model, kind="regular", steps=2, zero=True)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_simplex_two_bodies_in_contact(lib, model):
+    import simplex_cases
+    simplex_cases.check_two_bodies(lib, model, steps=2)
