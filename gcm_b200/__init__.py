@@ -7,7 +7,7 @@ fallback: `library()` raises ImportError when the native libraries are missing a
 there is no CUDA device.
 """
 from .capi import (Context, CubicBody, GcmError, HostEngine, Library, Q_PRESSURE_TRACE,  # noqa: F401
-                   host_matrices)
+                   SimplexHostEngine, host_matrices)
 
 _LIB = None
 

@@ -22,7 +22,7 @@ CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall"]
 CUDA_SOURCES = ["csrc/gcmb_capi.cu", "csrc/stage_dispatch.cu"]
 CUDA_HEADERS = ["csrc/internal.cuh", "csrc/thread_fns.h", "csrc/march_async.h", "csrc/ztile.h", "csrc/patterns.inc",
                 "csrc/simplex_fns.h", "csrc/simplex_capi.inc", "../include/gcm_b200.h"]
-HOST_SOURCES = ["host/models.cpp", "host/engine.cpp", "host/task_file.cpp", "host/host_capi.cpp", "host/simplex_mesh.cpp"]
+HOST_SOURCES = ["host/models.cpp", "host/engine.cpp", "host/task_file.cpp", "host/host_capi.cpp", "host/simplex_mesh.cpp", "host/simplex_engine.cpp"]
 HOST_HEADERS = ["host/gcmb_host.hpp", "../include/gcm_b200.h"]
 
 
@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
         _run(["nvcc", "-shared", "-Xlinker", "-Bsymbolic", "-o", lib] + objs + ["-ldl"])
     host = os.path.join(HERE, "libgcm_b200_host.so")
     host_src = [os.path.join(HERE, s) for s in HOST_SOURCES]
-    host_dep = host_src + [os.path.join(HERE, h) for h in HOST_HEADERS]
+    host_dep = host_src + [os.path.join(HERE, h) for h in HOST_HEADERS] + [os.path.abspath(__file__)]
     if force or _newer(host, host_dep):
         _run(["g++"] + CXX_FLAGS + ["-shared", "-o", host] + host_src +
              ["-L" + HERE, "-lgcm_b200", "-Wl,-rpath,$ORIGIN"])

@@ -103,6 +103,16 @@ HOST_ABI = {
     "gcmb_host_engine_seismogram": (ctypes.c_int, [vp, c_double_p, c_float_p, ctypes.c_int]),
     "gcmb_host_matrices": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
                                           c_double_p, c_double_p]),
+    "gcmb_host_simplex_box_mesh": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_double,
+                                                  ctypes.c_double, ctypes.c_uint, c_double_p, ctypes.c_int, c_int_p,
+                                                  c_double_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "gcmb_host_simplex_triangulation": (ctypes.c_int, [vp, c_int_p, c_double_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "gcmb_host_simplex_body_info": (ctypes.c_int, [vp, ctypes.c_size_t, c_int_p, c_double_p, c_double_p]),
+    "gcmb_host_simplex_body_pde": (ctypes.c_int, [vp, ctypes.c_size_t, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "gcmb_host_simplex_border_nodes": (ctypes.c_int, [vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, c_int_p, c_int_p, c_double_p]),
+    "gcmb_host_simplex_contact_nodes": (ctypes.c_int, [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, c_int_p, c_int_p,
+                                                       c_int_p, c_double_p]),
+    "gcmb_host_simplex_errors": (ctypes.c_int, [vp, c_int_p]),
 }
 
 
@@ -382,6 +392,63 @@ class HostEngine:
 
     def context_handle(self):
         return self.lib.h.gcmb_host_engine_context(self.handle)
+
+
+class SimplexHostEngine(HostEngine):
+    """the simplex engine of the host layer (gcm_b200/host/simplex_engine.cpp): task text with `grid simplex`"""
+
+    def triangulation(self):
+        sizes = np.zeros(3, dtype=np.int32)
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_triangulation(self.handle, ip(sizes), None, None, None, None, None, None))
+        nV, nC, ninc = (int(x) for x in sizes)
+        t = dict(xyz=np.zeros((nV, 3)), cell_v=np.zeros((nC, 4), dtype=np.int32), cell_n=np.zeros((nC, 4), dtype=np.int32),
+                 cell_grid=np.zeros(nC, dtype=np.int32), inc_off=np.zeros(nV + 1, dtype=np.int32),
+                 inc_cell=np.zeros(ninc, dtype=np.int32))
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_triangulation(self.handle, ip(sizes), dp(t["xyz"]), ip(t["cell_v"]), ip(t["cell_n"]),
+                                                                   ip(t["cell_grid"]), ip(t["inc_off"]), ip(t["inc_cell"])))
+        return t
+
+    def simplex_body_info(self, bid):
+        info = np.zeros(3, dtype=np.int32)
+        reals = np.zeros(3)
+        basis = np.zeros((3, 3))
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_body_info(self.handle, bid, ip(info), dp(reals), dp(basis)))
+        return dict(n_local=int(info[0]), M=int(info[1]), n_conditions=int(info[2]), average_height=reals[0],
+                    minimal_height=reals[1], maximal_eigenvalue=reals[2], basis=basis)
+
+    def simplex_pde(self, bid):
+        i = self.simplex_body_info(bid)
+        out = np.zeros((i["n_local"], i["M"]))
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_body_pde(self.handle, bid, dp(out), None, None, None))
+        return out
+
+    def simplex_matrices(self, bid):
+        M = self.simplex_body_info(bid)["M"]
+        U, U1, L = np.zeros((3, M, M)), np.zeros((3, M, M)), np.zeros((3, M))
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_body_pde(self.handle, bid, None, dp(U), dp(U1), dp(L)))
+        return U, U1, L
+
+    def border_nodes(self, bid, condition):
+        n = ctypes.c_int()
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_border_nodes(self.handle, bid, condition, 0, ctypes.byref(n), None, None))
+        nodes = np.zeros(n.value, dtype=np.int32)
+        normals = np.zeros((n.value, 3))
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_border_nodes(self.handle, bid, condition, n.value, ctypes.byref(n), ip(nodes), dp(normals)))
+        return nodes, normals
+
+    def contact_nodes(self, a, b):
+        n = ctypes.c_int()
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_contact_nodes(self.handle, a, b, 0, ctypes.byref(n), None, None, None))
+        first = np.zeros(n.value, dtype=np.int32)
+        second = np.zeros(n.value, dtype=np.int32)
+        normals = np.zeros((n.value, 3))
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_contact_nodes(self.handle, a, b, n.value, ctypes.byref(n), ip(first), ip(second), dp(normals)))
+        return first, second, normals
+
+    def errors(self):
+        c = ctypes.c_int()
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_errors(self.handle, ctypes.byref(c)))
+        return c.value
 
 
 def host_matrices(lib, model, D, material):

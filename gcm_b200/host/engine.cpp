@@ -462,9 +462,7 @@ void EngineBase::writeSnapshots(const int step_) {
 }  // namespace cubic
 
 std::shared_ptr<AbstractEngine> createEngine(const Task& task) {
-	if (task.globalSettings.gridId != Grids::T::CUBIC) {
-		throw Exception(GCMB_E_UNSUPPORTED, "createEngine: only cubic grids go through this factory");
-	}
+	if (task.globalSettings.gridId == Grids::T::SIMPLEX) { return std::make_shared<simplex::Engine>(task); }
 	switch (task.globalSettings.dimensionality) {
 		case 1: return std::make_shared<cubic::Engine<1>>(task);
 		case 2: return std::make_shared<cubic::Engine<2>>(task);

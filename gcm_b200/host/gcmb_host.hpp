@@ -43,6 +43,11 @@ struct Grids { enum class T { CUBIC, SIMPLEX }; };
 struct Models { enum class T { ELASTIC, ACOUSTIC, MAXWELL_ACOUSTIC }; };
 struct Snapshotters { enum class T { VTK, DETECTOR, SLICESNAP }; };
 struct Odes { enum class T { MAXWELL_VISCOSITY, CONTINUAL_DAMAGE, IDEAL_PLASTIC_FLOW }; };
+struct BorderConditions { enum class T { FIXED_FORCE, FIXED_VELOCITY }; };
+/// reference util/task/Task.hpp:12-22
+enum class BorderCalcMode { GLOBAL_BASIS, LOCAL_BASIS };
+enum class GcmType { ADVECT_RIEMANN_INVARIANTS, ADVECT_PDE_VECTORS };
+enum class SplittingType { PRODUCT, SUMM };
 
 // ---- areas (reference util/math/Area.hpp) ------------------------------------------------------
 struct Area {
@@ -133,6 +138,9 @@ int sigmaComponent(int D, int i, int j);
 /// Model::constructGcmMatrices in the global basis (reference ElasticModel.hpp:56-65,
 /// ElasticModel3D.cpp:432-448, ElasticModel2D.cpp:79-91, AcousticModel.hpp:57-65)
 GcmMatrices constructGcmMatrices(Models::T model, int D, const AbstractMaterial& material);
+/// the same for an isotropic material in any orthonormal calculation basis (row-major DxD; stage i runs along
+/// column i): ElasticModel.hpp:56-65, AcousticModel.hpp:57-65
+GcmMatrices constructGcmMatrices(Models::T model, int D, const IsotropicMaterial& material, const real* basis);
 /// column of U1 holding the given wave (reference rheology/models/Model.cpp:6-63)
 int waveColumn(Models::T model, Materials::T material, int D, Waves::T wave);
 /// component index, or GCMB_Q_PRESSURE_TRACE; throws if the model has no such quantity
@@ -160,6 +168,8 @@ struct Task {
 		int stepsPerSnap = 1;
 		real requiredTime = 0;
 		bool verboseTimeSteps = true;
+		GcmType gcmType = GcmType::ADVECT_RIEMANN_INVARIANTS;
+		SplittingType splittingType = SplittingType::PRODUCT;
 	} globalSettings;
 
 	struct CubicGrid {
@@ -171,6 +181,32 @@ struct Task {
 		int borderSize = 0;
 		std::map<size_t, Cube> cubics;
 	} cubicGrid;
+
+	/// reference util/task/Task.hpp:84-122.  The reference meshes with CGAL (not available here); the mesher
+	/// this build provides is a structured box cut into tetrahedra (host/simplex_mesh.cpp).
+	struct SimplexGrid {
+		enum class Mesher { CGAL_MESHER, INM_MESHER, BOX_MESHER } mesher = Mesher::BOX_MESHER;
+		real spatialStep = 0;            ///< edge of the box mesher's cubes
+		bool movable = false;
+		BorderCalcMode borderCalcMode = BorderCalcMode::GLOBAL_BASIS;
+		/// BOX_MESHER @{
+		std::array<int, 3> boxCubes = {{0, 0, 0}};
+		Real3 boxOrigin = {{0, 0, 0}};
+		real jitter = 0;                 ///< displacement of interior points, fraction of spatialStep
+		unsigned seed = 1;
+		struct BodyRegion {
+			size_t id;                   ///< cells whose centroid lies in the area belong to this body
+			std::shared_ptr<Area> area;  ///< later regions override earlier ones
+		};
+		std::vector<BodyRegion> bodies;  ///< cells in no region are empty space
+		std::vector<std::shared_ptr<Area>> cavities;  ///< cells whose centroid lies here are empty space
+		/// @}
+	} simplexGrid;
+
+	/// calculation basis of the simplex engine, row-major DxD; stage i runs along column i.  Empty = a new
+	/// random basis at every time step (reference util/task/Task.hpp:125-129)
+	std::vector<real> calculationBasis;
+	unsigned randomBasisSeed = 1;        ///< gcm_b200: the random bases are reproducible
 
 	struct MaterialCondition {
 		typedef std::shared_ptr<AbstractMaterial> Material;
@@ -219,8 +255,19 @@ struct Task {
 	};
 	std::map<size_t, std::vector<CubicBorderCondition>> cubicBorderConditions;
 
+	/// simplex grids (reference util/task/Task.hpp:204-213)
+	struct BorderCondition {
+		std::shared_ptr<Area> area;
+		bool useForMulticontactNodes = true;
+		BorderConditions::T type = BorderConditions::T::FIXED_FORCE;
+		std::vector<TimeDependency> values;  ///< as many as the model has outer characteristics
+	};
+	std::vector<BorderCondition> borderConditions;
+
 	struct ContactCondition {
+		typedef std::pair<size_t, size_t> GridsContact;
 		ContactConditions::T defaultCondition = ContactConditions::T::ADHESION;
+		std::map<GridsContact, ContactConditions::T> gridToGridConditions;
 	} contactCondition;
 
 	struct VtkSnapshotter {
@@ -368,6 +415,7 @@ public:
 namespace simplex {
 
 /// CGAL-free triangulation consumed by the simplex path (see host/simplex_mesh.cpp)
+static const int EmptySpaceFlag = -1;
 struct FlatTriangulation {
 	int nV = 0, nC = 0;
 	std::vector<double> xyz;     ///< [nV][3]
@@ -381,9 +429,109 @@ struct FlatTriangulation {
 FlatTriangulation makeBoxMesh(int nx, int ny, int nz, const Real3& origin, real h, real jitter, unsigned seed,
 		const Real3* voidMin, const Real3* voidMax, int gridId);
 
+/// host view of one body of the simplex engine (reference engine/simplex/AbstractMesh.hpp + DefaultMesh.hpp)
+class Mesh {
+public:
+	typedef int Iterator;   ///< local vertex index
+	GridId id = 0;
+	int M = 0;
+	Models::T modelType = Models::T::ELASTIC;
+	Materials::T materialType = Materials::T::ISOTROPIC;
+	~Mesh();
+	size_t sizeOfRealNodes() const { return globalOf.size(); }
+	Real3 coords(const Iterator it) const;
+	/// PDE vector of a vertex; the current layer is downloaded on first use after a step
+	const real* pde(const Iterator it) const;
+	const std::vector<real>& pdeAll() const;
+	real getMaximalEigenvalue() const { return maximalEigenvalue; }
+	real getAverageHeight() const { return averageHeight; }
+	real getMinimalHeight() const { return minimalHeight; }
+	gcmb_sbody* handle() const { return body; }
+	void invalidateHostCopy() const { hostValid = false; }
+
+	// filled by the engine
+	const FlatTriangulation* triangulation = nullptr;
+	gcmb_sbody* body = nullptr;
+	std::vector<int> globalOf, localOf;
+	std::vector<uint8_t> state;                 ///< 0 inner, 1 border, 2 contact, 3 multicontact
+	std::vector<real> borderNormals, commonNormals;
+	std::shared_ptr<AbstractMaterial> material;
+	GcmMatrices matrices;
+	real maximalEigenvalue = 0, averageHeight = 0, minimalHeight = 0;
+private:
+	mutable std::vector<real> host;
+	mutable bool hostValid = false;
+};
+
+/// reference engine/simplex/Engine.hpp:19-258 for Dimensionality = 3, on the flat triangulation
+class Engine : public AbstractEngine {
+public:
+	typedef std::pair<GridId, GridId> GridsPair;
+	Engine(const Task& task);
+	virtual ~Engine();
+	std::shared_ptr<const Mesh> getMesh(const GridId gridId) const { return getBody(gridId).mesh; }
+	const FlatTriangulation& getTriangulation() const { return triangulation; }
+	gcmb_ctx* context() const { return ctx; }
+	/// node computations the reference would have thrown on, over all bodies so far (sync)
+	int errorCount() const;
+	size_t numberOfContactNodes(const GridsPair& pair) const;
+	size_t numberOfBorderNodes(const GridId id, const size_t condition) const;
+	/// what Engine::addBorderNode / addContactNode collected (for tests and logs): local ids and normals
+	void borderNodes(const GridId id, const size_t condition, std::vector<int>& nodes, std::vector<real>& normals) const;
+	void contactNodes(const GridsPair& pair, std::vector<int>& first, std::vector<int>& second, std::vector<real>& normals) const;
+	size_t numberOfBorderConditions(const GridId id) const { return getBody(id).borders.size(); }
+	const real* calculationBasis() const { return basis; }
+protected:
+	void nextTimeStep() override;
+	real estimateTimeStep() override;
+	void writeSnapshots(const int) override { }
+private:
+	struct Border {
+		std::shared_ptr<Area> correctionArea;
+		bool useForMulticontactNodes = true;
+		BorderConditions::T type = BorderConditions::T::FIXED_FORCE;
+		std::vector<Task::TimeDependency> values;
+		std::vector<int> nodes;
+		std::vector<real> normals;
+	};
+	struct Body {
+		std::shared_ptr<Mesh> mesh;
+		std::vector<Border> borders;
+		std::vector<Odes::T> odes;
+	};
+	struct Contact {
+		ContactConditions::T condition = ContactConditions::T::ADHESION;
+		std::vector<int> first, second;
+		std::vector<real> normals;
+		gcmb_scontact* handle = nullptr;
+	};
+	gcmb_ctx* ctx = nullptr;
+	FlatTriangulation triangulation;
+	std::vector<Body> bodies;
+	std::map<GridsPair, Contact> contacts;
+	std::map<GridsPair, std::vector<real>> contactNormalsCache;  ///< set-up only
+	real basis[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	bool createNewRandomAtEachTimeStep = false;
+	unsigned long long randomState = 0;
+
+	Body& getBody(const GridId id);
+	const Body& getBody(const GridId id) const;
+	void createTriangulation(const Task& task);
+	void createMeshes(const Task& task);
+	void createContacts(const Task& task);
+	void addBorderOrContact(const int vertex);
+	void setMaterial(Body& body);
+	void applyInitialConditions(const Task& task, Body& body);
+	void changeCalculationBasis();
+	void gcmStage(const int stage, const real currentTime, const real timeStep);
+	void applyPlainBorderContactCorrection(const real timeForBorderCondition);
+	std::vector<real> borderValues(const Body& body, const real time) const;
+	real randomReal(real lo, real hi);
+};
+
 }  // namespace simplex
 
-/// reference engine/EngineFactory.hpp:11-36 (cubic grids only: the simplex engine is separate)
+/// reference engine/EngineFactory.hpp:11-36
 std::shared_ptr<AbstractEngine> createEngine(const Task& task);
 
 /// plain-text task files (DESIGN.md "task files")

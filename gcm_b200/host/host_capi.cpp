@@ -10,7 +10,13 @@ thread_local std::string hostError;
 struct Handle {
 	std::shared_ptr<AbstractEngine> engine;
 	cubic::EngineBase* base = nullptr;
+	simplex::Engine* sx = nullptr;
 };
+simplex::Engine& simplexOf(void* handle) {
+	simplex::Engine* e = static_cast<Handle*>(handle)->sx;
+	if (!e) { throw Exception(GCMB_E_INVALID_OP, "not a simplex engine"); }
+	return *e;
+}
 template<typename F> int guarded(F f) {
 	try { f(); return GCMB_OK; }
 	catch (const Exception& e) { hostError = e.what(); return e.code() == 0 ? GCMB_E_INVALID_OP : e.code(); }
@@ -34,6 +40,7 @@ int gcmb_host_engine_create(const char* task_text, int device, int slab_rank, in
 		auto* h = new Handle;
 		h->engine = createEngine(task);
 		h->base = dynamic_cast<cubic::EngineBase*>(h->engine.get());
+		h->sx = dynamic_cast<simplex::Engine*>(h->engine.get());
 		*out = h;
 	});
 }
@@ -80,7 +87,79 @@ void* gcmb_host_engine_body_handle(void* handle, size_t id) {
 	catch (...) { return nullptr; }
 }
 
-void* gcmb_host_engine_context(void* handle) { return static_cast<Handle*>(handle)->base->context(); }
+void* gcmb_host_engine_context(void* handle) {
+	Handle* h = static_cast<Handle*>(handle);
+	return h->base ? h->base->context() : (h->sx ? h->sx->context() : nullptr);
+}
+
+// ---- simplex engines ---------------------------------------------------------------------------
+/// sizes_out = {nV, nC, nIncident}; arrays may be null to query the sizes only
+int gcmb_host_simplex_triangulation(void* handle, int* sizes_out, double* xyz, int* cell_v, int* cell_n, int* cell_grid,
+		int* inc_off, int* inc_cell) {
+	return guarded([&] {
+		const simplex::FlatTriangulation& t = simplexOf(handle).getTriangulation();
+		sizes_out[0] = t.nV; sizes_out[1] = t.nC; sizes_out[2] = (int) t.incCell.size();
+		if (!xyz) { return; }
+		std::memcpy(xyz, t.xyz.data(), t.xyz.size() * sizeof(double));
+		std::memcpy(cell_v, t.cellV.data(), t.cellV.size() * sizeof(int));
+		std::memcpy(cell_n, t.cellN.data(), t.cellN.size() * sizeof(int));
+		std::memcpy(cell_grid, t.cellGrid.data(), t.cellGrid.size() * sizeof(int));
+		std::memcpy(inc_off, t.incOff.data(), t.incOff.size() * sizeof(int));
+		std::memcpy(inc_cell, t.incCell.data(), t.incCell.size() * sizeof(int));
+	});
+}
+
+/// info = {n_local, M, n_border_conditions}; reals = {average height, minimal height, maximal eigenvalue};
+/// basis = the current calculation basis (9)
+int gcmb_host_simplex_body_info(void* handle, size_t id, int* info, double* reals, double* basis) {
+	return guarded([&] {
+		simplex::Engine& e = simplexOf(handle);
+		auto mesh = e.getMesh(id);
+		info[0] = (int) mesh->sizeOfRealNodes(); info[1] = mesh->M; info[2] = (int) e.numberOfBorderConditions(id);
+		reals[0] = mesh->getAverageHeight(); reals[1] = mesh->getMinimalHeight(); reals[2] = mesh->getMaximalEigenvalue();
+		std::memcpy(basis, e.calculationBasis(), 9 * sizeof(double));
+	});
+}
+
+/// PDE vectors [n_local][M] of the current layer and, when not null, the U/U1 [3][M][M] and L [3][M] in use
+int gcmb_host_simplex_body_pde(void* handle, size_t id, double* pde, double* U, double* U1, double* L) {
+	return guarded([&] {
+		auto mesh = simplexOf(handle).getMesh(id);
+		if (pde) { const auto& v = mesh->pdeAll(); std::memcpy(pde, v.data(), v.size() * sizeof(double)); }
+		const GcmMatrices& g = mesh->matrices;
+		if (U) { std::memcpy(U, g.U.data(), g.U.size() * sizeof(double)); }
+		if (U1) { std::memcpy(U1, g.U1.data(), g.U1.size() * sizeof(double)); }
+		if (L) { std::memcpy(L, g.L.data(), g.L.size() * sizeof(double)); }
+	});
+}
+
+/// border nodes of one condition of a body; returns the count through *n (copies at most `capacity`)
+int gcmb_host_simplex_border_nodes(void* handle, size_t id, int condition, int capacity, int* n, int* nodes, double* normals) {
+	return guarded([&] {
+		std::vector<int> nd;
+		std::vector<real> nr;
+		simplexOf(handle).borderNodes(id, (size_t) condition, nd, nr);
+		*n = (int) nd.size();
+		for (int i = 0; i < *n && i < capacity; i++) { nodes[i] = nd[(size_t) i]; std::memcpy(normals + 3 * i, &nr[(size_t) 3 * i], 3 * sizeof(double)); }
+	});
+}
+
+int gcmb_host_simplex_contact_nodes(void* handle, size_t a, size_t b, int capacity, int* n, int* first, int* second, double* normals) {
+	return guarded([&] {
+		std::vector<int> f, s;
+		std::vector<real> nr;
+		simplexOf(handle).contactNodes({a, b}, f, s, nr);
+		*n = (int) f.size();
+		for (int i = 0; i < *n && i < capacity; i++) {
+			first[i] = f[(size_t) i]; second[i] = s[(size_t) i];
+			std::memcpy(normals + 3 * i, &nr[(size_t) 3 * i], 3 * sizeof(double));
+		}
+	});
+}
+
+int gcmb_host_simplex_errors(void* handle, int* count) {
+	return guarded([&] { *count = simplexOf(handle).errorCount(); });
+}
 
 /// eigen-systems of every material table of a body: U,U1 [tables][D][M][M], L [tables][D][M]
 int gcmb_host_engine_body_matrices(void* handle, size_t id, int* n_tables, double* U, double* U1, double* L) {

@@ -388,6 +388,30 @@ void orthotropic2D(const OrthotropicMaterial& m, GcmMatrices& g) {
 
 }  // namespace
 
+GcmMatrices constructGcmMatrices(Models::T model, int D, const IsotropicMaterial& material, const real* calcBasis) {
+	if (D < 1 || D > 3) { throw Exception(GCMB_E_INVALID_ARG, "dimensionality must be 1..3"); }
+	GcmMatrices g;
+	g.D = D;
+	g.M = pdeSize(model, D);
+	g.U.assign((size_t) D * g.M * g.M, 0.0);
+	g.U1.assign((size_t) D * g.M * g.M, 0.0);
+	g.L.assign((size_t) D * g.M, 0.0);
+	for (int s = 0; s < D; s++) {
+		real n[3] = {0, 0, 0};
+		for (int i = 0; i < D; i++) { n[i] = calcBasis[i * D + s]; }
+		real basis[3][3];
+		localBasis(D, n, basis);
+		real* U = g.U.data() + (size_t) s * g.M * g.M;
+		real* U1 = g.U1.data() + (size_t) s * g.M * g.M;
+		real* L = g.L.data() + (size_t) s * g.M;
+		if (model == Models::T::ELASTIC) { isotropicElasticDirection(D, material, basis, U, U1, L); }
+		else if (model == Models::T::ACOUSTIC) { acousticDirection(D, material, basis, U, U1, L); }
+		else { throw Exception(GCMB_E_UNSUPPORTED, "Unknown model type"); }
+	}
+	g.checkDecomposition(100 * 1e-9 * 1000);
+	return g;
+}
+
 GcmMatrices constructGcmMatrices(Models::T model, int D, const AbstractMaterial& material) {
 	if (D < 1 || D > 3) { throw Exception(GCMB_E_INVALID_ARG, "dimensionality must be 1..3"); }
 	GcmMatrices g;

@@ -7,6 +7,11 @@
 //   detector ID Q AREA [output-directory]
 //   AREA = infinite | box x0 y0 z0 x1 y1 z1 | sphere r cx cy cz | cylinder r bx by bz ex ey ez
 //   MATERIAL = isotropic rho lambda mu [tau0 t] | orthotropic rho c11 c12 c13 c22 c23 c33 c44 c55 c66 [tau0 t]
+// Simplex grids (box mesher):
+//   grid simplex | simplex_box nx ny nz ox oy oz h [jitter j] [seed s] | region ID AREA | cavity AREA
+//   body ID (elastic|acoustic) isotropic | material body ID MATERIAL | basis b00 b01 .. b22 | basis random [seed]
+//   border_condition AREA (fixed_force|fixed_velocity) [no_multicontact] (const c | sin amp omega)...
+//   contact (adhesion|slide) [ID ID]
 // The test suite feeds the same files to the unmodified reference.
 #include <cmath>
 #include <sstream>
@@ -176,6 +181,45 @@ Task parseTaskText(const std::string& text) {
 				bc.values[q] = timeDependency(t);
 			}
 			task.cubicBorderConditions[id].push_back(bc);
+		} else if (key == "grid") {
+			task.globalSettings.gridId = t.next() == "simplex" ? Grids::T::SIMPLEX : Grids::T::CUBIC;
+		} else if (key == "simplex_box") {
+			Task::SimplexGrid& g = task.simplexGrid;
+			for (size_t i = 0; i < 3; i++) { g.boxCubes[i] = t.inum(); }
+			g.boxOrigin = t.vec();
+			g.spatialStep = t.num();
+			while (!t.done()) {
+				const std::string sub = t.next();
+				if (sub == "jitter") { g.jitter = t.num(); }
+				else if (sub == "seed") { g.seed = (unsigned) t.inum(); }
+				else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown simplex_box option " + sub); }
+			}
+		} else if (key == "region") {
+			Task::SimplexGrid::BodyRegion r;
+			r.id = (size_t) t.inum();
+			r.area = area(t);
+			task.simplexGrid.bodies.push_back(r);
+		} else if (key == "cavity") {
+			task.simplexGrid.cavities.push_back(area(t));
+		} else if (key == "basis") {
+			task.calculationBasis.clear();
+			if (t.peek() == "random") { t.next(); if (!t.done()) { task.randomBasisSeed = (unsigned) t.inum(); } }
+			else { for (int i = 0; i < 9; i++) { task.calculationBasis.push_back(t.num()); } }
+		} else if (key == "border_condition") {
+			Task::BorderCondition bc;
+			bc.area = area(t);
+			const std::string type = t.next();
+			if (type == "fixed_force") { bc.type = BorderConditions::T::FIXED_FORCE; }
+			else if (type == "fixed_velocity") { bc.type = BorderConditions::T::FIXED_VELOCITY; }
+			else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown border condition type " + type); }
+			if (t.peek() == "no_multicontact") { t.next(); bc.useForMulticontactNodes = false; }
+			while (!t.done()) { bc.values.push_back(timeDependency(t)); }
+			task.borderConditions.push_back(bc);
+		} else if (key == "contact") {
+			const std::string type = t.next();
+			const ContactConditions::T c = type == "slide" ? ContactConditions::T::SLIDE : ContactConditions::T::ADHESION;
+			if (t.done()) { task.contactCondition.defaultCondition = c; }
+			else { const size_t a = (size_t) t.inum(), b = (size_t) t.inum(); task.contactCondition.gridToGridConditions[{a, b}] = c; }
 		} else if (key == "detector") {
 			task.detector.gridId = (size_t) t.inum();
 			task.detector.quantities = {quantity(t.next())};

@@ -326,3 +326,115 @@ def check_two_bodies(lib, model, steps=2, kind="layers"):
         b.close()
     ctx.close()
     return state
+
+
+# ---- the host engine (gcm_b200/host/simplex_engine.cpp) against the oracle driven in the reference's order ------
+def engine_scenario(model, bodies=2, basis="identity", cavity=True, steps=3):
+    """task text + the same border values as Python callables"""
+    import math
+    name = "elastic" if model == 0 else "acoustic"
+    outer = 3 if model == 0 else 1
+    lines = ["grid simplex", "dimensionality 3", "courant 0.7", "steps %d" % steps,
+             "simplex_box 5 4 6 0 0 0 0.5 jitter 0.3 seed 7"]
+    mats = [(2.0, 3.0, 1.2 if model == 0 else 0.0), (1.0, 2.0, 0.7 if model == 0 else 0.0)]
+    for b in range(bodies):
+        lines.append("body %d %s isotropic" % (b, name))
+        lines.append("material body %d isotropic %r %r %r" % ((b,) + mats[b]))
+    if bodies == 2:
+        lines.append("region 0 box -10 -10 -10 10 10 1.5")
+        lines.append("region 1 box -10 -10 1.5 10 10 10")
+        lines.append("contact %s" % ("adhesion" if model == 0 else "slide"))
+    if cavity:
+        lines.append("cavity box 0.9 0.6 2.2 1.6 1.4 2.8")
+    if basis == "identity":
+        lines.append("basis 1 0 0 0 1 0 0 0 1")
+    elif basis == "rotated":
+        c, s_ = math.cos(0.4), math.sin(0.4)
+        lines.append("basis %r %r 0 %r %r 0 0 0 1" % (c, -s_, s_, c))
+    else:
+        lines.append("basis random 5")
+    zero = " ".join(["const 0"] * outer)
+    lines.append("border_condition infinite fixed_force " + zero)
+    lines.append("border_condition box -10 -10 2.999 10 10 10 fixed_velocity no_multicontact "
+                 + " ".join(["const 0"] * (outer - 1) + ["sin 0.3 9"]))
+    lines.append("initial quantity PRESSURE 1 sphere 0.7 1.2 1.0 1.1")
+    values = lambda t: np.array([[0.0] * outer, [0.0] * (outer - 1) + [0.3 * math.sin(9 * t)]])
+    return "\n".join(lines) + "\n", values
+
+
+def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3):
+    L = oracle()
+    text, values = engine_scenario(model, bodies, basis, cavity, steps)
+    eng = capi.SimplexHostEngine(lib, text)
+    M = 9 if model == 0 else 4
+    tri = eng.triangulation()
+    ids = list(range(bodies))
+    meshes = [Mesh.from_arrays(tri, i) for i in ids]
+    views = [m.oracle_view() for m in meshes]
+    infos = [eng.simplex_body_info(i) for i in ids]
+    types = np.array([0, 1], dtype=np.int32)
+    border = []
+    for i in ids:
+        nodes, normals, conds = [], [], []
+        for c in range(infos[i]["n_conditions"]):
+            nd, nr = eng.border_nodes(i, c)
+            nodes.append(nd); normals.append(nr); conds.append(np.full(len(nd), c, dtype=np.int32))
+        border.append((np.concatenate(nodes).astype(np.int32), np.concatenate(normals).reshape(-1, 3), np.concatenate(conds).astype(np.int32)))
+        assert len(border[-1][0]) > 0
+    pairs = [(0, 1)] if bodies == 2 else []
+    contacts = {p: eng.contact_nodes(*p) for p in pairs}
+    for p, c in contacts.items():
+        assert len(c[0]) > 10
+    # the time step: Courant * average height / maximal eigenvalue, minimum over bodies (Engine.hpp:77-92)
+    _, time, tau = eng.info()
+    assert time == 0.0
+    expect = None
+    for i in ids:
+        h = np.zeros(2)
+        L.gcmo_simplex_heights(ctypes.byref(views[i]), _d(h))
+        assert h[0] == infos[i]["average_height"] and h[1] == infos[i]["minimal_height"]
+        U, U1, Lm = eng.simplex_matrices(i)
+        assert np.abs(Lm).max() == infos[i]["maximal_eigenvalue"]
+        t_i = 0.7 * h[0] / np.abs(Lm).max()
+        expect = t_i if expect is None else min(expect, t_i)
+    assert tau == expect
+    state = [eng.simplex_pde(i) for i in ids]
+    assert all(np.abs(s).max() > 0.5 for s in state[:1])
+    for step in range(steps):
+        eng.advance(1)
+        mats = [eng.simplex_matrices(i) for i in ids]            # the basis may change every step
+        basis_m = np.ascontiguousarray(eng.simplex_body_info(0)["basis"])
+        if basis == "identity":
+            assert np.array_equal(basis_m, np.eye(3))
+        else:
+            assert np.abs(basis_m.T @ basis_m - np.eye(3)).max() < 1e-12
+        b_next = values(time + tau)
+        for p, (fa, fb, fn) in contacts.items():
+            L.gcmo_simplex_plain_contact(model, M, len(fa), _i(fa), _i(fb), _d(fn), _d(state[p[0]]), _d(state[p[1]]))
+        for i in ids:
+            nodes, normals, conds = border[i]
+            L.gcmo_simplex_plain_border(model, M, len(nodes), _i(nodes), _d(normals), _i(conds), _i(types), _d(b_next), _d(state[i]))
+        for s in range(3):
+            nxt = [np.zeros_like(p) for p in state]
+            hs = [L.gcmo_sx_begin(ctypes.byref(views[i]), model, M, s, tau, _d(mats[i][0]), _d(mats[i][1]), _d(mats[i][2]),
+                                  _d(basis_m), _d(state[i]), _d(nxt[i])) for i in ids]
+            for h in hs:
+                L.gcmo_sx_nodes(h, 0)
+            for p, (fa, fb, fn) in contacts.items():
+                L.gcmo_sx_contact_correct(hs[p[0]], hs[p[1]], len(fa), _i(fa), _i(fb), _d(fn))
+            for i in ids:
+                nodes, normals, conds = border[i]
+                L.gcmo_sx_border_correct(hs[i], len(nodes), _i(nodes), _d(normals), _i(conds), 2, _i(types), _d(b_next))
+            for h in hs:
+                L.gcmo_sx_nodes(h, 1)
+            for h in hs:
+                assert L.gcmo_sx_end(h) == 0, (step, s)
+            state = nxt
+        time += tau
+        assert eng.info()[1] == time
+        for i in ids:
+            got = eng.simplex_pde(i)
+            assert np.array_equal(got, state[i]), (step, i, np.abs(got - state[i]).max())
+    assert eng.errors() == 0
+    assert all(np.isfinite(p).all() and np.abs(p).max() < 10 for p in state)
+    eng.close()

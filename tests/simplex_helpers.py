@@ -48,6 +48,17 @@ class Mesh:
         self.grid_id = grid_id
         self._index_body()
 
+    @classmethod
+    def from_arrays(cls, tri, grid_id):
+        """a body's view of a triangulation given as the dict SimplexHostEngine.triangulation() returns"""
+        m = cls.__new__(cls)
+        for k, v in tri.items():
+            setattr(m, k, v)
+        m.nV, m.nC = len(m.xyz), len(m.cell_v)
+        m.grid_id = grid_id
+        m._index_body()
+        return m
+
     def _index_body(self):
         used = np.zeros(self.nV, dtype=bool)
         used[self.cell_v[self.cell_grid == self.grid_id].ravel()] = True

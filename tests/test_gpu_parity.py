@@ -198,3 +198,11 @@ def test_simplex_zero_stays_zero_gpu(lib, model):
 def test_simplex_two_bodies_in_contact_gpu(lib, model, kind):
     import simplex_cases
     simplex_cases.check_two_bodies(lib, model, steps=3, kind=kind)
+
+
+@pytest.mark.parametrize("model,bodies,basis,cavity", [(0, 2, "identity", True), (1, 2, "rotated", True), (0, 1, "random", True),
+                                                      (0, 2, "random", False), (1, 1, "identity", False)])
+def test_simplex_engine_gpu(lib, model, bodies, basis, cavity):
+    """simplex::Engine of the host layer on the GPU == the oracle driven in the reference's order, bit for bit"""
+    import simplex_cases
+    simplex_cases.check_engine(lib, model, bodies=bodies, basis=basis, cavity=cavity, steps=4)

@@ -163,3 +163,10 @@ def test_simplex_zero_stays_zero(lib, model):
 def test_simplex_two_bodies_in_contact(lib, model):
     import simplex_cases
     simplex_cases.check_two_bodies(lib, model, steps=2)
+
+
+@pytest.mark.parametrize("model,bodies,basis", [(0, 2, "identity"), (1, 2, "rotated"), (0, 1, "random")])
+def test_simplex_engine(lib, model, bodies, basis):
+    """simplex::Engine of the host layer (task text -> run) == the oracle driven in the reference's order"""
+    import simplex_cases
+    simplex_cases.check_engine(lib, model, bodies=bodies, basis=basis, steps=2)
