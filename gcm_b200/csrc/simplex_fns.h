@@ -149,6 +149,8 @@ struct Tri {
 	const int* nbOff;       // [nLocal+1] neighbour vertices (ascending local id, at most MAX_NEIGHBORS)
 	const int* nbIdx;
 	const uint8_t* state;   // [nLocal] 0 inner, 1 border, 2 contact, 3 multicontact
+	const int* locOff;      // [nLocal+1] the body's own cells around a local vertex, ascending cell id ...
+	const int4* locABC;     // ... as {cell, a, b, c}: the other three vertices in the order findCrossedIncidentCell takes them
 
 	GCMB_HD V3 point(int g) const { return {xyz[3 * (long long) g], xyz[3 * (long long) g + 1], xyz[3 * (long long) g + 2]}; }
 	GCMB_HD V3 localPoint(int l) const { return point(globalOf[l]); }
@@ -163,12 +165,14 @@ struct Tri {
 	GCMB_HD int otherVertex(int cell, int a, int b, int c) const { return cellV[4 * (long long) cell + otherVertexIndex(cell, a, b, c)]; }
 };
 
-struct Found { int n; int p[4]; };
-GCMB_HD Found nothing() { return {0, {-1, -1, -1, -1}}; }
-GCMB_HD Found wholeCell(const Tri& t, int cell) {
+// n = 4: a cell, with the barycentric coordinates of the query that the containment test computed (the
+// interpolation needs exactly these: same points in the same order, same query)
+struct Found { int n; int p[4]; double l[4]; };
+GCMB_HD Found nothing() { return {0, {-1, -1, -1, -1}, {0, 0, 0, 0}}; }
+GCMB_HD Found wholeCell(const Tri& t, int cell, const double (&l)[4]) {
 	Found f;
 	f.n = 4;
-	for (int i = 0; i < 4; i++) { f.p[i] = t.localOf[t.cellV[4 * (long long) cell + i]]; }
+	for (int i = 0; i < 4; i++) { f.p[i] = t.localOf[t.cellV[4 * (long long) cell + i]]; f.l[i] = l[i]; }
 	return f;
 }
 
@@ -176,14 +180,47 @@ GCMB_HD Found wholeCell(const Tri& t, int cell) {
 // left the previous cell through are ever used
 struct Walked { int count, last, prev, exitSlot; };
 
-GCMB_HD int crossedIncidentCell(const Tri& t, int gv, V3 query, double eps, int& err) {
-	for (int i = t.incOff[gv]; i < t.incOff[gv + 1]; i++) {
-		const int cand = t.incCell[i];
-		if (!t.isLocal(cand)) { continue; }
-		const int a = t.otherVertex(cand, gv, gv, gv);
-		const int b = t.otherVertex(cand, gv, gv, a);
-		const int c = t.otherVertex(cand, gv, a, b);
-		if (solidAngleContains(t.point(gv), t.point(a), t.point(b), t.point(c), query, eps, err)) { return cand; }
+// exact value of (d / det < 0) without dividing: the quotient of two finite non-zero doubles has the sign of
+// d * det unless it underflows to zero, which the magnitude guard excludes
+GCMB_HD bool quotientNegative(double d, double det) {
+	if (d == 0) { return false; }
+	if (fabs(d) >= 1e-200 && fabs(det) <= 1e+100) { return (d < 0) != (det < 0); }
+	return d / det < 0;
+}
+
+// solidAngleContains(apex, b, c, d, q, eps = 0) (linal/geometry.hpp:326-334 through barycentricCoordinates
+// :201-217 and the Cramer solve linearSystems.hpp:104-129).  Same determinants as `barycentric`; the three
+// divisions are only carried out when the sign conditions that do not need them already hold, which leaves the
+// outcome unchanged: l0 <= 1 <=> d0 <= det (det > 0) or d0 >= det (det < 0) because rounding is monotonic and
+// 1 is representable; l1, l2 >= -0 <=> not (d / det < 0).
+GCMB_HD bool solidAngleContainsExact0(V3 a, V3 b, V3 c, V3 d, V3 q, int& err) {
+	const double T00 = a.x - d.x, T01 = b.x - d.x, T02 = c.x - d.x;
+	const double T10 = a.y - d.y, T11 = b.y - d.y, T12 = c.y - d.y;
+	const double T20 = a.z - d.z, T21 = b.z - d.z, T22 = c.z - d.z;
+	const double r0 = q.x - d.x, r1 = q.y - d.y, r2 = q.z - d.z;
+	const double det = det3(T00, T01, T02, T10, T11, T12, T20, T21, T22);
+	if (det == 0) { err = 1; return false; }
+	const double d1 = det3(T00, r0, T02, T10, r1, T12, T20, r2, T22);
+	if (quotientNegative(d1, det)) { return false; }
+	const double d2 = det3(T00, T01, r0, T10, T11, r1, T20, T21, r2);
+	if (quotientNegative(d2, det)) { return false; }
+	const double d0 = det3(r0, T01, T02, r1, T11, T12, r2, T21, T22);
+	if (det > 0 ? !(d0 <= det) : !(d0 >= det)) { return false; }
+	const double x0 = d0 / det, x1 = d1 / det, x2 = d2 / det;
+	const double l3 = 1 - x0 - x1 - x2;
+	return x0 <= 1 + 0.0 && x1 >= -0.0 && x2 >= -0.0 && l3 >= -0.0;
+}
+
+// Cgal3DTriangulation::findCrossedIncidentCell over the body's own cells around the vertex (table built at
+// body creation); returns the cell or -2
+GCMB_HD int crossedIncidentCell(const Tri& t, int lv, V3 query, double eps, int& err) {
+	const V3 apex = t.localPoint(lv);
+	for (int i = t.locOff[lv]; i < t.locOff[lv + 1]; i++) {
+		const int4 e = t.locABC[i];
+		const V3 pa = t.point(e.y), pb = t.point(e.z), pc = t.point(e.w);
+		const bool inside = eps == 0 ? solidAngleContainsExact0(apex, pa, pb, pc, query, err)
+		                             : solidAngleContains(apex, pa, pb, pc, query, eps, err);
+		if (inside) { return e.x; }
 	}
 	return -2;
 }
@@ -207,8 +244,8 @@ GCMB_HD Walked collectCells(const Tri& t, V3 q, V3 p, int cell, int u, int v, in
 	return ans;
 }
 
-GCMB_HD Walked walkFromVertex(const Tri& t, int gv, V3 p, int& err) {
-	const int cell = crossedIncidentCell(t, gv, p, 0, err);
+GCMB_HD Walked walkFromVertex(const Tri& t, int lv, int gv, V3 p, int& err) {
+	const int cell = crossedIncidentCell(t, lv, p, 0, err);
 	if (cell == -2) { return {0, -2, -2, -1}; }
 	int u = t.otherVertex(cell, gv, gv, gv);
 	int v = t.otherVertex(cell, gv, gv, u);
@@ -233,9 +270,10 @@ GCMB_HD Walked walkFromCell(const Tri& t, int cell, V3 q, V3 p, int& err) {
 	return collectCells(t, q, p, cell, u, v, w);
 }
 
-GCMB_HD bool cellContains(const Tri& t, int cell, V3 q, int& err) {
+GCMB_HD bool cellContains(const Tri& t, int cell, V3 q, double (&l)[4], int& err) {
 	const int* v = t.cellV + 4 * (long long) cell;
-	return tetrahedronContains(t.point(v[0]), t.point(v[1]), t.point(v[2]), t.point(v[3]), q, TOL, err);
+	if (!barycentric(t.point(v[0]), t.point(v[1]), t.point(v[2]), t.point(v[3]), q, l)) { err = 1; return false; }
+	return l[0] >= -TOL && l[1] >= -TOL && l[2] >= -TOL && l[3] >= -TOL;   // tetrahedronContains
 }
 
 GCMB_HD Found borderFacet(const Tri& t, int prev, int exitSlot, V3 start, V3 query, int& err) {
@@ -261,9 +299,10 @@ GCMB_HD Found borderFacet(const Tri& t, int prev, int exitSlot, V3 start, V3 que
 
 GCMB_HD Found checkWalk(const Tri& t, bool inner, Walked w, V3 start, V3 query, int& err) {
 	if (w.count == 0) { return nothing(); }
-	if (t.isLocal(w.last) && cellContains(t, w.last, query, err)) { return wholeCell(t, w.last); }
+	double l[4];
+	if (t.isLocal(w.last) && cellContains(t, w.last, query, l, err)) { return wholeCell(t, w.last, l); }
 	if (w.count == 1) { if (inner) { err = 1; } return nothing(); }
-	if (cellContains(t, w.prev, query, err)) { return wholeCell(t, w.prev); }
+	if (cellContains(t, w.prev, query, l, err)) { return wholeCell(t, w.prev, l); }
 	if (!inner) { return nothing(); }
 	if (!t.isLocal(w.last)) { return borderFacet(t, w.prev, w.exitSlot, start, query, err); }
 	return nothing();
@@ -275,13 +314,11 @@ GCMB_HD Found locate(const Tri& t, int lv, V3 shift, int& err) {
 	const bool inner = t.state[lv] == 0;
 	const V3 start = t.point(gv);
 	const V3 query = start + shift;
-	Found f = checkWalk(t, inner, walkFromVertex(t, gv, query, err), start, query, err);
+	Found f = checkWalk(t, inner, walkFromVertex(t, lv, gv, query, err), start, query, err);
 	if (f.n > 0) { return f; }
-	int startCell = crossedIncidentCell(t, gv, query, 0, err);
-	if (startCell == -2) { startCell = crossedIncidentCell(t, gv, query, TOL, err); }
-	if (startCell == -2) {
-		for (int i = t.incOff[gv]; i < t.incOff[gv + 1]; i++) { if (t.isLocal(t.incCell[i])) { startCell = t.incCell[i]; break; } }
-	}
+	int startCell = crossedIncidentCell(t, lv, query, 0, err);
+	if (startCell == -2) { startCell = crossedIncidentCell(t, lv, query, TOL, err); }
+	if (startCell == -2) { startCell = t.locABC[t.locOff[lv]].x; }
 	const int* cv = t.cellV + 4 * (long long) startCell;
 	const V3 center = (t.point(cv[0]) + t.point(cv[1]) + t.point(cv[2]) + t.point(cv[3])) / 4;
 	const double w = 1e-3;
@@ -350,42 +387,45 @@ GCMB_HD void matVec(const double* A, const double* x, double* y) {
 	}
 }
 
-// Differentiation::estimateGradient for one vertex: values [nLocal][M] -> grad [3][M] of that vertex
+// Differentiation::estimateGradient for one vertex: values [nLocal][M] -> grad [3][M] of that vertex.
+// One pass over the neighbours: every sum of the normal equations (A^T W A and A^T W b for all M right-hand
+// sides) is accumulated neighbour by neighbour in the reference's order, so nothing is staged in local memory.
 template<int M>
 GCMB_HD void gradientThread(const Tri& t, const double* values, int it, double* grad, int& err) {
 	const int n = t.nbOff[it + 1] - t.nbOff[it];
 	const int* nb = t.nbIdx + t.nbOff[it];
 	const V3 x0 = t.localPoint(it);
-	double A[MAX_NEIGHBORS][3], W[MAX_NEIGHBORS];
-	for (int i = 0; i < n; i++) {
-		const V3 d = t.localPoint(nb[i]) - x0;
-		A[i][0] = d.x; A[i][1] = d.y; A[i][2] = d.z;
-		W[i] = 1.0 / length(d);
+	double v0[M], b[M][3], N[3][3];
+	for (int c = 0; c < M; c++) { v0[c] = values[(long long) it * M + c]; }
+	for (int k = 0; k < n; k++) {
+		const V3 d = t.localPoint(nb[k]) - x0;
+		const double w = 1.0 / length(d);
+		const double A[3] = {d.x, d.y, d.z};
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+			const double term = A[i] * (w * A[j]);
+			N[i][j] = k == 0 ? term : N[i][j] + term;
+		}
+		const double* vk = values + (long long) nb[k] * M;
+		for (int c = 0; c < M; c++) {
+			const double bw = (vk[c] - v0[c]) * w;
+			for (int i = 0; i < 3; i++) {
+				const double term = bw * A[i];
+				b[c][i] = k == 0 ? term : b[c][i] + term;
+			}
+		}
 	}
-	double N[3][3];
-	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-		double r = 0;
-		for (int k = 0; k < n; k++) { const double term = A[k][i] * (W[k] * A[k][j]); r = k == 0 ? term : r + term; }
-		N[i][j] = r;
+	if (n == 0) {
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { N[i][j] = 0; }
+		for (int c = 0; c < M; c++) for (int i = 0; i < 3; i++) { b[c][i] = 0; }
 	}
 	const double det = det3(N[0][0], N[0][1], N[0][2], N[1][0], N[1][1], N[1][2], N[2][0], N[2][1], N[2][2]);
+	if (det == 0) { err = 1; }
 	for (int c = 0; c < M; c++) {
-		double b[3];
-		for (int i = 0; i < 3; i++) {
-			double r = 0;
-			for (int k = 0; k < n; k++) {
-				const double bk = values[(long long) nb[k] * M + c] - values[(long long) it * M + c];
-				const double term = (bk * W[k]) * A[k][i];
-				r = k == 0 ? term : r + term;
-			}
-			b[i] = r;
-		}
 		double g[3] = {0, 0, 0};
-		if (det == 0) { err = 1; }
-		else {
-			g[0] = det3(b[0], N[0][1], N[0][2], b[1], N[1][1], N[1][2], b[2], N[2][1], N[2][2]) / det;
-			g[1] = det3(N[0][0], b[0], N[0][2], N[1][0], b[1], N[1][2], N[2][0], b[2], N[2][2]) / det;
-			g[2] = det3(N[0][0], N[0][1], b[0], N[1][0], N[1][1], b[1], N[2][0], N[2][1], b[2]) / det;
+		if (det != 0) {
+			g[0] = det3(b[c][0], N[0][1], N[0][2], b[c][1], N[1][1], N[1][2], b[c][2], N[2][1], N[2][2]) / det;
+			g[1] = det3(N[0][0], b[c][0], N[0][2], N[1][0], b[c][1], N[1][2], N[2][0], b[c][2], N[2][2]) / det;
+			g[2] = det3(N[0][0], N[0][1], b[c][0], N[1][0], N[1][1], b[c][1], N[2][0], N[2][1], b[c][2]) / det;
 		}
 		for (int d = 0; d < 3; d++) { grad[d * M + c] = g[d]; }
 	}
@@ -393,51 +433,85 @@ GCMB_HD void gradientThread(const Tri& t, const double* values, int it, double* 
 
 GCMB_HD bool isInterpolation(const double (&l)[4]) { return l[0] > -TOL && l[1] > -TOL && l[2] > -TOL && l[3] > -TOL; }
 
-// TetrahedronInterpolator::hybridInterpolate of component k; grad is [nLocal][3][M]
+// TetrahedronInterpolator::hybridInterpolate, split so that characteristics with the same foot share the
+// geometry: the barycentric coordinates and q - c_i depend on the cell and the point only
+struct HybridGeom {
+	double l[4];
+	V3 d[4];       // q - c_i
+};
+GCMB_HD void hybridGeometry(const Tri& t, const int (&cell)[4], V3 q, HybridGeom& h, int& err) {
+	V3 c[4];
+	for (int i = 0; i < 4; i++) { c[i] = t.localPoint(cell[i]); h.d[i] = q - c[i]; }
+	if (!barycentric(c[0], c[1], c[2], c[3], q, h.l) || !isInterpolation(h.l)) { err = 1; }
+}
+// component k; grad is [nLocal][3][M]
 template<int M>
-GCMB_HD double hybridInterpolate(const Tri& t, const double* values, const double* grad, const int (&cell)[4], int k, V3 q, int& err) {
-	V3 c[4], g[4];
-	double v[4], l[4];
+GCMB_HD double hybridValue(const HybridGeom& h, const double* values, const double* grad, const int (&cell)[4], int k) {
+	V3 g[4];
+	double v[4];
 	for (int i = 0; i < 4; i++) {
-		c[i] = t.localPoint(cell[i]);
 		v[i] = values[(long long) cell[i] * M + k];
 		const double* gi = grad + (long long) cell[i] * 3 * M;
 		g[i] = {gi[0 * M + k], gi[1 * M + k], gi[2 * M + k]};
 	}
-	if (!barycentric(c[0], c[1], c[2], c[3], q, l) || !isInterpolation(l)) { err = 1; }
-	double quadratic = l[0] * (v[0] + dot(g[0], q - c[0]) / 2.0);
-	for (int i = 1; i < 4; i++) { quadratic = quadratic + l[i] * (v[i] + dot(g[i], q - c[i]) / 2.0); }
+	const double (&l)[4] = h.l;
+	double quadratic = l[0] * (v[0] + dot(g[0], h.d[0]) / 2.0);
+	for (int i = 1; i < 4; i++) { quadratic = quadratic + l[i] * (v[i] + dot(g[i], h.d[i]) / 2.0); }
 	const double lo = fmin(fmin(v[0], v[1]), fmin(v[2], v[3]));
 	const double hi = fmax(fmax(v[0], v[1]), fmax(v[2], v[3]));
 	const double limited = fmin(fmax(quadratic, lo), hi);
 	if (quadratic == limited) { return quadratic; }
 	return l[0] * v[0] + l[1] * v[1] + l[2] * v[2] + l[3] * v[3];
 }
+template<int M>
+GCMB_HD double hybridInterpolate(const Tri& t, const double* values, const double* grad, const int (&cell)[4], int k, V3 q, int& err) {
+	HybridGeom h;
+	hybridGeometry(t, cell, q, h, err);
+	return hybridValue<M>(h, values, grad, cell, k);
+}
 
-GCMB_HD double interpolateInOwner(const V3 (&c)[6], const double (&v)[6], V3 q, int& err) {
+// TetrahedronInterpolator::interpolateInOwner over the 15 tetrahedra of 6 points, split the same way: which
+// tetrahedron owns q and with what weights depends on the points only
+struct OwnerGeom {
+	int p[4];
+	double l[4];
+	bool found;
+};
+GCMB_HD void ownerGeometry(const V3 (&c)[6], V3 q, OwnerGeom& o, int& err) {
 	const int T[15][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 2, 5}, {0, 1, 3, 4}, {0, 1, 3, 5}, {0, 1, 4, 5}, {0, 2, 3, 4},
 			{0, 2, 3, 5}, {0, 2, 4, 5}, {0, 3, 4, 5}, {1, 2, 3, 4}, {1, 2, 3, 5}, {1, 2, 4, 5}, {1, 3, 4, 5}, {2, 3, 4, 5}};
+	o.found = false;
 	for (int i = 0; i < 15; i++) {
 		const int* p = T[i];
 		if (volume(c[p[0]], c[p[1]], c[p[2]], c[p[3]]) != 0) {
 			double l[4];
 			if (!barycentric(c[p[0]], c[p[1]], c[p[2]], c[p[3]], q, l)) { err = 1; continue; }
-			if (isInterpolation(l)) { return l[0] * v[p[0]] + l[1] * v[p[1]] + l[2] * v[p[2]] + l[3] * v[p[3]]; }
+			if (isInterpolation(l)) {
+				for (int j = 0; j < 4; j++) { o.p[j] = p[j]; o.l[j] = l[j]; }
+				o.found = true;
+				return;
+			}
 		}
 	}
 	err = 1;
-	return 0;
+}
+GCMB_HD double ownerValue(const OwnerGeom& o, const double (&v)[6]) {
+	if (!o.found) { return 0; }
+	return o.l[0] * v[o.p[0]] + o.l[1] * v[o.p[1]] + o.l[2] * v[o.p[2]] + o.l[3] * v[o.p[3]];
 }
 
-GCMB_HD double interpolateSpaceTime(V3 shift, V3 r0, const V3 (&r)[3], const double (&vc)[3], const double (&vn)[3], int& err) {
+// interpolateInSpaceTime (engine/simplex/common.hpp:70-108): where the ray leaves through the border facet
+// r[0..2], in the prism between the current layer (w = 0) and the next one (w = 1)
+GCMB_HD bool spaceTimeGeometry(V3 shift, V3 r0, const V3 (&r)[3], OwnerGeom& o, int& err) {
 	V3 rc;
-	if (!lineFlatIntersection(r[0], r[1], r[2], r0, r0 + shift, rc)) { err = 1; return 0; }
+	o.found = false;
+	if (!lineFlatIntersection(r[0], r[1], r[2], r0, r0 + shift, rc)) { err = 1; return false; }
 	double w[2];
-	if (!leastSquares2(r[1] - r[0], r[2] - r[0], rc - r[0], w)) { err = 1; return 0; }
+	if (!leastSquares2(r[1] - r[0], r[2] - r[0], rc - r[0], w)) { err = 1; return false; }
 	const V3 c[6] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}};
-	const double v[6] = {vc[0], vc[1], vc[2], vn[0], vn[1], vn[2]};
 	const V3 q = {w[0], w[1], 1 - length(rc - r0) / length(shift)};
-	return interpolateInOwner(c, v, q, err);
+	ownerGeometry(c, q, o, err);
+	return true;
 }
 
 // arguments of the stage kernels
@@ -449,6 +523,9 @@ struct StageS {
 	const double* U;        // [M*M] of this stage
 	const double* U1;
 	const double* L;        // [M]
+	int nFeet;              // distinct eigenvalues of this stage, in order of first appearance
+	double footLambda[9];
+	unsigned footMask[9];   // characteristics sharing the eigenvalue
 	double dir[3];          // calculation direction = column s of the basis
 	const double* cur;      // PDE vectors [nLocal][M]
 	double* riem;           // Riemann invariants of the current layer
@@ -458,59 +535,84 @@ struct StageS {
 	int* errors;            // counter of "the reference would have thrown"
 };
 
-// interpolateValuesAround for one vertex (…InRiemannInvariants.hpp:146-198 + :59-96 for border vertices)
+// interpolateValuesAround (…InRiemannInvariants.hpp:146-198) for the characteristics `same` of vertex `it`
+// that share the eigenvalue lambda, hence the foot x0 - tau*lambda*direction: the cell location and the
+// interpolation geometry are computed once per distinct foot (the reference recomputes them identically for
+// each characteristic).  Writes out[j] for every j in `same`; returns the characteristics that turned out outer.
 template<int M>
-GCMB_HD void nodeThread(const StageS& a, int it, bool borderPass) {
+GCMB_HD unsigned footCharacteristics(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err) {
 	const Tri& t = a.t;
-	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
-	const V3 direction = {a.dir[0], a.dir[1], a.dir[2]};
+	const double dx = -a.tau * lambda;
+	if (dx == 0) {
+		for (int j = 0; j < M; j++) { if ((same >> j) & 1u) { out[j] = a.riem[(long long) it * M + j]; } }
+		return 0;
+	}
 	const V3 x0 = t.localPoint(it);
+	const V3 shift = V3{a.dir[0], a.dir[1], a.dir[2]} * dx;
+	const Found f = locate(t, it, shift, err);
+	if (f.n == 4) {
+		const int cell[4] = {f.p[0], f.p[1], f.p[2], f.p[3]};
+		// hybridGeometry(t, cell, x0 + shift, h, err) with the coordinates the cell location already has
+		HybridGeom h;
+		const V3 q = x0 + shift;
+		for (int i = 0; i < 4; i++) { h.l[i] = f.l[i]; h.d[i] = q - t.localPoint(cell[i]); }
+		if (!isInterpolation(h.l)) { err = 1; }
+		for (int j = 0; j < M; j++) { if ((same >> j) & 1u) { out[j] = hybridValue<M>(h, a.riem, a.grad, cell, j); } }
+		return 0;
+	}
+	if (f.n == 3 && !borderPass) {
+		const V3 r[3] = {t.localPoint(f.p[0]), t.localPoint(f.p[1]), t.localPoint(f.p[2])};
+		OwnerGeom o;
+		spaceTimeGeometry(shift, x0, r, o, err);
+		for (int j = 0; j < M; j++) {
+			if (!((same >> j) & 1u)) { continue; }
+			double v[6];
+			for (int i = 0; i < 3; i++) {
+				v[i] = a.riem[(long long) f.p[i] * M + j];
+				v[3 + i] = a.next[(long long) f.p[i] * M + j];
+			}
+			out[j] = ownerValue(o, v);
+		}
+		return 0;
+	}
+	if (f.n == 2 && !borderPass) { err = 1; }   // THROW_UNSUPPORTED in 3-D
+	for (int j = 0; j < M; j++) { if ((same >> j) & 1u) { out[j] = 0; } }
+	return (f.n == 0 || (borderPass && f.n >= 2)) ? same : 0u;
+}
+
+GCMB_HD void countError(int* errors) {
+#ifdef __CUDA_ARCH__
+	atomicAdd(errors, 1);
+#else
+	(*errors)++;
+#endif
+}
+
+// border and contact vertices (…InRiemannInvariants.hpp:59-96): all characteristics of one vertex, then the
+// bookkeeping of its outer invariants
+template<int M>
+GCMB_HD void borderNodeThread(const StageS& a, int it) {
+	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
 	unsigned outers = 0;
 	int err = 0;
 	double ans[M];
-	for (int k = 0; k < M; k++) {
-		const double dx = -a.tau * a.L[k];
-		if (dx == 0) { ans[k] = a.riem[(long long) it * M + k]; continue; }
-		const V3 shift = direction * dx;
-		const Found f = locate(t, it, shift, err);
-		double u = 0;
-		if (f.n == 4) {
-			const int cell[4] = {f.p[0], f.p[1], f.p[2], f.p[3]};
-			u = hybridInterpolate<M>(t, a.riem, a.grad, cell, k, x0 + shift, err);
-		} else if (f.n == 0) {
-			outers |= 1u << k;
-		} else if (f.n == 3) {
-			if (!borderPass) {
-				V3 r[3];
-				double vc[3], vn[3];
-				for (int i = 0; i < 3; i++) {
-					r[i] = t.localPoint(f.p[i]);
-					vc[i] = a.riem[(long long) f.p[i] * M + k];
-					vn[i] = a.next[(long long) f.p[i] * M + k];
-				}
-				u = interpolateSpaceTime(shift, x0, r, vc, vn, err);
-			} else { outers |= 1u << k; }
-		} else if (f.n == 2) {
-			if (!borderPass) { err = 1; } else { outers |= 1u << k; }
-		}
-		ans[k] = u;
+	for (int f = 0; f < a.nFeet; f++) { outers |= footCharacteristics<M>(a, it, a.footLambda[f], a.footMask[f], true, ans, err); }
+	if (outers != RIGHT && outers != LEFT && outers != (LEFT | RIGHT) && outers != 0) {
+		if (outers & RIGHT) { outers |= RIGHT; }
+		if (outers & LEFT) { outers |= LEFT; }
+		for (int k = 0; k < M; k++) { if ((outers >> k) & 1u) { ans[k] = 0; } }
 	}
-	if (borderPass) {
-		if (outers != RIGHT && outers != LEFT && outers != (LEFT | RIGHT) && outers != 0) {
-			if (outers & RIGHT) { outers |= RIGHT; }
-			if (outers & LEFT) { outers |= LEFT; }
-			for (int k = 0; k < M; k++) { if ((outers >> k) & 1u) { ans[k] = 0; } }
-		}
-		a.waves[it] = outers;
-	}
+	a.waves[it] = outers;
 	for (int k = 0; k < M; k++) { a.next[(long long) it * M + k] = ans[k]; }
-	if (err) {
-#ifdef __CUDA_ARCH__
-		atomicAdd(a.errors, 1);
-#else
-		(*a.errors)++;
-#endif
-	}
+	if (err) { countError(a.errors); }
+}
+
+// inner vertices (…InRiemannInvariants.hpp:99-113): one thread per (vertex, distinct foot)
+template<int M>
+GCMB_HD void innerFootThread(const StageS& a, int it, int foot) {
+	int err = 0;
+	footCharacteristics<M>(a, it, a.footLambda[foot], a.footMask[foot], false, a.next + (long long) it * M, err);
+	if (err) { countError(a.errors); }
 }
 
 // ---- border conditions -----------------------------------------------------------------------
