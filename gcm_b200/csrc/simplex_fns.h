@@ -212,17 +212,24 @@ GCMB_HD bool solidAngleContainsExact0(V3 a, V3 b, V3 c, V3 d, V3 q, int& err) {
 }
 
 // Cgal3DTriangulation::findCrossedIncidentCell over the body's own cells around the vertex (table built at
-// body creation); returns the cell or -2
-GCMB_HD int crossedIncidentCell(const Tri& t, int lv, V3 query, double eps, int& err) {
+// body creation); returns the table entry {cell, a, b, c} or cell = -2.  The loop is software-pipelined: the
+// entry two cells ahead and the points of the next cell are in flight while the current cell is tested.
+GCMB_HD int4 crossedIncidentCell(const Tri& t, int lv, V3 query, double eps, int& err) {
 	const V3 apex = t.localPoint(lv);
-	for (int i = t.locOff[lv]; i < t.locOff[lv + 1]; i++) {
-		const int4 e = t.locABC[i];
-		const V3 pa = t.point(e.y), pb = t.point(e.z), pc = t.point(e.w);
+	const int begin = t.locOff[lv], end = t.locOff[lv + 1];
+	int4 e = t.locABC[begin];
+	int4 e1 = begin + 1 < end ? t.locABC[begin + 1] : e;
+	V3 pa = t.point(e.y), pb = t.point(e.z), pc = t.point(e.w);
+	for (int i = begin; i < end; i++) {
+		const int4 e2 = i + 2 < end ? t.locABC[i + 2] : e1;
+		const V3 na = t.point(e1.y), nb = t.point(e1.z), nc = t.point(e1.w);
 		const bool inside = eps == 0 ? solidAngleContainsExact0(apex, pa, pb, pc, query, err)
 		                             : solidAngleContains(apex, pa, pb, pc, query, eps, err);
-		if (inside) { return e.x; }
+		if (inside) { return e; }
+		e = e1; e1 = e2;
+		pa = na; pb = nb; pc = nc;
 	}
-	return -2;
+	return make_int4(-2, -1, -1, -1);
 }
 
 GCMB_HD Walked collectCells(const Tri& t, V3 q, V3 p, int cell, int u, int v, int w) {
@@ -245,11 +252,11 @@ GCMB_HD Walked collectCells(const Tri& t, V3 q, V3 p, int cell, int u, int v, in
 }
 
 GCMB_HD Walked walkFromVertex(const Tri& t, int lv, int gv, V3 p, int& err) {
-	const int cell = crossedIncidentCell(t, lv, p, 0, err);
+	const int4 e = crossedIncidentCell(t, lv, p, 0, err);
+	const int cell = e.x;
 	if (cell == -2) { return {0, -2, -2, -1}; }
-	int u = t.otherVertex(cell, gv, gv, gv);
-	int v = t.otherVertex(cell, gv, gv, u);
-	const int w = t.otherVertex(cell, gv, u, v);
+	int u = e.y, v = e.z;   // otherVertex(cell, gv, gv, gv), (cell, gv, gv, u), (cell, gv, u, v)
+	const int w = e.w;
 	if (orientedVolume(t.point(u), t.point(v), t.point(w), t.point(gv)) < 0) { const int x = u; u = v; v = x; }
 	return collectCells(t, t.point(gv), p, cell, u, v, w);
 }
@@ -300,7 +307,8 @@ GCMB_HD Found borderFacet(const Tri& t, int prev, int exitSlot, V3 start, V3 que
 GCMB_HD Found checkWalk(const Tri& t, bool inner, Walked w, V3 start, V3 query, int& err) {
 	if (w.count == 0) { return nothing(); }
 	double l[4];
-	if (t.isLocal(w.last) && cellContains(t, w.last, query, l, err)) { return wholeCell(t, w.last, l); }
+	// a walk of one cell ends in its start cell, which belongs to the body
+	if ((w.count == 1 || t.isLocal(w.last)) && cellContains(t, w.last, query, l, err)) { return wholeCell(t, w.last, l); }
 	if (w.count == 1) { if (inner) { err = 1; } return nothing(); }
 	if (cellContains(t, w.prev, query, l, err)) { return wholeCell(t, w.prev, l); }
 	if (!inner) { return nothing(); }
@@ -316,8 +324,8 @@ GCMB_HD Found locate(const Tri& t, int lv, V3 shift, int& err) {
 	const V3 query = start + shift;
 	Found f = checkWalk(t, inner, walkFromVertex(t, lv, gv, query, err), start, query, err);
 	if (f.n > 0) { return f; }
-	int startCell = crossedIncidentCell(t, lv, query, 0, err);
-	if (startCell == -2) { startCell = crossedIncidentCell(t, lv, query, TOL, err); }
+	int startCell = crossedIncidentCell(t, lv, query, 0, err).x;
+	if (startCell == -2) { startCell = crossedIncidentCell(t, lv, query, TOL, err).x; }
 	if (startCell == -2) { startCell = t.locABC[t.locOff[lv]].x; }
 	const int* cv = t.cellV + 4 * (long long) startCell;
 	const V3 center = (t.point(cv[0]) + t.point(cv[1]) + t.point(cv[2]) + t.point(cv[3])) / 4;
