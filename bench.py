@@ -161,6 +161,80 @@ def pick_size(free_bytes, want):
     return 64
 
 
+SIMPLEX_TASK = """grid simplex
+dimensionality 3
+courant 0.7
+steps 1000000
+simplex_box {nx} {ny} {nz} 0 0 0 {h!r} jitter 0.3 seed 1
+cavity box {c0!r} {c0!r} {c1!r} {c2!r} {c2!r} {c3!r}
+body 0 elastic isotropic
+material body 0 isotropic 7800 1.2e11 8.0e10
+basis 1 0 0 0 1 0 0 0 1
+border_condition infinite fixed_force const 0 const 0 const 0
+initial quantity PRESSURE 1 sphere {r!r} {sx!r} {sx!r} {sz!r}
+"""
+
+
+def simplex_task(nx, ny, nz, h):
+    """a 4:4:1 plate of tetrahedra with an inner cavity (the geometry of
+    meshes/layers_with_fracture.off, meshed by our box mesher), isotropic elastic, fixed identity calculation
+    basis, zero fixed force on every border, pressure-sphere source"""
+    lx, lz = nx * h, nz * h
+    return SIMPLEX_TASK.format(nx=nx, ny=ny, nz=nz, h=h, c0=0.4 * lx, c2=0.6 * lx, c1=0.35 * lz, c3=0.65 * lz,
+                               r=0.08 * lx, sx=0.3 * lx, sz=0.5 * lz)
+
+
+def simplex_section(lib, device, steps, warmup, with_cpu):
+    """the simplex (tetrahedral) path, SURVEY.md §8 rows a13-a21: vertex-updates/s through simplex::Engine"""
+    import numpy as np
+    from gcm_b200 import capi
+    nx, ny, nz = (int(x) for x in os.environ.get("GCMB_BENCH_SIMPLEX_CUBES", "160,160,40").split(","))
+    h = 0.16 / nx
+    eng = capi.SimplexHostEngine(lib, simplex_task(nx, ny, nz, h), device=device)
+    info = eng.simplex_body_info(0)
+    ctxh = eng.context_handle()
+    eng.advance(warmup)
+    lib.check(lib.c.gcmb_sync(ctxh))
+    launches0 = lib.c.gcmb_launch_count(ctxh)
+    lib.check(lib.c.gcmb_timer_start(ctxh))
+    t0 = time.perf_counter()
+    eng.advance(steps)
+    ms = capi.ctypes.c_float()
+    lib.check(lib.c.gcmb_timer_stop(ctxh, capi.ctypes.byref(ms)))
+    state = eng.simplex_pde(0)
+    wall = time.perf_counter() - t0
+    assert eng.errors() == 0 and np.isfinite(state).all() and np.abs(state).max() > 0
+    out = {"metric": "simplex GCM vertex-updates/s (3-D isotropic elastic tetrahedra, SURVEY.md §8d C5)",
+           "value": info["n_local"] * steps / (ms.value * 1e-3), "unit": "vertex-updates/s", "ms_per_step": ms.value / steps,
+           "e2e": {"value": info["n_local"] * steps / wall, "unit": "vertex-updates/s", "d2h_bytes_per_step": info["n_local"] * 72 // steps,
+                   "what": "simplex::Engine::run loop incl. border functors on the host and the final state read-back"},
+           "gpu_launches": int(lib.c.gcmb_launch_count(ctxh) - launches0),
+           "config": {"workload": "%dx%dx%d cubes of edge %g cut into 6 tetrahedra each, jitter 0.3, inner cavity: %d vertices; "
+                                  "identity calculation basis, fixed zero force on all borders, Courant 0.7" % (nx, ny, nz, h, info["n_local"])},
+           "parity": "unpinned (the reference's simplex engine needs CGAL; oracle/simplex_oracle.c restates it)"}
+    eng.close()
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import simplex_host
+        small = capi.SimplexHostEngine(lib, simplex_task(24, 24, 6, h), device=device)
+        i2 = small.simplex_body_info(0)
+        tri = small.triangulation()
+        U, U1, L = small.simplex_matrices(0)
+        nodes, normals = small.border_nodes(0, 0)
+        pde0 = small.simplex_pde(0)
+        tau = small.info()[2]
+        cpu_steps = 2
+        ref, spent = simplex_host.run_single_body(tri, 0, 0, U, U1, L, np.eye(3), nodes, normals, np.zeros(len(nodes), dtype=np.int32),
+                                                  np.zeros(1, dtype=np.int32), lambda t: np.zeros((1, 3)), pde0, tau, cpu_steps)
+        small.advance(cpu_steps)
+        same = bool(np.array_equal(small.simplex_pde(0), ref))
+        small.close()
+        out["cpu_baseline"] = {"value": i2["n_local"] * cpu_steps / spent, "unit": "vertex-updates/s", "cores": 1, "kind": "port",
+                               "sample": "%d steps of the same task at 24x24x6 cubes (%d vertices) through oracle/simplex_oracle.c" % (cpu_steps, i2["n_local"]),
+                               "gpu_equals_port_bitwise": same}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +244,7 @@ def main():
     ap.add_argument("--size", type=int, default=1024, help="cube edge per GPU")
     ap.add_argument("--ref-size", type=int, default=64, help="cube edge of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-simplex", action="store_true", help="skip the secondary simplex-path measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -323,8 +398,15 @@ def main():
         if not args.no_cpu_baseline:
             base = cpu_baseline(args.ref_size, 5)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
     eng.close()
+    if rank == 0:
+        if world == 1 and not args.no_simplex:
+            # secondary measurement (never the headline): the tetrahedral path of SURVEY.md §8 a13-a21
+            try:
+                line["simplex"] = simplex_section(lib, local, 20, 3, not args.no_cpu_baseline)
+            except Exception as e:  # the headline line must survive a failure here
+                line["simplex"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

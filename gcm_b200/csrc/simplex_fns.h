@@ -531,9 +531,11 @@ struct StageS {
 	const double* U;        // [M*M] of this stage
 	const double* U1;
 	const double* L;        // [M]
-	int nFeet;              // distinct eigenvalues of this stage, in order of first appearance
+	int nFeet;              // distinct NON-ZERO eigenvalues of this stage, in order of first appearance
 	double footLambda[9];
 	unsigned footMask[9];   // characteristics sharing the eigenvalue
+	unsigned zeroMask;      // characteristics with a zero eigenvalue: the invariant is carried over
+	int footMajor;          // thread mapping of the inner pass: 1 = a warp shares the foot, 0 = adjacent lanes share the vertex
 	double dir[3];          // calculation direction = column s of the basis
 	const double* cur;      // PDE vectors [nLocal][M]
 	double* riem;           // Riemann invariants of the current layer
@@ -604,6 +606,7 @@ GCMB_HD void borderNodeThread(const StageS& a, int it) {
 	unsigned outers = 0;
 	int err = 0;
 	double ans[M];
+	footCharacteristics<M>(a, it, 0.0, a.zeroMask, true, ans, err);
 	for (int f = 0; f < a.nFeet; f++) { outers |= footCharacteristics<M>(a, it, a.footLambda[f], a.footMask[f], true, ans, err); }
 	if (outers != RIGHT && outers != LEFT && outers != (LEFT | RIGHT) && outers != 0) {
 		if (outers & RIGHT) { outers |= RIGHT; }
@@ -619,6 +622,7 @@ GCMB_HD void borderNodeThread(const StageS& a, int it) {
 template<int M>
 GCMB_HD void innerFootThread(const StageS& a, int it, int foot) {
 	int err = 0;
+	if (foot == 0) { footCharacteristics<M>(a, it, 0.0, a.zeroMask, false, a.next + (long long) it * M, err); }
 	footCharacteristics<M>(a, it, a.footLambda[foot], a.footMask[foot], false, a.next + (long long) it * M, err);
 	if (err) { countError(a.errors); }
 }
@@ -935,7 +939,7 @@ GCMB_HD bool contactWaveCorrection(const double* uA, const double* OmA, const do
 // (ElasticModel.hpp:156-189), acoustic SLIDE (AcousticModel.hpp:95-117); ContactCorrector.hpp:443-481
 template<int M>
 GCMB_HD void contactMatrix(int model, int which, V3 n, double* B) {
-	const int outer = model == 0 ? 3 : 1;
+	constexpr int outer = M == 9 ? 3 : 1;   // elastic: 3 outer waves, acoustic: 1
 	for (int i = 0; i < outer * M; i++) { B[i] = 0; }
 	if (model == 1) {
 		if (which == 1) { B[0] = n.x; B[1] = n.y; B[2] = n.z; } else { B[3] = 1; }
