@@ -598,24 +598,36 @@ GCMB_HD void countError(int* errors) {
 #endif
 }
 
-// border and contact vertices (…InRiemannInvariants.hpp:59-96): all characteristics of one vertex, then the
-// bookkeeping of its outer invariants
+// border and contact vertices (…InRiemannInvariants.hpp:59-96), one thread per (vertex, distinct foot): the
+// invariants go straight to the next layer, the outer ones are collected in waves[it] (zeroed before the pass)
 template<int M>
-GCMB_HD void borderNodeThread(const StageS& a, int it) {
-	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
-	unsigned outers = 0;
+GCMB_HD void borderFootThread(const StageS& a, int it, int foot) {
 	int err = 0;
-	double ans[M];
-	footCharacteristics<M>(a, it, 0.0, a.zeroMask, true, ans, err);
-	for (int f = 0; f < a.nFeet; f++) { outers |= footCharacteristics<M>(a, it, a.footLambda[f], a.footMask[f], true, ans, err); }
+	double* out = a.next + (long long) it * M;
+	if (foot == 0) { footCharacteristics<M>(a, it, 0.0, a.zeroMask, true, out, err); }
+	const unsigned outers = footCharacteristics<M>(a, it, a.footLambda[foot], a.footMask[foot], true, out, err);
+	if (outers) {
+#ifdef __CUDA_ARCH__
+		atomicOr(a.waves + it, outers);
+#else
+		a.waves[it] |= outers;
+#endif
+	}
+	if (err) { countError(a.errors); }
+}
+
+// ... then, per vertex, the bookkeeping of its outer invariants (…InRiemannInvariants.hpp:73-85): a vertex with
+// only part of a family outer gets the whole family marked and zeroed
+template<int M>
+GCMB_HD void borderFinishThread(const StageS& a, int it) {
+	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
+	unsigned outers = a.waves[it];
 	if (outers != RIGHT && outers != LEFT && outers != (LEFT | RIGHT) && outers != 0) {
 		if (outers & RIGHT) { outers |= RIGHT; }
 		if (outers & LEFT) { outers |= LEFT; }
-		for (int k = 0; k < M; k++) { if ((outers >> k) & 1u) { ans[k] = 0; } }
+		for (int k = 0; k < M; k++) { if ((outers >> k) & 1u) { a.next[(long long) it * M + k] = 0; } }
+		a.waves[it] = outers;
 	}
-	a.waves[it] = outers;
-	for (int k = 0; k < M; k++) { a.next[(long long) it * M + k] = ans[k]; }
-	if (err) { countError(a.errors); }
 }
 
 // inner vertices (…InRiemannInvariants.hpp:99-113): one thread per (vertex, distinct foot)
