@@ -534,6 +534,7 @@ struct StageS {
 	int nFeet;              // distinct NON-ZERO eigenvalues of this stage, in order of first appearance
 	double footLambda[9];
 	unsigned footMask[9];   // characteristics sharing the eigenvalue
+	int pdeMode;            // GcmType::ADVECT_PDE_VECTORS: `riem` is the current layer itself, `next` receives U*V rows
 	unsigned zeroMask;      // characteristics with a zero eigenvalue: the invariant is carried over
 	int footMajor;          // thread mapping of the inner pass: 1 = a warp shares the foot, 0 = adjacent lanes share the vertex
 	double dir[3];          // calculation direction = column s of the basis
@@ -590,6 +591,84 @@ GCMB_HD unsigned footCharacteristics(const StageS& a, int it, double lambda, uns
 	return (f.n == 0 || (borderPass && f.n >= 2)) ? same : 0u;
 }
 
+// The same for GcmType::ADVECT_PDE_VECTORS (…InPdeVectors.hpp:103-169 + localGcmStep): the whole PDE vector is
+// interpolated at the foot (TetrahedronInterpolator<PdeVector>::hybridInterpolate: linear as soon as ANY
+// component of the quadratic interpolant leaves the [min, max] of the four values), and the characteristics k
+// sharing the foot get r_k = sum_j U(k,j) * v_j -- row k of diagonalMultiply(U, V) (linal/functions.hpp:254-267).
+template<int M>
+GCMB_HD unsigned footVectors(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err) {
+	const Tri& t = a.t;
+	const double dx = -a.tau * lambda;
+	double v[M];
+	unsigned outers = 0;
+	for (int j = 0; j < M; j++) { v[j] = 0; }
+	if (dx == 0) {
+		for (int j = 0; j < M; j++) { v[j] = a.riem[(long long) it * M + j]; }
+	} else {
+		const V3 x0 = t.localPoint(it);
+		const V3 shift = V3{a.dir[0], a.dir[1], a.dir[2]} * dx;
+		const Found f = locate(t, it, shift, err);
+		if (f.n == 4) {
+			const int cell[4] = {f.p[0], f.p[1], f.p[2], f.p[3]};
+			HybridGeom h;
+			const V3 q = x0 + shift;
+			for (int i = 0; i < 4; i++) { h.l[i] = f.l[i]; h.d[i] = q - t.localPoint(cell[i]); }
+			if (!isInterpolation(h.l)) { err = 1; }
+			bool quadraticHolds = true;
+			for (int j = 0; j < M; j++) {
+				double w[4];
+				V3 g[4];
+				for (int i = 0; i < 4; i++) {
+					w[i] = a.riem[(long long) cell[i] * M + j];
+					const double* gi = a.grad + (long long) cell[i] * 3 * M;
+					g[i] = {gi[0 * M + j], gi[1 * M + j], gi[2 * M + j]};
+				}
+				double quadratic = h.l[0] * (w[0] + dot(g[0], h.d[0]) / 2.0);
+				for (int i = 1; i < 4; i++) { quadratic = quadratic + h.l[i] * (w[i] + dot(g[i], h.d[i]) / 2.0); }
+				const double lo = fmin(fmin(w[0], w[1]), fmin(w[2], w[3]));
+				const double hi = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
+				if (!(quadratic == fmin(fmax(quadratic, lo), hi))) { quadraticHolds = false; }
+				v[j] = quadratic;
+			}
+			if (!quadraticHolds) {
+				for (int j = 0; j < M; j++) {
+					double w[4];
+					for (int i = 0; i < 4; i++) { w[i] = a.riem[(long long) cell[i] * M + j]; }
+					v[j] = h.l[0] * w[0] + h.l[1] * w[1] + h.l[2] * w[2] + h.l[3] * w[3];
+				}
+			}
+		} else if (f.n == 3 && !borderPass) {
+			const V3 r[3] = {t.localPoint(f.p[0]), t.localPoint(f.p[1]), t.localPoint(f.p[2])};
+			OwnerGeom o;
+			spaceTimeGeometry(shift, x0, r, o, err);
+			for (int j = 0; j < M; j++) {
+				double w[6];
+				for (int i = 0; i < 3; i++) {
+					w[i] = a.riem[(long long) f.p[i] * M + j];
+					w[3 + i] = a.next[(long long) f.p[i] * M + j];
+				}
+				v[j] = ownerValue(o, w);
+			}
+		} else {
+			if (f.n == 2 && !borderPass) { err = 1; }
+			if (f.n == 0 || (borderPass && f.n >= 2)) { outers = same; }
+		}
+	}
+	for (int k = 0; k < M; k++) {
+		if (!((same >> k) & 1u)) { continue; }
+		double r = a.U[k * M] * v[0];
+		for (int j = 1; j < M; j++) { r += a.U[k * M + j] * v[j]; }
+		out[k] = r;
+	}
+	return outers;
+}
+
+template<int M>
+GCMB_HD unsigned footAny(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err) {
+	return a.pdeMode ? footVectors<M>(a, it, lambda, same, borderPass, out, err)
+	                 : footCharacteristics<M>(a, it, lambda, same, borderPass, out, err);
+}
+
 GCMB_HD void countError(int* errors) {
 #ifdef __CUDA_ARCH__
 	atomicAdd(errors, 1);
@@ -604,8 +683,8 @@ template<int M>
 GCMB_HD void borderFootThread(const StageS& a, int it, int foot) {
 	int err = 0;
 	double* out = a.next + (long long) it * M;
-	if (foot == 0) { footCharacteristics<M>(a, it, 0.0, a.zeroMask, true, out, err); }
-	const unsigned outers = footCharacteristics<M>(a, it, a.footLambda[foot], a.footMask[foot], true, out, err);
+	if (foot == 0) { footAny<M>(a, it, 0.0, a.zeroMask, true, out, err); }
+	const unsigned outers = footAny<M>(a, it, a.footLambda[foot], a.footMask[foot], true, out, err);
 	if (outers) {
 #ifdef __CUDA_ARCH__
 		atomicOr(a.waves + it, outers);
@@ -620,6 +699,14 @@ GCMB_HD void borderFootThread(const StageS& a, int it, int foot) {
 // only part of a family outer gets the whole family marked and zeroed
 template<int M>
 GCMB_HD void borderFinishThread(const StageS& a, int it) {
+	if (a.pdeMode) {
+		// …InPdeVectors.hpp:52-72: the outer invariants stay as found; u = U1 * (rows of U*V)
+		double r[M], u[M];
+		for (int k = 0; k < M; k++) { r[k] = a.next[(long long) it * M + k]; }
+		matVec<M>(a.U1, r, u);
+		for (int k = 0; k < M; k++) { a.next[(long long) it * M + k] = u[k]; }
+		return;
+	}
 	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
 	unsigned outers = a.waves[it];
 	if (outers != RIGHT && outers != LEFT && outers != (LEFT | RIGHT) && outers != 0) {
@@ -634,8 +721,8 @@ GCMB_HD void borderFinishThread(const StageS& a, int it) {
 template<int M>
 GCMB_HD void innerFootThread(const StageS& a, int it, int foot) {
 	int err = 0;
-	if (foot == 0) { footCharacteristics<M>(a, it, 0.0, a.zeroMask, false, a.next + (long long) it * M, err); }
-	footCharacteristics<M>(a, it, a.footLambda[foot], a.footMask[foot], false, a.next + (long long) it * M, err);
+	if (foot == 0) { footAny<M>(a, it, 0.0, a.zeroMask, false, a.next + (long long) it * M, err); }
+	footAny<M>(a, it, a.footLambda[foot], a.footMask[foot], false, a.next + (long long) it * M, err);
 	if (err) { countError(a.errors); }
 }
 
@@ -750,6 +837,7 @@ GCMB_HD void outerColumns(int outer, const double* U1, unsigned mask, double* Om
 }
 
 struct BorderS {
+	int pdeMode;            // the next layer already holds PDE variables (BorderCorrectorInPdeVectors)
 	int model, type;        // condition type 0 FIXED_FORCE, 1 FIXED_VELOCITY
 	const double* U;        // this stage
 	const double* U1;
@@ -776,7 +864,8 @@ GCMB_HD void borderCorrectThread(const BorderS& a, int i) {
 	const int node = a.node[i];
 	const V3 normal = {a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2]};
 	double u[M], w[M];
-	matVec<M>(a.U1, a.next + (long long) node * M, u);
+	if (a.pdeMode) { for (int k = 0; k < M; k++) { u[k] = a.next[(long long) node * M + k]; } }
+	else { matVec<M>(a.U1, a.next + (long long) node * M, u); }
 	borderMatrix<M>(a.model, a.type, normal, B);
 	const unsigned outers = a.waves[node];
 	if (outers == RIGHT || outers == LEFT) {
@@ -792,7 +881,8 @@ GCMB_HD void borderCorrectThread(const BorderS& a, int i) {
 		if (okr && okl) { for (int k = 0; k < M; k++) { u[k] += (vr[k] + vl[k]) / 2; } }
 		else { plainBorder(a.model, a.type, normal, a.b, u); }
 	}
-	matVec<M>(a.U, u, w);
+	if (a.pdeMode) { for (int k = 0; k < M; k++) { w[k] = u[k]; } }
+	else { matVec<M>(a.U, u, w); }
 	for (int k = 0; k < M; k++) { a.next[(long long) node * M + k] = w[k]; }
 }
 
@@ -1015,6 +1105,7 @@ GCMB_HD void outerColumnsBoth(const double* U1, unsigned RIGHT, unsigned LEFT, d
 GCMB_HD int popcountU(unsigned x) { int c = 0; while (x) { c += (int) (x & 1u); x >>= 1; } return c; }
 
 struct ContactS {
+	int pdeMode;                         // ContactCorrectorInPdeVectors: no matching, no conversions
 	int model, n;
 	const double *UA, *U1A, *UB, *U1B;   // this stage, body A and body B
 	double dir[3];
@@ -1046,7 +1137,7 @@ GCMB_HD void contactCorrectThread(const ContactS& a, int i) {
 	unsigned wa = a.wavesA[a.nodeA[i]], wb = a.wavesB[a.nodeB[i]];
 	// matchInnersAndOuters (:381-410)
 	const int N = (popcountU(wa) + popcountU(wb)) / O;
-	if (N % 2 != 0) {
+	if (!a.pdeMode && N % 2 != 0) {
 		if (N == 3) { wa = wb = LEFT | RIGHT; }
 		else if (wa == 0) { if (wb == LEFT) { wa = RIGHT; } else { if (wb != RIGHT) { err = 1; } wa = LEFT; } }
 		else { if (wb != 0) { err = 1; } if (wa == LEFT) { wb = RIGHT; } else { if (wa != RIGHT) { err = 1; } wb = LEFT; } }
@@ -1054,8 +1145,8 @@ GCMB_HD void contactCorrectThread(const ContactS& a, int i) {
 	}
 	a.wavesA[a.nodeA[i]] = wa; a.wavesB[a.nodeB[i]] = wb;
 	double uA[M], uB[M], w[M];
-	matVec<M>(a.U1A, ra, uA);
-	matVec<M>(a.U1B, rb, uB);
+	if (a.pdeMode) { for (int k = 0; k < M; k++) { uA[k] = ra[k]; uB[k] = rb[k]; } }
+	else { matVec<M>(a.U1A, ra, uA); matVec<M>(a.U1B, rb, uB); }
 	const V3 normal = {a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2]};
 	contactMatrix<M>(a.model, 1, normal, B1A); contactMatrix<M>(a.model, 1, normal, B1B);
 	contactMatrix<M>(a.model, 2, normal, B2A); contactMatrix<M>(a.model, 2, normal, B2B);
@@ -1091,10 +1182,13 @@ GCMB_HD void contactCorrectThread(const ContactS& a, int i) {
 		if (ok1 && ok2) { for (int k = 0; k < M; k++) { uA[k] += (vA[k] + vA2[k]) / 2; uB[k] += (vB[k] + vB2[k]) / 2; } }
 		else { plainContact(a.model, true, normal, uA, uB); }
 	}
-	matVec<M>(a.UA, uA, w);
-	for (int k = 0; k < M; k++) { ra[k] = w[k]; }
-	matVec<M>(a.UB, uB, w);
-	for (int k = 0; k < M; k++) { rb[k] = w[k]; }
+	if (a.pdeMode) { for (int k = 0; k < M; k++) { ra[k] = uA[k]; rb[k] = uB[k]; } }
+	else {
+		matVec<M>(a.UA, uA, w);
+		for (int k = 0; k < M; k++) { ra[k] = w[k]; }
+		matVec<M>(a.UB, uB, w);
+		for (int k = 0; k < M; k++) { rb[k] = w[k]; }
+	}
 	if (err) {
 #ifdef __CUDA_ARCH__
 		atomicAdd(a.errors, 1);

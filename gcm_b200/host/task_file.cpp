@@ -11,7 +11,7 @@
 //   grid simplex | simplex_box nx ny nz ox oy oz h [jitter j] [seed s] | region ID AREA | cavity AREA
 //   body ID (elastic|acoustic) isotropic | material body ID MATERIAL | basis b00 b01 .. b22 | basis random [seed]
 //   border_condition AREA (fixed_force|fixed_velocity) [no_multicontact] (const c | sin amp omega)...
-//   contact (adhesion|slide) [ID ID]
+//   contact (adhesion|slide) [ID ID] | gcm_type (riemann_invariants|pde_vectors)
 // The test suite feeds the same files to the unmodified reference.
 #include <cmath>
 #include <sstream>
@@ -183,6 +183,11 @@ Task parseTaskText(const std::string& text) {
 			task.cubicBorderConditions[id].push_back(bc);
 		} else if (key == "grid") {
 			task.globalSettings.gridId = t.next() == "simplex" ? Grids::T::SIMPLEX : Grids::T::CUBIC;
+		} else if (key == "gcm_type") {
+			const std::string type = t.next();
+			if (type == "riemann_invariants") { task.globalSettings.gcmType = GcmType::ADVECT_RIEMANN_INVARIANTS; }
+			else if (type == "pde_vectors") { task.globalSettings.gcmType = GcmType::ADVECT_PDE_VECTORS; }
+			else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown gcm_type " + type); }
 		} else if (key == "simplex_box") {
 			Task::SimplexGrid& g = task.simplexGrid;
 			for (size_t i = 0; i < 3; i++) { g.boxCubes[i] = t.inum(); }

@@ -200,6 +200,10 @@ int gcmb_simplex_stage(gcmb_sbody* body, int s, double tau, const double* values
  * that contacts between bodies are corrected in the reference's order:
  *   before_stage (every body) -> border_contact_stage (every body) -> contact_correct (every contact)
  *   -> border_correct (every body) -> inner_stage (every body) -> after_stage (every body; swaps the layers) */
+/* GcmType of the task (util/task/Task.hpp:15-18,62): 0 ADVECT_RIEMANN_INVARIANTS (default,
+ * engine/simplex/GridCharacteristicMethodInRiemannInvariants.hpp), 1 ADVECT_PDE_VECTORS (…InPdeVectors.hpp with
+ * BorderCorrectorInPdeVectors / ContactCorrectorInPdeVectors) */
+int gcmb_simplex_set_gcm_type(gcmb_sbody* body, int gcm_type);
 int gcmb_simplex_before_stage(gcmb_sbody* body, int s, double tau);
 int gcmb_simplex_border_contact_stage(gcmb_sbody* body);
 int gcmb_simplex_border_correct(gcmb_sbody* body, const double* values /* [n_cond][outer] at t+tau */);

@@ -918,11 +918,12 @@ struct gcmo_sstage {
 	double *riem, *grad, *next;
 	unsigned* waves;
 	int errors;
+	int pde_mode;          /* GcmType::ADVECT_PDE_VECTORS: riem holds the PDE vectors themselves */
 };
 
 /* beforeStage (…InRiemannInvariants.hpp:44-56) */
 gcmo_sstage* gcmo_sx_begin(const gcmo_tri* t, int model, int M, int s, double tau, const double* U_, const double* U1_,
-		const double* L_, const double* basis, const double* cur, double* next) {
+		const double* L_, const double* basis, const double* cur, double* next, int gcm_type) {
 	gcmo_sstage* h = (gcmo_sstage*) calloc(1, sizeof(gcmo_sstage));
 	const int n = t->n_local;
 	h->t = t; h->model = model; h->M = M; h->s = s; h->tau = tau;
@@ -934,7 +935,9 @@ gcmo_sstage* gcmo_sx_begin(const gcmo_tri* t, int model, int M, int s, double ta
 	h->grad = (double*) malloc((size_t) n * 3 * M * sizeof(double));
 	h->waves = (unsigned*) calloc((size_t) n, sizeof(unsigned));
 	h->next = next;
-	for (int v = 0; v < n; v++) { mat_vec(M, h->U, cur + (size_t) v * M, h->riem + (size_t) v * M); }
+	h->pde_mode = gcm_type == 1;
+	if (h->pde_mode) { memcpy(h->riem, cur, (size_t) n * M * sizeof(double)); }   /* …InPdeVectors.hpp:37-44 */
+	else { for (int v = 0; v < n; v++) { mat_vec(M, h->U, cur + (size_t) v * M, h->riem + (size_t) v * M); } }
 	h->errors += gcmo_simplex_gradient(t, M, h->riem, h->grad);
 	const R3 direction = {{basis[0 * 3 + s], basis[1 * 3 + s], basis[2 * 3 + s]}};
 	h->direction = direction;
@@ -943,7 +946,10 @@ gcmo_sstage* gcmo_sx_begin(const gcmo_tri* t, int model, int M, int s, double ta
 
 /* pass 0: contactAndBorderStage (…InRiemannInvariants.hpp:59-96), pass 1: innerStage (:99-113); both through
  * interpolateValuesAround (:146-198) */
+static void nodes_pde_vectors(gcmo_sstage* h, int pass);
+
 void gcmo_sx_nodes(gcmo_sstage* h, int pass) {
+	if (h->pde_mode) { nodes_pde_vectors(h, pass); return; }
 	const gcmo_tri* t = h->t;
 	const int M = h->M;
 	for (int it = 0; it < t->n_local; it++) {
@@ -1021,7 +1027,8 @@ void gcmo_sx_border_correct(gcmo_sstage* h, int n_border, const int* border_node
 			const int node = border_node[i];
 			const R3 normal = r3(border_normal + 3 * i);
 			double u[9], w[9];
-			mat_vec(M, U1, next + (size_t) node * M, u);          /* to PDE variables */
+			if (h->pde_mode) { memcpy(u, next + (size_t) node * M, (size_t) M * sizeof(double)); }
+			else { mat_vec(M, U1, next + (size_t) node * M, u); }  /* to PDE variables */
 			border_matrix(model, M, cond_type[c], normal, B);
 			const unsigned outers = h->waves[node];
 			if (outers == h->RIGHT || outers == h->LEFT) {
@@ -1038,7 +1045,8 @@ void gcmo_sx_border_correct(gcmo_sstage* h, int n_border, const int* border_node
 				if (okr && okl) { for (int k = 0; k < M; k++) { u[k] += (vr[k] + vl[k]) / 2; } }
 				else { plain_border(model, M, cond_type[c], normal, b, u); }
 			}
-			mat_vec(M, U, u, w);                                   /* back to invariants */
+			if (h->pde_mode) { memcpy(w, u, (size_t) M * sizeof(double)); }
+			else { mat_vec(M, U, u, w); }                           /* back to invariants */
 			memcpy(next + (size_t) node * M, w, (size_t) M * sizeof(double));
 		}
 	}
@@ -1068,7 +1076,7 @@ void gcmo_sx_contact_correct(gcmo_sstage* a, gcmo_sstage* b, int n, const int* n
 		unsigned wa = a->waves[node_a[i]], wb = b->waves[node_b[i]];
 		/* matchInnersAndOuters */
 		const int N = (popcount_u(wa) + popcount_u(wb)) / o;
-		if (N % 2 != 0) {
+		if (!a->pde_mode && N % 2 != 0) {
 			if (N == 3) { wa = wb = LEFT | RIGHT; }
 			else if (wa == 0) { if (wb == LEFT) { wa = RIGHT; } else { if (wb != RIGHT) { a->errors++; } wa = LEFT; } }
 			else { if (wb != 0) { a->errors++; } if (wa == LEFT) { wb = RIGHT; } else { if (wa != RIGHT) { a->errors++; } wb = LEFT; } }
@@ -1076,8 +1084,8 @@ void gcmo_sx_contact_correct(gcmo_sstage* a, gcmo_sstage* b, int n, const int* n
 		}
 		a->waves[node_a[i]] = wa; b->waves[node_b[i]] = wb;
 		double uA[9], uB[9], w[9];
-		mat_vec(M, a->U1, ra, uA);
-		mat_vec(M, b->U1, rb, uB);
+		if (a->pde_mode) { memcpy(uA, ra, (size_t) M * sizeof(double)); memcpy(uB, rb, (size_t) M * sizeof(double)); }
+		else { mat_vec(M, a->U1, ra, uA); mat_vec(M, b->U1, rb, uB); }
 		const R3 normal = r3(normals + 3 * i);
 		contact_matrix(model, M, 1, normal, B1A); contact_matrix(model, M, 1, normal, B1B);
 		contact_matrix(model, M, 2, normal, B2A); contact_matrix(model, M, 2, normal, B2B);
@@ -1115,15 +1123,18 @@ void gcmo_sx_contact_correct(gcmo_sstage* a, gcmo_sstage* b, int n, const int* n
 			if (ok1 && ok2) { for (int k = 0; k < M; k++) { uA[k] += (vA[k] + vA2[k]) / 2; uB[k] += (vB[k] + vB2[k]) / 2; } }
 			else { plain_contact(model, 1, normal, uA, uB); }
 		}
-		mat_vec(M, a->U, uA, w); memcpy(ra, w, (size_t) M * sizeof(double));
-		mat_vec(M, b->U, uB, w); memcpy(rb, w, (size_t) M * sizeof(double));
+		if (a->pde_mode) { memcpy(ra, uA, (size_t) M * sizeof(double)); memcpy(rb, uB, (size_t) M * sizeof(double)); }
+		else {
+			mat_vec(M, a->U, uA, w); memcpy(ra, w, (size_t) M * sizeof(double));
+			mat_vec(M, b->U, uB, w); memcpy(rb, w, (size_t) M * sizeof(double));
+		}
 	}
 }
 
 /* afterStage (…InRiemannInvariants.hpp:116-127); frees the handle and returns its error count */
 int gcmo_sx_end(gcmo_sstage* h) {
 	const int M = h->M;
-	for (int v = 0; v < h->t->n_local; v++) {
+	for (int v = 0; v < h->t->n_local && !h->pde_mode; v++) {
 		double w[9];
 		mat_vec(M, h->U1, h->next + (size_t) v * M, w);
 		memcpy(h->next + (size_t) v * M, w, (size_t) M * sizeof(double));
@@ -1138,7 +1149,7 @@ int gcmo_simplex_stage(const gcmo_tri* t, int model, int M, int s, double tau,
 		int n_border, const int* border_node, const double* border_normal, const int* border_cond,
 		int n_cond, const int* cond_type, const double* cond_b,
 		const double* cur, double* next) {
-	gcmo_sstage* h = gcmo_sx_begin(t, model, M, s, tau, U_, U1_, L_, basis, cur, next);
+	gcmo_sstage* h = gcmo_sx_begin(t, model, M, s, tau, U_, U1_, L_, basis, cur, next, 0);
 	gcmo_sx_nodes(h, 0);
 	gcmo_sx_border_correct(h, n_border, border_node, border_normal, border_cond, n_cond, cond_type, cond_b);
 	gcmo_sx_nodes(h, 1);
@@ -1185,4 +1196,98 @@ void gcmo_simplex_heights(const gcmo_tri* t, double out[2]) {
 	out[0] = dot_sum / count;
 	out[1] = lo;
 	free(h);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* GcmType::ADVECT_PDE_VECTORS (engine/simplex/GridCharacteristicMethodInPdeVectors.hpp:37-169)  */
+/* ------------------------------------------------------------------------------------------ */
+/* TetrahedronInterpolator<PdeVector>::hybridInterpolate (…Interpolator.hpp:44-104): the quadratic interpolant of
+ * the whole vector, replaced by the linear one as soon as ANY component leaves the [min, max] of the 4 values */
+static void hybrid_interpolate_vector(const gcmo_tri* t, int M, const double* values, const double* grad,
+		const int cell[4], R3 q, double* out, int* err) {
+	R3 c[4];
+	double l[4], quadratic[9];
+	for (int i = 0; i < 4; i++) { c[i] = point(t, t->global_of[cell[i]]); }
+	if (barycentric4(c[0], c[1], c[2], c[3], q, l) || !is_interpolation(l)) { *err = 1; }
+	int same = 1;
+	for (int k = 0; k < M; k++) {
+		double v[4];
+		R3 g[4];
+		for (int i = 0; i < 4; i++) {
+			v[i] = values[(size_t) cell[i] * M + k];
+			for (int d = 0; d < 3; d++) { g[i].v[d] = grad[((size_t) cell[i] * 3 + d) * M + k]; }
+		}
+		double x = l[0] * (v[0] + dot(g[0], sub(q, c[0])) / 2.0);
+		for (int i = 1; i < 4; i++) { x = x + l[i] * (v[i] + dot(g[i], sub(q, c[i])) / 2.0); }
+		quadratic[k] = x;
+		const double mn = fmin(fmin(v[0], v[1]), fmin(v[2], v[3]));
+		const double mx = fmax(fmax(v[0], v[1]), fmax(v[2], v[3]));
+		if (!(x == fmin(fmax(x, mn), mx))) { same = 0; }
+	}
+	for (int k = 0; k < M; k++) {
+		if (same) { out[k] = quadratic[k]; continue; }
+		double v[4];
+		for (int i = 0; i < 4; i++) { v[i] = values[(size_t) cell[i] * M + k]; }
+		out[k] = l[0] * v[0] + l[1] * v[1] + l[2] * v[2] + l[3] * v[3];
+	}
+}
+
+static void nodes_pde_vectors(gcmo_sstage* h, int pass) {
+	const gcmo_tri* t = h->t;
+	const int M = h->M;
+	for (int it = 0; it < t->n_local; it++) {
+		const int state = gcmo_simplex_border_state(t, it);
+		if ((pass == 0) != (state != 0)) { continue; }
+		const int can_st = pass == 1;
+		unsigned outers = 0;
+		double V[9][9];   /* V[j][k]: component j of the vector interpolated at the foot of characteristic k */
+		const R3 x0 = point(t, t->global_of[it]);
+		for (int k = 0; k < M; k++) {
+			double u[9];
+			memset(u, 0, sizeof u);
+			const double dx = -h->tau * h->L[k];
+			if (dx == 0) {
+				memcpy(u, h->riem + (size_t) it * M, (size_t) M * sizeof(double));
+			} else {
+				const R3 shift = scale(h->direction, dx);
+				int cell[5];
+				h->errors += gcmo_simplex_locate(t, it, shift.v, cell);
+				if (cell[0] == 4) {
+					int e = 0;
+					hybrid_interpolate_vector(t, M, h->riem, h->grad, cell + 1, add(x0, shift), u, &e);
+					h->errors += e;
+				} else if (cell[0] == 0) {
+					outers |= 1u << k;
+				} else if (cell[0] == 3) {
+					if (can_st) {
+						R3 r[3];
+						for (int i = 0; i < 3; i++) { r[i] = point(t, t->global_of[cell[1 + i]]); }
+						for (int j = 0; j < M; j++) {
+							double vc[3], vn[3];
+							for (int i = 0; i < 3; i++) {
+								vc[i] = h->riem[(size_t) cell[1 + i] * M + j];
+								vn[i] = h->next[(size_t) cell[1 + i] * M + j];
+							}
+							int e = 0;
+							u[j] = interpolate_space_time(shift, x0, r, vc, vn, &e);
+							h->errors += e;
+						}
+					} else { outers |= 1u << k; }
+				} else if (cell[0] == 2) {
+					if (can_st) { h->errors++; } else { outers |= 1u << k; }
+				}
+			}
+			for (int j = 0; j < M; j++) { V[j][k] = u[j]; }
+		}
+		/* localGcmStep (util/math/GridCharacteristicMethod.hpp:10-17): U1 * diagonalMultiply(U, V) */
+		double r[9], w[9];
+		for (int k = 0; k < M; k++) {
+			double x = h->U[k * M] * V[0][k];
+			for (int j = 1; j < M; j++) { x += h->U[k * M + j] * V[j][k]; }
+			r[k] = x;
+		}
+		mat_vec(M, h->U1, r, w);
+		memcpy(h->next + (size_t) it * M, w, (size_t) M * sizeof(double));
+		if (pass == 0) { h->waves[it] = outers; }
+	}
 }

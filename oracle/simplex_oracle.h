@@ -86,8 +86,9 @@ int gcmo_simplex_stage(const gcmo_tri* t, int model, int M, int s, double tau,
  *   begin (all bodies) -> nodes(pass 0) (all) -> contact_correct (every contact) -> border_correct (all)
  *   -> nodes(pass 1) (all) -> end (all) */
 typedef struct gcmo_sstage gcmo_sstage;
+/* gcm_type: 0 GcmType::ADVECT_RIEMANN_INVARIANTS (…InRiemannInvariants.hpp), 1 ADVECT_PDE_VECTORS (…InPdeVectors.hpp) */
 gcmo_sstage* gcmo_sx_begin(const gcmo_tri* t, int model, int M, int s, double tau, const double* U, const double* U1,
-                           const double* L, const double* basis, const double* cur, double* next);
+                           const double* L, const double* basis, const double* cur, double* next, int gcm_type);
 void gcmo_sx_nodes(gcmo_sstage* h, int pass);
 void gcmo_sx_border_correct(gcmo_sstage* h, int n_border, const int* border_node, const double* border_normal,
                             const int* border_cond, int n_cond, const int* cond_type, const double* cond_b);

@@ -180,7 +180,7 @@ def check_stage(lib, model, kind="jitter_void", steps=2, zero=False):
     return cur
 
 
-def check_two_bodies(lib, model, steps=2, kind="layers"):
+def check_two_bodies(lib, model, steps=2, kind="layers", gcm_type=0):
     """two bodies glued (elastic, ADHESION) or sliding (acoustic, SLIDE) along a jittered interface, different
     materials, free/forced outer borders: whole time steps in the order of simplex::Engine::nextTimeStep
     (engine/simplex/Engine.cpp:97-141) == the oracle driven in the same order, bit for bit"""
@@ -201,6 +201,7 @@ def check_two_bodies(lib, model, steps=2, kind="layers"):
     bodies = [SimplexBody(lib, ctx, m, model) for m in meshes]
     for b, (U, U1, Lm) in zip(bodies, mat3):
         b.set_material(U, U1, Lm, basis)
+        b.set_gcm_type(gcm_type)
 
     # Engine::addBorderOrContact (Engine.cpp:250-309)
     inc = base.incident_grids()
@@ -296,7 +297,7 @@ def check_two_bodies(lib, model, steps=2, kind="layers"):
             for b in bodies:
                 b.after_stage()
             nxt = [np.zeros_like(p) for p in state]
-            hs = [L.gcmo_sx_begin(ctypes.byref(v), model, M, s, tau, _d(m3[0]), _d(m3[1]), _d(m3[2]), _d(basis), _d(cur), _d(nx))
+            hs = [L.gcmo_sx_begin(ctypes.byref(v), model, M, s, tau, _d(m3[0]), _d(m3[1]), _d(m3[2]), _d(basis), _d(cur), _d(nx), gcm_type)
                   for v, m3, cur, nx in zip(views, mat3, state, nxt)]
             for h in hs:
                 L.gcmo_sx_nodes(h, 0)
@@ -329,7 +330,7 @@ def check_two_bodies(lib, model, steps=2, kind="layers"):
 
 
 # ---- the host engine (gcm_b200/host/simplex_engine.cpp) against the oracle driven in the reference's order ------
-def engine_scenario(model, bodies=2, basis="identity", cavity=True, steps=3):
+def engine_scenario(model, bodies=2, basis="identity", cavity=True, steps=3, gcm_type=0):
     """task text + the same border values as Python callables"""
     import math
     name = "elastic" if model == 0 else "acoustic"
@@ -358,13 +359,14 @@ def engine_scenario(model, bodies=2, basis="identity", cavity=True, steps=3):
     lines.append("border_condition box -10 -10 2.999 10 10 10 fixed_velocity no_multicontact "
                  + " ".join(["const 0"] * (outer - 1) + ["sin 0.3 9"]))
     lines.append("initial quantity PRESSURE 1 sphere 0.7 1.2 1.0 1.1")
+    lines.append("gcm_type " + ("pde_vectors" if gcm_type == 1 else "riemann_invariants"))
     values = lambda t: np.array([[0.0] * outer, [0.0] * (outer - 1) + [0.3 * math.sin(9 * t)]])
     return "\n".join(lines) + "\n", values
 
 
-def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3):
+def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3, gcm_type=0):
     L = oracle()
-    text, values = engine_scenario(model, bodies, basis, cavity, steps)
+    text, values = engine_scenario(model, bodies, basis, cavity, steps, gcm_type)
     eng = capi.SimplexHostEngine(lib, text)
     M = 9 if model == 0 else 4
     tri = eng.triangulation()
@@ -417,7 +419,7 @@ def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3):
         for s in range(3):
             nxt = [np.zeros_like(p) for p in state]
             hs = [L.gcmo_sx_begin(ctypes.byref(views[i]), model, M, s, tau, _d(mats[i][0]), _d(mats[i][1]), _d(mats[i][2]),
-                                  _d(basis_m), _d(state[i]), _d(nxt[i])) for i in ids]
+                                  _d(basis_m), _d(state[i]), _d(nxt[i]), gcm_type) for i in ids]
             for h in hs:
                 L.gcmo_sx_nodes(h, 0)
             for p, (fa, fb, fn) in contacts.items():

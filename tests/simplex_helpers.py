@@ -120,7 +120,7 @@ def oracle():
     L.gcmo_simplex_stage.argtypes = [tp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp,
                                      ctypes.c_int, ip, dp, ip, ctypes.c_int, ip, dp, dp, dp]
     L.gcmo_simplex_plain_border.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, dp, ip, ip, dp, dp]
-    L.gcmo_sx_begin.argtypes = [tp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp, dp, dp]
+    L.gcmo_sx_begin.argtypes = [tp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp, dp, dp, ctypes.c_int]
     L.gcmo_sx_begin.restype = ctypes.c_void_p
     L.gcmo_sx_nodes.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.gcmo_sx_nodes.restype = None
@@ -223,6 +223,9 @@ class SimplexBody:
     def stage(self, s, tau, values):
         v = np.ascontiguousarray(values, dtype=np.float64)
         self.lib.check(self.lib.c.gcmb_simplex_stage(self.handle, s, tau, _d(v)))
+
+    def set_gcm_type(self, gcm_type):
+        self.lib.check(self.lib.c.gcmb_simplex_set_gcm_type(self.handle, gcm_type))
 
     def before_stage(self, s, tau):
         self.lib.check(self.lib.c.gcmb_simplex_before_stage(self.handle, s, tau))

@@ -206,3 +206,11 @@ def test_simplex_engine_gpu(lib, model, bodies, basis, cavity):
     """simplex::Engine of the host layer on the GPU == the oracle driven in the reference's order, bit for bit"""
     import simplex_cases
     simplex_cases.check_engine(lib, model, bodies=bodies, basis=basis, cavity=cavity, steps=4)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_simplex_pde_vectors_gpu(lib, model):
+    """GcmType::ADVECT_PDE_VECTORS: two bodies in contact, then the engine with a random basis"""
+    import simplex_cases
+    simplex_cases.check_two_bodies(lib, model, steps=3, kind="layers_void", gcm_type=1)
+    simplex_cases.check_engine(lib, model, bodies=2, basis="random", cavity=True, steps=3, gcm_type=1)

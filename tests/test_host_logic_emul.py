@@ -170,3 +170,15 @@ def test_simplex_engine(lib, model, bodies, basis):
     """simplex::Engine of the host layer (task text -> run) == the oracle driven in the reference's order"""
     import simplex_cases
     simplex_cases.check_engine(lib, model, bodies=bodies, basis=basis, steps=2)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_simplex_pde_vectors_two_bodies(lib, model):
+    """GcmType::ADVECT_PDE_VECTORS (engine/simplex/GridCharacteristicMethodInPdeVectors.hpp) with contacts"""
+    import simplex_cases
+    simplex_cases.check_two_bodies(lib, model, steps=2, kind="layers_void", gcm_type=1)
+
+
+def test_simplex_pde_vectors_engine(lib):
+    import simplex_cases
+    simplex_cases.check_engine(lib, 0, bodies=2, basis="rotated", steps=2, gcm_type=1)
