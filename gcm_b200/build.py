@@ -64,6 +64,11 @@ def build(force=False, verbose=False):
     if force or _newer(host, host_dep):
         _run(["g++"] + CXX_FLAGS + ["-shared", "-o", host] + host_src +
              ["-L" + HERE, "-lgcm_b200", "-Wl,-rpath,$ORIGIN"])
+    # gcmb_exe: the reference launcher's command line (src/launcher/main.cpp) on top of the host layer
+    exe = os.path.join(HERE, "gcmb_exe")
+    exe_src = os.path.join(HERE, "host", "launcher.cpp")
+    if force or _newer(exe, [exe_src, host]):
+        _run(["g++"] + CXX_FLAGS + ["-o", exe, exe_src, "-L" + HERE, "-lgcm_b200_host", "-lgcm_b200", "-Wl,-rpath,$ORIGIN"])
     return lib, host
 
 

@@ -35,3 +35,17 @@ def build_host_emul():
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out] + srcs +
                        ["-L" + HERE, "-lgcm_b200_emul", "-Wl,-rpath,$ORIGIN"], check=True)
     return out
+
+
+def build_launcher_emul():
+    """gcm_b200/host/launcher.cpp linked against the stepping harness (command-line logic on the build machine)."""
+    host = build_host_emul()
+    out = os.path.join(HERE, "gcmb_exe_emul")
+    src = os.path.join(ROOT, "gcm_b200", "host", "launcher.cpp")
+    if not _fresh(out, [src, host]):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", out, src, "-L" + HERE,
+                        "-lgcm_b200_host_emul", "-lgcm_b200_emul", "-Wl,-rpath,$ORIGIN"], check=True)
+    tasks = os.path.join(HERE, "tasks")
+    if not os.path.islink(tasks):
+        os.symlink(os.path.join(ROOT, "gcm_b200", "tasks"), tasks)
+    return out

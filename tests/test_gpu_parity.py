@@ -214,3 +214,30 @@ def test_simplex_pde_vectors_gpu(lib, model):
     import simplex_cases
     simplex_cases.check_two_bodies(lib, model, steps=3, kind="layers_void", gcm_type=1)
     simplex_cases.check_engine(lib, model, bodies=2, basis="random", cavity=True, steps=3, gcm_type=1)
+
+
+@pytest.mark.parametrize("task", ["cubic2d", "cubic3d", "acoustic"])
+def test_launcher_gpu(task):
+    """gcm_b200/gcmb_exe --task <id>: the reference launcher's cubic demo tasks (src/launcher/main.cpp:332-467) on
+    the GPU against the unmodified reference's step count, end time and checksum"""
+    import json
+    import re
+    exe = os.path.join(ROOT, "gcm_b200", "gcmb_exe")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "launcher_tasks.json")))[task]
+    out = subprocess.run([exe, "--task", task, "-q"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    steps, time = re.search(r"steps = (\d+), time = (\S+)", out.stdout).groups()
+    assert int(steps) == gold["steps"] and float(time) == gold["time"]
+    checksum = float(re.search(r"body 0 checksum = (\S+)", out.stdout).group(1))
+    assert abs(checksum - gold["checksum"]) <= 1e-10 * gold["abs_sum"]
+
+
+def test_launcher_simplex_plate_gpu():
+    import re
+    exe = os.path.join(ROOT, "gcm_b200", "gcmb_exe")
+    out = subprocess.run([exe, "--task", "simplex_plate", "-q"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert re.search(r"steps = 50,", out.stdout)
+    assert "would have thrown on = 0" in out.stdout
+    checksum = float(re.search(r"checksum = (\S+)", out.stdout).group(1))
+    assert np.isfinite(checksum) and checksum != 0

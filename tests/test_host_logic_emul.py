@@ -182,3 +182,26 @@ def test_simplex_pde_vectors_two_bodies(lib, model):
 def test_simplex_pde_vectors_engine(lib):
     import simplex_cases
     simplex_cases.check_engine(lib, 0, bodies=2, basis="rotated", steps=2, gcm_type=1)
+
+
+@pytest.mark.parametrize("task", ["cubic2d", "acoustic"])
+def test_launcher_command_line(task):
+    """gcmb_exe --task <id> (src/launcher/main.cpp:22-71) on the shipped demo tasks: step count, end time and state
+    checksum against the unmodified reference's (tests/golden/launcher_tasks.json)"""
+    import json
+    import re
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    import build_emul
+    exe = build_emul.build_launcher_emul()
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "launcher_tasks.json")))[task]
+    out = subprocess.run([exe, "--task", task, "-q"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    steps, time = re.search(r"steps = (\d+), time = (\S+)", out.stdout).groups()
+    assert int(steps) == gold["steps"] and float(time) == gold["time"]
+    checksum = float(re.search(r"body 0 checksum = (\S+)", out.stdout).group(1))
+    assert abs(checksum - gold["checksum"]) <= 1e-10 * gold["abs_sum"]
+    bad = subprocess.run([exe, "--task", "no_such_task"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "Invalid task file" in bad.stderr
