@@ -22,7 +22,7 @@ CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall"]
 CUDA_SOURCES = ["csrc/gcmb_capi.cu", "csrc/stage_dispatch.cu"]
 CUDA_HEADERS = ["csrc/internal.cuh", "csrc/thread_fns.h", "csrc/march_async.h", "csrc/ztile.h", "csrc/patterns.inc",
                 "csrc/simplex_fns.h", "csrc/simplex_capi.inc", "../include/gcm_b200.h"]
-HOST_SOURCES = ["host/models.cpp", "host/engine.cpp", "host/task_file.cpp", "host/host_capi.cpp", "host/simplex_mesh.cpp", "host/simplex_engine.cpp"]
+HOST_SOURCES = ["host/models.cpp", "host/engine.cpp", "host/task_file.cpp", "host/host_capi.cpp", "host/simplex_mesh.cpp", "host/simplex_engine.cpp", "host/vtk_writer.cpp"]
 HOST_HEADERS = ["host/gcmb_host.hpp", "../include/gcm_b200.h"]
 
 

@@ -23,6 +23,13 @@ namespace {
 
 GCMB_GLOBAL void k_border(BorderArgs b, long long n_face) {
 	const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (b.axis == 2) {
+		// a face across the contiguous axis: the ghost layers of one face node share memory sectors with each
+		// other (and so do the inner layers they mirror), so one thread fills all of them
+		if (t >= n_face) { return; }
+		for (int a = 1; a <= b.g.bs; a++) { border_thread(b, t, a); }
+		return;
+	}
 	if (t >= n_face * b.g.bs) { return; }
 	// consecutive threads walk the face (contiguous along z when the face contains z)
 	const long long f = t % n_face;
@@ -588,6 +595,20 @@ int gcmb_cubic_download_state(gcmb_body* body, void* aos_pde, int with_ghosts) {
 	return transfer(body, aos_pde, with_ghosts, false);
 }
 
+int gcmb_cubic_download_tables(gcmb_body* b, uint8_t* node_table_id) {
+	if (!b || !node_table_id) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	const Geom& g = b->g;
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	std::vector<uint8_t> all((size_t) g.comp);
+	GCMB_CUDA(cudaMemcpyAsync(all.data(), b->node_table, all.size(), cudaMemcpyDeviceToHost, b->ctx->stream));
+	GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+	size_t r = 0;
+	for (int i0 = 0; i0 < g.n[0]; i0++) for (int i1 = 0; i1 < g.n[1]; i1++) for (int i2 = 0; i2 < g.n[2]; i2++) {
+		node_table_id[r++] = all[(size_t) g.index(i0, i1, i2)];
+	}
+	return GCMB_OK;
+}
+
 int gcmb_cubic_set_materials(gcmb_body* b, int n_tables, const double* U, const double* U1,
                              const double* L, const uint8_t* node_table_id) {
 	if (!b || !U || !U1 || !L) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
@@ -733,7 +754,7 @@ int gcmb_cubic_border_apply(gcmb_body* b, int dir, int n_values, const double* v
 			a.pde = b->buf[b->cur]; a.mask = c.mask[s]; a.g = g; a.axis = axis; a.side = s;
 			a.nq = (int) c.q.size();
 			for (int i = 0; i < a.nq; i++) { a.q[i] = c.q[(size_t) i]; a.val[i] = values[used + i]; }
-			const long long n = nf * g.bs;
+			const long long n = axis == 2 ? nf : nf * g.bs;
 			Launch l(b->ctx, 3);
 			GCMB_LAUNCH(k_border, (unsigned) ((n + 127) / 128), 128, b->ctx->stream, a, nf);
 		}

@@ -455,7 +455,33 @@ void EngineBase::writeSnapshots(const int step_) {
 	if (step_ % task.globalSettings.stepsPerSnap != 0) { return; }
 	for (const Snapshotters::T s : task.globalSettings.snapshottersId) {
 		if (s == Snapshotters::T::SLICESNAP) { sliceSnapshot(step_); }
-		// Snapshotters::T::VTK: next row of SURVEY.md §8(f); not written in this build
+		if (s == Snapshotters::T::VTK) { vtkSnapshot(step_); }
+	}
+}
+
+/// VtkSnapshotter::snapshotImpl (util/snapshot/VtkSnapshotter.hpp:20-61) for every body of this process
+void EngineBase::vtkSnapshot(const int step_) {
+	const Task& task = taskCopy;
+	for (Body& body : bodies) {
+		const Mesh& m = *body.mesh;
+		const int n[3] = {m.sizes[0], m.sizes[1], m.sizes[2]};   // unused axes have size 1
+		const size_t total = m.sizeOfRealNodes();
+		std::vector<uint8_t> tables(total);
+		check(gcmb_cubic_download_tables(m.body, tables.data()));
+		// VTK point order: x fastest (linal::SlowZFastX); ours: x slowest
+		std::vector<size_t> order(total);
+		std::vector<float> points(3 * total), material(total);
+		size_t i = 0;
+		for (int z = 0; z < n[2]; z++) for (int y = 0; y < n[1]; y++) for (int x = 0; x < n[0]; x++, i++) {
+			const Mesh::Iterator it = {{x, y, z}};
+			order[i] = ((size_t) x * (size_t) n[1] + (size_t) y) * (size_t) n[2] + (size_t) z;
+			const Real3 c = m.coords(it);
+			for (size_t d = 0; d < 3; d++) { points[3 * i + d] = (float) c[d]; }
+			material[i] = (float) m.materials[tables[order[i]]]->materialNumber;
+		}
+		const auto fields = vtk::snapshotFields(m.modelType, D, m.M, m.pdeRealNodes(), order, task.vtkSnapshotter.quantitiesToSnap, material);
+		vtk::writeStructuredGrid(vtk::snapshotFileName(task.globalSettings.outputDirectory, "vtk", m.id, slabRank, step_, "vts"),
+				n, points, fields);
 	}
 }
 

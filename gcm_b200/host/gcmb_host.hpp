@@ -8,6 +8,7 @@
 // description, the per-material eigen-systems and lazily downloaded copies for accessors/snapshots.
 #pragma once
 #include <array>
+#include <cstdint>
 #include <functional>
 #include <map>
 #include <memory>
@@ -401,6 +402,7 @@ private:
 	void setUpPde(const Task& task, Body& body);
 	void setUpBorders(const Task& task, Body& body);
 	void sliceSnapshot(const int step);
+	void vtkSnapshot(const int step);
 };
 
 template<int Dimensionality>
@@ -484,8 +486,12 @@ public:
 protected:
 	void nextTimeStep() override;
 	real estimateTimeStep() override;
-	void writeSnapshots(const int) override { }
+	void writeSnapshots(const int step) override;
 private:
+	Task::VtkSnapshotter vtkSettings;
+	std::vector<Snapshotters::T> snapshotters;
+	std::string outputDirectory;
+	int stepsPerSnap = 1;
 	struct Border {
 		std::shared_ptr<Area> correctionArea;
 		bool useForMulticontactNodes = true;
@@ -530,6 +536,22 @@ private:
 };
 
 }  // namespace simplex
+
+/// VTK XML snapshots (host/vtk_writer.cpp; reference util/snapshot/VtkSnapshotter.hpp, VtkUtils.hpp)
+namespace vtk {
+struct Field {
+	std::string name;
+	int components = 1;
+	std::vector<float> data;
+};
+std::string snapshotFileName(const std::string& outputDirectory, const std::string& folder, size_t meshId, int rank, int step,
+		const std::string& extension);
+void writeStructuredGrid(const std::string& path, const int (&n)[3], const std::vector<float>& points, const std::vector<Field>& fields);
+void writeUnstructuredGrid(const std::string& path, const std::vector<float>& points, const std::vector<int32_t>& tetrahedra,
+		const std::vector<Field>& fields);
+std::vector<Field> snapshotFields(Models::T model, int D, int M, const std::vector<real>& pde, const std::vector<size_t>& order,
+		const std::vector<PhysicalQuantities::T>& quantities, const std::vector<float>& materialIndex);
+}  // namespace vtk
 
 /// reference engine/EngineFactory.hpp:11-36
 std::shared_ptr<AbstractEngine> createEngine(const Task& task);

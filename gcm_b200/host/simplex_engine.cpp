@@ -114,6 +114,10 @@ Engine::Engine(const Task& task) : AbstractEngine(task) {
 		throw Exception(GCMB_E_UNSUPPORTED, "SplittingType::SUMM is not built");
 	}
 	if (task.simplexGrid.movable) { throw Exception(GCMB_E_UNSUPPORTED, "movable grids are not built"); }
+	vtkSettings = task.vtkSnapshotter;
+	snapshotters = task.globalSettings.snapshottersId;
+	outputDirectory = task.globalSettings.outputDirectory;
+	stepsPerSnap = task.globalSettings.stepsPerSnap;
 	check(gcmb_create(task.device.device, 8, &ctx));
 	try {
 		createTriangulation(task);
@@ -483,6 +487,33 @@ real Engine::estimateTimeStep() {
 		if (bodyTimeStep < minimalTimeStep) { minimalTimeStep = bodyTimeStep; }
 	}
 	return minimalTimeStep;
+}
+
+/// Engine::writeSnapshots (engine/simplex/Engine.cpp:313-320) -> VtkSnapshotter::snapshotImpl
+/// (util/snapshot/VtkSnapshotter.hpp:20-61): the body's vertices and its own cells as a .vtu
+void Engine::writeSnapshots(const int step_) {
+	if (step_ % stepsPerSnap != 0) { return; }
+	for (const Snapshotters::T s : snapshotters) {
+		if (s != Snapshotters::T::VTK) { continue; }
+		for (const Body& body : bodies) {
+			const Mesh& m = *body.mesh;
+			const size_t n = m.sizeOfRealNodes();
+			std::vector<size_t> order(n);
+			std::vector<float> points(3 * n), material(n, (float) m.material->materialNumber);
+			for (size_t l = 0; l < n; l++) {
+				order[l] = l;
+				const Real3 c = m.coords((int) l);
+				for (size_t d = 0; d < 3; d++) { points[3 * l + d] = (float) c[d]; }
+			}
+			std::vector<int32_t> cells;
+			for (int c = 0; c < triangulation.nC; c++) {
+				if (triangulation.cellGrid[(size_t) c] != (int) m.id) { continue; }
+				for (int k = 0; k < 4; k++) { cells.push_back(m.localOf[(size_t) triangulation.cellV[(size_t) 4 * c + k]]); }
+			}
+			const auto fields = vtk::snapshotFields(m.modelType, 3, m.M, m.pdeAll(), order, vtkSettings.quantitiesToSnap, material);
+			vtk::writeUnstructuredGrid(vtk::snapshotFileName(outputDirectory, "vtk", m.id, 0, step_, "vtu"), points, cells, fields);
+		}
+	}
 }
 
 int Engine::errorCount() const {

@@ -4,7 +4,7 @@
 //   material default MATERIAL | material area AREA MATERIAL | material body ID MATERIAL
 //   initial quantity Q value AREA | initial wave W direction Q value AREA
 //   border ID direction AREA {Q (const c | sin amp omega)}...
-//   detector ID Q AREA [output-directory]
+//   detector ID Q AREA [output-directory] | vtk [every N] Q... | output DIRECTORY
 //   AREA = infinite | box x0 y0 z0 x1 y1 z1 | sphere r cx cy cz | cylinder r bx by bz ex ey ez
 //   MATERIAL = isotropic rho lambda mu [tau0 t] | orthotropic rho c11 c12 c13 c22 c23 c33 c44 c55 c66 [tau0 t]
 // Simplex grids (box mesher):
@@ -225,6 +225,13 @@ Task parseTaskText(const std::string& text) {
 			const ContactConditions::T c = type == "slide" ? ContactConditions::T::SLIDE : ContactConditions::T::ADHESION;
 			if (t.done()) { task.contactCondition.defaultCondition = c; }
 			else { const size_t a = (size_t) t.inum(), b = (size_t) t.inum(); task.contactCondition.gridToGridConditions[{a, b}] = c; }
+		} else if (key == "vtk") {
+			// vtk [every N] Q...: Snapshotters::T::VTK with vtkSnapshotter.quantitiesToSnap
+			task.globalSettings.snapshottersId.push_back(Snapshotters::T::VTK);
+			if (t.peek() == "every") { t.next(); task.globalSettings.stepsPerSnap = t.inum(); }
+			while (!t.done()) { task.vtkSnapshotter.quantitiesToSnap.push_back(quantity(t.next())); }
+		} else if (key == "output") {
+			task.globalSettings.outputDirectory = t.next();
 		} else if (key == "detector") {
 			task.detector.gridId = (size_t) t.inum();
 			task.detector.quantities = {quantity(t.next())};

@@ -84,6 +84,9 @@ void gcmb_cubic_body_destroy(gcmb_body* body);
  * prod(sizes+2*border) nodes; 0: real nodes only (prod(sizes)).  Both sync. */
 int gcmb_cubic_upload_state(gcmb_body* body, const void* aos_pde, int with_ghosts);
 int gcmb_cubic_download_state(gcmb_body* body, void* aos_pde, int with_ghosts);
+/* material table id of every REAL node, x slowest (DefaultMesh::material(it), engine/cubic/DefaultMesh.hpp:96-110;
+ * read by VtkSnapshotter for its material_index field, util/snapshot/VtkSnapshotter.hpp:49-56). sync */
+int gcmb_cubic_download_tables(gcmb_body* body, uint8_t* node_table_id);
 
 /* Eigen-system tables of the materials present in the body (GcmMatrices, reference
  * util/math/GridCharacteristicMethod.hpp:33-111): U, U1 are [n_tables][D][M][M] row-major,

@@ -29,7 +29,7 @@ def build_host_emul():
     emul = build_emul()
     out = os.path.join(HERE, "libgcm_b200_host_emul.so")
     hdir = os.path.join(ROOT, "gcm_b200", "host")
-    srcs = [os.path.join(hdir, f) for f in ("models.cpp", "engine.cpp", "task_file.cpp", "host_capi.cpp", "simplex_mesh.cpp", "simplex_engine.cpp")]
+    srcs = [os.path.join(hdir, f) for f in ("models.cpp", "engine.cpp", "task_file.cpp", "host_capi.cpp", "simplex_mesh.cpp", "simplex_engine.cpp", "vtk_writer.cpp")]
     deps = srcs + [os.path.join(hdir, "gcmb_host.hpp"), emul]
     if not _fresh(out, deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out] + srcs +

@@ -99,3 +99,19 @@ def random_stage_check(lib, cases, seed=7):
                                                     np.abs(nxt[real] - got).max())
         body.close()
     ctx.close()
+
+
+def read_vtk_appended(path):
+    """arrays of a VTK XML file written with one raw appended block (gcm_b200/host/vtk_writer.cpp)"""
+    import re
+    raw = open(path, "rb").read()
+    head, _, tail = raw.partition(b'<AppendedData encoding="raw">')
+    data = tail[tail.index(b"_") + 1:]
+    types = {"Float32": np.float32, "Int32": np.int32, "UInt8": np.uint8}
+    out = {"header": head.decode()}
+    for m in re.finditer(r'<DataArray type="(\w+)" Name="(\w+)" NumberOfComponents="(\d+)" format="appended" offset="(\d+)"/>', out["header"]):
+        kind, name, comps, offset = m.group(1), m.group(2), int(m.group(3)), int(m.group(4))
+        nbytes = int(np.frombuffer(data[offset:offset + 4], dtype=np.uint32)[0])
+        arr = np.frombuffer(data[offset + 4:offset + 4 + nbytes], dtype=types[kind])
+        out[name] = arr.reshape(-1, comps) if comps > 1 else arr
+    return out

@@ -10,6 +10,7 @@ import os
 import numpy as np
 import pytest
 
+from gcm_b200 import capi
 from helpers import compare_with_golden, emul_library, golden, run_engine
 from scenarios import SCENARIOS
 
@@ -205,3 +206,47 @@ def test_launcher_command_line(task):
     assert abs(checksum - gold["checksum"]) <= 1e-10 * gold["abs_sum"]
     bad = subprocess.run([exe, "--task", "no_such_task"], capture_output=True, text=True)
     assert bad.returncode != 0 and "Invalid task file" in bad.stderr
+
+
+def test_vtk_snapshots_cubic(lib, tmp_path, monkeypatch):
+    """VtkSnapshotter fields and file names (util/snapshot/VtkSnapshotter.hpp:20-61, Snapshotter.hpp:53-68) for a
+    layered 3-D elastic body: .vts in VTK point order with Velocity, the requested scalars and material_index"""
+    from helpers import read_vtk_appended
+    from scenarios import elastic3d_layers
+    monkeypatch.chdir(tmp_path)
+    text = elastic3d_layers(n=10, steps=4) + "vtk every 2 PRESSURE Sxy\noutput run1\n"
+    eng = capi.HostEngine(lib, text).run()
+    D, M, sizes, _ = eng.body_info(0)
+    u = eng.body_pde(0).reshape(tuple(sizes) + (M,))
+    files = sorted(os.listdir(tmp_path / "snapshots" / "run1" / "vtk"))
+    # numberOfSnaps = 4 snapshots of stepsPerSnap = 2 steps each, plus the initial one (AbstractEngine.cpp:30-46)
+    assert files == ["mesh0core00snap%04d.vts" % s for s in (0, 2, 4, 6, 8)]
+    v = read_vtk_appended(tmp_path / "snapshots" / "run1" / "vtk" / files[-1])
+    nx, ny, nz = (int(s) for s in sizes)
+    assert 'WholeExtent="0 %d 0 %d 0 %d"' % (nx - 1, ny - 1, nz - 1) in v["header"]
+    vtk_order = u.transpose(2, 1, 0, 3).reshape(-1, M)          # x fastest
+    assert np.array_equal(v["Velocity"], vtk_order[:, :3].astype(np.float32))
+    assert np.array_equal(v["Sxy"], vtk_order[:, 4].astype(np.float32))
+    pressure = -(vtk_order[:, 3] + vtk_order[:, 6] + vtk_order[:, 8]) / 3
+    assert np.array_equal(v["pressure"], pressure.astype(np.float32))
+    assert v["Points"].shape == (nx * ny * nz, 3) and v["Points"][1, 0] > v["Points"][0, 0] and v["Points"][1, 1] == v["Points"][0, 1]
+    assert set(np.unique(v["material_index"])) <= {0.0, 1.0, 2.0, 3.0} and len(np.unique(v["material_index"])) >= 1
+    eng.close()
+
+
+def test_vtk_snapshots_simplex(lib, tmp_path, monkeypatch):
+    from helpers import read_vtk_appended
+    import simplex_cases
+    monkeypatch.chdir(tmp_path)
+    text, _ = simplex_cases.engine_scenario(0, bodies=2, steps=2)
+    eng = capi.SimplexHostEngine(lib, text + "vtk PRESSURE\n").run()
+    tri = eng.triangulation()
+    for body in (0, 1):
+        v = read_vtk_appended(tmp_path / "snapshots" / "vtk" / ("mesh%dcore00snap0002.vtu" % body))
+        u = eng.simplex_pde(body)
+        assert np.array_equal(v["Velocity"], u[:, :3].astype(np.float32))
+        assert np.array_equal(v["pressure"], (-(u[:, 3] + u[:, 6] + u[:, 8]) / 3).astype(np.float32))
+        n_cells = int((tri["cell_grid"] == body).sum())
+        assert v["connectivity"].shape == (4 * n_cells,) and v["connectivity"].max() == len(u) - 1
+        assert np.array_equal(v["offsets"], 4 * np.arange(1, n_cells + 1)) and (v["types"] == 10).all()
+    eng.close()
