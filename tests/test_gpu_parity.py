@@ -217,14 +217,14 @@ def test_simplex_pde_vectors_gpu(lib, model):
 
 
 @pytest.mark.parametrize("task", ["cubic2d", "cubic3d", "acoustic"])
-def test_launcher_gpu(task):
+def test_launcher_gpu(task, tmp_path):
     """gcm_b200/gcmb_exe --task <id>: the reference launcher's cubic demo tasks (src/launcher/main.cpp:332-467) on
     the GPU against the unmodified reference's step count, end time and checksum"""
     import json
     import re
     exe = os.path.join(ROOT, "gcm_b200", "gcmb_exe")
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "launcher_tasks.json")))[task]
-    out = subprocess.run([exe, "--task", task, "-q"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, "--task", task, "-q"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
     assert out.returncode == 0, out.stderr
     steps, time = re.search(r"steps = (\d+), time = (\S+)", out.stdout).groups()
     assert int(steps) == gold["steps"] and float(time) == gold["time"]
@@ -232,10 +232,10 @@ def test_launcher_gpu(task):
     assert abs(checksum - gold["checksum"]) <= 1e-10 * gold["abs_sum"]
 
 
-def test_launcher_simplex_plate_gpu():
+def test_launcher_simplex_plate_gpu(tmp_path):
     import re
     exe = os.path.join(ROOT, "gcm_b200", "gcmb_exe")
-    out = subprocess.run([exe, "--task", "simplex_plate", "-q"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, "--task", "simplex_plate", "-q"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
     assert out.returncode == 0, out.stderr
     assert re.search(r"steps = 50,", out.stdout)
     assert "would have thrown on = 0" in out.stdout

@@ -186,7 +186,7 @@ def test_simplex_pde_vectors_engine(lib):
 
 
 @pytest.mark.parametrize("task", ["cubic2d", "acoustic"])
-def test_launcher_command_line(task):
+def test_launcher_command_line(task, tmp_path):
     """gcmb_exe --task <id> (src/launcher/main.cpp:22-71) on the shipped demo tasks: step count, end time and state
     checksum against the unmodified reference's (tests/golden/launcher_tasks.json)"""
     import json
@@ -198,7 +198,7 @@ def test_launcher_command_line(task):
     import build_emul
     exe = build_emul.build_launcher_emul()
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "launcher_tasks.json")))[task]
-    out = subprocess.run([exe, "--task", task, "-q"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, "--task", task, "-q"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
     assert out.returncode == 0, out.stderr
     steps, time = re.search(r"steps = (\d+), time = (\S+)", out.stdout).groups()
     assert int(steps) == gold["steps"] and float(time) == gold["time"]
