@@ -115,6 +115,7 @@ HOST_ABI = {
     "gcmb_host_simplex_contact_nodes": (ctypes.c_int, [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, c_int_p, c_int_p,
                                                        c_int_p, c_double_p]),
     "gcmb_host_simplex_errors": (ctypes.c_int, [vp, c_int_p]),
+    "gcmb_host_simplex_save_inm": (ctypes.c_int, [vp, ctypes.c_char_p]),
 }
 
 
@@ -446,6 +447,9 @@ class SimplexHostEngine(HostEngine):
         normals = np.zeros((n.value, 3))
         self.lib.hcheck(self.lib.h.gcmb_host_simplex_contact_nodes(self.handle, a, b, n.value, ctypes.byref(n), ip(first), ip(second), dp(normals)))
         return first, second, normals
+
+    def save_inm(self, path):
+        self.lib.hcheck(self.lib.h.gcmb_host_simplex_save_inm(self.handle, str(path).encode()))
 
     def errors(self):
         c = ctypes.c_int()

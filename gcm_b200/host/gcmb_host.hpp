@@ -188,6 +188,8 @@ struct Task {
 	struct SimplexGrid {
 		enum class Mesher { CGAL_MESHER, INM_MESHER, BOX_MESHER } mesher = Mesher::BOX_MESHER;
 		real spatialStep = 0;            ///< edge of the box mesher's cubes
+		std::string fileName;            ///< INM_MESHER: the mesh file
+		real scale = 1;                  ///< denominator to scale the points after loading
 		bool movable = false;
 		BorderCalcMode borderCalcMode = BorderCalcMode::GLOBAL_BASIS;
 		/// BOX_MESHER @{
@@ -430,6 +432,10 @@ struct FlatTriangulation {
 };
 FlatTriangulation makeBoxMesh(int nx, int ny, int nz, const Real3& origin, real h, real jitter, unsigned seed,
 		const Real3* voidMin, const Real3* voidMax, int gridId);
+
+/// INM mesh files (reference grid/simplex/mesh_loaders/InmMeshLoader.hpp): the file's cells are the triangulation
+FlatTriangulation loadInmMesh(const std::string& fileName, real scale = 1);
+void saveInmMesh(const FlatTriangulation& t, const std::string& fileName);
 
 /// host view of one body of the simplex engine (reference engine/simplex/AbstractMesh.hpp + DefaultMesh.hpp)
 class Mesh {

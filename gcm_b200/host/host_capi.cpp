@@ -157,6 +157,11 @@ int gcmb_host_simplex_contact_nodes(void* handle, size_t a, size_t b, int capaci
 	});
 }
 
+/// the engine's triangulation as an INM mesh file (grid/simplex/mesh_loaders/InmMeshLoader.hpp format)
+int gcmb_host_simplex_save_inm(void* handle, const char* file_name) {
+	return guarded([&] { simplex::saveInmMesh(simplexOf(handle).getTriangulation(), file_name); });
+}
+
 int gcmb_host_simplex_errors(void* handle, int* count) {
 	return guarded([&] { *count = simplexOf(handle).errorCount(); });
 }

@@ -180,8 +180,18 @@ const Engine::Body& Engine::getBody(const GridId id) const {
 /// CgalTriangulation built by the mesher, grid/simplex/cgal/Cgal3DTriangulation.hpp:56-76)
 void Engine::createTriangulation(const Task& task) {
 	const Task::SimplexGrid& g = task.simplexGrid;
+	if (g.mesher == Task::SimplexGrid::Mesher::INM_MESHER) {
+		// the cells of the file carry the body ids (InmMeshLoader.hpp:60-83); ids without a Task::Body are an error
+		triangulation = loadInmMesh(g.fileName, g.scale);
+		for (const int id : triangulation.cellGrid) {
+			if (id != EmptySpaceFlag && !task.bodies.count((size_t) id)) {
+				throw Exception(GCMB_E_INVALID_ARG, "the mesh file has cells of body " + std::to_string(id) + " which the task does not describe");
+			}
+		}
+		return;
+	}
 	if (g.mesher != Task::SimplexGrid::Mesher::BOX_MESHER) {
-		throw Exception(GCMB_E_UNSUPPORTED, "only the structured box mesher is available (CGAL is not part of this build)");
+		throw Exception(GCMB_E_UNSUPPORTED, "CGAL meshing is not part of this build: use the box mesher or an INM mesh file");
 	}
 	if (g.boxCubes[0] < 1 || g.boxCubes[1] < 1 || g.boxCubes[2] < 1 || !(g.spatialStep > 0)) {
 		throw Exception(GCMB_E_INVALID_ARG, "box mesher needs positive sizes and spatial step");

@@ -8,7 +8,9 @@
 // CellInfo::EmptySpaceFlag; the exterior of the convex hull is neighbour -1 (CGAL's infinite cells).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <map>
 
 #include "gcmb_host.hpp"
@@ -100,6 +102,57 @@ FlatTriangulation makeBoxMesh(int nx, int ny, int nz, const Real3& origin, real 
 	}
 	t.buildTopology();
 	return t;
+}
+
+/// INM mesh files (the reference's grid/simplex/mesh_loaders/InmMeshLoader.hpp:96-168): number of points, one
+/// "x y z" line per point, number of cells, one "v1 v2 v3 v4 material" line per cell (1-based vertex numbers), a
+/// closing "0".  The reference feeds the points to CGAL's Delaunay triangulation and keeps the materials of the
+/// cells it finds again (:36-94); here the file's own cells ARE the triangulation (nothing is re-meshed, no cell
+/// is missed): the material number becomes the body id of the cell, and facets without a neighbour border on
+/// empty space.
+FlatTriangulation loadInmMesh(const std::string& fileName, real scale) {
+	std::ifstream in(fileName);
+	if (!in) { throw Exception(GCMB_E_INVALID_ARG, "cannot open mesh file " + fileName); }
+	FlatTriangulation t;
+	size_t nPoints = 0, nCells = 0;
+	if (!(in >> nPoints) || nPoints < 4) { throw Exception(GCMB_E_BAD_MESH, "INM mesh: bad number of points"); }
+	t.xyz.resize(nPoints * 3);
+	for (size_t i = 0; i < nPoints * 3; i++) {
+		if (!(in >> t.xyz[i])) { throw Exception(GCMB_E_BAD_MESH, "INM mesh: bad point"); }
+		t.xyz[i] /= scale;   // Task::SimplexGrid::scale: "denominator to scale the points after meshing"
+	}
+	if (!(in >> nCells) || nCells < 1) { throw Exception(GCMB_E_BAD_MESH, "INM mesh: bad number of cells"); }
+	t.cellV.resize(nCells * 4);
+	t.cellGrid.resize(nCells);
+	for (size_t c = 0; c < nCells; c++) {
+		for (int k = 0; k < 4; k++) {
+			long long v = 0;
+			if (!(in >> v) || v < 1 || (size_t) v > nPoints) { throw Exception(GCMB_E_BAD_MESH, "INM mesh: bad cell vertex"); }
+			t.cellV[4 * c + (size_t) k] = (int) (v - 1);
+		}
+		if (!(in >> t.cellGrid[c])) { throw Exception(GCMB_E_BAD_MESH, "INM mesh: bad cell material"); }
+	}
+	int zero = -1;
+	if (!(in >> zero) || zero != 0) { throw Exception(GCMB_E_BAD_MESH, "INM mesh: the closing 0 is missing"); }
+	t.buildTopology();
+	return t;
+}
+
+void saveInmMesh(const FlatTriangulation& t, const std::string& fileName) {
+	FILE* f = std::fopen(fileName.c_str(), "w");
+	if (!f) { throw Exception(GCMB_E_INVALID_OP, "cannot write " + fileName); }
+	std::fprintf(f, "%d\n", t.nV);
+	for (int v = 0; v < t.nV; v++) { std::fprintf(f, "%.17e %.17e %.17e\n", t.xyz[(size_t) 3 * v], t.xyz[(size_t) 3 * v + 1], t.xyz[(size_t) 3 * v + 2]); }
+	int cells = 0;
+	for (int c = 0; c < t.nC; c++) { if (t.cellGrid[(size_t) c] != EmptySpaceFlag) { cells++; } }
+	std::fprintf(f, "%d\n", cells);
+	for (int c = 0; c < t.nC; c++) {
+		if (t.cellGrid[(size_t) c] == EmptySpaceFlag) { continue; }
+		const int* v = &t.cellV[(size_t) 4 * c];
+		std::fprintf(f, "%d %d %d %d %d\n", v[0] + 1, v[1] + 1, v[2] + 1, v[3] + 1, t.cellGrid[(size_t) c]);
+	}
+	std::fprintf(f, "0\n");
+	std::fclose(f);
 }
 
 }  // namespace simplex

@@ -9,6 +9,7 @@
 //   MATERIAL = isotropic rho lambda mu [tau0 t] | orthotropic rho c11 c12 c13 c22 c23 c33 c44 c55 c66 [tau0 t]
 // Simplex grids (box mesher):
 //   grid simplex | simplex_box nx ny nz ox oy oz h [jitter j] [seed s] | region ID AREA | cavity AREA
+//   simplex_mesh FILE [scale S]   (INM mesh file instead of the box mesher)
 //   body ID (elastic|acoustic) isotropic | material body ID MATERIAL | basis b00 b01 .. b22 | basis random [seed]
 //   border_condition AREA (fixed_force|fixed_velocity) [no_multicontact] (const c | sin amp omega)...
 //   contact (adhesion|slide) [ID ID] | gcm_type (riemann_invariants|pde_vectors)
@@ -199,6 +200,12 @@ Task parseTaskText(const std::string& text) {
 				else if (sub == "seed") { g.seed = (unsigned) t.inum(); }
 				else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown simplex_box option " + sub); }
 			}
+		} else if (key == "simplex_mesh") {
+			// simplex_mesh FILE [scale S]: an INM mesh file (Task::SimplexGrid::Mesher::INM_MESHER)
+			Task::SimplexGrid& g = task.simplexGrid;
+			g.mesher = Task::SimplexGrid::Mesher::INM_MESHER;
+			g.fileName = t.next();
+			if (t.peek() == "scale") { t.next(); g.scale = t.num(); }
 		} else if (key == "region") {
 			Task::SimplexGrid::BodyRegion r;
 			r.id = (size_t) t.inum();

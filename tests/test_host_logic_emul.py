@@ -250,3 +250,33 @@ def test_vtk_snapshots_simplex(lib, tmp_path, monkeypatch):
         assert v["connectivity"].shape == (4 * n_cells,) and v["connectivity"].max() == len(u) - 1
         assert np.array_equal(v["offsets"], 4 * np.arange(1, n_cells + 1)) and (v["types"] == 10).all()
     eng.close()
+
+
+def test_inm_mesh_file_round_trip(lib, tmp_path):
+    """INM mesh files (grid/simplex/mesh_loaders/InmMeshLoader.hpp:96-168): a two-body box mesh with a cavity saved
+    in that format and loaded back gives the same bodies, borders, contacts and, after 2 steps, the same bits"""
+    import simplex_cases
+    text, _ = simplex_cases.engine_scenario(0, bodies=2, steps=2)
+    # one engine at a time: like the reference's, the Clock is a process-wide static (engine/GlobalVariables.hpp:16-40)
+    a = capi.SimplexHostEngine(lib, text)
+    path = tmp_path / "mesh.out"
+    a.save_inm(path)
+    head = open(path).read().split("\n")
+    ta = a.triangulation()
+    assert int(head[0]) == len(ta["xyz"]) and open(path).read().rstrip().endswith("\n0")
+    a.run()
+    ref = {body: a.simplex_pde(body) for body in (0, 1)}
+    ref_contacts = a.contact_nodes(0, 1)[0]
+    assert a.errors() == 0
+    a.close()
+    keep = [ln for ln in text.split("\n") if not ln.startswith(("simplex_box", "region", "cavity"))]
+    b = capi.SimplexHostEngine(lib, "\n".join(keep) + "\nsimplex_mesh %s\n" % path)
+    tb = b.triangulation()
+    assert np.array_equal(ta["xyz"], tb["xyz"])
+    assert (ta["cell_grid"] >= 0).sum() == len(tb["cell_grid"])       # empty cells are not stored in the file
+    b.run()
+    assert np.array_equal(ref_contacts, b.contact_nodes(0, 1)[0])
+    for body in (0, 1):
+        assert np.abs(ref[body]).max() > 0.1 and np.array_equal(ref[body], b.simplex_pde(body))
+    assert b.errors() == 0
+    b.close()
