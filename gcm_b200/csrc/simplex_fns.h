@@ -534,6 +534,11 @@ struct StageS {
 	int nFeet;              // distinct NON-ZERO eigenvalues of this stage, in order of first appearance
 	double footLambda[9];
 	unsigned footMask[9];   // characteristics sharing the eigenvalue
+	// feet of the inner vertices found in an earlier step with the same time step, basis and eigenvalues (the
+	// mesh does not move, so the cell location of a foot is the same in every step): 0 off, 1 fill, 2 use
+	int cacheMode;
+	int4* cacheCell;        // [foot][inner index] local vertex ids of the cell, x = -1: not a plain cell hit
+	double* cacheLam;       // [foot][inner index][4] barycentric coordinates of the foot
 	int pdeMode;            // GcmType::ADVECT_PDE_VECTORS: `riem` is the current layer itself, `next` receives U*V rows
 	unsigned zeroMask;      // characteristics with a zero eigenvalue: the invariant is carried over
 	int footMajor;          // thread mapping of the inner pass: 1 = a warp shares the foot, 0 = adjacent lanes share the vertex
@@ -546,12 +551,34 @@ struct StageS {
 	int* errors;            // counter of "the reference would have thrown"
 };
 
+// SimplexGrid::findCellCrossedByTheRay through the cache of feet: slot < 0 = no caching for this call
+GCMB_HD Found locateFoot(const StageS& a, int it, V3 shift, long long slot, int& err) {
+	if (slot >= 0 && a.cacheMode == 2) {
+		const int4 c = a.cacheCell[slot];
+		if (c.x >= 0) {
+			Found f;
+			f.n = 4;
+			f.p[0] = c.x; f.p[1] = c.y; f.p[2] = c.z; f.p[3] = c.w;
+			for (int i = 0; i < 4; i++) { f.l[i] = a.cacheLam[4 * slot + i]; }
+			return f;
+		}
+	}
+	const Found f = locate(a.t, it, shift, err);
+	if (slot >= 0 && a.cacheMode == 1) {
+		const bool plain = f.n == 4 && !err;
+		a.cacheCell[slot] = plain ? make_int4(f.p[0], f.p[1], f.p[2], f.p[3]) : make_int4(-1, -1, -1, -1);
+		for (int i = 0; i < 4; i++) { a.cacheLam[4 * slot + i] = f.l[i]; }
+	}
+	return f;
+}
+
 // interpolateValuesAround (…InRiemannInvariants.hpp:146-198) for the characteristics `same` of vertex `it`
 // that share the eigenvalue lambda, hence the foot x0 - tau*lambda*direction: the cell location and the
 // interpolation geometry are computed once per distinct foot (the reference recomputes them identically for
 // each characteristic).  Writes out[j] for every j in `same`; returns the characteristics that turned out outer.
 template<int M>
-GCMB_HD unsigned footCharacteristics(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err) {
+GCMB_HD unsigned footCharacteristics(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err,
+                                     long long slot = -1) {
 	const Tri& t = a.t;
 	const double dx = -a.tau * lambda;
 	if (dx == 0) {
@@ -560,7 +587,7 @@ GCMB_HD unsigned footCharacteristics(const StageS& a, int it, double lambda, uns
 	}
 	const V3 x0 = t.localPoint(it);
 	const V3 shift = V3{a.dir[0], a.dir[1], a.dir[2]} * dx;
-	const Found f = locate(t, it, shift, err);
+	const Found f = locateFoot(a, it, shift, slot, err);
 	if (f.n == 4) {
 		const int cell[4] = {f.p[0], f.p[1], f.p[2], f.p[3]};
 		// hybridGeometry(t, cell, x0 + shift, h, err) with the coordinates the cell location already has
@@ -596,7 +623,8 @@ GCMB_HD unsigned footCharacteristics(const StageS& a, int it, double lambda, uns
 // component of the quadratic interpolant leaves the [min, max] of the four values), and the characteristics k
 // sharing the foot get r_k = sum_j U(k,j) * v_j -- row k of diagonalMultiply(U, V) (linal/functions.hpp:254-267).
 template<int M>
-GCMB_HD unsigned footVectors(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err) {
+GCMB_HD unsigned footVectors(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err,
+                             long long slot = -1) {
 	const Tri& t = a.t;
 	const double dx = -a.tau * lambda;
 	double v[M];
@@ -607,7 +635,7 @@ GCMB_HD unsigned footVectors(const StageS& a, int it, double lambda, unsigned sa
 	} else {
 		const V3 x0 = t.localPoint(it);
 		const V3 shift = V3{a.dir[0], a.dir[1], a.dir[2]} * dx;
-		const Found f = locate(t, it, shift, err);
+		const Found f = locateFoot(a, it, shift, slot, err);
 		if (f.n == 4) {
 			const int cell[4] = {f.p[0], f.p[1], f.p[2], f.p[3]};
 			HybridGeom h;
@@ -664,9 +692,10 @@ GCMB_HD unsigned footVectors(const StageS& a, int it, double lambda, unsigned sa
 }
 
 template<int M>
-GCMB_HD unsigned footAny(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err) {
-	return a.pdeMode ? footVectors<M>(a, it, lambda, same, borderPass, out, err)
-	                 : footCharacteristics<M>(a, it, lambda, same, borderPass, out, err);
+GCMB_HD unsigned footAny(const StageS& a, int it, double lambda, unsigned same, bool borderPass, double* out, int& err,
+                         long long slot = -1) {
+	return a.pdeMode ? footVectors<M>(a, it, lambda, same, borderPass, out, err, slot)
+	                 : footCharacteristics<M>(a, it, lambda, same, borderPass, out, err, slot);
 }
 
 GCMB_HD void countError(int* errors) {
@@ -719,10 +748,10 @@ GCMB_HD void borderFinishThread(const StageS& a, int it) {
 
 // inner vertices (…InRiemannInvariants.hpp:99-113): one thread per (vertex, distinct foot)
 template<int M>
-GCMB_HD void innerFootThread(const StageS& a, int it, int foot) {
+GCMB_HD void innerFootThread(const StageS& a, int it, int foot, long long slot) {
 	int err = 0;
 	if (foot == 0) { footAny<M>(a, it, 0.0, a.zeroMask, false, a.next + (long long) it * M, err); }
-	footAny<M>(a, it, a.footLambda[foot], a.footMask[foot], false, a.next + (long long) it * M, err);
+	footAny<M>(a, it, a.footLambda[foot], a.footMask[foot], false, a.next + (long long) it * M, err, slot);
 	if (err) { countError(a.errors); }
 }
 

@@ -149,8 +149,9 @@ def test_simplex_gradient(lib):
 
 @pytest.mark.parametrize("model", [0, 1])
 def test_simplex_time_steps(lib, model):
+    """4 steps: the cache of located feet is keyed in step 1, filled in step 2 and used from step 3 on"""
     import simplex_cases
-    simplex_cases.check_stage(lib, model, steps=2)
+    simplex_cases.check_stage(lib, model, steps=4)
 
 
 @pytest.mark.parametrize("model", [0, 1])
@@ -182,7 +183,7 @@ def test_simplex_pde_vectors_two_bodies(lib, model):
 
 def test_simplex_pde_vectors_engine(lib):
     import simplex_cases
-    simplex_cases.check_engine(lib, 0, bodies=2, basis="rotated", steps=2, gcm_type=1)
+    simplex_cases.check_engine(lib, 0, bodies=2, basis="rotated", steps=4, gcm_type=1)
 
 
 @pytest.mark.parametrize("task", ["cubic2d", "acoustic"])
