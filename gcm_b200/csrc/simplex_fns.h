@@ -399,7 +399,7 @@ GCMB_HD void matVec(const double* A, const double* x, double* y) {
 // One pass over the neighbours: every sum of the normal equations (A^T W A and A^T W b for all M right-hand
 // sides) is accumulated neighbour by neighbour in the reference's order, so nothing is staged in local memory.
 template<int M>
-GCMB_HD void gradientThread(const Tri& t, const double* values, int it, double* grad, int& err) {
+GCMB_HD void gradientThread(const Tri& t, const double* values, int it, double4* vg /* [M] of this vertex: {value, gradient} */, int& err) {
 	const int n = t.nbOff[it + 1] - t.nbOff[it];
 	const int* nb = t.nbIdx + t.nbOff[it];
 	const V3 x0 = t.localPoint(it);
@@ -435,7 +435,9 @@ GCMB_HD void gradientThread(const Tri& t, const double* values, int it, double* 
 			g[1] = det3(N[0][0], b[c][0], N[0][2], N[1][0], b[c][1], N[1][2], N[2][0], b[c][2], N[2][2]) / det;
 			g[2] = det3(N[0][0], N[0][1], b[c][0], N[1][0], N[1][1], b[c][1], N[2][0], N[2][1], b[c][2]) / det;
 		}
-		for (int d = 0; d < 3; d++) { grad[d * M + c] = g[d]; }
+		// value and gradient of a component side by side: one 32-byte sector per (vertex, component) for the
+		// interpolation's gathers
+		vg[c] = make_double4(v0[c], g[0], g[1], g[2]);
 	}
 }
 
@@ -454,13 +456,13 @@ GCMB_HD void hybridGeometry(const Tri& t, const int (&cell)[4], V3 q, HybridGeom
 }
 // component k; grad is [nLocal][3][M]
 template<int M>
-GCMB_HD double hybridValue(const HybridGeom& h, const double* values, const double* grad, const int (&cell)[4], int k) {
+GCMB_HD double hybridValue(const HybridGeom& h, const double4* vg, const int (&cell)[4], int k) {
 	V3 g[4];
 	double v[4];
 	for (int i = 0; i < 4; i++) {
-		v[i] = values[(long long) cell[i] * M + k];
-		const double* gi = grad + (long long) cell[i] * 3 * M;
-		g[i] = {gi[0 * M + k], gi[1 * M + k], gi[2 * M + k]};
+		const double4 x = vg[(long long) cell[i] * M + k];
+		v[i] = x.x;
+		g[i] = {x.y, x.z, x.w};
 	}
 	const double (&l)[4] = h.l;
 	double quadratic = l[0] * (v[0] + dot(g[0], h.d[0]) / 2.0);
@@ -472,10 +474,10 @@ GCMB_HD double hybridValue(const HybridGeom& h, const double* values, const doub
 	return l[0] * v[0] + l[1] * v[1] + l[2] * v[2] + l[3] * v[3];
 }
 template<int M>
-GCMB_HD double hybridInterpolate(const Tri& t, const double* values, const double* grad, const int (&cell)[4], int k, V3 q, int& err) {
+GCMB_HD double hybridInterpolate(const Tri& t, const double4* vg, const int (&cell)[4], int k, V3 q, int& err) {
 	HybridGeom h;
 	hybridGeometry(t, cell, q, h, err);
-	return hybridValue<M>(h, values, grad, cell, k);
+	return hybridValue<M>(h, vg, cell, k);
 }
 
 // TetrahedronInterpolator::interpolateInOwner over the 15 tetrahedra of 6 points, split the same way: which
@@ -545,7 +547,7 @@ struct StageS {
 	double dir[3];          // calculation direction = column s of the basis
 	const double* cur;      // PDE vectors [nLocal][M]
 	double* riem;           // Riemann invariants of the current layer
-	double* grad;           // [nLocal][3][M]
+	double4* vg;            // [nLocal][M] {invariant, its gradient} (the values repeat riem)
 	double* next;           // next layer (invariants until the last kernel)
 	unsigned* waves;        // outer invariants of border vertices (bit k)
 	int* errors;            // counter of "the reference would have thrown"
@@ -595,7 +597,7 @@ GCMB_HD unsigned footCharacteristics(const StageS& a, int it, double lambda, uns
 		const V3 q = x0 + shift;
 		for (int i = 0; i < 4; i++) { h.l[i] = f.l[i]; h.d[i] = q - t.localPoint(cell[i]); }
 		if (!isInterpolation(h.l)) { err = 1; }
-		for (int j = 0; j < M; j++) { if ((same >> j) & 1u) { out[j] = hybridValue<M>(h, a.riem, a.grad, cell, j); } }
+		for (int j = 0; j < M; j++) { if ((same >> j) & 1u) { out[j] = hybridValue<M>(h, a.vg, cell, j); } }
 		return 0;
 	}
 	if (f.n == 3 && !borderPass) {
@@ -647,9 +649,9 @@ GCMB_HD unsigned footVectors(const StageS& a, int it, double lambda, unsigned sa
 				double w[4];
 				V3 g[4];
 				for (int i = 0; i < 4; i++) {
-					w[i] = a.riem[(long long) cell[i] * M + j];
-					const double* gi = a.grad + (long long) cell[i] * 3 * M;
-					g[i] = {gi[0 * M + j], gi[1 * M + j], gi[2 * M + j]};
+					const double4 x = a.vg[(long long) cell[i] * M + j];
+					w[i] = x.x;
+					g[i] = {x.y, x.z, x.w};
 				}
 				double quadratic = h.l[0] * (w[0] + dot(g[0], h.d[0]) / 2.0);
 				for (int i = 1; i < 4; i++) { quadratic = quadratic + h.l[i] * (w[i] + dot(g[i], h.d[i]) / 2.0); }
