@@ -312,12 +312,11 @@ def main():
     lib.check(lib.c.gcmb_timer_start(ctxh))
     for _ in range(K):
         for d in range(3):
+            if d == 2:
+                lib.check(lib.c.gcmb_cubic_border_apply(body, 2, 3, capi.dp(zeros3)))
             if d == 0 and world > 1:
                 lib.check(lib.c.gcmb_cubic_halo_exchange(body))
-            if d == 1:  # the free-surface ghost fill of direction 2 rides on the stage before it
-                lib.check(lib.c.gcmb_cubic_stage_then_border(body, 1, tau, 2, 3, capi.dp(zeros3)))
-            else:
-                lib.check(lib.c.gcmb_cubic_stage(body, d, tau))
+            lib.check(lib.c.gcmb_cubic_stage(body, d, tau))
     ms = capi.ctypes.c_float()
     lib.check(lib.c.gcmb_timer_stop(ctxh, capi.ctypes.byref(ms)))
     barrier()

@@ -60,7 +60,6 @@ C_ABI = {
     "gcmb_cubic_halo_put": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "gcmb_comm_allreduce_sum": (ctypes.c_int, [vp, c_double_p, ctypes.c_int]),
     "gcmb_cubic_checksum": (ctypes.c_int, [vp, c_double_p]),
-    "gcmb_cubic_stage_then_border": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, c_double_p]),
     "gcmb_cubic_download_tables": (ctypes.c_int, [vp, c_u8_p]),
     "gcmb_simplex_body_create": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_int_p, c_int_p,
                                                 c_int_p, c_int_p, c_int_p, ctypes.c_int, ctypes.POINTER(vp)]),

@@ -794,36 +794,9 @@ int gcmb_cubic_contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_m
 }
 
 // ---- stage -----------------------------------------------------------------------------------
-namespace {
-
-// the ghost fills gcmb_cubic_border_apply(b, dir, values) would launch, on the buffer `pde`, in its order
-int collect_border_args(gcmb_body* b, int dir, int n_values, const double* values, double* pde, std::vector<BorderArgs>& out) {
-	int need = 0;
-	for (auto& kv : b->borders) { if (kv.second.dir == dir) { need += (int) kv.second.q.size(); } }
-	if (need != n_values || (need > 0 && !values)) { GCMB_FAIL(GCMB_E_INVALID_ARG, "wrong number of border values"); }
-	const Geom& g = b->g;
-	int used = 0;
-	for (auto& kv : b->borders) {
-		BorderCond& c = kv.second;
-		if (c.dir != dir) { continue; }
-		for (int s = 0; s < 2; s++) {
-			if (!c.side_on[s]) { continue; }
-			BorderArgs a;
-			std::memset(&a, 0, sizeof a);
-			a.pde = pde; a.mask = c.mask[s]; a.g = g; a.axis = dir + g.shift; a.side = s;
-			a.nq = (int) c.q.size();
-			for (int i = 0; i < a.nq; i++) { a.q[i] = c.q[(size_t) i]; a.val[i] = values[used + i]; }
-			out.push_back(a);
-		}
-		used += (int) c.q.size();
-	}
-	return GCMB_OK;
-}
-
-int stage_impl(gcmb_body* b, int dir, double tau, int border_dir, int n_values, const double* values) {
+int gcmb_cubic_stage(gcmb_body* b, int dir, double tau) {
 	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
 	if (dir < 0 || dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "direction out of range"); }
-	if (border_dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "border direction out of range"); }
 	if (!b->tables) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
 	if (!(b->tables_tau == tau)) {
@@ -842,45 +815,20 @@ int stage_impl(gcmb_body* b, int dir, double tau, int border_dir, int n_values, 
 	a.dir = dir;
 	a.x_begin = 0;
 	a.x_end = b->g.n[0];
-	a.n_fused = 0;
 	StageLauncher launch = nullptr;
 	const int p = b->pattern_of_dir[dir];
-	const bool sparse = p >= 0 && !b->any_k0;
-	if (sparse) { launch = b->g.bs == 1 ? pattern(p).launch_bs1 : pattern(p).launch_bs2; }
+	if (p >= 0 && !b->any_k0) {
+		launch = b->g.bs == 1 ? pattern(p).launch_bs1 : pattern(p).launch_bs2;
+	}
 	if (!launch) { launch = dense_launcher(b->g.M); }
 	if (!launch) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "no stage kernel for this PDE size"); }
-	// the ghost fill that follows: by the marching kernel itself when it is the one chosen and the faces lie across
-	// the contiguous axis (the expensive case for a separate kernel: one 128-byte line per 16 useful bytes)
-	std::vector<BorderArgs> fills;
-	bool fused = false;
-	if (border_dir >= 0) {
-		const int rc = collect_border_args(b, border_dir, n_values, values, a.nxt, fills);
-		if (rc) { return rc; }
-		static const bool allow = !std::getenv("GCMB_NO_FUSED_BORDER");
-		if (allow && sparse && border_dir + b->g.shift == 2 && march_async_selected(a) && !fills.empty() &&
-		    (int) fills.size() <= MAX_FUSED_BORDERS) {
-			a.n_fused = (int) fills.size();
-			for (int i = 0; i < a.n_fused; i++) { a.fused[i] = fills[(size_t) i]; }
-			fused = true;
-		}
-	}
 	{
 		Launch l(b->ctx, a.axis);
 		launch(a, b->ctx->stream);
 	}
 	GCMB_CUDA(cudaGetLastError());
 	b->cur = 1 - b->cur;  // swapCurrAndNextPdeTimeLayer
-	if (border_dir >= 0 && !fused) { return gcmb_cubic_border_apply(b, border_dir, n_values, values); }
 	return GCMB_OK;
-}
-
-}  // namespace
-
-int gcmb_cubic_stage(gcmb_body* b, int dir, double tau) { return stage_impl(b, dir, tau, -1, 0, nullptr); }
-
-int gcmb_cubic_stage_then_border(gcmb_body* b, int dir, double tau, int border_dir, int n_values, const double* values) {
-	if (border_dir < 0) { GCMB_FAIL(GCMB_E_INVALID_ARG, "border direction out of range"); }
-	return stage_impl(b, dir, tau, border_dir, n_values, values);
 }
 
 const char* gcmb_cubic_stage_kernel_name(gcmb_body* b, int dir) {

@@ -69,20 +69,6 @@ struct StageTable {
 	int dir[MAXM];           // +1 / -1 : side the foot lies on (dx_k > 0 ? +1 : -1)
 };
 
-// one ghost fill of a face: arguments of k_border, and of the fill fused into a stage kernel
-struct BorderArgs {
-	double* pde;
-	const uint8_t* mask;  // face mask or nullptr
-	Geom g;
-	int axis;             // internal axis
-	int side;             // 0 left (inner sign +1), 1 right (inner sign -1)
-	int nq;
-	int q[MAXM + 1];
-	double val[MAXM + 1];
-};
-
-constexpr int MAX_FUSED_BORDERS = 2;
-
 struct StageArgs {
 	const double* cur;
 	double* nxt;
@@ -94,10 +80,6 @@ struct StageArgs {
 	int axis;                 // internal axis of the sweep
 	int dir;                  // reference direction
 	int x_begin, x_end;       // range of internal axis 0 to process (slab sub-ranges for overlap)
-	// ghost fills of the contiguous-axis faces of `nxt`, done by the marching kernel after its sweep (see
-	// fused_border_pass); 0 = none
-	int n_fused;
-	BorderArgs fused[MAX_FUSED_BORDERS];
 };
 
 typedef void (*StageLauncher)(const StageArgs&, cudaStream_t);
@@ -150,7 +132,6 @@ inline bool table_shares_as_pattern(const PatternInfo& p, int bs, const StageTab
 
 // stage_dispatch.cu
 int pattern_count();
-bool march_async_selected(const StageArgs& a);
 const PatternInfo& pattern(int i);
 StageLauncher dense_launcher(int M);
 

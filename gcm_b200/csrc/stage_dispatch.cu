@@ -80,10 +80,7 @@ GCMB_GLOBAL void GCMB_BOUNDS2(MARCH_ZT, MINB) k_stage_march_async(const StageArg
 	const int perp = a.axis == 0 ? (int) blockIdx.z : (int) blockIdx.z + a.x_begin;
 	GCMB_BLOCK_THREADS(tid) {
 		const int i2 = blockIdx.y * MARCH_ZT + tid;
-		if (i2 < a.g.n[2]) {
-			stage_thread_march_async<P, BS, LEAD>(a, ring, tab, tid, perp, i2, s_begin, s_end);
-			if (a.n_fused) { fused_border_pass(a, perp, i2, s_begin, s_end); }
-		}
+		if (i2 < a.g.n[2]) { stage_thread_march_async<P, BS, LEAD>(a, ring, tab, tid, perp, i2, s_begin, s_end); }
 	}
 }
 
@@ -116,12 +113,6 @@ GCMB_GLOBAL void GCMB_BOUNDS(ZTILE) k_stage_ztile(const StageArgs a, int rows) {
 static int env_int(const char* name, int dflt) {
 	const char* v = getenv(name);
 	return v ? atoi(v) : dflt;
-}
-
-// does launch_sparse pick the cp.async marching kernel (the one that can take fused ghost fills) for these arguments?
-bool march_async_selected(const StageArgs& a) {
-	static const int impl = env_int("GCMB_STAGE_IMPL", 2);
-	return impl == 2 && a.axis != 2 && a.packed && a.n_tables <= SMEM_TABLES;
 }
 
 template<class P, int BS>

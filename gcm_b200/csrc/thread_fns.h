@@ -276,6 +276,17 @@ GCMB_HD void face_node(const Geom& g, int axis, long long f, int fixed, int (&it
 // ---------------------------------------------------------------------------------------------
 // border ghost fill (reference engine/cubic/BorderConditions.hpp:97-114): thread = (face node, a)
 // ---------------------------------------------------------------------------------------------
+struct BorderArgs {
+	double* pde;
+	const uint8_t* mask;  // face mask or nullptr
+	Geom g;
+	int axis;             // internal axis
+	int side;             // 0 left (inner sign +1), 1 right (inner sign -1)
+	int nq;
+	int q[MAXM + 1];
+	double val[MAXM + 1];
+};
+
 GCMB_HD void border_thread(const BorderArgs& b, long long f, int a /* 1..bs */) {
 	if (b.mask && !b.mask[f]) { return; }
 	int it[3];
@@ -294,23 +305,6 @@ GCMB_HD void border_thread(const BorderArgs& b, long long f, int a /* 1..bs */) 
 		set_quantity(b.g.D, b.g.M, b.q[j], ghostValue, ghost);
 	}
 	for (int c = 0; c < b.g.M; c++) { b.pde[c * b.g.comp + gi] = ghost[c]; }
-}
-
-// Ghost fill of the faces across the contiguous axis done by the marching stage kernel on its own output: the
-// thread that just wrote the inner layer `a` of a face (its z is fixed, it marched over [s_begin, s_end) along
-// `axis` at the perpendicular index `perp`) mirrors it into ghost layer `a` while the rows are still in L2.
-// Same arithmetic and the same order over the conditions as k_border running after the stage.
-GCMB_HD void fused_border_pass(const StageArgs& a, int perp, int i2, int s_begin, int s_end) {
-	for (int k = 0; k < a.n_fused; k++) {
-		const BorderArgs& b = a.fused[k];
-		const int fixed = b.side == 0 ? 0 : b.g.n[2] - 1;
-		const int layer = b.side == 0 ? i2 - fixed : fixed - i2;
-		if (layer < 1 || layer > b.g.bs) { continue; }
-		for (int s = s_begin; s < s_end; s++) {
-			const long long f = a.axis == 0 ? (long long) s * b.g.n[1] + perp : (long long) perp * b.g.n[1] + s;
-			border_thread(b, f, layer);
-		}
-	}
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -344,26 +344,14 @@ void EngineBase::setUpBorders(const Task& task, Body& body) {
 
 /// reference engine/cubic/Engine.cpp:92-121
 void EngineBase::nextTimeStep() {
-	// values of a body's border conditions of one direction at the current time, in the order of the conditions
-	auto borderValues = [](const Body& body, int direction, bool& any) {
-		std::vector<double> values;
-		any = false;
-		for (const Border& b : body.borders) {
-			if (b.direction != direction) { continue; }
-			any = true;
-			for (const auto& f : b.values) { values.push_back(f(Clock::Time())); }
-		}
-		return values;
-	};
 	for (int stage = 0; stage < D; stage++) {
-		// the ghost fill of the last direction is handed to the stage before it (gcmb_cubic_stage_then_border):
-		// it only reads and writes its own body, so it may follow that body's previous stage directly
-		const bool filledByPreviousStage = D >= 2 && stage == D - 1;
 		for (Body& body : bodies) {
-			if (filledByPreviousStage) { continue; }
-			bool any;
-			const std::vector<double> values = borderValues(body, stage, any);
-			if (any || !body.borders.empty()) {
+			std::vector<double> values;
+			for (const Border& b : body.borders) {
+				if (b.direction != stage) { continue; }
+				for (const auto& f : b.values) { values.push_back(f(Clock::Time())); }
+			}
+			if (!values.empty() || !body.borders.empty()) {
 				check(gcmb_cubic_border_apply(body.mesh->body, stage, (int) values.size(), values.data()));
 			}
 		}
@@ -379,14 +367,7 @@ void EngineBase::nextTimeStep() {
 			for (Body& body : bodies) { check(gcmb_cubic_halo_exchange(body.mesh->body)); }
 		}
 		for (Body& body : bodies) {
-			bool any = false;
-			std::vector<double> values;
-			if (D >= 2 && stage == D - 2) { values = borderValues(body, D - 1, any); }
-			if (any) {
-				check(gcmb_cubic_stage_then_border(body.mesh->body, stage, Clock::TimeStep(), D - 1, (int) values.size(), values.data()));
-			} else {
-				check(gcmb_cubic_stage(body.mesh->body, stage, Clock::TimeStep()));
-			}
+			check(gcmb_cubic_stage(body.mesh->body, stage, Clock::TimeStep()));
 		}
 	}
 	for (Body& body : bodies) {

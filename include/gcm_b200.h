@@ -129,12 +129,6 @@ int gcmb_cubic_contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_m
 /* computes the next time layer of all real nodes along reference direction `dir` and swaps the two
  * layers, like cubic/Engine.cpp:110-111 */
 int gcmb_cubic_stage(gcmb_body* body, int dir, double tau);
-/* gcmb_cubic_stage(body, dir, tau) followed by gcmb_cubic_border_apply(body, border_dir, n_values, values): the
- * result is the same, but when border_dir is the contiguous (last) direction the stage kernel fills those ghost
- * layers itself while its output rows are still in cache.  A body's ghost fill for the next stage only reads and
- * writes that body, so it may follow the previous stage directly (engine/cubic/Engine.cpp:92-113 runs it after all
- * bodies finished that stage; contact copies still come later). */
-int gcmb_cubic_stage_then_border(gcmb_body* body, int dir, double tau, int border_dir, int n_values, const double* values);
 
 /* ---- Maxwell viscosity (rheology/ode/Ode.hpp:28-38): sigma *= decay[table of the node];
  * decay = exp(-tau/tau0) is evaluated by the caller with the host libm, like the reference ------- */

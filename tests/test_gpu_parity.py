@@ -37,10 +37,9 @@ def test_cuda_engine_matches_reference_bitwise(lib, name):
 
 
 @pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "5"},
-                                 {"GCMB_MARCH_SEG": "0"}, {"GCMB_NO_FUSED_BORDER": "1"}])
+                                 {"GCMB_MARCH_SEG": "0"}])
 def test_kernel_variants_match_reference(env):
-    """dense / direct / marching-with-odd-segments kernels, ghost fill fused into the stage or not: every variant
-    reproduces the reference bits."""
+    """dense / direct / marching-with-odd-segments kernels: every variant reproduces the reference bits."""
     code = ("import sys; sys.path[:0] = [%r, %r]\n"
             "import gcm_b200\n"
             "from helpers import compare_with_golden\n"
@@ -242,31 +241,3 @@ def test_launcher_simplex_plate_gpu(tmp_path):
     assert "would have thrown on = 0" in out.stdout
     checksum = float(re.search(r"checksum = (\S+)", out.stdout).group(1))
     assert np.isfinite(checksum) and checksum != 0
-
-
-def test_fused_border_fill_is_used_and_equal(lib):
-    """gcmb_cubic_stage_then_border: same state (ghosts included) as stage + border_apply, one launch fewer"""
-    from scenarios import acoustic3d_free
-    text = acoustic3d_free(n=40, steps=3)
-    states, launches = [], []
-    for fused in (True, False):
-        eng = gcm_b200.HostEngine(lib, text)
-        body, ctx = eng.body_handle(0), eng.context_handle()
-        tau = eng.info()[2]
-        n0 = lib.c.gcmb_launch_count(ctx)
-        zeros = np.zeros(1)   # one condition (PRESSURE) on both z faces
-        for d in range(3):
-            if d == 1 and fused:
-                lib.check(lib.c.gcmb_cubic_stage_then_border(body, 1, tau, 2, 1, capi.dp(zeros)))
-            else:
-                lib.check(lib.c.gcmb_cubic_stage(body, d, tau))
-                if d == 1:
-                    lib.check(lib.c.gcmb_cubic_border_apply(body, 2, 1, capi.dp(zeros)))
-        launches.append(lib.c.gcmb_launch_count(ctx) - n0)
-        D, M, sizes, _ = eng.body_info(0)
-        full = np.zeros(int(np.prod(np.array(sizes) + 4)) * M)
-        lib.check(lib.c.gcmb_cubic_download_state(body, full.ctypes.data_as(capi.vp), 1))
-        states.append(full)
-        eng.close()
-    assert np.array_equal(states[0], states[1]) and np.abs(states[0]).max() > 0
-    assert launches[0] == 3 and launches[1] == 5, launches
