@@ -286,3 +286,57 @@ def protocol_queries(mesh, n_dirs=16, lengths=9, scale=1.0, vertices=None):
     sh = (dirs[None, :, None, :] * lens[None, None, :, None]).reshape(1, -1, 3)
     sh = np.broadcast_to(sh, (len(vs), sh.shape[1], 3)).reshape(-1, 3).copy()
     return v, sh
+
+
+def write_flat_dump(tri, path):
+    """the mesh file of oracle/_ref/gcm_ref_simplex (oracle/shim/CGAL/flat_triangulation_3.h): "nV nC", points,
+    then per cell 4 vertices, 4 neighbours, grid id"""
+    with open(path, "w") as f:
+        f.write("%d %d\n" % (len(tri["xyz"]), len(tri["cell_v"])))
+        for p in tri["xyz"]:
+            f.write("%.17e %.17e %.17e\n" % tuple(p))
+        for v, n, g in zip(tri["cell_v"], tri["cell_n"], tri["cell_grid"]):
+            f.write("%d %d %d %d %d %d %d %d %d\n" % (tuple(v) + tuple(n) + (g,)))
+
+
+def run_reference_simplex(task_text, tri, workdir, bodies, M):
+    """the UNMODIFIED reference simplex engine (with the CGAL stand-in) on the given triangulation: returns
+    {body: (coords [n,3], pde [n,M])}, meta"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(oh.__file__)), "_ref", "gcm_ref_simplex")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-j8", "-C", os.path.dirname(exe) + "/..", "ref_simplex"], check=True)
+    os.makedirs(os.path.join(workdir, "snapshots"), exist_ok=True)
+    mesh = os.path.join(workdir, "mesh.flat")
+    write_flat_dump(tri, mesh)
+    task = os.path.join(workdir, "task.txt")
+    open(task, "w").write(task_text + "\nsimplex_flat %s\n" % mesh)
+    r = subprocess.run([exe, task, os.path.join(workdir, "out")], cwd=workdir, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcm_ref_simplex failed: " + r.stdout[-2000:] + r.stderr[-2000:])
+    meta = {}
+    for line in open(os.path.join(workdir, "out.meta")):
+        w = line.split()
+        if w[0] == "body":
+            meta[("body", int(w[1]))] = {w[i]: float(w[i + 1]) for i in range(2, len(w), 2)}
+        else:
+            meta[w[0]] = float(w[1])
+    meta["cell_grid"] = np.loadtxt(os.path.join(workdir, "out.cells"), dtype=np.int64).astype(np.int32)
+    out = {}
+    for b in bodies:
+        raw = np.fromfile(os.path.join(workdir, "out.body%d.f64" % b)).reshape(-1, 3 + M)
+        out[b] = (raw[:, :3].copy(), raw[:, 3:].copy())
+    return out, meta
+
+
+def write_inm_all_cells(tri, cell_grid, path):
+    """INM-format mesh file that keeps EVERY cell (empty ones with material -1) in the triangulation's order, so that
+    a body built from it sees the same cells, neighbours and incident lists as the flat dump"""
+    with open(path, "w") as f:
+        f.write("%d\n" % len(tri["xyz"]))
+        for p in tri["xyz"]:
+            f.write("%.17e %.17e %.17e\n" % tuple(p))
+        f.write("%d\n" % len(tri["cell_v"]))
+        for v, g in zip(tri["cell_v"], cell_grid):
+            f.write("%d %d %d %d %d\n" % (v[0] + 1, v[1] + 1, v[2] + 1, v[3] + 1, g))
+        f.write("0\n")
