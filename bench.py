@@ -211,7 +211,7 @@ def simplex_section(lib, device, steps, warmup, with_cpu):
            "gpu_launches": int(lib.c.gcmb_launch_count(ctxh) - launches0),
            "config": {"workload": "%dx%dx%d cubes of edge %g cut into 6 tetrahedra each, jitter 0.3, inner cavity: %d vertices; "
                                   "identity calculation basis, fixed zero force on all borders, Courant 0.7" % (nx, ny, nz, h, info["n_local"])},
-           "parity": "unpinned (the reference's simplex engine needs CGAL; oracle/simplex_oracle.c restates it)"}
+           "parity": "bit-identical to the unmodified reference simplex engine built against a CGAL stand-in (tests/golden/simplex_*.npz)"}
     eng.close()
     if with_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -31,7 +31,7 @@ def build_oracle():
     """Compile oracle/_ref/libgcm_oracle.so (and gcm_ref when the reference tree is present)."""
     subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
     if os.path.isdir("/root/reference/src"):
-        subprocess.run(["make", "-s", "-j8", "-C", HERE, "ref"], check=True)
+        subprocess.run(["make", "-s", "-j8", "-C", HERE, "ref", "ref_simplex"], check=True)
 
 
 def lib():

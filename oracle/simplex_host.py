@@ -1,5 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY — drives oracle/simplex_oracle.c (CPU restatement of the reference's simplex GCM, parity
-unpinned: see the header of simplex_oracle.h) over whole time steps of one body.  Used by bench.py's cpu_baseline
+"""TEST INFRASTRUCTURE ONLY — drives oracle/simplex_oracle.c (CPU restatement of the reference's simplex GCM, pinned
+against the unmodified reference engine: see the header of simplex_oracle.h) over whole time steps of one body.  Used by bench.py's cpu_baseline
 leg; nothing under gcm_b200/ may import this."""
 import ctypes
 import time

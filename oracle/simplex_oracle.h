@@ -2,13 +2,22 @@
  * TEST INFRASTRUCTURE ONLY — plain-C CPU restatement of the reference's simplex (tetrahedral) GCM path.
  * Nothing under gcm_b200/ may include, link or call this.
  *
- * Parity status: **parity unpinned**.  The reference's simplex engine needs CGAL (absent from this image and
- * not vendored: `find_package(CGAL 4.8)`, /root/reference/CMakeLists.txt:41-43), so it cannot be compiled here,
- * and none of its tests pins a cell index or a non-trivial field value.  This file restates the
- * published algorithm line by line from the reference sources cited at every function and is anchored on the
- * reference tests' PROPERTIES (tests/test_simplex_*.py): containment of the query in the returned cell for
- * every vertex x 16x16 directions x 9 lengths (src/test/sequence/TestLineWalkSearch3D.cpp:120-154), interpolator
- * exactness on linear/quadratic fields (TestInterpolator.cpp:129-252), zero stays zero (TestSimplexGcm.cpp:29-67).
+ * Parity status: **pinned**.  The reference's simplex engine needs CGAL (absent from this image and not vendored:
+ * `find_package(CGAL 4.8)`, /root/reference/CMakeLists.txt:41-43), but CGAL is only its container: oracle/Makefile
+ * builds oracle/_ref/gcm_ref_simplex from the UNMODIFIED reference sources (engine/simplex/Engine.cpp,
+ * grid/simplex/SimplexGrid.cpp, grid/simplex/cgal/CgalTriangulation.cpp + .hpp, Cgal3DTriangulation.hpp, LineWalker.hpp,
+ * both GCMs, the correctors, interpolators, linal) against a stand-in for the handful of CGAL calls they make
+ * (shim/CGAL/flat_triangulation_3.h: cells from a file instead of a Delaunay triangulation) and a restatement of
+ * GSL's LU (shim/libgcm/util/math/GslUtils.hpp).  tests/golden/simplex_*.npz hold that engine's results on five
+ * scenarios (cavity, two bodies in contact, rotated basis, both GCM types, elastic and acoustic); this restatement,
+ * driven in the reference's order, reproduces every value bit for bit (tests/test_host_logic_emul.py
+ * ::test_simplex_oracle_matches_reference_bitwise), and so does the product (…::test_simplex_engine_matches_
+ * reference_bitwise on the stepping harness, tests/test_gpu_parity.py::test_simplex_cuda_engine_matches_reference_
+ * bitwise on the GPU).  What stays outside the pin: CGAL's own meshing/Delaunay code and its (unspecified) order of
+ * incident cells, which both sides replace by ascending cell ids.  The reference tests' PROPERTIES are asserted as
+ * well: containment of the query in the returned cell for every vertex x 16x16 directions x 9 lengths
+ * (src/test/sequence/TestLineWalkSearch3D.cpp:120-154), gradient exactness on linear fields, zero stays zero
+ * (TestSimplexGcm.cpp:29-67).
  *
  * Topology is a flat triangulation (our own, CGAL-free): points, 4 vertex ids and 4 neighbour ids per cell
  * (neighbour i is opposite vertex i, -1 outside the hull), a grid id per cell (EMPTY = no body), and the

@@ -1,0 +1,58 @@
+"""Golden vectors of the simplex path from the UNMODIFIED reference engine.
+
+oracle/_ref/gcm_ref_simplex is the reference's simplex::Engine<3, CgalTriangulation> (engine/simplex/Engine.cpp,
+grid/simplex/SimplexGrid.cpp, cgal/CgalTriangulation.cpp, LineWalker.hpp, the GCMs, correctors, interpolators, linal --
+compiled where they lie) with CGAL replaced by the flat container of oracle/shim/CGAL/flat_triangulation_3.h and GSL's
+LU by its restatement (oracle/shim/libgcm/util/math/GslUtils.hpp).  For each scenario this script
+  1. builds a triangulation with the product's box mesher (host library on the stepping harness: mesh generation is
+     plain host C++),
+  2. runs the reference engine on it; the reference first cleans the triangulation's body ids (hanged cells,
+     disconnected cell sets: CgalTriangulation.cpp:8-112) and the cleaned ids are kept,
+  3. stores the triangulation with the cleaned ids, the task text and the reference's final PDE values per body.
+Run in the build container:  python tests/golden/make_simplex_golden.py"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import helpers  # noqa: E402
+import simplex_cases  # noqa: E402
+from gcm_b200 import capi  # noqa: E402
+from simplex_helpers import run_reference_simplex  # noqa: E402
+
+SCENARIOS = {
+    # name: (model, bodies, gcm_type, basis, steps)
+    "elastic_cavity": (0, 1, 0, "identity", 4),
+    "elastic_contact": (0, 2, 0, "identity", 4),
+    "acoustic_contact_rotated": (1, 2, 0, "rotated", 4),
+    "elastic_contact_pde_vectors": (0, 2, 1, "rotated", 4),
+    "acoustic_pde_vectors": (1, 1, 1, "identity", 4),
+}
+
+
+def main():
+    lib = helpers.emul_library()
+    for name, (model, bodies, gcm, basis, steps) in SCENARIOS.items():
+        text = simplex_cases.golden_scenario(model, bodies, gcm, basis, steps)
+        eng = capi.SimplexHostEngine(lib, text)
+        tri = eng.triangulation()
+        eng.close()
+        M = 9 if model == 0 else 4
+        ref, meta = run_reference_simplex(text, tri, tempfile.mkdtemp(), range(bodies), M)
+        out = dict(task=np.array(text), xyz=tri["xyz"], cell_v=tri["cell_v"], cell_n=tri["cell_n"], cell_grid=meta["cell_grid"],
+                   cell_grid_before_cleanup=tri["cell_grid"], time=meta["time"], tau=meta["tau"], steps=int(meta["steps"]), model=model,
+                   bodies=bodies, gcm_type=gcm)
+        for b in range(bodies):
+            out["coords%d" % b], out["pde%d" % b] = ref[b]
+            out["average_height%d" % b] = meta[("body", b)]["average_height"]
+        np.savez_compressed(os.path.join(HERE, "simplex_%s.npz" % name), **out)
+        print(name, "cells", len(tri["cell_v"]), "changed by the reference clean-up", int((meta["cell_grid"] != tri["cell_grid"]).sum()),
+              "max |u|", max(np.abs(ref[b][1]).max() for b in range(bodies)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,7 @@
 """Simplex-path checks shared by the CPU (stepping harness) and GPU test modules.
-The oracle is oracle/simplex_oracle.c — parity UNPINNED by the reference (no CGAL here, no pinned values in its
-tests); these checks therefore also assert the PROPERTIES the reference's own tests assert."""
+The oracle is oracle/simplex_oracle.c, pinned by the fixtures of the unmodified reference engine
+(tests/golden/simplex_*.npz, see check_engine_against_reference / check_oracle_against_reference below); the checks
+also assert the PROPERTIES the reference's own tests assert."""
 import ctypes
 
 import numpy as np
@@ -364,9 +365,12 @@ def engine_scenario(model, bodies=2, basis="identity", cavity=True, steps=3, gcm
     return "\n".join(lines) + "\n", values
 
 
-def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3, gcm_type=0):
+def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3, gcm_type=0, text=None, golden=None):
+    """the host engine, step by step, against oracle/simplex_oracle.c driven in the reference's order; with `golden`
+    (a fixture of the unmodified reference engine) the restatement's final state must equal the reference's too"""
     L = oracle()
-    text, values = engine_scenario(model, bodies, basis, cavity, steps, gcm_type)
+    scenario_text, values = engine_scenario(model, bodies, basis, cavity, steps, gcm_type)
+    text = scenario_text if text is None else text
     eng = capi.SimplexHostEngine(lib, text)
     M = 9 if model == 0 else 4
     tri = eng.triangulation()
@@ -439,4 +443,78 @@ def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3, g
             assert np.array_equal(got, state[i]), (step, i, np.abs(got - state[i]).max())
     assert eng.errors() == 0
     assert all(np.isfinite(p).all() and np.abs(p).max() < 10 for p in state)
+    if golden is not None:
+        assert time == float(golden["time"]) and tau == float(golden["tau"])
+        for i in ids:
+            assert np.array_equal(state[i], golden["pde%d" % i]), "the restatement differs from the reference engine"
+    eng.close()
+
+
+def check_oracle_against_reference(lib, name, workdir):
+    """oracle/simplex_oracle.c (driven in the reference's order from the host engine's set-up) reproduces the
+    unmodified reference engine's final state bit for bit: this pins the restatement"""
+    g = load_golden(name)
+    basis = "identity" if "basis 1 0 0 0 1 0 0 0 1" in str(g["task"]) else "rotated"
+    check_engine(lib, int(g["model"]), bodies=int(g["bodies"]), basis=basis, steps=int(g["steps"]), gcm_type=int(g["gcm_type"]),
+                 text=golden_task_with_mesh(g, workdir), golden=g)
+
+
+# ---- golden vectors from the unmodified reference engine (tests/golden/make_simplex_golden.py) -------------------
+def golden_scenario(model, bodies, gcm, basis, steps):
+    """engine_scenario on a 7x6x8 box with a cavity of about 100 cells that survives the reference's clean-up"""
+    text, _ = engine_scenario(model, bodies=bodies, steps=steps, gcm_type=gcm, cavity=True, basis=basis)
+    lines = []
+    for ln in text.split("\n"):
+        if ln.startswith("simplex_box"):
+            ln = "simplex_box 7 6 8 0 0 0 0.5 jitter 0.3 seed 7"
+        if ln.startswith("cavity"):
+            ln = "cavity box 1.1 0.9 1.6 2.3 2.1 2.9"
+        if ln.startswith("region 0"):
+            ln = "region 0 box -10 -10 -10 10 10 2.0"
+        if ln.startswith("region 1"):
+            ln = "region 1 box -10 -10 2.0 10 10 10"
+        if ln.startswith("border_condition box"):
+            ln = ln.replace("2.999", "3.999")
+        if ln.startswith("initial quantity"):
+            ln = "initial quantity PRESSURE 1 sphere 0.9 1.6 1.4 1.8"
+        lines.append(ln)
+    return "\n".join(lines)
+
+
+GOLDEN_SIMPLEX = ["elastic_cavity", "elastic_contact", "acoustic_contact_rotated", "elastic_contact_pde_vectors", "acoustic_pde_vectors"]
+
+
+def load_golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "simplex_%s.npz" % name))
+
+
+def golden_task_with_mesh(g, workdir):
+    """the fixture's task text reading the fixture's triangulation (with the reference-cleaned body ids) from an INM file"""
+    import os
+    from simplex_helpers import write_inm_all_cells
+    tri = dict(xyz=g["xyz"], cell_v=g["cell_v"], cell_n=g["cell_n"], cell_grid=g["cell_grid"])
+    inm = os.path.join(str(workdir), "mesh.inm")
+    write_inm_all_cells(tri, g["cell_grid"], inm)
+    keep = [ln for ln in str(g["task"]).split("\n") if not ln.startswith(("simplex_box", "region", "cavity"))]
+    return "\n".join(keep) + "\nsimplex_mesh %s\n" % inm
+
+
+def check_engine_against_reference(lib, name, workdir):
+    """the product's simplex::Engine == the unmodified reference engine: time step, step count and every PDE value
+    of every body, bit for bit"""
+    g = load_golden(name)
+    eng = capi.SimplexHostEngine(lib, golden_task_with_mesh(g, workdir))
+    tri = eng.triangulation()
+    assert np.array_equal(tri["cell_n"], g["cell_n"])        # the topology built from the file is the fixture's
+    eng.run()
+    steps, time, tau = eng.info()
+    assert (steps, time, tau) == (int(g["steps"]), float(g["time"]), float(g["tau"]))
+    for b in range(int(g["bodies"])):
+        assert eng.simplex_body_info(b)["average_height"] == float(g["average_height%d" % b])
+        got = eng.simplex_pde(b)
+        ref = g["pde%d" % b]
+        assert got.shape == ref.shape and np.abs(ref).max() > 0.05
+        assert np.array_equal(got, ref), (name, b, np.abs(got - ref).max())
+    assert eng.errors() == 0
     eng.close()

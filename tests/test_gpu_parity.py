@@ -151,7 +151,7 @@ def test_reference_two_layers(lib, vary):
         assert abs(rs - rs_theory) < 1e-2 and abs(rv - rv_theory) < 1e-2, (rs, rs_theory, rv, rv_theory)
 
 
-# ---- simplex path on the device; oracle: oracle/simplex_oracle.c (parity unpinned) --------
+# ---- simplex path on the device; oracle: oracle/simplex_oracle.c (pinned by tests/golden/simplex_*.npz) --------
 def test_simplex_vertex_info_gpu(lib):
     import simplex_cases
     simplex_cases.check_vertex_info(lib)
@@ -241,3 +241,13 @@ def test_launcher_simplex_plate_gpu(tmp_path):
     assert "would have thrown on = 0" in out.stdout
     checksum = float(re.search(r"checksum = (\S+)", out.stdout).group(1))
     assert np.isfinite(checksum) and checksum != 0
+
+
+import simplex_cases as _sx  # noqa: E402
+
+
+@pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX)
+def test_simplex_cuda_engine_matches_reference_bitwise(lib, name, tmp_path):
+    """the CUDA simplex path == the UNMODIFIED reference simplex engine (compiled against a CGAL stand-in,
+    tests/golden/make_simplex_golden.py): time step, step count and every PDE value of every body"""
+    _sx.check_engine_against_reference(lib, name, tmp_path)

@@ -128,7 +128,7 @@ def test_reference_two_layers(lib, vary):
         assert abs(rs - rs_theory) < 1e-2 and abs(rv - rv_theory) < 1e-2, (rs, rs_theory, rv, rv_theory)
 
 
-# ---- simplex path on the stepping harness (oracle: oracle/simplex_oracle.c, parity unpinned) -----------------
+# ---- simplex path on the stepping harness (oracle: oracle/simplex_oracle.c, pinned by tests/golden/simplex_*.npz) -----------------
 def test_simplex_vertex_info(lib):
     import simplex_cases
     simplex_cases.check_vertex_info(lib)
@@ -281,3 +281,17 @@ def test_inm_mesh_file_round_trip(lib, tmp_path):
         assert np.abs(ref[body]).max() > 0.1 and np.array_equal(ref[body], b.simplex_pde(body))
     assert b.errors() == 0
     b.close()
+
+
+# ---- simplex path against the UNMODIFIED reference engine (fixtures: tests/golden/make_simplex_golden.py) ----------
+import simplex_cases as _sx  # noqa: E402
+
+
+@pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX)
+def test_simplex_engine_matches_reference_bitwise(lib, name, tmp_path):
+    _sx.check_engine_against_reference(lib, name, tmp_path)
+
+
+@pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX)
+def test_simplex_oracle_matches_reference_bitwise(lib, name, tmp_path):
+    _sx.check_oracle_against_reference(lib, name, tmp_path)
