@@ -7,7 +7,7 @@
 // service for this code; the cell location itself is the reference's own line walk).  The mesh is a "flat" dump
 // written by the tests from the product's box mesher, so both sides work on the very same triangulation.
 //
-// usage: gcm_ref_simplex <task-file> <dump-prefix>
+// usage: gcm_ref_simplex <task-file> <dump-prefix> [--locate <queries-file>]
 //   task file: the simplex subset of the plain-text task format (gcm_b200/host/task_file.cpp) with
 //              "simplex_flat FILE" naming the mesh dump (simplex_box/region/cavity lines are ignored)
 //   <dump-prefix>.body<ID>.f64  per local vertex: x y z, then the M PDE values (raw doubles)
@@ -151,9 +151,33 @@ void dumpBody(const Engine3& engine, const size_t id, const std::string& prefix,
 }  // namespace
 
 
+/// --locate: SimplexGrid::findCellCrossedByTheRay (grid/simplex/SimplexGrid.cpp:61-112) of the reference for a list of
+/// queries "body local_vertex sx sy sz"; one answer "n p0 p1 p2 p3" per line (local vertex indices, -1 padding), or
+/// "throw" where the reference throws.  The grids are built on the reference-cleaned triangulation, like the engine's.
+int locateMode(const Task& task, const std::string& queriesFile, const std::string& outFile) {
+	CgalTriangulation<3, VertexInfo, CellInfoT<4>> triangulation(task);
+	std::map<size_t, std::shared_ptr<Grid3>> grids;
+	for (const auto& b : task.bodies) { grids[b.first] = std::make_shared<Grid3>(b.first, Grid3::ConstructionPack({&triangulation})); }
+	std::ifstream in(queriesFile);
+	std::ofstream out(outFile);
+	size_t body, vertex;
+	Real3 shift;
+	while (in >> body >> vertex >> shift(0) >> shift(1) >> shift(2)) {
+		try {
+			const Grid3::Cell c = grids.at(body)->findCellCrossedByTheRay(Grid3::Iterator(vertex), shift);
+			out << c.n;
+			for (int i = 0; i < 4; i++) { out << " " << (i < c.n ? (long) c(i).iter : -1L); }
+			out << "\n";
+		} catch (Exception&) {
+			out << "throw\n";
+		}
+	}
+	return 0;
+}
+
 int main(int argc, char** argv) {
 	if (argc < 3) {
-		fprintf(stderr, "usage: %s <task-file> <dump-prefix>\n", argv[0]);
+		fprintf(stderr, "usage: %s <task-file> <dump-prefix> [--locate <queries-file>]\n", argv[0]);
 		return 2;
 	}
 	MPI_Init(&argc, &argv);
@@ -161,6 +185,7 @@ int main(int argc, char** argv) {
 		Task task;
 		std::map<size_t, bool> acousticBodies;
 		parseTaskFile(argv[1], task, acousticBodies);
+		if (argc > 4 && std::string(argv[3]) == "--locate") { return locateMode(task, argv[4], std::string(argv[2]) + ".located"); }
 		{
 			// grid ids of the finite cells after the reference's own clean-up of the triangulation
 			// (CgalTriangulation.cpp:8-112: hanged cells, disconnected cell sets), in file order

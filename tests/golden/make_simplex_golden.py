@@ -54,5 +54,37 @@ def main():
               "max |u|", max(np.abs(ref[b][1]).max() for b in range(bodies)))
 
 
+def locate_golden():
+    """SimplexGrid::findCellCrossedByTheRay of the reference over the protocol of TestLineWalkSearch3D.cpp:120-154
+    (16 x 16 directions x 9 lengths) from every third vertex of both bodies of the elastic_contact fixture"""
+    import subprocess
+    from simplex_helpers import Mesh, protocol_queries, write_flat_dump
+    g = simplex_cases.load_golden("elastic_contact")
+    tri = dict(xyz=g["xyz"], cell_v=g["cell_v"], cell_n=g["cell_n"], cell_grid=g["cell_grid"])
+    wd = tempfile.mkdtemp()
+    os.makedirs(os.path.join(wd, "snapshots"))   # the reference's grids write cell-height histograms there
+    write_flat_dump(tri, os.path.join(wd, "mesh.flat"))
+    open(os.path.join(wd, "task.txt"), "w").write(str(g["task"]) + "\nsimplex_flat %s\n" % os.path.join(wd, "mesh.flat"))
+    out = {}
+    for body in (0, 1):
+        m = Mesh.from_arrays(dict(tri, inc_off=None, inc_cell=None), body)
+        vs = np.arange(0, m.n_local, 3)
+        v, sh = protocol_queries(m, 16, 9, scale=0.4, vertices=vs)
+        with open(os.path.join(wd, "queries.txt"), "w") as f:
+            for a, s in zip(v, sh):
+                f.write("%d %d %.17e %.17e %.17e\n" % (body, a, s[0], s[1], s[2]))
+        exe = os.path.join(ROOT, "oracle", "_ref", "gcm_ref_simplex")
+        subprocess.run([exe, os.path.join(wd, "task.txt"), os.path.join(wd, "out"), "--locate", os.path.join(wd, "queries.txt")], check=True, cwd=wd)
+        rows = []
+        for line in open(os.path.join(wd, "out.located")):
+            rows.append([-9] * 5 if line.startswith("throw") else [int(x) for x in line.split()])
+        out["located%d" % body] = np.array(rows, dtype=np.int16)
+        out["vertices%d" % body] = vs.astype(np.int32)
+        print("body", body, "queries", len(rows), "histogram of n", np.bincount(np.maximum(out["located%d" % body][:, 0], 0), minlength=5),
+              "throws", int((out["located%d" % body][:, 0] == -9).sum()))
+    np.savez_compressed(os.path.join(HERE, "simplex_locate_protocol.npz"), **out)
+
+
 if __name__ == "__main__":
     main()
+    locate_golden()

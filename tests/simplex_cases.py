@@ -518,3 +518,38 @@ def check_engine_against_reference(lib, name, workdir):
         assert np.array_equal(got, ref), (name, b, np.abs(got - ref).max())
     assert eng.errors() == 0
     eng.close()
+
+
+def check_locate_against_reference(lib, with_oracle=False):
+    """gcmb_simplex_locate == SimplexGrid::findCellCrossedByTheRay of the UNMODIFIED reference
+    (grid/simplex/SimplexGrid.cpp:61-112) over the protocol of src/test/sequence/TestLineWalkSearch3D.cpp:120-154:
+    16 x 16 directions x 9 lengths from every third vertex of both bodies of the elastic_contact fixture,
+    428 544 queries, integer for integer"""
+    import os
+    g = load_golden("elastic_contact")
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "simplex_locate_protocol.npz"))
+    tri = dict(xyz=np.ascontiguousarray(g["xyz"]), cell_v=np.ascontiguousarray(g["cell_v"]), cell_n=np.ascontiguousarray(g["cell_n"]),
+               cell_grid=np.ascontiguousarray(g["cell_grid"]))
+    # incident cells of every vertex in ascending cell id
+    order = np.argsort(tri["cell_v"].ravel(), kind="stable")
+    counts = np.bincount(tri["cell_v"].ravel(), minlength=len(tri["xyz"]))
+    tri["inc_off"] = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    tri["inc_cell"] = (order // 4).astype(np.int32)
+    ctx = capi.Context(lib)
+    L = oracle() if with_oracle else None
+    for body in (0, 1):
+        m = Mesh.from_arrays(tri, body)
+        vs = ref["vertices%d" % body]
+        v, sh = protocol_queries(m, 16, 9, scale=0.4, vertices=vs)
+        want = ref["located%d" % body].astype(np.int32)
+        assert len(want) == len(v) and (want[:, 0] >= 0).all()
+        sb = SimplexBody(lib, ctx, m, 0)
+        got = sb.locate(v, sh)
+        assert sb.errors() == 0
+        assert np.array_equal(got, want), "cell location differs from the reference in %d of %d queries" % ((got != want).any(axis=1).sum(), len(v))
+        sb.close()
+        if with_oracle:
+            pick = np.arange(0, len(v), 7)
+            o, errs = oracle_locate_all(L, m, v[pick], sh[pick])
+            assert errs == 0 and np.array_equal(o, want[pick])
+    ctx.close()

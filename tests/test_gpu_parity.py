@@ -251,3 +251,7 @@ def test_simplex_cuda_engine_matches_reference_bitwise(lib, name, tmp_path):
     """the CUDA simplex path == the UNMODIFIED reference simplex engine (compiled against a CGAL stand-in,
     tests/golden/make_simplex_golden.py): time step, step count and every PDE value of every body"""
     _sx.check_engine_against_reference(lib, name, tmp_path)
+
+
+def test_simplex_cuda_cell_location_matches_reference(lib):
+    _sx.check_locate_against_reference(lib)

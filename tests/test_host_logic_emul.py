@@ -295,3 +295,7 @@ def test_simplex_engine_matches_reference_bitwise(lib, name, tmp_path):
 @pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX)
 def test_simplex_oracle_matches_reference_bitwise(lib, name, tmp_path):
     _sx.check_oracle_against_reference(lib, name, tmp_path)
+
+
+def test_simplex_cell_location_matches_reference(lib):
+    _sx.check_locate_against_reference(lib, with_oracle=True)
