@@ -429,6 +429,7 @@ struct FlatTriangulation {
 	std::vector<int> incOff;     ///< [nV+1]
 	std::vector<int> incCell;    ///< incident cells, ascending id
 	void buildTopology();        ///< orientation, neighbours, incidence from xyz + cellV (+ cellGrid)
+	int cleanBodyIds();          ///< the reference's clean-up of hanged cells and disconnected cell sets
 };
 FlatTriangulation makeBoxMesh(int nx, int ny, int nz, const Real3& origin, real h, real jitter, unsigned seed,
 		const Real3* voidMin, const Real3* voidMax, int gridId);

@@ -188,6 +188,7 @@ void Engine::createTriangulation(const Task& task) {
 				throw Exception(GCMB_E_INVALID_ARG, "the mesh file has cells of body " + std::to_string(id) + " which the task does not describe");
 			}
 		}
+		triangulation.cleanBodyIds();
 		return;
 	}
 	if (g.mesher != Task::SimplexGrid::Mesher::BOX_MESHER) {
@@ -216,6 +217,7 @@ void Engine::createTriangulation(const Task& task) {
 		for (const auto& cavity : g.cavities) { if (cavity->contains(center)) { id = EmptySpaceFlag; } }
 		triangulation.cellGrid[(size_t) c] = id;
 	}
+	triangulation.cleanBodyIds();   // CgalTriangulation's constructor (grid/simplex/cgal/CgalTriangulation.cpp:8-39)
 }
 
 /// engine/simplex/Engine.cpp:52-91 + DefaultMesh::setUpPde (DefaultMesh.hpp:63-70,227-267)

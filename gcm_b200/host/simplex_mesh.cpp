@@ -9,9 +9,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <list>
 #include <map>
+#include <set>
 
 #include "gcmb_host.hpp"
 
@@ -102,6 +105,137 @@ FlatTriangulation makeBoxMesh(int nx, int ny, int nz, const Real3& origin, real 
 	}
 	t.buildTopology();
 	return t;
+}
+
+/// The clean-up of the body ids that the reference's triangulation constructor runs after meshing
+/// (grid/simplex/cgal/CgalTriangulation.cpp:8-112 with CgalTriangulation.hpp:206-290): cells none of whose four
+/// neighbours carries their id take the most common neighbouring id ("hanged cells"), and around every vertex
+/// where some id forms several disconnected sets of cells, all but the largest set of the id with the most sets are
+/// handed to another id; repeated until nothing changes, at most ten times.  The hull's outside counts as empty
+/// space (CGAL's infinite cells: one per hull facet, joined across the hull edges).  Ids compare as the reference's
+/// GridId (size_t): empty space, (size_t)(-1), is the largest.  Where the reference picks "a random other id" it
+/// calls libc's rand(); so does this (the outcome then depends on the process' rand() state, as the reference's).
+/// Returns the number of cells whose id changed.
+int FlatTriangulation::cleanBodyIds() {
+	typedef unsigned long long Id;
+	auto idOf = [this](int cell) -> Id { return (Id) (long long) cellGrid[(size_t) cell]; };   // -1 -> max
+	// infinite cells: ids nC.., vertices (a, b, c, infinite = -1), neighbours like CGAL's
+	std::vector<std::array<int, 4>> infV, infN;
+	std::vector<std::array<int, 4>> nb((size_t) nC);
+	std::map<std::array<int, 2>, std::vector<std::array<int, 2>>> hullEdges;
+	for (int c = 0; c < nC; c++) for (int k = 0; k < 4; k++) { nb[(size_t) c][(size_t) k] = cellN[(size_t) 4 * c + k]; }
+	for (int c = 0; c < nC; c++) for (int k = 0; k < 4; k++) {
+		if (cellN[(size_t) 4 * c + k] >= 0) { continue; }
+		std::array<int, 4> v = {{-1, -1, -1, -1}};
+		int m = 0;
+		for (int j = 0; j < 4; j++) { if (j != k) { v[(size_t) m++] = cellV[(size_t) 4 * c + j]; } }
+		const int me = nC + (int) infV.size();
+		infV.push_back(v);
+		infN.push_back({{-1, -1, -1, c}});
+		nb[(size_t) c][(size_t) k] = me;
+		for (int a = 0; a < 3; a++) {
+			std::array<int, 2> e = {{v[(size_t) ((a + 1) % 3)], v[(size_t) ((a + 2) % 3)]}};
+			if (e[1] < e[0]) { std::swap(e[0], e[1]); }
+			hullEdges[e].push_back({{me, a}});
+		}
+	}
+	for (const auto& e : hullEdges) {
+		if (e.second.size() != 2) { throw Exception(GCMB_E_BAD_MESH, "the hull of the triangulation is not a closed surface"); }
+		infN[(size_t) (e.second[0][0] - nC)][(size_t) e.second[0][1]] = e.second[1][0];
+		infN[(size_t) (e.second[1][0] - nC)][(size_t) e.second[1][1]] = e.second[0][0];
+	}
+	const Id EMPTY = (Id) (long long) EmptySpaceFlag;
+	auto id = [&](int cell) -> Id { return cell >= nC ? EMPTY : idOf(cell); };
+	auto hasVertex = [&](int cell, int v) {
+		if (cell >= nC) { const auto& x = infV[(size_t) (cell - nC)]; return x[0] == v || x[1] == v || x[2] == v; }
+		const int* x = &cellV[(size_t) 4 * cell];
+		return x[0] == v || x[1] == v || x[2] == v || x[3] == v;
+	};
+	auto neighbor = [&](int cell, int k) { return cell >= nC ? infN[(size_t) (cell - nC)][(size_t) k] : nb[(size_t) cell][(size_t) k]; };
+	// incident cells of every vertex, finite ones first in ascending id, then the infinite ones
+	std::vector<std::vector<int>> incident((size_t) nV);
+	for (int v = 0; v < nV; v++) { incident[(size_t) v].assign(incCell.begin() + incOff[(size_t) v], incCell.begin() + incOff[(size_t) v + 1]); }
+	for (size_t i = 0; i < infV.size(); i++) for (int k = 0; k < 3; k++) { incident[(size_t) infV[i][(size_t) k]].push_back(nC + (int) i); }
+
+	const std::vector<int> before = cellGrid;
+	int hanged = 1, disconnected = 1, iterations = 0;
+	long long guard = 0;
+	while (disconnected > 0 || hanged > 0) {
+		if (++iterations > 10) { break; }
+		// correctHangedCells (CgalTriangulation.cpp:42-66)
+		hanged = 0;
+		for (int c = 0; c < nC; c++) {
+			std::multiset<Id> around;
+			for (int k = 0; k < 4; k++) { around.insert(id(neighbor(c, k))); }
+			if (around.find(idOf(c)) != around.end()) { continue; }
+			++hanged;
+			Id common = *around.begin();
+			for (const Id x : around) { if (around.count(x) > around.count(common)) { common = x; } }
+			cellGrid[(size_t) c] = (int) (long long) common;
+		}
+		// clearFromDisconnectedCellSets for every vertex (CgalTriangulation.cpp:69-111)
+		disconnected = 0;
+		for (int v = 0; v < nV; v++) {
+			while (true) {
+				std::set<Id> unique;
+				for (const int c : incident[(size_t) v]) { unique.insert(id(c)); }
+				if (unique.size() == 1) { break; }
+				// connected sets of equal-id cells around the vertex, in the order the reference builds them
+				struct Set { Id id; std::set<int> cells; };
+				std::vector<Set> sets;   // kept sorted by id, equal ids in insertion order (std::multiset)
+				std::set<int> all(incident[(size_t) v].begin(), incident[(size_t) v].end());
+				while (!all.empty()) {
+					Set s;
+					s.id = id(*all.begin());
+					std::vector<int> stack = {*all.begin()};
+					while (!stack.empty()) {
+						const int c = stack.back();
+						stack.pop_back();
+						if (!(hasVertex(c, v) && id(c) == s.id) || !s.cells.insert(c).second) { continue; }
+						for (int k = 0; k < 4; k++) { stack.push_back(neighbor(c, k)); }
+					}
+					size_t at = sets.size();
+					while (at > 0 && s.id < sets[at - 1].id) { at--; }
+					sets.insert(sets.begin() + (long) at, s);
+					for (const int c : s.cells) { all.erase(c); }
+				}
+				struct Info { Id id; size_t nSets = 0, nCells = 0; };
+				std::list<Info> byCells;
+				for (const Id x : unique) {
+					Info info;
+					info.id = x;
+					for (const Set& s : sets) { if (s.id == x) { ++info.nSets; info.nCells += s.cells.size(); } }
+					byCells.push_back(info);
+				}
+				byCells.sort([](const Info& a, const Info& b) { return a.nCells > b.nCells; });
+				std::list<Info> bySets(byCells);
+				bySets.sort([](const Info& a, const Info& b) { return a.nSets < b.nSets; });
+				const Info toRemove = bySets.back();
+				if (toRemove.nSets == 1) { break; }
+				// Utils::chooseRandomElementExceptSpecified (util/Utils.hpp:57-76): libc rand(), which the reference has not
+				// seeded yet when its triangulation is constructed (AbstractEngine::run seeds it later)
+				std::set<Id> others(unique);
+				others.erase(toRemove.id);
+				const real upTo = (1 - 1e-9) * (real) others.size();
+				const int pick = (int) ((upTo * std::rand()) / RAND_MAX + 0);
+				auto chosen = others.begin();
+				for (int i = 0; i < pick; i++) { ++chosen; }
+				const Id toInsert = *chosen;
+				if (++guard > 100000) { throw Exception(GCMB_E_BAD_MESH, "the clean-up of body ids does not terminate"); }
+				// removeDCS: every set of that id but the (first) largest changes its id
+				const Set* largest = nullptr;
+				for (const Set& s : sets) { if (s.id == toRemove.id && (!largest || largest->cells.size() < s.cells.size())) { largest = &s; } }
+				for (const Set& s : sets) {
+					if (s.id != toRemove.id || &s == largest) { continue; }
+					for (const int c : s.cells) { if (c < nC) { cellGrid[(size_t) c] = (int) (long long) toInsert; } }
+				}
+				++disconnected;
+			}
+		}
+	}
+	int changed = 0;
+	for (int c = 0; c < nC; c++) { if (cellGrid[(size_t) c] != before[(size_t) c]) { changed++; } }
+	return changed;
 }
 
 /// INM mesh files (the reference's grid/simplex/mesh_loaders/InmMeshLoader.hpp:96-168): number of points, one

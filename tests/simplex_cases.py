@@ -553,3 +553,21 @@ def check_locate_against_reference(lib, with_oracle=False):
             o, errs = oracle_locate_all(L, m, v[pick], sh[pick])
             assert errs == 0 and np.array_equal(o, want[pick])
     ctx.close()
+
+
+def check_mesh_cleanup_against_reference(lib, name):
+    """the box mesher + the host's restatement of the reference's clean-up of body ids == the ids the reference's
+    CgalTriangulation constructor leaves (grid/simplex/cgal/CgalTriangulation.cpp:8-112), and the task run straight
+    from the mesher then reproduces the reference engine's values"""
+    g = load_golden(name)
+    # the clean-up draws from libc's rand() like the reference's, which runs it in a fresh process: same state here
+    ctypes.CDLL(None).srand(1)
+    eng = capi.SimplexHostEngine(lib, str(g["task"]))
+    tri = eng.triangulation()
+    assert np.array_equal(tri["xyz"], g["xyz"]) and np.array_equal(tri["cell_v"], g["cell_v"])
+    assert (g["cell_grid"] != g["cell_grid_before_cleanup"]).sum() > 0      # the clean-up had something to do
+    assert np.array_equal(tri["cell_grid"], g["cell_grid"])
+    eng.run()
+    for b in range(int(g["bodies"])):
+        assert np.array_equal(eng.simplex_pde(b), g["pde%d" % b])
+    eng.close()

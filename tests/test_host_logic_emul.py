@@ -299,3 +299,8 @@ def test_simplex_oracle_matches_reference_bitwise(lib, name, tmp_path):
 
 def test_simplex_cell_location_matches_reference(lib):
     _sx.check_locate_against_reference(lib, with_oracle=True)
+
+
+@pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX)
+def test_simplex_mesh_cleanup_matches_reference(lib, name):
+    _sx.check_mesh_cleanup_against_reference(lib, name)
