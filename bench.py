@@ -164,7 +164,7 @@ def pick_size(free_bytes, want):
 SIMPLEX_TASK = """grid simplex
 dimensionality 3
 courant 0.7
-steps 1000000
+steps {steps}
 simplex_box {nx} {ny} {nz} 0 0 0 {h!r} jitter 0.3 seed 1
 cavity box {c0!r} {c0!r} {c1!r} {c2!r} {c2!r} {c3!r}
 body 0 elastic isotropic
@@ -175,12 +175,12 @@ initial quantity PRESSURE 1 sphere {r!r} {sx!r} {sx!r} {sz!r}
 """
 
 
-def simplex_task(nx, ny, nz, h):
+def simplex_task(nx, ny, nz, h, steps=1000000):
     """a 4:4:1 plate of tetrahedra with an inner cavity (the geometry of
     meshes/layers_with_fracture.off, meshed by our box mesher), isotropic elastic, fixed identity calculation
     basis, zero fixed force on every border, pressure-sphere source"""
     lx, lz = nx * h, nz * h
-    return SIMPLEX_TASK.format(nx=nx, ny=ny, nz=nz, h=h, c0=0.4 * lx, c2=0.6 * lx, c1=0.35 * lz, c3=0.65 * lz,
+    return SIMPLEX_TASK.format(steps=steps, nx=nx, ny=ny, nz=nz, h=h, c0=0.4 * lx, c2=0.6 * lx, c1=0.35 * lz, c3=0.65 * lz,
                                r=0.08 * lx, sx=0.3 * lx, sz=0.5 * lz)
 
 
@@ -214,24 +214,39 @@ def simplex_section(lib, device, steps, warmup, with_cpu):
            "parity": "bit-identical to the unmodified reference simplex engine built against a CGAL stand-in (tests/golden/simplex_*.npz)"}
     eng.close()
     if with_cpu:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import simplex_host
-        small = capi.SimplexHostEngine(lib, simplex_task(24, 24, 6, h), device=device)
+        # CPU baseline on a bounded sample of the same task: the UNMODIFIED reference simplex engine
+        # (oracle/_ref/gcm_ref_simplex, built against a CGAL stand-in) when it was built, else the C port
+        sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+        cpu_steps = 10
+        text = simplex_task(24, 24, 6, 0.16 / 24, steps=cpu_steps)
+        small = capi.SimplexHostEngine(lib, text, device=device)
         i2 = small.simplex_body_info(0)
         tri = small.triangulation()
-        U, U1, L = small.simplex_matrices(0)
-        nodes, normals = small.border_nodes(0, 0)
-        pde0 = small.simplex_pde(0)
-        tau = small.info()[2]
-        cpu_steps = 2
-        ref, spent = simplex_host.run_single_body(tri, 0, 0, U, U1, L, np.eye(3), nodes, normals, np.zeros(len(nodes), dtype=np.int32),
-                                                  np.zeros(1, dtype=np.int32), lambda t: np.zeros((1, 3)), pde0, tau, cpu_steps)
-        small.advance(cpu_steps)
-        same = bool(np.array_equal(small.simplex_pde(0), ref))
+        exe = os.path.join(ROOT, "oracle", "_ref", "gcm_ref_simplex")
+        if os.path.exists(exe):
+            from simplex_helpers import run_reference_simplex
+            ref, meta = run_reference_simplex(text, tri, tempfile.mkdtemp(prefix="gcmb_sx_"), [0], 9)
+            small.run()
+            same = bool(np.array_equal(small.simplex_pde(0), ref[0][1]) and small.info()[2] == meta["tau"])
+            out["cpu_baseline"] = {"value": i2["n_local"] * cpu_steps / meta["run_seconds"], "unit": "vertex-updates/s", "cores": 1,
+                                   "kind": "reference",
+                                   "sample": "%d steps of the same task at 24x24x6 cubes (%d vertices) by the reference's "
+                                             "simplex::Engine::run(), %.2f s" % (cpu_steps, i2["n_local"], meta["run_seconds"]),
+                                   "gpu_equals_reference_bitwise": same}
+        else:
+            import simplex_host
+            U, U1, L = small.simplex_matrices(0)
+            nodes, normals = small.border_nodes(0, 0)
+            pde0 = small.simplex_pde(0)
+            tau = small.info()[2]
+            ref, spent = simplex_host.run_single_body(tri, 0, 0, U, U1, L, np.eye(3), nodes, normals, np.zeros(len(nodes), dtype=np.int32),
+                                                      np.zeros(1, dtype=np.int32), lambda t: np.zeros((1, 3)), pde0, tau, cpu_steps)
+            small.advance(cpu_steps)
+            same = bool(np.array_equal(small.simplex_pde(0), ref))
+            out["cpu_baseline"] = {"value": i2["n_local"] * cpu_steps / spent, "unit": "vertex-updates/s", "cores": 1, "kind": "port",
+                                   "sample": "%d steps of the same task at 24x24x6 cubes (%d vertices) through oracle/simplex_oracle.c" % (cpu_steps, i2["n_local"]),
+                                   "gpu_equals_port_bitwise": same}
         small.close()
-        out["cpu_baseline"] = {"value": i2["n_local"] * cpu_steps / spent, "unit": "vertex-updates/s", "cores": 1, "kind": "port",
-                               "sample": "%d steps of the same task at 24x24x6 cubes (%d vertices) through oracle/simplex_oracle.c" % (cpu_steps, i2["n_local"]),
-                               "gpu_equals_port_bitwise": same}
     return out
 
 
