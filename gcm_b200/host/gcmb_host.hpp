@@ -525,6 +525,7 @@ private:
 	std::map<GridsPair, std::vector<real>> contactNormalsCache;  ///< set-up only
 	real basis[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 	bool createNewRandomAtEachTimeStep = false;
+	bool summSplitting = false;
 	unsigned long long randomState = 0;
 
 	Body& getBody(const GridId id);

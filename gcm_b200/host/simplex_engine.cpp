@@ -1,7 +1,7 @@
 // simplex::Engine — the reference's engine/simplex/Engine.{hpp,cpp} for 3-D bodies on the flat triangulation,
 // driving the gcmb_simplex_* device calls.  Supported: both GCM types (Riemann invariants -- the reference's
 // default -- and PDE vectors), GLOBAL_BASIS borders and contacts, PRODUCT splitting, isotropic elastic/acoustic
-// bodies, fixed or per-step random calculation basis.
+// bodies, fixed or per-step random calculation basis, PRODUCT and SUMM splitting by directions.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -110,9 +110,7 @@ Engine::Engine(const Task& task) : AbstractEngine(task) {
 	if (task.simplexGrid.borderCalcMode != BorderCalcMode::GLOBAL_BASIS) {
 		throw Exception(GCMB_E_UNSUPPORTED, "BorderCalcMode::LOCAL_BASIS is not built");
 	}
-	if (task.globalSettings.splittingType != SplittingType::PRODUCT) {
-		throw Exception(GCMB_E_UNSUPPORTED, "SplittingType::SUMM is not built");
-	}
+	summSplitting = task.globalSettings.splittingType == SplittingType::SUMM;
 	if (task.simplexGrid.movable) { throw Exception(GCMB_E_UNSUPPORTED, "movable grids are not built"); }
 	vtkSettings = task.vtkSnapshotter;
 	snapshotters = task.globalSettings.snapshottersId;
@@ -240,6 +238,7 @@ void Engine::createMeshes(const Task& task) {
 		check(gcmb_simplex_body_create(ctx, m.modelType == Models::T::ACOUSTIC ? 1 : 0, t.nV, t.nC, t.xyz.data(), t.cellV.data(),
 				t.cellN.data(), t.cellGrid.data(), t.incOff.data(), t.incCell.data(), (int) m.id, &m.body));
 		check(gcmb_simplex_set_gcm_type(m.body, task.globalSettings.gcmType == GcmType::ADVECT_PDE_VECTORS ? 1 : 0));
+		check(gcmb_simplex_set_splitting(m.body, summSplitting ? 1 : 0));
 		int nLocal = 0, M = 0, nBorder = 0;
 		check(gcmb_simplex_info(m.body, &nLocal, &M, &nBorder));
 		m.globalOf.resize((size_t) nLocal);
@@ -474,6 +473,7 @@ void Engine::nextTimeStep() {
 	changeCalculationBasis();
 	applyPlainBorderContactCorrection(Clock::Time() + Clock::TimeStep());
 	for (int stage = 0; stage < 3; stage++) { gcmStage(stage, Clock::Time(), Clock::TimeStep()); }
+	if (summSplitting) { for (const Body& body : bodies) { check(gcmb_simplex_average_layers(body.mesh->body)); } }
 	for (const Body& body : bodies) { body.mesh->invalidateHostCopy(); }
 }
 

@@ -207,6 +207,12 @@ int gcmb_simplex_stage(gcmb_sbody* body, int s, double tau, const double* values
  * engine/simplex/GridCharacteristicMethodInRiemannInvariants.hpp), 1 ADVECT_PDE_VECTORS (…InPdeVectors.hpp with
  * BorderCorrectorInPdeVectors / ContactCorrectorInPdeVectors) */
 int gcmb_simplex_set_gcm_type(gcmb_sbody* body, int gcm_type);
+/* SplittingType of the task (util/task/Task.hpp:19-22,64; engine/simplex/Engine.hpp:135-160): 0 PRODUCT -- every stage
+ * starts from the result of the previous one (default); 1 SUMM -- every stage starts from the same layer and fills a
+ * layer of its own, gcmb_simplex_average_layers then averages them into the current layer
+ * (DefaultMesh::averageNewPdeLayersToCurrent, engine/simplex/DefaultMesh.hpp:160-169; Engine.cpp:104-108) */
+int gcmb_simplex_set_splitting(gcmb_sbody* body, int splitting);
+int gcmb_simplex_average_layers(gcmb_sbody* body);
 int gcmb_simplex_before_stage(gcmb_sbody* body, int s, double tau);
 int gcmb_simplex_border_contact_stage(gcmb_sbody* body);
 int gcmb_simplex_border_correct(gcmb_sbody* body, const double* values /* [n_cond][outer] at t+tau */);

@@ -114,6 +114,8 @@ void parseTaskFile(const std::string& fileName, Task& task, std::map<size_t, boo
 			q.value = tk.num();
 			q.area = parseArea(tk);
 			task.initialCondition.quantities.push_back(q);
+		} else if (key == "splitting") {
+			task.globalSettings.splittingType = tk.next() == "summ" ? SplittingType::SUMM : SplittingType::PRODUCT;
 		} else if (key == "gcm_type") {
 			task.globalSettings.gcmType = tk.next() == "pde_vectors" ? GcmType::ADVECT_PDE_VECTORS : GcmType::ADVECT_RIEMANN_INVARIANTS;
 		} else {

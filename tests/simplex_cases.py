@@ -481,7 +481,8 @@ def golden_scenario(model, bodies, gcm, basis, steps):
     return "\n".join(lines)
 
 
-GOLDEN_SIMPLEX = ["elastic_cavity", "elastic_contact", "acoustic_contact_rotated", "elastic_contact_pde_vectors", "acoustic_pde_vectors"]
+GOLDEN_SIMPLEX = ["elastic_cavity", "elastic_contact", "acoustic_contact_rotated", "elastic_contact_pde_vectors", "acoustic_pde_vectors",
+                  "elastic_contact_summ"]
 
 
 def load_golden(name):
