@@ -420,6 +420,8 @@ def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3, g
         for i in ids:
             nodes, normals, conds = border[i]
             L.gcmo_simplex_plain_border(model, M, len(nodes), _i(nodes), _d(normals), _i(conds), _i(types), _d(b_next), _d(state[i]))
+        summ = "splitting summ" in text   # SplittingType::SUMM: every stage from the same layer, then the average
+        layers = []
         for s in range(3):
             nxt = [np.zeros_like(p) for p in state]
             hs = [L.gcmo_sx_begin(ctypes.byref(views[i]), model, M, s, tau, _d(mats[i][0]), _d(mats[i][1]), _d(mats[i][2]),
@@ -435,7 +437,12 @@ def check_engine(lib, model, bodies=2, basis="identity", cavity=True, steps=3, g
                 L.gcmo_sx_nodes(h, 1)
             for h in hs:
                 assert L.gcmo_sx_end(h) == 0, (step, s)
-            state = nxt
+            if summ:
+                layers.append(nxt)
+            else:
+                state = nxt
+        if summ:   # DefaultMesh::averageNewPdeLayersToCurrent: pde = 0; pde += new_s / 3
+            state = [((0.0 + layers[0][i] / 3.0) + layers[1][i] / 3.0) + layers[2][i] / 3.0 for i in ids]
         time += tau
         assert eng.info()[1] == time
         for i in ids:
