@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--ref-size", type=int, default=64, help="cube edge of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-simplex", action="store_true", help="skip the secondary simplex-path measurement")
+    ap.add_argument("--no-host-roundtrip", action="store_true", help="skip the host-resident-state measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -414,6 +415,42 @@ def main():
             base = cpu_baseline(args.ref_size, 5)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     eng.close()
+    if rank == 0 and world == 1 and not args.no_host_roundtrip:
+        # ---- (3) the pessimistic bound of a drop-in that keeps the reference's HOST-resident mesh: the whole state
+        #          (reference AoS layout with ghost nodes) goes up from pinned host memory before EVERY step and comes
+        #          back after it.  Measured on a 512^3 body (9.8 GB each way) so that the pinned buffer fits any host.
+        try:
+            m = min(n, 512)
+            small = capi.HostEngine(lib, task_text(m, m, m, steps=10 ** 6, detector=False), device=local)
+            sbody, sctx = small.body_handle(0), small.context_handle()
+            stau = small.info()[2]
+            count = (m + 4) ** 3 * 9
+            host = torch.empty(count, dtype=torch.float64, pin_memory=True)
+            hp = capi.ctypes.c_void_p(host.data_ptr())
+            lib.check(lib.c.gcmb_cubic_download_state(sbody, hp, 1))
+            lib.check(lib.c.gcmb_sync(sctx))
+            reps = 2
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                lib.check(lib.c.gcmb_cubic_upload_state(sbody, hp, 1))
+                for d in range(3):
+                    if d == 2:
+                        lib.check(lib.c.gcmb_cubic_border_apply(sbody, 2, 3, capi.dp(zeros3)))
+                    lib.check(lib.c.gcmb_cubic_stage(sbody, d, stau))
+                lib.check(lib.c.gcmb_cubic_download_state(sbody, hp, 1))
+            lib.check(lib.c.gcmb_sync(sctx))
+            dt = (time.perf_counter() - t0) / reps
+            assert bool(torch.isfinite(host[:: 4097]).all())
+            line["e2e_host_state_every_step"] = {
+                "value": m ** 3 / dt, "unit": "node-updates/s", "ms_per_step": 1e3 * dt,
+                "h2d_bytes_per_step": count * 8, "d2h_bytes_per_step": count * 8,
+                "what": "gcmb_cubic_upload_state from pinned host memory + one time step + gcmb_cubic_download_state, "
+                        "%d^3 body: what a binding that leaves the mesh in host memory (reference DefaultMesh) would "
+                        "pay per step; PCIe-bound, the reason INTEGRATION.md keeps the mesh resident in HBM" % m}
+            small.close()
+            del host
+        except Exception as e:
+            line["e2e_host_state_every_step"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         if world == 1 and not args.no_simplex:
             # secondary measurement (never the headline): the tetrahedral path of SURVEY.md §8 a13-a21
