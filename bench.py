@@ -366,7 +366,7 @@ def main():
 
     # ---- roofline of the dominant kernel (the slowest of the three stage kernels) ------------------
     peak, peak_src = measured_hbm_peak()
-    stage_ms = [prof_ms[a] / max(1, prof_n[a]) for a in range(3)]
+    stage_ms = [prof_ms[a] / K for a in range(3)]   # per stage and step (the x stage is three launches when the halo exchange overlaps it)
     dom = int(np.argmax(stage_ms))
     bytes_per_launch = BYTES_PER_NODE_STAGE * nodes_per_gpu
     achieved = bytes_per_launch / (stage_ms[dom] * 1e-3) / 1e9

@@ -209,7 +209,21 @@ struct gcmb_ctx {
 	ncclComm_t comm = nullptr;
 	int n_ranks = 1, rank = 0;
 	double* scratch = nullptr;  // small device scratch (reductions)
+	// halo exchange overlapped with the interior of the x stage: NCCL runs on comm_stream between ev_ready (state
+	// complete on `stream`) and ev_halo (ghost planes received); the next launch on `stream` waits for ev_halo
+	// unless it is the interior part of the x stage (halo_defer)
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
+	bool halo_pending = false, halo_defer = false;
 };
+
+// make `stream` wait for a halo exchange in flight (no-op when there is none)
+static void wait_halo(gcmb_ctx* ctx) {
+	if (ctx->halo_pending) {
+		cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0);
+		ctx->halo_pending = false;
+	}
+}
 
 struct BorderCond {
 	int cond = 0, dir = 0;
@@ -245,6 +259,7 @@ struct Launch {
 	int cls;
 	ProfileSpan span;
 	Launch(gcmb_ctx* c, int cls_) : ctx(c), cls(cls_) {
+		if (ctx->halo_pending && !ctx->halo_defer) { wait_halo(ctx); }
 		if (ctx->profiling) {
 			span.cls = cls;
 			cudaEventCreate(&span.a);
@@ -435,7 +450,9 @@ void gcmb_destroy(gcmb_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	while (!ctx->bodies.empty()) { gcmb_cubic_body_destroy(ctx->bodies.back()); }
 	for (ProfileSpan& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+	if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); }
 	if (ctx->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->comm); }
+	if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_halo); }
 	cudaFree(ctx->scratch);
 	cudaEventDestroy(ctx->timer_a);
 	cudaEventDestroy(ctx->timer_b);
@@ -452,6 +469,7 @@ int gcmb_set_stream(gcmb_ctx* ctx, void* cuda_stream) {
 
 int gcmb_sync(gcmb_ctx* ctx) {
 	GCMB_CUDA(cudaSetDevice(ctx->device));
+	wait_halo(ctx);
 	GCMB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return GCMB_OK;
 }
@@ -462,6 +480,7 @@ int gcmb_timer_start(gcmb_ctx* ctx) {
 }
 
 int gcmb_timer_stop(gcmb_ctx* ctx, float* ms) {
+	wait_halo(ctx);
 	GCMB_CUDA(cudaEventRecord(ctx->timer_b, ctx->stream));
 	GCMB_CUDA(cudaEventSynchronize(ctx->timer_b));
 	GCMB_CUDA(cudaEventElapsedTime(ms, ctx->timer_a, ctx->timer_b));
@@ -822,9 +841,23 @@ int gcmb_cubic_stage(gcmb_body* b, int dir, double tau) {
 	}
 	if (!launch) { launch = dense_launcher(b->g.M); }
 	if (!launch) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "no stage kernel for this PDE size"); }
-	{
-		Launch l(b->ctx, a.axis);
-		launch(a, b->ctx->stream);
+	gcmb_ctx* ctx = b->ctx;
+	const int bs = b->g.g[0];
+	if (ctx->halo_pending && a.axis == 0 && bs > 0 && b->g.n[0] > 2 * bs) {
+		// the nodes at least `bs` planes away from both slab faces read no ghost plane: they go first, while the
+		// halo exchange is still in flight; the two boundary strips follow once the ghost planes have arrived
+		StageArgs part = a;
+		part.x_begin = bs; part.x_end = b->g.n[0] - bs;
+		ctx->halo_defer = true;
+		{ Launch l(ctx, a.axis); launch(part, ctx->stream); }
+		ctx->halo_defer = false;
+		part.x_begin = 0; part.x_end = bs;
+		{ Launch l(ctx, a.axis); launch(part, ctx->stream); }
+		part.x_begin = b->g.n[0] - bs; part.x_end = b->g.n[0];
+		{ Launch l(ctx, a.axis); launch(part, ctx->stream); }
+	} else {
+		Launch l(ctx, a.axis);
+		launch(a, ctx->stream);
 	}
 	GCMB_CUDA(cudaGetLastError());
 	b->cur = 1 - b->cur;  // swapCurrAndNextPdeTimeLayer
@@ -984,19 +1017,38 @@ int gcmb_cubic_halo_exchange(gcmb_body* b) {
 	// outermost real planes [bs, 2bs) and [n0, n0+bs)
 	const size_t count = (size_t) g.g[0] * (size_t) g.plane;
 	double* base = b->buf[b->cur];
+	// on a stream of its own, so that the interior of the following x stage (which reads no ghost plane) overlaps it
+	static const bool overlap = !std::getenv("GCMB_NO_HALO_OVERLAP");
+	if (overlap && !ctx->comm_stream) {
+		int least = 0, greatest = 0;
+		GCMB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+		GCMB_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, greatest));
+		GCMB_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+		GCMB_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+	}
+	wait_halo(ctx);
+	cudaStream_t comm_stream = overlap ? ctx->comm_stream : ctx->stream;
+	if (overlap) {
+		GCMB_CUDA(cudaEventRecord(ctx->ev_ready, ctx->stream));
+		GCMB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0));
+	}
 	GCMB_NCCL(g_nccl.GroupStart());
 	for (int c = 0; c < g.M; c++) {
 		double* v = base + (long long) c * g.comp;
 		if (ctx->rank > 0) {
-			GCMB_NCCL(g_nccl.Send(v + (long long) g.g[0] * g.plane, count, ncclDouble, ctx->rank - 1, ctx->comm, ctx->stream));
-			GCMB_NCCL(g_nccl.Recv(v, count, ncclDouble, ctx->rank - 1, ctx->comm, ctx->stream));
+			GCMB_NCCL(g_nccl.Send(v + (long long) g.g[0] * g.plane, count, ncclDouble, ctx->rank - 1, ctx->comm, comm_stream));
+			GCMB_NCCL(g_nccl.Recv(v, count, ncclDouble, ctx->rank - 1, ctx->comm, comm_stream));
 		}
 		if (ctx->rank < ctx->n_ranks - 1) {
-			GCMB_NCCL(g_nccl.Send(v + (long long) g.n[0] * g.plane, count, ncclDouble, ctx->rank + 1, ctx->comm, ctx->stream));
-			GCMB_NCCL(g_nccl.Recv(v + (long long) (g.n[0] + g.g[0]) * g.plane, count, ncclDouble, ctx->rank + 1, ctx->comm, ctx->stream));
+			GCMB_NCCL(g_nccl.Send(v + (long long) g.n[0] * g.plane, count, ncclDouble, ctx->rank + 1, ctx->comm, comm_stream));
+			GCMB_NCCL(g_nccl.Recv(v + (long long) (g.n[0] + g.g[0]) * g.plane, count, ncclDouble, ctx->rank + 1, ctx->comm, comm_stream));
 		}
 	}
 	GCMB_NCCL(g_nccl.GroupEnd());
+	if (overlap) {
+		GCMB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+		ctx->halo_pending = true;
+	}
 	ctx->launches++;
 	return GCMB_OK;
 }
@@ -1011,6 +1063,7 @@ static int halo_host(gcmb_body* b, int side, void* host, bool get) {
 	const Geom& g = b->g;
 	if (g.g[0] == 0) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "slab decomposition needs the x axis to be the slowest internal axis (3-D grids)"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	wait_halo(b->ctx);
 	const size_t count = (size_t) g.g[0] * (size_t) g.plane;
 	// real planes next to the face: [bs, 2bs) left, [n0, n0+bs) right; ghost planes: [0, bs) / [n0+bs, n0+2bs)
 	const long long first = get ? (side == 0 ? g.g[0] : g.n[0]) : (side == 0 ? 0 : g.n[0] + g.g[0]);

@@ -72,6 +72,10 @@ using std::max;
 #define cudaSetDevice(d) gcmb_emul::ok()
 #define cudaStreamCreateWithFlags(p, f) (*(p) = nullptr, cudaSuccess)
 #define cudaStreamSynchronize(s) gcmb_emul::ok()
+#define cudaStreamCreateWithPriority(p, f, prio) (*(p) = nullptr, cudaSuccess)
+#define cudaDeviceGetStreamPriorityRange(lo, hi) (*(lo) = 0, *(hi) = 0, cudaSuccess)
+#define cudaStreamWaitEvent(s, e, f) gcmb_emul::ok()
+#define cudaEventCreateWithFlags(p, f) gcmb_emul::ev_create(p)
 #define cudaStreamDestroy(s) gcmb_emul::ok()
 #define cudaEventCreate(p) gcmb_emul::ev_create(p)
 #define cudaEventRecord(e, s) gcmb_emul::ev_record(e)
