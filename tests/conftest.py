@@ -16,3 +16,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _run_in_tmp_dir(tmp_path, monkeypatch):
+    """engines with a detector write snapshots/ into the working directory like the reference does: keep the tree clean"""
+    monkeypatch.chdir(tmp_path)
