@@ -541,6 +541,11 @@ struct StageS {
 	int cacheMode;
 	int4* cacheCell;        // [foot][inner index] local vertex ids of the cell, x = -1: not a plain cell hit
 	double* cacheLam;       // [foot][inner index][4] barycentric coordinates of the foot
+	// BorderCalcMode::LOCAL_BASIS: border and contact vertices carry eigen-systems of their own, written in a basis
+	// whose first axis is their normal (engine/simplex/DefaultMesh.hpp:245-266); null = every vertex uses U/U1/dir
+	const int* slotOf;          // [nLocal] index of the vertex' tables or -1
+	const double* nodeTables;   // [slot][3 stages][U 81 | U1 81 | L 9]
+	const double* nodeDirs;     // [slot][3 stages][3] calculation direction of the vertex at each stage
 	int pdeMode;            // GcmType::ADVECT_PDE_VECTORS: `riem` is the current layer itself, `next` receives U*V rows
 	unsigned zeroMask;      // characteristics with a zero eigenvalue: the invariant is carried over
 	int footMajor;          // thread mapping of the inner pass: 1 = a warp shares the foot, 0 = adjacent lanes share the vertex
@@ -552,6 +557,19 @@ struct StageS {
 	unsigned* waves;        // outer invariants of border vertices (bit k)
 	int* errors;            // counter of "the reference would have thrown"
 };
+
+// eigen-system and calculation direction of a vertex at the stage in flight
+GCMB_HD const double* vertexU(const StageS& a, int it) {
+	const int slot = a.slotOf ? a.slotOf[it] : -1;
+	return slot < 0 ? a.U : a.nodeTables + ((long long) slot * 3 + a.s) * 171;
+}
+GCMB_HD const double* vertexU1(const StageS& a, int it) { return vertexU(a, it) + 81; }
+GCMB_HD V3 vertexDirection(const StageS& a, int it) {
+	const int slot = a.slotOf ? a.slotOf[it] : -1;
+	if (slot < 0) { return {a.dir[0], a.dir[1], a.dir[2]}; }
+	const double* d = a.nodeDirs + ((long long) slot * 3 + a.s) * 3;
+	return {d[0], d[1], d[2]};
+}
 
 // SimplexGrid::findCellCrossedByTheRay through the cache of feet: slot < 0 = no caching for this call
 GCMB_HD Found locateFoot(const StageS& a, int it, V3 shift, long long slot, int& err) {
@@ -588,7 +606,7 @@ GCMB_HD unsigned footCharacteristics(const StageS& a, int it, double lambda, uns
 		return 0;
 	}
 	const V3 x0 = t.localPoint(it);
-	const V3 shift = V3{a.dir[0], a.dir[1], a.dir[2]} * dx;
+	const V3 shift = vertexDirection(a, it) * dx;
 	const Found f = locateFoot(a, it, shift, slot, err);
 	if (f.n == 4) {
 		const int cell[4] = {f.p[0], f.p[1], f.p[2], f.p[3]};
@@ -636,7 +654,7 @@ GCMB_HD unsigned footVectors(const StageS& a, int it, double lambda, unsigned sa
 		for (int j = 0; j < M; j++) { v[j] = a.riem[(long long) it * M + j]; }
 	} else {
 		const V3 x0 = t.localPoint(it);
-		const V3 shift = V3{a.dir[0], a.dir[1], a.dir[2]} * dx;
+		const V3 shift = vertexDirection(a, it) * dx;
 		const Found f = locateFoot(a, it, shift, slot, err);
 		if (f.n == 4) {
 			const int cell[4] = {f.p[0], f.p[1], f.p[2], f.p[3]};
@@ -686,8 +704,9 @@ GCMB_HD unsigned footVectors(const StageS& a, int it, double lambda, unsigned sa
 	}
 	for (int k = 0; k < M; k++) {
 		if (!((same >> k) & 1u)) { continue; }
-		double r = a.U[k * M] * v[0];
-		for (int j = 1; j < M; j++) { r += a.U[k * M + j] * v[j]; }
+		const double* U = vertexU(a, it);
+		double r = U[k * M] * v[0];
+		for (int j = 1; j < M; j++) { r += U[k * M + j] * v[j]; }
 		out[k] = r;
 	}
 	return outers;
@@ -734,7 +753,7 @@ GCMB_HD void borderFinishThread(const StageS& a, int it) {
 		// …InPdeVectors.hpp:52-72: the outer invariants stay as found; u = U1 * (rows of U*V)
 		double r[M], u[M];
 		for (int k = 0; k < M; k++) { r[k] = a.next[(long long) it * M + k]; }
-		matVec<M>(a.U1, r, u);
+		matVec<M>(vertexU1(a, it), r, u);
 		for (int k = 0; k < M; k++) { a.next[(long long) it * M + k] = u[k]; }
 		return;
 	}
@@ -868,6 +887,10 @@ GCMB_HD void outerColumns(int outer, const double* U1, unsigned mask, double* Om
 }
 
 struct BorderS {
+	int local;              // applyInLocalBasis: the vertex' own stage-0 tables, right invariants, no validity threshold
+	const int* slotOf;
+	const double* nodeTables;
+	int* errors;
 	int pdeMode;            // the next layer already holds PDE variables (BorderCorrectorInPdeVectors)
 	int model, type;        // condition type 0 FIXED_FORCE, 1 FIXED_VELOCITY
 	const double* U;        // this stage
@@ -882,8 +905,31 @@ struct BorderS {
 };
 
 // BorderCorrectorInRiemannInvariants::applyInGlobalBasis for one border node
+// BorderCorrectorInRiemannInvariants / InPdeVectors ::applyInLocalBasis (BorderCorrector.hpp:101-120, 226-239)
+template<int M>
+GCMB_HD void borderCorrectLocalThread(const BorderS& a, int i) {
+	const int outer = a.model == 0 ? 3 : 1;
+	const unsigned RIGHT = a.model == 0 ? 0x2au : 0x2u;
+	const int node = a.node[i];
+	const int slot = a.slotOf[node];
+	const double* U = slot < 0 ? a.U : a.nodeTables + (long long) slot * 3 * 171;   // stage 0
+	const double* U1 = U + 81;
+	const V3 normal = {a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2]};
+	double Omega[M * 3], B[3 * M], u[M], w[M], value[M], det;
+	outerColumns<M>(outer, U1, RIGHT, Omega);
+	borderMatrix<M>(a.model, a.type, normal, B);
+	if (a.pdeMode) { for (int k = 0; k < M; k++) { u[k] = a.next[(long long) node * M + k]; } }
+	else { matVec<M>(U1, a.next + (long long) node * M, u); }
+	if (!outerWaveCorrection<M>(outer, u, Omega, B, a.b, 0, value, det)) { countError(a.errors); }   // assert_true(isSuccessful)
+	for (int k = 0; k < M; k++) { u[k] += value[k]; }
+	if (a.pdeMode) { for (int k = 0; k < M; k++) { w[k] = u[k]; } }
+	else { matVec<M>(U, u, w); }
+	for (int k = 0; k < M; k++) { a.next[(long long) node * M + k] = w[k]; }
+}
+
 template<int M>
 GCMB_HD void borderCorrectThread(const BorderS& a, int i) {
+	if (a.local) { borderCorrectLocalThread<M>(a, i); return; }
 	const int outer = a.model == 0 ? 3 : 1;
 	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
 	double Omega[M * 3], B[3 * M], zero[M], value[M], det;
@@ -1136,6 +1182,9 @@ GCMB_HD void outerColumnsBoth(const double* U1, unsigned RIGHT, unsigned LEFT, d
 GCMB_HD int popcountU(unsigned x) { int c = 0; while (x) { c += (int) (x & 1u); x >>= 1; } return c; }
 
 struct ContactS {
+	int local;                           // applyInLocalBasis: the vertices' own stage-0 tables, right invariants
+	const int *slotOfA, *slotOfB;
+	const double *nodeTablesA, *nodeTablesB;
 	int pdeMode;                         // ContactCorrectorInPdeVectors: no matching, no conversions
 	int model, n;
 	const double *UA, *U1A, *UB, *U1B;   // this stage, body A and body B
@@ -1149,8 +1198,39 @@ struct ContactS {
 
 // ContactCorrectorInRiemannInvariants::applyInGlobalBasis for one pair of nodes (ContactCorrector.hpp:334-410
 // around :133-253)
+// ContactCorrectorInRiemannInvariants / InPdeVectors ::applyInLocalBasis (ContactCorrector.hpp:104-131, 320-332)
+template<int M, int O>
+GCMB_HD void contactCorrectLocalThread(const ContactS& a, int i) {
+	const unsigned RIGHT = a.model == 0 ? 0x2au : 0x2u;
+	int err = 0;
+	const int slotA = a.slotOfA[a.nodeA[i]], slotB = a.slotOfB[a.nodeB[i]];
+	const double* UA = slotA < 0 ? a.UA : a.nodeTablesA + (long long) slotA * 3 * 171;
+	const double* UB = slotB < 0 ? a.UB : a.nodeTablesB + (long long) slotB * 3 * 171;
+	double OmA[M * O], OmB[M * O], B1A[O * M], B1B[O * M], B2A[O * M], B2B[O * M], uA[M], uB[M], vA[M], vB[M], w[M], det1, det2;
+	outerColumns<M>(O, UA + 81, RIGHT, OmA);
+	outerColumns<M>(O, UB + 81, RIGHT, OmB);
+	const V3 normal = {a.normal[3 * i], a.normal[3 * i + 1], a.normal[3 * i + 2]};
+	contactMatrix<M>(a.model, 1, normal, B1A); contactMatrix<M>(a.model, 1, normal, B1B);
+	contactMatrix<M>(a.model, 2, normal, B2A); contactMatrix<M>(a.model, 2, normal, B2B);
+	double* ra = a.nextA + (long long) a.nodeA[i] * M;
+	double* rb = a.nextB + (long long) a.nodeB[i] * M;
+	if (a.pdeMode) { for (int k = 0; k < M; k++) { uA[k] = ra[k]; uB[k] = rb[k]; } }
+	else { matVec<M>(UA + 81, ra, uA); matVec<M>(UB + 81, rb, uB); }
+	if (!contactWaveCorrection<M, O>(uA, OmA, B1A, B2A, uB, OmB, B1B, B2B, 0, 0, vA, vB, det1, det2, err)) { err = 1; }
+	for (int k = 0; k < M; k++) { uA[k] += vA[k]; uB[k] += vB[k]; }
+	if (a.pdeMode) { for (int k = 0; k < M; k++) { ra[k] = uA[k]; rb[k] = uB[k]; } }
+	else {
+		matVec<M>(UA, uA, w);
+		for (int k = 0; k < M; k++) { ra[k] = w[k]; }
+		matVec<M>(UB, uB, w);
+		for (int k = 0; k < M; k++) { rb[k] = w[k]; }
+	}
+	if (err) { countError(a.errors); }
+}
+
 template<int M, int O>
 GCMB_HD void contactCorrectThread(const ContactS& a, int i) {
+	if (a.local) { contactCorrectLocalThread<M, O>(a, i); return; }
 	const unsigned LEFT = a.model == 0 ? 0x15u : 0x1u, RIGHT = a.model == 0 ? 0x2au : 0x2u;
 	int err = 0;
 	double OmA[M * 2 * O], OmB[M * O], B1A[O * M], B1B[O * M], B2A[O * M], B2B[O * M], zero[M], vA[M], vB[M], det1, det2;

@@ -526,6 +526,7 @@ private:
 	real basis[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 	bool createNewRandomAtEachTimeStep = false;
 	bool summSplitting = false;
+	bool localBasis = false;
 	unsigned long long randomState = 0;
 
 	Body& getBody(const GridId id);

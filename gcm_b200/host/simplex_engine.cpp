@@ -1,7 +1,8 @@
 // simplex::Engine — the reference's engine/simplex/Engine.{hpp,cpp} for 3-D bodies on the flat triangulation,
 // driving the gcmb_simplex_* device calls.  Supported: both GCM types (Riemann invariants -- the reference's
 // default -- and PDE vectors), GLOBAL_BASIS borders and contacts, PRODUCT splitting, isotropic elastic/acoustic
-// bodies, fixed or per-step random calculation basis, PRODUCT and SUMM splitting by directions.
+// bodies, fixed or per-step random calculation basis, PRODUCT and SUMM splitting by directions, borders and contacts
+// in the GLOBAL_BASIS or in the LOCAL_BASIS of every border vertex.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -107,9 +108,7 @@ Engine::Engine(const Task& task) : AbstractEngine(task) {
 	if (task.globalSettings.dimensionality != 3) {
 		throw Exception(GCMB_E_UNSUPPORTED, "the simplex engine of this build is three-dimensional");
 	}
-	if (task.simplexGrid.borderCalcMode != BorderCalcMode::GLOBAL_BASIS) {
-		throw Exception(GCMB_E_UNSUPPORTED, "BorderCalcMode::LOCAL_BASIS is not built");
-	}
+	localBasis = task.simplexGrid.borderCalcMode == BorderCalcMode::LOCAL_BASIS;
 	summSplitting = task.globalSettings.splittingType == SplittingType::SUMM;
 	if (task.simplexGrid.movable) { throw Exception(GCMB_E_UNSUPPORTED, "movable grids are not built"); }
 	vtkSettings = task.vtkSnapshotter;
@@ -287,6 +286,53 @@ void Engine::setMaterial(Body& body) {
 	m.matrices = constructGcmMatrices(m.modelType, 3, iso, basis);
 	m.maximalEigenvalue = m.matrices.getMaximalEigenvalue();
 	check(gcmb_simplex_set_material(m.body, m.matrices.U.data(), m.matrices.U1.data(), m.matrices.L.data(), basis));
+	if (!localBasis) { return; }
+	// DefaultMesh::applyMaterialsCondition, LOCAL_BASIS (engine/simplex/DefaultMesh.hpp:245-266): border (and
+	// multicontact) vertices in a basis whose first axis is their border normal, contact vertices in one along the
+	// normal towards the body they touch; linal::createLocalBasisWithX (linal/basis.hpp:104-110)
+	const FlatTriangulation& t = triangulation;
+	std::map<int, std::vector<real>> contactNormals;   // towards a neighbouring body, for every local vertex
+	std::vector<int> nodes;
+	std::vector<real> U, U1, L, bases;
+	for (size_t l = 0; l < m.globalOf.size(); l++) {
+		if (m.state[l] == 0) { continue; }
+		real n[3];
+		if (m.state[l] == 2) {
+			const int g = m.globalOf[l];
+			int other = EmptySpaceFlag;
+			for (int i = t.incOff[(size_t) g]; i < t.incOff[(size_t) g + 1]; i++) {
+				const int id = t.cellGrid[(size_t) t.incCell[(size_t) i]];
+				if (id != (int) m.id) { other = id; }
+			}
+			std::vector<real>& all = contactNormals[other];
+			if (all.empty()) {
+				all.resize(m.globalOf.size() * 3);
+				check(gcmb_simplex_contact_normals(m.body, other, all.data()));
+			}
+			std::copy(&all[3 * l], &all[3 * l] + 3, n);
+		} else {
+			std::copy(&m.borderNormals[3 * l], &m.borderNormals[3 * l] + 3, n);
+		}
+		if (n[0] == 0 && n[1] == 0 && n[2] == 0) {
+			throw Exception(GCMB_E_UNSUPPORTED, "LOCAL_BASIS: a multicontact vertex without a border normal has no local basis");
+		}
+		// tau_1 = -perpendicularClockwise(n) (linal/geometry.hpp:46-52), tau_2 = n x tau_1
+		real p[3] = {n[1], -n[0], 0};
+		if (n[0] == 0 && n[1] == 0) { p[0] = n[2]; p[1] = 0; p[2] = 0; }
+		const real lenN = length({{n[0], n[1], n[2]}}), lenP = length({{p[0], p[1], p[2]}});
+		real t1[3];
+		for (int i = 0; i < 3; i++) { t1[i] = -(p[i] * lenN / lenP); }
+		const Real3 t2 = cross({{n[0], n[1], n[2]}}, {{t1[0], t1[1], t1[2]}});
+		const real local[9] = {n[0], t1[0], t2[0], n[1], t1[1], t2[1], n[2], t1[2], t2[2]};
+		const GcmMatrices g = constructGcmMatrices(m.modelType, 3, iso, local);
+		if (g.getMaximalEigenvalue() > m.maximalEigenvalue) { m.maximalEigenvalue = g.getMaximalEigenvalue(); }
+		nodes.push_back((int) l);
+		U.insert(U.end(), g.U.begin(), g.U.end());
+		U1.insert(U1.end(), g.U1.begin(), g.U1.end());
+		L.insert(L.end(), g.L.begin(), g.L.end());
+		bases.insert(bases.end(), local, local + 9);
+	}
+	check(gcmb_simplex_set_local_bases(m.body, (int) nodes.size(), nodes.data(), U.data(), U1.data(), L.data(), bases.data()));
 }
 
 /// the reference's applyInitialConditions on vertex coordinates (DefaultMesh.hpp:63-70 ->

@@ -12,7 +12,7 @@
 //   simplex_mesh FILE [scale S]   (INM mesh file instead of the box mesher)
 //   body ID (elastic|acoustic) isotropic | material body ID MATERIAL | basis b00 b01 .. b22 | basis random [seed]
 //   border_condition AREA (fixed_force|fixed_velocity) [no_multicontact] (const c | sin amp omega)...
-//   contact (adhesion|slide) [ID ID] | gcm_type (riemann_invariants|pde_vectors) | splitting (product|summ)
+//   contact (adhesion|slide) [ID ID] | gcm_type (riemann_invariants|pde_vectors) | splitting (product|summ) | border_calc_mode (global|local)
 // The test suite feeds the same files to the unmodified reference.
 #include <cmath>
 #include <sstream>
@@ -189,6 +189,11 @@ Task parseTaskText(const std::string& text) {
 			if (type == "riemann_invariants") { task.globalSettings.gcmType = GcmType::ADVECT_RIEMANN_INVARIANTS; }
 			else if (type == "pde_vectors") { task.globalSettings.gcmType = GcmType::ADVECT_PDE_VECTORS; }
 			else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown gcm_type " + type); }
+		} else if (key == "border_calc_mode") {
+			const std::string mode = t.next();
+			if (mode == "global") { task.simplexGrid.borderCalcMode = BorderCalcMode::GLOBAL_BASIS; }
+			else if (mode == "local") { task.simplexGrid.borderCalcMode = BorderCalcMode::LOCAL_BASIS; }
+			else { throw Exception(GCMB_E_INVALID_ARG, "task text: unknown border_calc_mode " + mode); }
 		} else if (key == "splitting") {
 			const std::string type = t.next();
 			if (type == "product") { task.globalSettings.splittingType = SplittingType::PRODUCT; }

@@ -212,6 +212,13 @@ int gcmb_simplex_set_gcm_type(gcmb_sbody* body, int gcm_type);
  * layer of its own, gcmb_simplex_average_layers then averages them into the current layer
  * (DefaultMesh::averageNewPdeLayersToCurrent, engine/simplex/DefaultMesh.hpp:160-169; Engine.cpp:104-108) */
 int gcmb_simplex_set_splitting(gcmb_sbody* body, int splitting);
+/* BorderCalcMode::LOCAL_BASIS (util/task/Task.hpp:12-14; engine/simplex/DefaultMesh.hpp:245-266): the listed border and
+ * contact vertices get eigen-systems of their own, U/U1 [n][3][M][M] and L [n][3][M], written in the bases [n][9]
+ * (row-major; stage s runs along column s, the first column is the vertex' normal).  From then on
+ * gcmb_simplex_border_correct / contact_correct act as applyInLocalBasis and only at stage 0
+ * (Engine::correctContactsAndBorders, engine/simplex/Engine.cpp:170-187).  n = 0 returns to GLOBAL_BASIS. */
+int gcmb_simplex_set_local_bases(gcmb_sbody* body, int n, const int* nodes, const double* U, const double* U1,
+                                 const double* L, const double* bases);
 int gcmb_simplex_average_layers(gcmb_sbody* body);
 int gcmb_simplex_before_stage(gcmb_sbody* body, int s, double tau);
 int gcmb_simplex_border_contact_stage(gcmb_sbody* body);

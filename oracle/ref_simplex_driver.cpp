@@ -114,6 +114,8 @@ void parseTaskFile(const std::string& fileName, Task& task, std::map<size_t, boo
 			q.value = tk.num();
 			q.area = parseArea(tk);
 			task.initialCondition.quantities.push_back(q);
+		} else if (key == "border_calc_mode") {
+			task.simplexGrid.borderCalcMode = tk.next() == "local" ? BorderCalcMode::LOCAL_BASIS : BorderCalcMode::GLOBAL_BASIS;
 		} else if (key == "splitting") {
 			task.globalSettings.splittingType = tk.next() == "summ" ? SplittingType::SUMM : SplittingType::PRODUCT;
 		} else if (key == "gcm_type") {

@@ -34,6 +34,8 @@ SCENARIOS = {
     "elastic_contact_pde_vectors": (0, 2, 1, "rotated", 4),
     "acoustic_pde_vectors": (1, 1, 1, "identity", 4),
     "elastic_contact_summ": (0, 2, 0, "rotated", 4, "splitting summ"),
+    "elastic_contact_local_basis": (0, 2, 0, "rotated", 4, "border_calc_mode local"),
+    "acoustic_cavity_local_basis_pde_vectors": (1, 1, 1, "identity", 4, "border_calc_mode local"),
 }
 
 

@@ -246,7 +246,7 @@ def test_launcher_simplex_plate_gpu(tmp_path):
 import simplex_cases as _sx  # noqa: E402
 
 
-@pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX)
+@pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX + _sx.GOLDEN_SIMPLEX_LOCAL)
 def test_simplex_cuda_engine_matches_reference_bitwise(lib, name, tmp_path):
     """the CUDA simplex path == the UNMODIFIED reference simplex engine (compiled against a CGAL stand-in,
     tests/golden/make_simplex_golden.py): time step, step count and every PDE value of every body"""

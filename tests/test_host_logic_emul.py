@@ -287,7 +287,7 @@ def test_inm_mesh_file_round_trip(lib, tmp_path):
 import simplex_cases as _sx  # noqa: E402
 
 
-@pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX)
+@pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX + _sx.GOLDEN_SIMPLEX_LOCAL)
 def test_simplex_engine_matches_reference_bitwise(lib, name, tmp_path):
     _sx.check_engine_against_reference(lib, name, tmp_path)
 
