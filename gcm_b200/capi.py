@@ -76,6 +76,7 @@ C_ABI = {
     "gcmb_simplex_stage": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double, c_double_p]),
     "gcmb_simplex_gradient": (ctypes.c_int, [vp, c_double_p, c_double_p]),
     "gcmb_simplex_set_gcm_type": (ctypes.c_int, [vp, ctypes.c_int]),
+    "gcmb_simplex_ode_maxwell": (ctypes.c_int, [vp, ctypes.c_double]),
     "gcmb_simplex_set_splitting": (ctypes.c_int, [vp, ctypes.c_int]),
     "gcmb_simplex_set_local_bases": (ctypes.c_int, [vp, ctypes.c_int, c_int_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "gcmb_simplex_average_layers": (ctypes.c_int, [vp]),

@@ -224,8 +224,11 @@ void Engine::createMeshes(const Task& task) {
 		if (taskBody.second.modelId != Models::T::ELASTIC && taskBody.second.modelId != Models::T::ACOUSTIC) {
 			throw Exception(GCMB_E_UNSUPPORTED, "Unknown model type");
 		}
-		if (!taskBody.second.odes.empty()) { throw Exception(GCMB_E_UNSUPPORTED, "ODEs on simplex grids are not built"); }
 		Body body;
+		for (const Odes::T ode : taskBody.second.odes) {
+			if (ode != Odes::T::MAXWELL_VISCOSITY) { throw Exception(GCMB_E_UNSUPPORTED, "only the Maxwell viscosity ODE exists"); }
+			body.odes.push_back(ode);
+		}
 		body.mesh = std::make_shared<Mesh>();
 		Mesh& m = *body.mesh;
 		m.id = taskBody.first;
@@ -520,6 +523,12 @@ void Engine::nextTimeStep() {
 	applyPlainBorderContactCorrection(Clock::Time() + Clock::TimeStep());
 	for (int stage = 0; stage < 3; stage++) { gcmStage(stage, Clock::Time(), Clock::TimeStep()); }
 	if (summSplitting) { for (const Body& body : bodies) { check(gcmb_simplex_average_layers(body.mesh->body)); } }
+	for (const Body& body : bodies) {   // engine/simplex/Engine.cpp:110-114
+		for (size_t o = 0; o < body.odes.size(); o++) {
+			const auto& iso = dynamic_cast<const IsotropicMaterial&>(*body.mesh->material);
+			check(gcmb_simplex_ode_maxwell(body.mesh->body, std::exp(-Clock::TimeStep() / iso.tau0)));
+		}
+	}
 	for (const Body& body : bodies) { body.mesh->invalidateHostCopy(); }
 }
 

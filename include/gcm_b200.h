@@ -211,6 +211,9 @@ int gcmb_simplex_set_gcm_type(gcmb_sbody* body, int gcm_type);
  * starts from the result of the previous one (default); 1 SUMM -- every stage starts from the same layer and fills a
  * layer of its own, gcmb_simplex_average_layers then averages them into the current layer
  * (DefaultMesh::averageNewPdeLayersToCurrent, engine/simplex/DefaultMesh.hpp:160-169; Engine.cpp:104-108) */
+/* MaxwellViscosityOde::apply on a simplex mesh (rheology/ode/Ode.hpp:28-38, engine/simplex/Engine.cpp:110-114):
+ * stress components *= decay, decay = exp(-tau / tau0) evaluated by the caller's libm like the reference's */
+int gcmb_simplex_ode_maxwell(gcmb_sbody* body, double decay);
 int gcmb_simplex_set_splitting(gcmb_sbody* body, int splitting);
 /* BorderCalcMode::LOCAL_BASIS (util/task/Task.hpp:12-14; engine/simplex/DefaultMesh.hpp:245-266): the listed border and
  * contact vertices get eigen-systems of their own, U/U1 [n][3][M][M] and L [n][3][M], written in the bases [n][9]

@@ -89,12 +89,16 @@ void parseTaskFile(const std::string& fileName, Task& task, std::map<size_t, boo
 			const bool acoustic = tk.next() == "acoustic";
 			acousticBodies[id] = acoustic;
 			task.bodies[id] = {Materials::T::ISOTROPIC, acoustic ? Models::T::ACOUSTIC : Models::T::ELASTIC, {}};
+			tk.next();  // isotropic
+			if (tk.peek() == "ode") { tk.next(); tk.next(); task.bodies[id].odes.push_back(Odes::T::MAXWELL_VISCOSITY); }
 		} else if (key == "material") {
 			if (tk.next() != "body") { THROW_INVALID_ARG("simplex tasks take materials by bodies"); }
 			const size_t id = (size_t) tk.inum();
 			tk.next();  // isotropic
 			const real rho = tk.num(), la = tk.num(), mu = tk.num();
-			task.materialConditions.byBodies.bodyMaterialMap[id] = std::make_shared<IsotropicMaterial>(rho, la, mu);
+			real tau0 = 0;
+			if (tk.peek() == "tau0") { tk.next(); tau0 = tk.num(); }
+			task.materialConditions.byBodies.bodyMaterialMap[id] = std::make_shared<IsotropicMaterial>(rho, la, mu, 0, 0, 0, tau0);
 		} else if (key == "basis") {
 			task.calculationBasis.clear();
 			for (int i = 0; i < 9; i++) { task.calculationBasis.push_back(tk.num()); }

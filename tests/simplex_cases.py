@@ -490,8 +490,9 @@ def golden_scenario(model, bodies, gcm, basis, steps):
 
 GOLDEN_SIMPLEX = ["elastic_cavity", "elastic_contact", "acoustic_contact_rotated", "elastic_contact_pde_vectors", "acoustic_pde_vectors",
                   "elastic_contact_summ"]
-# BorderCalcMode::LOCAL_BASIS: pinned on the engine level only (the C restatement keeps to GLOBAL_BASIS)
-GOLDEN_SIMPLEX_LOCAL = ["elastic_contact_local_basis", "acoustic_cavity_local_basis_pde_vectors"]
+# BorderCalcMode::LOCAL_BASIS and the Maxwell ODE: pinned on the engine level only (the C restatement keeps to
+# GLOBAL_BASIS and has no ODE)
+GOLDEN_SIMPLEX_LOCAL = ["elastic_contact_local_basis", "acoustic_cavity_local_basis_pde_vectors", "elastic_maxwell"]
 
 
 def load_golden(name):
