@@ -573,6 +573,8 @@ GCMB_HD V3 vertexDirection(const StageS& a, int it) {
 
 // SimplexGrid::findCellCrossedByTheRay through the cache of feet: slot < 0 = no caching for this call
 GCMB_HD Found locateFoot(const StageS& a, int it, V3 shift, long long slot, int& err) {
+	// cache entry: x >= 0: a cell (x, y, z, w) with its barycentrics; x <= -10: the other outcomes, n = -(x + 10)
+	// vertices in (y, z, w); x = -1: not cached (the location raised an error: recomputed, and counted, every time)
 	if (slot >= 0 && a.cacheMode == 2) {
 		const int4 c = a.cacheCell[slot];
 		if (c.x >= 0) {
@@ -582,11 +584,18 @@ GCMB_HD Found locateFoot(const StageS& a, int it, V3 shift, long long slot, int&
 			for (int i = 0; i < 4; i++) { f.l[i] = a.cacheLam[4 * slot + i]; }
 			return f;
 		}
+		if (c.x <= -10) {
+			Found f = nothing();
+			f.n = -(c.x + 10);
+			f.p[0] = c.y; f.p[1] = c.z; f.p[2] = c.w;
+			return f;
+		}
 	}
 	const Found f = locate(a.t, it, shift, err);
 	if (slot >= 0 && a.cacheMode == 1) {
-		const bool plain = f.n == 4 && !err;
-		a.cacheCell[slot] = plain ? make_int4(f.p[0], f.p[1], f.p[2], f.p[3]) : make_int4(-1, -1, -1, -1);
+		int4 c = make_int4(-1, -1, -1, -1);
+		if (!err) { c = f.n == 4 ? make_int4(f.p[0], f.p[1], f.p[2], f.p[3]) : make_int4(-10 - f.n, f.p[0], f.p[1], f.p[2]); }
+		a.cacheCell[slot] = c;
 		for (int i = 0; i < 4; i++) { a.cacheLam[4 * slot + i] = f.l[i]; }
 	}
 	return f;
@@ -730,11 +739,11 @@ GCMB_HD void countError(int* errors) {
 // border and contact vertices (…InRiemannInvariants.hpp:59-96), one thread per (vertex, distinct foot): the
 // invariants go straight to the next layer, the outer ones are collected in waves[it] (zeroed before the pass)
 template<int M>
-GCMB_HD void borderFootThread(const StageS& a, int it, int foot) {
+GCMB_HD void borderFootThread(const StageS& a, int it, int foot, long long slot) {
 	int err = 0;
 	double* out = a.next + (long long) it * M;
 	if (foot == 0) { footAny<M>(a, it, 0.0, a.zeroMask, true, out, err); }
-	const unsigned outers = footAny<M>(a, it, a.footLambda[foot], a.footMask[foot], true, out, err);
+	const unsigned outers = footAny<M>(a, it, a.footLambda[foot], a.footMask[foot], true, out, err, slot);
 	if (outers) {
 #ifdef __CUDA_ARCH__
 		atomicOr(a.waves + it, outers);
