@@ -37,6 +37,7 @@ SCENARIOS = {
     "elastic_contact_local_basis": (0, 2, 0, "rotated", 4, "border_calc_mode local"),
     "acoustic_cavity_local_basis_pde_vectors": (1, 1, 1, "identity", 4, "border_calc_mode local"),
     "elastic_maxwell": (0, 1, 0, "identity", 4, "MAXWELL"),
+    "elastic_three_bodies": (0, 3, 0, "rotated", 4),
 }
 
 

@@ -469,7 +469,11 @@ def check_oracle_against_reference(lib, name, workdir):
 # ---- golden vectors from the unmodified reference engine (tests/golden/make_simplex_golden.py) -------------------
 def golden_scenario(model, bodies, gcm, basis, steps):
     """engine_scenario on a 7x6x8 box with a cavity of about 100 cells that survives the reference's clean-up"""
-    text, _ = engine_scenario(model, bodies=bodies, steps=steps, gcm_type=gcm, cavity=True, basis=basis)
+    text, _ = engine_scenario(model, bodies=min(bodies, 2), steps=steps, gcm_type=gcm, cavity=True, basis=basis)
+    if bodies == 3:
+        # a third body along x: lines where three bodies meet (multicontact vertices without empty space around)
+        name = "elastic" if model == 0 else "acoustic"
+        text += "body 2 %s isotropic\nmaterial body 2 isotropic 1.5 2.5 %r\nregion 2 box 2.0 -10 -10 10 10 10\n" % (name, 0.9 if model == 0 else 0.0)
     lines = []
     for ln in text.split("\n"):
         if ln.startswith("simplex_box"):
@@ -492,7 +496,8 @@ GOLDEN_SIMPLEX = ["elastic_cavity", "elastic_contact", "acoustic_contact_rotated
                   "elastic_contact_summ"]
 # BorderCalcMode::LOCAL_BASIS and the Maxwell ODE: pinned on the engine level only (the C restatement keeps to
 # GLOBAL_BASIS and has no ODE)
-GOLDEN_SIMPLEX_LOCAL = ["elastic_contact_local_basis", "acoustic_cavity_local_basis_pde_vectors", "elastic_maxwell"]
+GOLDEN_SIMPLEX_LOCAL = ["elastic_contact_local_basis", "acoustic_cavity_local_basis_pde_vectors", "elastic_maxwell",
+                        "elastic_three_bodies"]
 
 
 def load_golden(name):
@@ -521,6 +526,8 @@ def check_engine_against_reference(lib, name, workdir):
     eng.run()
     steps, time, tau = eng.info()
     assert (steps, time, tau) == (int(g["steps"]), float(g["time"]), float(g["tau"]))
+    if int(g["bodies"]) == 3:   # every pair of bodies is in contact, and there are vertices where all three meet
+        assert all(len(eng.contact_nodes(a, b)[0]) > 0 for a, b in ((0, 1), (0, 2), (1, 2)))
     for b in range(int(g["bodies"])):
         assert eng.simplex_body_info(b)["average_height"] == float(g["average_height%d" % b])
         got = eng.simplex_pde(b)
