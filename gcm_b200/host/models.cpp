@@ -386,6 +386,315 @@ void orthotropic2D(const OrthotropicMaterial& m, GcmMatrices& g) {
 	}
 }
 
+
+// ---- rotated orthotropic material, 3-D (ElasticModel3D.cpp:8-283, AbstractMaterial.hpp:27-133) ------------------
+namespace rotated {
+
+/// gsl_poly_solve_cubic (GSL poly/solve_cubic.c), which the reference calls through
+/// gsl_utils::solveThirdOrderPolynomial (util/math/GslUtils.hpp:163-204): roots of x^3 + a x^2 + b x + c
+int solveCubic(double a, double b, double c, double* x0, double* x1, double* x2) {
+	const double q = (a * a - 3 * b);
+	const double r = (2 * a * a * a - 9 * a * b + 27 * c);
+	const double Q = q / 9;
+	const double R = r / 54;
+	const double Q3 = Q * Q * Q;
+	const double R2 = R * R;
+	const double CR2 = 729 * r * r;
+	const double CQ3 = 2916 * q * q * q;
+	if (R == 0 && Q == 0) {
+		*x0 = -a / 3; *x1 = -a / 3; *x2 = -a / 3;
+		return 3;
+	} else if (CR2 == CQ3) {
+		const double sqrtQ = std::sqrt(Q);
+		if (R > 0) { *x0 = -2 * sqrtQ - a / 3; *x1 = sqrtQ - a / 3; *x2 = sqrtQ - a / 3; }
+		else { *x0 = -sqrtQ - a / 3; *x1 = -sqrtQ - a / 3; *x2 = 2 * sqrtQ - a / 3; }
+		return 3;
+	} else if (R2 < Q3) {
+		const double sgnR = (R >= 0 ? 1 : -1);
+		const double ratio = sgnR * std::sqrt(R2 / Q3);
+		const double theta = std::acos(ratio);
+		const double norm = -2 * std::sqrt(Q);
+		*x0 = norm * std::cos(theta / 3) - a / 3;
+		*x1 = norm * std::cos((theta + 2.0 * M_PI) / 3) - a / 3;
+		*x2 = norm * std::cos((theta - 2.0 * M_PI) / 3) - a / 3;
+		if (*x0 > *x1) { std::swap(*x0, *x1); }
+		if (*x1 > *x2) {
+			std::swap(*x1, *x2);
+			if (*x0 > *x1) { std::swap(*x0, *x1); }
+		}
+		return 3;
+	}
+	const double sgnR = (R >= 0 ? 1 : -1);
+	const double A = -sgnR * std::pow(std::fabs(R) + std::sqrt(R2 - Q3), 1.0 / 3.0);
+	const double B = Q / A;
+	*x0 = A + B - a / 3;
+	return 1;
+}
+
+/// gsl_utils::solveThirdOrderPolynomial: three real roots, a pair of (nearly) equal ones moved to the end
+void solveThirdOrderPolynomial(const double (&p)[3], double (&x)[3]) {
+	const double eps = 1e-2;
+	double x1 = 0, x2 = 0, x3 = 0;
+	if (solveCubic(p[0], p[1], p[2], &x1, &x2, &x3) != 3) {
+		throw Exception(GCMB_E_UNSUPPORTED, "rotated orthotropic material: the characteristic polynomial has complex roots");
+	}
+	if (std::fabs(x1 - x2) < std::fmax(std::fabs(x1), std::fabs(x2)) * eps) {
+		if (std::fabs(x3 - x2) < std::fmax(std::fabs(x3), std::fabs(x2)) * eps) {
+			x1 = x2 = x3 = (x1 + x2 + x3) / 3;
+		} else {
+			x2 = (x1 + x2) / 2;
+			x1 = x3;
+			x3 = x2;
+		}
+	} else if (std::fabs(x1 - x3) < std::fmax(std::fabs(x1), std::fabs(x3)) * eps) {
+		x3 = (x1 + x3) / 2;
+		x1 = x2;
+		x2 = x3;
+	} else if (std::fabs(x2 - x3) < std::fmax(std::fabs(x2), std::fabs(x3)) * eps) {
+		x2 = x3 = (x2 + x3) / 2;
+	}
+	x[0] = x1; x[1] = x2; x[2] = x3;
+}
+
+inline int sym3(int i, int j) { if (i > j) { std::swap(i, j); } return i * 3 - ((i - 1) * i) / 2 + j - i; }
+inline int sym6(int i, int j) { if (i > j) { std::swap(i, j); } return i * 6 - ((i - 1) * i) / 2 + j - i; }
+
+/// AbstractMaterial::rotate(ElasticMatrix, phi): 6x6 -> 3^4 tensor -> rotation by G = Z(phi2) Y(phi1) X(phi0) -> 6x6
+/// (AbstractMaterial.hpp:27-133; symmetric storage throughout, like linal::SymmetricMatrix)
+void rotatedElasticMatrix(const OrthotropicMaterial& m, double (&c)[21]) {
+	double c0[21];
+	for (double& x : c0) { x = 0; }
+	c0[sym6(0, 0)] = m.c[0]; c0[sym6(0, 1)] = m.c[1]; c0[sym6(0, 2)] = m.c[2];
+	c0[sym6(1, 1)] = m.c[3]; c0[sym6(1, 2)] = m.c[4]; c0[sym6(2, 2)] = m.c[5];
+	c0[sym6(3, 3)] = m.c[6]; c0[sym6(4, 4)] = m.c[7]; c0[sym6(5, 5)] = m.c[8];
+	// convert(ElasticMatrix) -> tensor t[sym3(i,j)][sym3(k,l)]
+	static const int voigt[6][2] = {{0, 0}, {1, 1}, {2, 2}, {1, 2}, {0, 2}, {0, 1}};
+	double t[6][6];
+	for (auto& row : t) for (double& x : row) { x = 0; }
+	for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) {
+		const int ij = sym3(voigt[a][0], voigt[a][1]), kl = sym3(voigt[b][0], voigt[b][1]);
+		t[ij][kl] = t[kl][ij] = c0[sym6(a, b)];
+	}
+	const double phi = m.anglesOfRotation[0], teta = m.anglesOfRotation[1], khi = m.anglesOfRotation[2];
+	const double X[9] = {1.0, 0.0, 0.0, 0.0, std::cos(phi), std::sin(phi), 0.0, -std::sin(phi), std::cos(phi)};
+	const double Y[9] = {std::cos(teta), 0.0, -std::sin(teta), 0.0, 1.0, 0.0, std::sin(teta), 0.0, std::cos(teta)};
+	const double Z[9] = {std::cos(khi), std::sin(khi), 0.0, -std::sin(khi), std::cos(khi), 0.0, 0.0, 0.0, 1.0};
+	auto mul = [](const double* a, const double* b, double* out) {
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+			double r = a[i * 3] * b[j];
+			for (int k = 1; k < 3; k++) { r += a[i * 3 + k] * b[k * 3 + j]; }
+			out[i * 3 + j] = r;
+		}
+	};
+	double zy[9], G[9];
+	mul(Z, Y, zy);
+	mul(zy, X, G);
+	double ans[6][6];
+	for (auto& row : ans) for (double& x : row) { x = 0; }
+	for (int mm = 0; mm < 3; mm++) for (int n = mm; n < 3; n++) for (int p = 0; p < 3; p++) for (int q = p; q < 3; q++) {
+		double& acc = ans[sym3(mm, n)][sym3(p, q)];
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) {
+			acc += G[mm * 3 + i] * G[n * 3 + j] * G[p * 3 + k] * G[q * 3 + l] * t[sym3(i, j)][sym3(k, l)];
+		}
+	}
+	// convert(ElasticTensor) -> 6x6 (the reference reads q(a)(b) with a <= b in Voigt order)
+	for (double& x : c) { x = 0; }
+	for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) {
+		// the reference's table takes (min, max) pairs such that the FIRST index pair is the "earlier" Voigt entry,
+		// except for the shear-shear block where it reads q(0,2)(1,2), q(0,1)(1,2), q(0,1)(0,2)
+		int first = a, second = b;
+		if (a >= 3 && b >= 3 && a != b) { first = b; second = a; }
+		c[sym6(a, b)] = ans[sym3(voigt[first][0], voigt[first][1])][sym3(voigt[second][0], voigt[second][1])];
+	}
+}
+
+/// linal::solveDegenerateLinearSystem for long double 3x3 (linal/linearSystems.hpp:169-244)
+void solveDegenerate(const long double (&A)[3][3], int numberOfSolutions, long double (&x)[3], long double (&y)[3]) {
+	if (numberOfSolutions == 1) {
+		int I = 0, J = 1, P = 0, Q = 1;
+		long double det = 0;
+		for (int i = 0; i < 2; i++) for (int j = i + 1; j < 3; j++) {
+			for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+				if (std::fabs(A[p][i] * A[q][j] - A[q][i] * A[p][j]) > std::fabs(det)) {
+					det = A[p][i] * A[q][j] - A[q][i] * A[p][j];
+					I = i; J = j; P = p; Q = q;
+				}
+			}
+		}
+		int U = 2;
+		for (int k = 0; k < 2; k++) { if (k != I && k != J) { U = k; break; } }
+		x[U] = 1;
+		x[I] = (-A[P][U] * A[Q][J] + A[Q][U] * A[P][J]) / det;
+		x[J] = (-A[P][I] * A[Q][U] + A[Q][I] * A[P][U]) / det;
+		return;
+	}
+	int I = 0, J = 0;
+	long double det = 0;
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+		if (std::fabs(det) < std::fabs(A[i][j])) { det = A[i][j]; I = i; J = j; }
+	}
+	int p, q;
+	if (J == 0) { p = 1; q = 2; } else if (J == 1) { p = 0; q = 2; } else { p = 0; q = 1; }
+	x[p] = y[q] = 1;
+	x[q] = y[p] = 0;
+	x[J] = -A[I][p] / det;
+	y[J] = -A[I][q] / det;
+}
+
+void columnsWithRho(int stage, int& i, int& j, int& k) {
+	if (stage == 0) { i = 3; j = 4; k = 5; } else if (stage == 1) { i = 4; j = 6; k = 7; } else { i = 5; j = 7; k = 8; }
+}
+void zeroColumns(int stage, int& i, int& j, int& k) {
+	if (stage == 0) { i = 6; j = 7; k = 8; } else if (stage == 1) { i = 3; j = 5; k = 8; } else { i = 3; j = 4; k = 6; }
+}
+
+/// findEigenvectors (vectors = true) / findEigenstrings (false) of ElasticModel3D.cpp:74-148
+void eigen(bool vectors, long double l, const double (&A)[9][9], int stage, int count, long double (&out)[2][9]) {
+	int i, j, k, p, q, m;
+	columnsWithRho(stage, i, j, k);
+	zeroColumns(stage, p, q, m);
+	const long double r = A[0][i];
+	long double M[3][3];
+	if (vectors) {
+		const long double init[3][3] = {{A[i][0] - l * l / r, A[i][1], A[i][2]}, {A[j][0], A[j][1] - l * l / r, A[j][2]},
+		                                {A[k][0], A[k][1], A[k][2] - l * l / r}};
+		for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { M[a][b] = init[a][b]; }
+	} else {
+		const long double init[3][3] = {{A[i][0] - l * l / r, A[j][0], A[k][0]}, {A[i][1], A[j][1] - l * l / r, A[k][1]},
+		                                {A[i][2], A[j][2], A[k][2] - l * l / r}};
+		for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { M[a][b] = init[a][b]; }
+	}
+	long double sol[2][3] = {{0, 0, 0}, {0, 0, 0}};
+	solveDegenerate(M, count, sol[0], sol[1]);
+	for (int n = 0; n < count; n++) {
+		long double* ev = out[n];
+		for (int a = 0; a < 9; a++) { ev[a] = 0; }
+		if (vectors) {
+			ev[0] = sol[n][0]; ev[1] = sol[n][1]; ev[2] = sol[n][2];
+			ev[i] = l / r * ev[0];
+			ev[j] = l / r * ev[1];
+			ev[k] = l / r * ev[2];
+			ev[p] = (A[p][0] * ev[0] + A[p][1] * ev[1] + A[p][2] * ev[2]) / l;
+			ev[q] = (A[q][0] * ev[0] + A[q][1] * ev[1] + A[q][2] * ev[2]) / l;
+			ev[m] = (A[m][0] * ev[0] + A[m][1] * ev[1] + A[m][2] * ev[2]) / l;
+		} else {
+			ev[i] = sol[n][0]; ev[j] = sol[n][1]; ev[k] = sol[n][2];
+			ev[0] = l / r * ev[i];
+			ev[1] = l / r * ev[j];
+			ev[2] = l / r * ev[k];
+			ev[p] = 0; ev[q] = 0; ev[m] = 0;
+		}
+	}
+}
+
+long double det3l(long double a11, long double a12, long double a13, long double a21, long double a22, long double a23,
+                  long double a31, long double a32, long double a33) {
+	return a11 * (a22 * a33 - a23 * a32) - a12 * (a21 * a33 - a23 * a31) + a13 * (a21 * a32 - a22 * a31);
+}
+
+}  // namespace rotated
+
+/// ElasticModel<3>::constructRotated (ElasticModel3D.cpp:151-283)
+void orthotropicRotated3D(const OrthotropicMaterial& material, GcmMatrices& g) {
+	using namespace rotated;
+	const double rho = material.rho;
+	double c21[21];
+	rotatedElasticMatrix(material, c21);
+	auto c = [&c21](int i, int j) { return c21[sym6(i, j)]; };
+	double A3[3][9][9];
+	for (auto& a : A3) for (auto& row : a) for (double& x : row) { x = 0; }
+	// columns of stress rates per velocity component, rows 3..8 (ElasticModel3D.cpp:163-203)
+	static const int rhoCol[3][3] = {{3, 4, 5}, {4, 6, 7}, {5, 7, 8}};
+	static const int cIdx[3][6][3][2] = {
+		{{{0, 0}, {0, 5}, {0, 4}}, {{0, 5}, {5, 5}, {4, 5}}, {{0, 4}, {4, 5}, {4, 4}}, {{0, 1}, {1, 5}, {1, 4}}, {{0, 3}, {3, 5}, {3, 4}}, {{0, 2}, {2, 5}, {2, 4}}},
+		{{{0, 5}, {0, 1}, {0, 3}}, {{5, 5}, {1, 5}, {3, 5}}, {{4, 5}, {1, 4}, {3, 4}}, {{1, 5}, {1, 1}, {1, 3}}, {{3, 5}, {1, 3}, {3, 3}}, {{2, 5}, {1, 2}, {2, 3}}},
+		{{{0, 4}, {0, 3}, {0, 2}}, {{4, 5}, {3, 5}, {2, 5}}, {{4, 4}, {3, 4}, {2, 4}}, {{1, 4}, {1, 3}, {1, 2}}, {{3, 4}, {3, 3}, {2, 3}}, {{2, 4}, {2, 3}, {2, 2}}}};
+	for (int s = 0; s < 3; s++) {
+		for (int v = 0; v < 3; v++) { A3[s][v][rhoCol[s][v]] = -1.0 / rho; }
+		for (int row = 0; row < 6; row++) for (int v = 0; v < 3; v++) { A3[s][3 + row][v] = -c(cIdx[s][row][v][0], cIdx[s][row][v][1]); }
+	}
+	for (int stage = 0; stage < 3; stage++) {
+		const double (&A)[9][9] = A3[stage];
+		double* U = g.U.data() + stage * 81;
+		double* U1 = g.U1.data() + stage * 81;
+		double* L = g.L.data() + stage * 9;
+		int i, j, k;
+		columnsWithRho(stage, i, j, k);
+		// constructEigenvaluesPolynomial (ElasticModel3D.cpp:50-71)
+		const long double r = A[0][i];
+		long double pl[3];
+		pl[0] = r * (-A[k][2] - A[j][1] - A[i][0]);
+		pl[1] = r * r * ((A[j][1] + A[i][0]) * A[k][2] - A[j][2] * A[k][1] - A[i][2] * A[k][0] + A[i][0] * A[j][1] - A[i][1] * A[j][0]);
+		pl[2] = r * r * r * ((-A[i][0] * A[j][1] + A[i][1] * A[j][0]) * A[k][2] + (A[i][0] * A[j][2] - A[i][2] * A[j][0]) * A[k][1] +
+		                     (-A[i][1] * A[j][2] + A[i][2] * A[j][1]) * A[k][0]);
+		const double pd[3] = {(double) pl[0], (double) pl[1], (double) pl[2]};
+		double sq[3];
+		solveThirdOrderPolynomial(pd, sq);
+		const double s1w = (double) std::sqrt(sq[2]), s2w = (double) std::sqrt(sq[1]), pw = (double) std::sqrt(sq[0]);
+		const double Ls[9] = {-s1w, s1w, -s2w, s2w, -pw, pw, 0, 0, 0};
+		for (int n = 0; n < 9; n++) { L[n] = Ls[n]; }
+		long double ev[2][9];
+		auto setColumn = [&](int col, const long double* v) { for (int a = 0; a < 9; a++) { U1[a * 9 + col] = (double) v[a]; } };
+		auto setRow = [&](int row, const long double* v) { for (int a = 0; a < 9; a++) { U[row * 9 + a] = (double) v[a]; } };
+		if (sq[1] != sq[2]) {
+			for (int n = 0; n < 6; n++) {
+				eigen(true, L[n], A, stage, 1, ev);
+				setColumn(n, ev[0]);
+				eigen(false, L[n], A, stage, 1, ev);
+				setRow(n, ev[0]);
+			}
+		} else {
+			for (int n = 4; n < 6; n++) {
+				eigen(true, L[n], A, stage, 1, ev);
+				setColumn(n, ev[0]);
+				eigen(false, L[n], A, stage, 1, ev);
+				setRow(n, ev[0]);
+			}
+			for (int n = 0; n < 2; n++) {
+				eigen(true, L[n], A, stage, 2, ev);
+				setColumn(n, ev[0]);
+				setColumn(n + 2, ev[1]);
+				eigen(false, L[n], A, stage, 2, ev);
+				setRow(n, ev[0]);
+				setRow(n + 2, ev[1]);
+			}
+		}
+		int p, q, rr;
+		zeroColumns(stage, p, q, rr);
+		U1[p * 9 + 6] = U1[q * 9 + 7] = U1[rr * 9 + 8] = 1;
+		U[6 * 9 + p] = U[7 * 9 + q] = U[8 * 9 + rr] = 1;
+		// rows 6..8 of U: solve M x = -A(row, 0..2) by Cramer's rule in long double (ElasticModel3D.cpp:253-270)
+		const long double M[3][3] = {{A[i][0], A[j][0], A[k][0]}, {A[i][1], A[j][1], A[k][1]}, {A[i][2], A[j][2], A[k][2]}};
+		const int zero[3] = {p, q, rr};
+		for (int z = 0; z < 3; z++) {
+			const double b[3] = {-A[zero[z]][0], -A[zero[z]][1], -A[zero[z]][2]};
+			// determinant(A) of a long double matrix resolves to the Matrix33 (double) overload in the reference
+			// (linal/determinants.hpp:56-60): the denominator is computed in double, the numerators in long double
+			const double Md[3][3] = {{(double) M[0][0], (double) M[0][1], (double) M[0][2]}, {(double) M[1][0], (double) M[1][1], (double) M[1][2]},
+			                         {(double) M[2][0], (double) M[2][1], (double) M[2][2]}};
+			const double det = Md[0][0] * (Md[1][1] * Md[2][2] - Md[1][2] * Md[2][1]) - Md[0][1] * (Md[1][0] * Md[2][2] - Md[1][2] * Md[2][0]) +
+			                   Md[0][2] * (Md[1][0] * Md[2][1] - Md[1][1] * Md[2][0]);
+			if (det == 0) { throw Exception(GCMB_E_INVALID_ARG, "SLE determinant is zero"); }
+			const long double d1 = det3l(b[0], M[0][1], M[0][2], b[1], M[1][1], M[1][2], b[2], M[2][1], M[2][2]);
+			const long double d2 = det3l(M[0][0], b[0], M[0][2], M[1][0], b[1], M[1][2], M[2][0], b[2], M[2][2]);
+			const long double d3 = det3l(M[0][0], M[0][1], b[0], M[1][0], M[1][1], b[1], M[2][0], M[2][1], b[2]);
+			U[(6 + z) * 9 + i] = (double) (d1 / det);
+			U[(6 + z) * 9 + j] = (double) (d2 / det);
+			U[(6 + z) * 9 + k] = (double) (d3 / det);
+		}
+		// U*U1 is diagonal now: normalise to the identity (ElasticModel3D.cpp:272-279)
+		for (int n = 0; n < 9; n++) {
+			double diag = U[n * 9] * U1[n];
+			for (int a = 1; a < 9; a++) { diag += U[n * 9 + a] * U1[a * 9 + n]; }
+			const double normalizer = std::sqrt(std::fabs(diag));
+			if (diag == 0) { throw Exception(GCMB_E_INVALID_ARG, "degenerate eigen-system of a rotated orthotropic material"); }
+			const int sign = diag > 0 ? 1 : -1;
+			for (int a = 0; a < 9; a++) { U1[a * 9 + n] = U1[a * 9 + n] / normalizer; }
+			for (int a = 0; a < 9; a++) { U[n * 9 + a] = (sign * U[n * 9 + a]) / normalizer; }
+		}
+	}
+}
+
 }  // namespace
 
 GcmMatrices constructGcmMatrices(Models::T model, int D, const IsotropicMaterial& material, const real* calcBasis) {
@@ -438,10 +747,10 @@ GcmMatrices constructGcmMatrices(Models::T model, int D, const AbstractMaterial&
 		g.checkDecomposition(100 * 1e-9 * 1000);
 	} else if (ortho) {
 		if (model != Models::T::ELASTIC) { throw Exception(GCMB_E_UNSUPPORTED, "Unknown or inappropriate model type"); }
-		if (ortho->anglesOfRotation[0] != 0 || ortho->anglesOfRotation[1] != 0 || ortho->anglesOfRotation[2] != 0) {
-			throw Exception(GCMB_E_UNSUPPORTED, "rotated orthotropic materials are not supported yet");
-		}
-		if (D == 3) { orthotropic3D(*ortho, g); }
+		const bool isRotated = ortho->anglesOfRotation[0] != 0 || ortho->anglesOfRotation[1] != 0 || ortho->anglesOfRotation[2] != 0;
+		if (isRotated && D != 3) { throw Exception(GCMB_E_UNSUPPORTED, "rotated orthotropic materials exist in 3-D only"); }
+		if (D == 3 && isRotated) { orthotropicRotated3D(*ortho, g); g.checkDecomposition(1e-2); }
+		else if (D == 3) { orthotropic3D(*ortho, g); }
 		else if (D == 2) { orthotropic2D(*ortho, g); g.checkDecomposition(1e-9 * 1000); }
 		else { throw Exception(GCMB_E_UNSUPPORTED, "OrthotropicMaterial in 1D is meaningless"); }
 	} else {

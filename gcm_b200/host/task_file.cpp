@@ -6,7 +6,7 @@
 //   border ID direction AREA {Q (const c | sin amp omega)}...
 //   detector ID Q AREA [output-directory] | vtk [every N] Q... | output DIRECTORY
 //   AREA = infinite | box x0 y0 z0 x1 y1 z1 | sphere r cx cy cz | cylinder r bx by bz ex ey ez
-//   MATERIAL = isotropic rho lambda mu [tau0 t] | orthotropic rho c11 c12 c13 c22 c23 c33 c44 c55 c66 [tau0 t]
+//   MATERIAL = isotropic rho lambda mu [tau0 t] | orthotropic rho c11 c12 c13 c22 c23 c33 c44 c55 c66 [angles a b c] [tau0 t]
 // Simplex grids (box mesher):
 //   grid simplex | simplex_box nx ny nz ox oy oz h [jitter j] [seed s] | region ID AREA | cavity AREA
 //   simplex_mesh FILE [scale S]   (INM mesh file instead of the box mesher)
@@ -62,10 +62,12 @@ Task::MaterialCondition::Material material(Words& t) {
 		real c[9];
 		for (real& x : c) { x = t.num(); }
 		real tau0 = 0;
+		Real3 angles = {{0, 0, 0}};
+		if (t.peek() == "angles") { t.next(); angles = t.vec(); }   // rotation of the material axes (radians)
 		if (t.peek() == "tau0") { t.next(); tau0 = t.num(); }
 		ans = std::make_shared<OrthotropicMaterial>(rho,
 				std::initializer_list<real>{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]},
-				0, 0, Real3{{0, 0, 0}}, tau0);
+				0, 0, angles, tau0);
 	} else {
 		throw Exception(GCMB_E_INVALID_ARG, "task text: unknown material " + kind);
 	}

@@ -364,6 +364,248 @@ void gcmo_elastic_orthotropic(int D, double rho, const double c[9], double* U, d
 /* interpolation: util/math/interpolation/EqualDistanceLineInterpolator.hpp                    */
 /* ------------------------------------------------------------------------------------------ */
 
+
+/* ---- rotated orthotropic material, 3-D ---------------------------------------------------------------------------
+ * rheology/models/ElasticModel3D.cpp:8-283 (constructRotated and its helpers), rheology/materials/AbstractMaterial.hpp:27-133
+ * (rotation of the elastic matrix through the rank-4 tensor), util/math/GslUtils.hpp:163-204 (cubic roots, around
+ * GSL's gsl_poly_solve_cubic, poly/solve_cubic.c of GSL, restated here since GSL is absent),
+ * linal/linearSystems.hpp:104-129,169-244 (Cramer, degenerate systems).  long double where the reference uses it. */
+typedef long double ldbl;
+#ifndef M_PI
+#define M_PI 3.14159265358979323846 /* <math.h> hides it under -std=c11 */
+#endif
+
+static int gsl_cubic(double a, double b, double c, double x[3]) {
+	const double q = (a * a - 3 * b), r = (2 * a * a * a - 9 * a * b + 27 * c);
+	const double Q = q / 9, R = r / 54;
+	const double Q3 = Q * Q * Q, R2 = R * R;
+	const double CR2 = 729 * r * r, CQ3 = 2916 * q * q * q;
+	if (R == 0 && Q == 0) { x[0] = x[1] = x[2] = -a / 3; return 3; }
+	if (CR2 == CQ3) {
+		const double sq = sqrt(Q);
+		if (R > 0) { x[0] = -2 * sq - a / 3; x[1] = sq - a / 3; x[2] = sq - a / 3; }
+		else { x[0] = -sq - a / 3; x[1] = -sq - a / 3; x[2] = 2 * sq - a / 3; }
+		return 3;
+	}
+	if (R2 < Q3) {
+		const double sgn = (R >= 0 ? 1 : -1);
+		const double theta = acos(sgn * sqrt(R2 / Q3));
+		const double norm = -2 * sqrt(Q);
+		double t;
+		x[0] = norm * cos(theta / 3) - a / 3;
+		x[1] = norm * cos((theta + 2.0 * M_PI) / 3) - a / 3;
+		x[2] = norm * cos((theta - 2.0 * M_PI) / 3) - a / 3;
+		if (x[0] > x[1]) { t = x[0]; x[0] = x[1]; x[1] = t; }
+		if (x[1] > x[2]) {
+			t = x[1]; x[1] = x[2]; x[2] = t;
+			if (x[0] > x[1]) { t = x[0]; x[0] = x[1]; x[1] = t; }
+		}
+		return 3;
+	}
+	return 1; /* one real root: the reference would go on to gsl_poly_complex_solve_cubic */
+}
+
+/* GslUtils.hpp:163-204: nearly equal roots (relative 1e-2) are averaged and moved to the end */
+static int third_order_roots(const double p[3], double out[3]) {
+	const double eps = 1e-2;
+	double x[3];
+	if (gsl_cubic(p[0], p[1], p[2], x) != 3) { return -1; }
+	double x1 = x[0], x2 = x[1], x3 = x[2];
+	if (fabs(x1 - x2) < fmax(fabs(x1), fabs(x2)) * eps) {
+		if (fabs(x3 - x2) < fmax(fabs(x3), fabs(x2)) * eps) { x1 = x2 = x3 = (x1 + x2 + x3) / 3; }
+		else { x2 = (x1 + x2) / 2; x1 = x3; x3 = x2; }
+	} else if (fabs(x1 - x3) < fmax(fabs(x1), fabs(x3)) * eps) {
+		x3 = (x1 + x3) / 2; x1 = x2; x2 = x3;
+	} else if (fabs(x2 - x3) < fmax(fabs(x2), fabs(x3)) * eps) {
+		x2 = x3 = (x2 + x3) / 2;
+	}
+	out[0] = x1; out[1] = x2; out[2] = x3;
+	return 0;
+}
+
+static const int VOIGT[6][2] = {{0, 0}, {1, 1}, {2, 2}, {1, 2}, {0, 2}, {0, 1}};
+static int pair3(int i, int j) { return i <= j ? i * 3 - ((i - 1) * i) / 2 + j - i : pair3(j, i); }
+
+/* AbstractMaterial.hpp:27-133: C (Voigt 6x6) -> c_ijkl -> G G G G c -> Voigt, G = Z(a2) Y(a1) X(a0) */
+static void rotate_stiffness(const double c9[9], const double ang[3], double C[6][6]) {
+	double C0[6][6] = {{0}};
+	C0[0][0] = c9[0]; C0[0][1] = C0[1][0] = c9[1]; C0[0][2] = C0[2][0] = c9[2];
+	C0[1][1] = c9[3]; C0[1][2] = C0[2][1] = c9[4]; C0[2][2] = c9[5];
+	C0[3][3] = c9[6]; C0[4][4] = c9[7]; C0[5][5] = c9[8];
+	double t[6][6], r[6][6] = {{0}};
+	for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) {
+		t[pair3(VOIGT[a][0], VOIGT[a][1])][pair3(VOIGT[b][0], VOIGT[b][1])] = C0[a][b];
+	}
+	const double X[3][3] = {{1.0, 0.0, 0.0}, {0.0, cos(ang[0]), sin(ang[0])}, {0.0, -sin(ang[0]), cos(ang[0])}};
+	const double Y[3][3] = {{cos(ang[1]), 0.0, -sin(ang[1])}, {0.0, 1.0, 0.0}, {sin(ang[1]), 0.0, cos(ang[1])}};
+	const double Z[3][3] = {{cos(ang[2]), sin(ang[2]), 0.0}, {-sin(ang[2]), cos(ang[2]), 0.0}, {0.0, 0.0, 1.0}};
+	double ZY[3][3], G[3][3];
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+		ZY[i][j] = Z[i][0] * Y[0][j]; ZY[i][j] += Z[i][1] * Y[1][j]; ZY[i][j] += Z[i][2] * Y[2][j];
+	}
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+		G[i][j] = ZY[i][0] * X[0][j]; G[i][j] += ZY[i][1] * X[1][j]; G[i][j] += ZY[i][2] * X[2][j];
+	}
+	for (int m = 0; m < 3; m++) for (int n = m; n < 3; n++) for (int p = 0; p < 3; p++) for (int q = p; q < 3; q++) {
+		double acc = 0;
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) {
+			acc += G[m][i] * G[n][j] * G[p][k] * G[q][l] * t[pair3(i, j)][pair3(k, l)];
+		}
+		r[pair3(m, n)][pair3(p, q)] = acc;
+	}
+	/* back to Voigt: the reference reads the upper triangle, and within the shear block takes (later, earlier) */
+	for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) {
+		const int f = (a >= 3 && b > a) ? b : a, g = (a >= 3 && b > a) ? a : b;
+		C[a][b] = C[b][a] = r[pair3(VOIGT[f][0], VOIGT[f][1])][pair3(VOIGT[g][0], VOIGT[g][1])];
+	}
+}
+
+static const int RHO_COLS[3][3] = {{3, 4, 5}, {4, 6, 7}, {5, 7, 8}};   /* getColumnsWithRho, ElasticModel3D.cpp:8-22 */
+static const int ZERO_COLS[3][3] = {{6, 7, 8}, {3, 5, 8}, {3, 4, 6}};  /* getZeroColumns, :25-39 */
+
+/* linal/linearSystems.hpp:169-244 for a 3x3 long double matrix of rank 2 (one solution) or 1 (two) */
+static void degenerate_solutions(ldbl A[3][3], int count, ldbl x[3], ldbl y[3]) {
+	x[0] = x[1] = x[2] = y[0] = y[1] = y[2] = 0;
+	if (count == 1) {
+		int I = 0, J = 1, P = 0, Q = 1;
+		ldbl det = 0;
+		for (int i = 0; i < 2; i++) for (int j = i + 1; j < 3; j++) for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+			const ldbl d = A[p][i] * A[q][j] - A[q][i] * A[p][j];
+			if (fabsl(d) > fabsl(det)) { det = A[p][i] * A[q][j] - A[q][i] * A[p][j]; I = i; J = j; P = p; Q = q; }
+		}
+		int U = 2;
+		for (int k = 0; k < 2; k++) { if (k != I && k != J) { U = k; break; } }
+		x[U] = 1;
+		x[I] = (-A[P][U] * A[Q][J] + A[Q][U] * A[P][J]) / det;
+		x[J] = (-A[P][I] * A[Q][U] + A[Q][I] * A[P][U]) / det;
+		return;
+	}
+	int I = 0, J = 0;
+	ldbl det = 0;
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+		if (fabsl(det) < fabsl(A[i][j])) { det = A[i][j]; I = i; J = j; }
+	}
+	const int p = (J == 0) ? 1 : 0, q = (J == 2) ? 1 : 2;
+	x[p] = y[q] = 1;
+	x[J] = -A[I][p] / det;
+	y[J] = -A[I][q] / det;
+}
+
+/* findEigenvectors / findEigenstrings, ElasticModel3D.cpp:74-148 */
+static void eigen_of(int vectors, ldbl l, double A[9][9], int s, int count, ldbl out[2][9]) {
+	const int i = RHO_COLS[s][0], j = RHO_COLS[s][1], k = RHO_COLS[s][2];
+	const int rows[3] = {i, j, k};
+	const ldbl r = A[0][i];
+	ldbl m[3][3], sol[2][3];
+	for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+		m[a][b] = vectors ? (ldbl) A[rows[a]][b] : (ldbl) A[rows[b]][a];
+		if (a == b) { m[a][b] = A[rows[a]][a] - l * l / r; }
+	}
+	degenerate_solutions(m, count, sol[0], sol[1]);
+	for (int n = 0; n < count; n++) {
+		ldbl* e = out[n];
+		for (int a = 0; a < 9; a++) { e[a] = 0; }
+		if (vectors) {
+			for (int a = 0; a < 3; a++) { e[a] = sol[n][a]; }
+			for (int a = 0; a < 3; a++) { e[rows[a]] = l / r * e[a]; }
+			for (int z = 0; z < 3; z++) {
+				const int p = ZERO_COLS[s][z];
+				e[p] = (A[p][0] * e[0] + A[p][1] * e[1] + A[p][2] * e[2]) / l;
+			}
+		} else {
+			for (int a = 0; a < 3; a++) { e[rows[a]] = sol[n][a]; }
+			for (int a = 0; a < 3; a++) { e[a] = l / r * e[rows[a]]; }
+		}
+	}
+}
+
+static ldbl det3_ld(ldbl a11, ldbl a12, ldbl a13, ldbl a21, ldbl a22, ldbl a23, ldbl a31, ldbl a32, ldbl a33) {
+	return a11 * (a22 * a33 - a23 * a32) - a12 * (a21 * a33 - a23 * a31) + a13 * (a21 * a32 - a22 * a31);
+}
+
+/* ElasticModel<3>::constructRotated, ElasticModel3D.cpp:151-283.  Returns 0, or -1 when the characteristic cubic has
+ * complex roots (the reference's fallback needs gsl_poly_complex_solve_cubic), -2 for a singular system. */
+int gcmo_elastic_orthotropic_rotated(double rho, const double c9[9], const double angles[3], double* U, double* U1, double* L) {
+	double C[6][6];
+	rotate_stiffness(c9, angles, C);
+	memset(U, 0, 3 * 81 * sizeof(double));
+	memset(U1, 0, 3 * 81 * sizeof(double));
+	memset(L, 0, 3 * 9 * sizeof(double));
+	/* sigma rows in PDE order xx xy xz yy yz zz = Voigt 0 5 4 1 3 2; velocity-gradient columns of stage s:
+	 * d v_x / d x_s, d v_y / d x_s, d v_z / d x_s pair with Voigt entries of (x,s), (y,s), (z,s) */
+	static const int ROW_VOIGT[6] = {0, 5, 4, 1, 3, 2};
+	static const int COL_VOIGT[3][3] = {{0, 5, 4}, {5, 1, 3}, {4, 3, 2}};
+	for (int s = 0; s < 3; s++) {
+		double A[9][9] = {{0}};
+		for (int v = 0; v < 3; v++) { A[v][RHO_COLS[s][v]] = -1.0 / rho; }
+		for (int row = 0; row < 6; row++) for (int v = 0; v < 3; v++) { A[3 + row][v] = -C[ROW_VOIGT[row]][COL_VOIGT[s][v]]; }
+		double* Us = U + s * 81;
+		double* U1s = U1 + s * 81;
+		double* Ls = L + s * 9;
+		const int i = RHO_COLS[s][0], j = RHO_COLS[s][1], k = RHO_COLS[s][2];
+		/* constructEigenvaluesPolynomial, :50-71 */
+		const ldbl r = A[0][i];
+		const ldbl p0 = r * (-A[k][2] - A[j][1] - A[i][0]);
+		const ldbl p1 = r * r * ((A[j][1] + A[i][0]) * A[k][2] - A[j][2] * A[k][1] - A[i][2] * A[k][0] + A[i][0] * A[j][1] - A[i][1] * A[j][0]);
+		const ldbl p2 = r * r * r * ((-A[i][0] * A[j][1] + A[i][1] * A[j][0]) * A[k][2] + (A[i][0] * A[j][2] - A[i][2] * A[j][0]) * A[k][1] +
+		                             (-A[i][1] * A[j][2] + A[i][2] * A[j][1]) * A[k][0]);
+		const double pd[3] = {(double) p0, (double) p1, (double) p2};
+		double sq[3];
+		if (third_order_roots(pd, sq) != 0) { return -1; }
+		const double s1 = sqrt(sq[2]), s2 = sqrt(sq[1]), pw = sqrt(sq[0]);
+		const double lam[9] = {-s1, s1, -s2, s2, -pw, pw, 0, 0, 0};
+		memcpy(Ls, lam, sizeof lam);
+		ldbl e[2][9];
+#define GCMO_COL(col, v) for (int a = 0; a < 9; a++) { U1s[a * 9 + (col)] = (double) (v)[a]; }
+#define GCMO_ROW(row, v) for (int a = 0; a < 9; a++) { Us[(row) * 9 + a] = (double) (v)[a]; }
+		const int single_from = (sq[1] != sq[2]) ? 0 : 4;
+		for (int n = single_from; n < 6; n++) {
+			eigen_of(1, Ls[n], A, s, 1, e); GCMO_COL(n, e[0]);
+			eigen_of(0, Ls[n], A, s, 1, e); GCMO_ROW(n, e[0]);
+		}
+		if (single_from == 4) {
+			for (int n = 0; n < 2; n++) {
+				eigen_of(1, Ls[n], A, s, 2, e); GCMO_COL(n, e[0]); GCMO_COL(n + 2, e[1]);
+				eigen_of(0, Ls[n], A, s, 2, e); GCMO_ROW(n, e[0]); GCMO_ROW(n + 2, e[1]);
+			}
+		}
+#undef GCMO_COL
+#undef GCMO_ROW
+		for (int z = 0; z < 3; z++) {
+			const int zc = ZERO_COLS[s][z];
+			U1s[zc * 9 + 6 + z] = 1;
+			Us[(6 + z) * 9 + zc] = 1;
+		}
+		/* rows 6..8: Cramer's rule; determinant(M) of the long double matrix binds to the double overload
+		 * (linal/determinants.hpp:56-60), the three numerators stay long double */
+		const double Md[3][3] = {{A[i][0], A[j][0], A[k][0]}, {A[i][1], A[j][1], A[k][1]}, {A[i][2], A[j][2], A[k][2]}};
+		const double det = Md[0][0] * (Md[1][1] * Md[2][2] - Md[1][2] * Md[2][1]) - Md[0][1] * (Md[1][0] * Md[2][2] - Md[1][2] * Md[2][0]) +
+		                   Md[0][2] * (Md[1][0] * Md[2][1] - Md[1][1] * Md[2][0]);
+		if (det == 0) { return -2; }
+		for (int z = 0; z < 3; z++) {
+			const int zc = ZERO_COLS[s][z];
+			const double b[3] = {-A[zc][0], -A[zc][1], -A[zc][2]};
+			const ldbl d1 = det3_ld(b[0], Md[0][1], Md[0][2], b[1], Md[1][1], Md[1][2], b[2], Md[2][1], Md[2][2]);
+			const ldbl d2 = det3_ld(Md[0][0], b[0], Md[0][2], Md[1][0], b[1], Md[1][2], Md[2][0], b[2], Md[2][2]);
+			const ldbl d3 = det3_ld(Md[0][0], Md[0][1], b[0], Md[1][0], Md[1][1], b[1], Md[2][0], Md[2][1], b[2]);
+			Us[(6 + z) * 9 + i] = (double) (d1 / det);
+			Us[(6 + z) * 9 + j] = (double) (d2 / det);
+			Us[(6 + z) * 9 + k] = (double) (d3 / det);
+		}
+		/* U * U1 is diagonal: scale to the identity (:272-279) */
+		for (int n = 0; n < 9; n++) {
+			double d = Us[n * 9] * U1s[n];
+			for (int a = 1; a < 9; a++) { d += Us[n * 9 + a] * U1s[a * 9 + n]; }
+			if (d == 0) { return -2; }
+			const double nz = sqrt(fabs(d));
+			const int sg = d > 0 ? 1 : -1;
+			for (int a = 0; a < 9; a++) { U1s[a * 9 + n] = U1s[a * 9 + n] / nz; }
+			for (int a = 0; a < 9; a++) { Us[n * 9 + a] = (sg * Us[n * 9 + a]) / nz; }
+		}
+	}
+	return 0;
+}
+
 /* :56-71  Newton forward interpolation; src (n vectors of m) is overwritten */
 int gcmo_interpolate(int m, int n, double* src, double q, double* out) {
 	for (int c = 0; c < m; c++) { out[c] = src[c]; }

@@ -32,6 +32,8 @@ int gcmo_pde_size(int model /*0 elastic,1 acoustic*/, int D);
 void gcmo_elastic_isotropic(int D, double rho, double lambda, double mu,
                             double* U, double* U1, double* L);
 void gcmo_elastic_orthotropic(int D, double rho, const double c[9], double* U, double* U1, double* L);
+/* rotated material axes, 3-D only (ElasticModel3D.cpp:151-283); 0 = ok */
+int gcmo_elastic_orthotropic_rotated(double rho, const double c[9], const double angles[3], double* U, double* U1, double* L);
 void gcmo_acoustic(int D, double rho, double lambda, double* U, double* U1, double* L);
 
 /* ---- interpolation (util/math/interpolation/EqualDistanceLineInterpolator.hpp:18-71) ---- */

@@ -49,6 +49,8 @@ def lib():
         L.gcmo_all_nodes.argtypes = [ctypes.c_int, ip, ctypes.c_int]
         L.gcmo_elastic_isotropic.argtypes = [ctypes.c_int] + [ctypes.c_double] * 3 + [dp] * 3
         L.gcmo_elastic_orthotropic.argtypes = [ctypes.c_int, ctypes.c_double, dp, dp, dp, dp]
+        L.gcmo_elastic_orthotropic_rotated.argtypes = [ctypes.c_double, dp, dp, dp, dp, dp]
+        L.gcmo_elastic_orthotropic_rotated.restype = ctypes.c_int
         L.gcmo_acoustic.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, dp, dp, dp]
         L.gcmo_minmax_interpolate.argtypes = [ctypes.c_int, ctypes.c_int, dp, ctypes.c_double, dp]
         L.gcmo_interpolate.argtypes = [ctypes.c_int, ctypes.c_int, dp, ctypes.c_double, dp]
@@ -116,7 +118,10 @@ def parse_material(tk):
     if kind == "isotropic":
         m = {"kind": kind, "rho": tk.num(), "lambda": tk.num(), "mu": tk.num(), "tau0": 0.0}
     elif kind == "orthotropic":
-        m = {"kind": kind, "rho": tk.num(), "c": [tk.num() for _ in range(9)], "tau0": 0.0}
+        m = {"kind": kind, "rho": tk.num(), "c": [tk.num() for _ in range(9)], "tau0": 0.0, "angles": [0.0, 0.0, 0.0]}
+        if tk.peek() == "angles":
+            tk.next()
+            m["angles"] = [tk.num() for _ in range(3)]
     else:
         raise ValueError("unknown material " + kind)
     if tk.peek() == "tau0":
@@ -279,7 +284,14 @@ def matrices_for(model, D, mat):
         L.gcmo_elastic_isotropic(D, mat["rho"], mat["lambda"], mat["mu"], _dp(U), _dp(U1), _dp(Lm))
     else:
         c = np.array(mat["c"], dtype=np.float64)
-        L.gcmo_elastic_orthotropic(D, mat["rho"], _dp(c), _dp(U), _dp(U1), _dp(Lm))
+        if any(a != 0 for a in mat.get("angles", [0, 0, 0])):   # ElasticModel3D.cpp:151 (3-D only, like the reference)
+            if D != 3:
+                raise ValueError("rotated orthotropic materials exist in 3-D only")
+            angles = np.array(mat["angles"], dtype=np.float64)
+            if L.gcmo_elastic_orthotropic_rotated(mat["rho"], _dp(c), _dp(angles), _dp(U), _dp(U1), _dp(Lm)) != 0:
+                raise ValueError("rotated orthotropic material: no real eigen-system")
+        else:
+            L.gcmo_elastic_orthotropic(D, mat["rho"], _dp(c), _dp(U), _dp(U1), _dp(Lm))
     return U, U1, Lm
 
 

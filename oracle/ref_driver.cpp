@@ -76,10 +76,12 @@ Task::MaterialCondition::Material parseMaterial(Tokens& tk) {
 		real c[9];
 		for (int i = 0; i < 9; i++) { c[i] = tk.num(); }
 		real tau0 = 0;
+		Real3 angles = Real3::Zeros();
+		if (tk.peek() == "angles") { tk.next(); for (int i = 0; i < 3; i++) { angles(i) = tk.num(); } }
 		if (tk.peek() == "tau0") { tk.next(); tau0 = tk.num(); }
 		return std::make_shared<OrthotropicMaterial>(rho,
 				std::initializer_list<real>({c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]}),
-				0, 0, Real3::Zeros(), tau0);
+				0, 0, angles, tau0);
 	}
 	THROW_INVALID_ARG("task file: unknown material " + kind);
 }

@@ -4,7 +4,8 @@
 // partial pivoting in GSL's loop order, the determinant as signum * product of the diagonal, the solve as permute +
 // forward substitution (unit lower) + back substitution.  Only the simplex contact corrector's "both families outer"
 // sub-case reaches them (engine/simplex/ContactCorrector.hpp:180-222: a 6x6 system for elastic bodies).
-// solveThirdOrderPolynomial (rotated orthotropic materials) is not provided.
+// solveThirdOrderPolynomial (rotated orthotropic materials, rheology/models/ElasticModel3D.cpp:208) keeps the
+// reference's own root-sorting wrapper around a restatement of gsl_poly_solve_cubic.
 #ifndef LIBGCM_GSLUTILS_HPP
 #define LIBGCM_GSLUTILS_HPP
 #include <cmath>
@@ -82,8 +83,68 @@ solveLinearSystem(const linal::MatrixBase<TM, TM, real, linal::NonSymmetric, C>&
 	for (int i = 0; i < TM; i++) { ans(i) = x[i]; }
 	return ans;
 }
-inline linal::Vector<3> solveThirdOrderPolynomial(const linal::Vector<3>) {
-	THROW_UNSUPPORTED("GSL is not available in the oracle build");
+/// gsl_poly_solve_cubic (GSL poly/solve_cubic.c) restated: real roots of x^3 + a x^2 + b x + c, ascending
+inline int polySolveCubicStandIn(double a, double b, double c, double* x0, double* x1, double* x2) {
+	const double q = (a * a - 3 * b);
+	const double r = (2 * a * a * a - 9 * a * b + 27 * c);
+	const double Q = q / 9;
+	const double R = r / 54;
+	const double Q3 = Q * Q * Q;
+	const double R2 = R * R;
+	const double CR2 = 729 * r * r;
+	const double CQ3 = 2916 * q * q * q;
+	if (R == 0 && Q == 0) {
+		*x0 = -a / 3; *x1 = -a / 3; *x2 = -a / 3;
+		return 3;
+	} else if (CR2 == CQ3) {
+		const double sqrtQ = std::sqrt(Q);
+		if (R > 0) { *x0 = -2 * sqrtQ - a / 3; *x1 = sqrtQ - a / 3; *x2 = sqrtQ - a / 3; }
+		else { *x0 = -sqrtQ - a / 3; *x1 = -sqrtQ - a / 3; *x2 = 2 * sqrtQ - a / 3; }
+		return 3;
+	} else if (R2 < Q3) {
+		const double sgnR = (R >= 0 ? 1 : -1);
+		const double ratio = sgnR * std::sqrt(R2 / Q3);
+		const double theta = std::acos(ratio);
+		const double norm = -2 * std::sqrt(Q);
+		*x0 = norm * std::cos(theta / 3) - a / 3;
+		*x1 = norm * std::cos((theta + 2.0 * M_PI) / 3) - a / 3;
+		*x2 = norm * std::cos((theta - 2.0 * M_PI) / 3) - a / 3;
+		if (*x0 > *x1) { std::swap(*x0, *x1); }
+		if (*x1 > *x2) {
+			std::swap(*x1, *x2);
+			if (*x0 > *x1) { std::swap(*x0, *x1); }
+		}
+		return 3;
+	}
+	const double sgnR = (R >= 0 ? 1 : -1);
+	const double A = -sgnR * std::pow(std::fabs(R) + std::sqrt(R2 - Q3), 1.0 / 3.0);
+	const double B = Q / A;
+	*x0 = A + B - a / 3;
+	return 1;
+}
+
+/// the reference's own wrapper (util/math/GslUtils.hpp:163-204) around the cubic solver: two (nearly) equal roots go
+/// to the end.  The complex-root fallback (gsl_poly_complex_solve_cubic) is not provided.
+inline linal::Vector<3> solveThirdOrderPolynomial(const linal::Vector<3> p) {
+	double x1 = 0, x2 = 0, x3 = 0;
+	const int numberOfRoots = polySolveCubicStandIn(p(0), p(1), p(2), &x1, &x2, &x3);
+	if (numberOfRoots != 3) { THROW_UNSUPPORTED("complex roots: gsl_poly_complex_solve_cubic is not available in the oracle build"); }
+	if (std::fabs(x1 - x2) < std::fmax(std::fabs(x1), std::fabs(x2)) * eps) {
+		if (std::fabs(x3 - x2) < std::fmax(std::fabs(x3), std::fabs(x2)) * eps) {
+			x1 = x2 = x3 = (x1 + x2 + x3) / 3;
+		} else {
+			x2 = (x1 + x2) / 2;
+			x1 = x3;
+			x3 = x2;
+		}
+	} else if (std::fabs(x1 - x3) < std::fmax(std::fabs(x1), std::fabs(x3)) * eps) {
+		x3 = (x1 + x3) / 2;
+		x1 = x2;
+		x2 = x3;
+	} else if (std::fabs(x2 - x3) < std::fmax(std::fabs(x2), std::fabs(x3)) * eps) {
+		x2 = x3 = (x2 + x3) / 2;
+	}
+	return {x1, x2, x3};
 }
 }
 }

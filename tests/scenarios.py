@@ -76,6 +76,21 @@ initial quantity PRESSURE 1 sphere 0.3 0.5 0.5 0.5
 """
 
 
+def elastic3d_ortho_rotated(n=14, steps=4):
+    # rotated axes of the material (ElasticModel3D.cpp:151-283): dense eigen-systems from the cubic's roots
+    h = _h(n)
+    return f"""
+dimensionality 3
+courant 0.9
+border_size 2
+h {h} {h} {h}
+steps {steps}
+body 0 elastic orthotropic sizes {n} {n} {n} start 0 0 0
+material default orthotropic 4 360 70 70 180 70 90 10 20 30 angles 0.3 -0.5 1.1
+initial quantity PRESSURE 1 sphere 0.3 0.5 0.5 0.5
+"""
+
+
 def ortho3d_contact(n=16, steps=5):
     # BASELINE config 4 at reduced size: two orthotropic bodies glued along y + fixed velocity on a disc
     h = _h(n)
@@ -90,6 +105,27 @@ body 0 elastic orthotropic sizes {n} {half} {n} start 0 0 0
 body 1 elastic orthotropic sizes {n} {half} {n} start 0 {half} 0
 material body 0 orthotropic 1580 10.30e9 6.96e9 6.96e9 23.25e9 6.96e9 10.30e9 5.01e9 1.67e9 5.01e9
 material body 1 orthotropic 4 360 70 70 180 70 90 10 10 10
+initial quantity PRESSURE 1 sphere 0.35 0.5 0.5 0.5
+border 1 1 sphere 0.3 0.5 1.0 0.5 Vy sin 1.0 5.0
+"""
+
+
+def ortho3d_rotated_plies(n=14, steps=4):
+    # BASELINE config 4 with the plies turned +-45 degrees about y (the stacking axis): rotated orthotropic materials
+    # in two glued bodies, one of them with a Maxwell relaxation time
+    h = _h(n)
+    half = n // 2
+    ply = "1580 10.30e9 6.96e9 6.96e9 23.25e9 6.96e9 10.30e9 5.01e9 1.67e9 5.01e9"
+    return f"""
+dimensionality 3
+courant 0.9
+border_size 2
+h {h} {h} {h}
+steps {steps}
+body 0 elastic orthotropic sizes {n} {half} {n} start 0 0 0
+body 1 elastic orthotropic sizes {n} {half} {n} start 0 {half} 0
+material body 0 orthotropic {ply} angles 0 0.7853981633974483 0
+material body 1 orthotropic {ply} angles 0 -0.7853981633974483 0
 initial quantity PRESSURE 1 sphere 0.35 0.5 0.5 0.5
 border 1 1 sphere 0.3 0.5 1.0 0.5 Vy sin 1.0 5.0
 """
@@ -240,7 +276,9 @@ SCENARIOS = {
     "acoustic3d_free": acoustic3d_free(),
     "elastic3d_layers": elastic3d_layers(),
     "elastic3d_ortho": elastic3d_ortho(),
+    "elastic3d_ortho_rotated": elastic3d_ortho_rotated(),
     "ortho3d_contact": ortho3d_contact(),
+    "ortho3d_rotated_plies": ortho3d_rotated_plies(),
     "elastic2d_pwave": elastic2d_pwave(),
     "elastic2d_courant45": elastic2d_courant45(),
     "elastic2d_ortho": elastic2d_ortho(),
