@@ -241,6 +241,7 @@ struct gcmb_body {
 	int n_tables = 0;
 	std::vector<double> U, U1, L;         // host copies [n][D][M*M] / [n][D][M]
 	StageTable* tables = nullptr;         // device [n*D]
+	std::vector<StageTable> host_tables;  // the same tables on the host
 	double tables_tau = NAN;
 	bool any_k0 = false;                  // some characteristic foot beyond the first cell (Courant > 1)
 	int pattern_of_dir[3] = {-1, -1, -1};
@@ -320,7 +321,8 @@ long long face_size(const Geom& g, int axis) {
 int build_tables(gcmb_body* b, double tau) {
 	const Geom& g = b->g;
 	const int M = g.M, D = g.D;
-	std::vector<StageTable> host((size_t) b->n_tables * D);
+	std::vector<StageTable>& host = b->host_tables;
+	host.assign((size_t) b->n_tables * D, StageTable());
 	b->any_k0 = false;
 	for (int t = 0; t < b->n_tables; t++) {
 		for (int s = 0; s < D; s++) {
@@ -834,10 +836,18 @@ int gcmb_cubic_stage(gcmb_body* b, int dir, double tau) {
 	a.dir = dir;
 	a.x_begin = 0;
 	a.x_end = b->g.n[0];
+	a.host_tables = b->host_tables.data();
 	StageLauncher launch = nullptr;
 	const int p = b->pattern_of_dir[dir];
 	if (p >= 0 && !b->any_k0) {
 		launch = b->g.bs == 1 ? pattern(p).launch_bs1 : pattern(p).launch_bs2;
+	}
+	static const bool literal_dense = std::getenv("GCMB_DENSE_LITERAL") != nullptr;
+	if (!launch && !b->any_k0 && !literal_dense) {
+		launch = dense_k0_launcher(b->g.M, b->g.bs);
+		if (launch && p < 0) {
+			b->kernel_name[dir] = std::string(b->n_tables == 1 ? "dense_k0_one:M" : "dense_k0:M") + std::to_string(b->g.M) + "/bs" + std::to_string(b->g.bs);
+		}
 	}
 	if (!launch) { launch = dense_launcher(b->g.M); }
 	if (!launch) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "no stage kernel for this PDE size"); }

@@ -80,6 +80,7 @@ struct StageArgs {
 	int axis;                 // internal axis of the sweep
 	int dir;                  // reference direction
 	int x_begin, x_end;       // range of internal axis 0 to process (slab sub-ranges for overlap)
+	const StageTable* host_tables; // HOST copy of `tables` (launchers only: coefficients passed as kernel parameters)
 };
 
 typedef void (*StageLauncher)(const StageArgs&, cudaStream_t);
@@ -134,6 +135,7 @@ inline bool table_shares_as_pattern(const PatternInfo& p, int bs, const StageTab
 int pattern_count();
 const PatternInfo& pattern(int i);
 StageLauncher dense_launcher(int M);
+StageLauncher dense_k0_launcher(int M, int bs);
 
 // error handling ------------------------------------------------------------------------------
 void set_error(const std::string& msg);

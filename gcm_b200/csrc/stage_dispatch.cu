@@ -53,6 +53,18 @@ GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_dense(const StageArgs a) {
 	if (block_node(a, i0, i1, i2)) { stage_thread_dense<M>(a, i0, i1, i2); }
 }
 
+template<int M, int BS>
+GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_dense_k0(const StageArgs a) {
+	int i0, i1, i2;
+	if (block_node(a, i0, i1, i2)) { stage_thread_dense_k0<M, BS>(a, i0, i1, i2); }
+}
+
+template<int M, int BS>
+GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_dense_k0_one(const StageArgs a, const DenseParamCoef<M, BS> co) {
+	int i0, i1, i2;
+	if (block_node(a, i0, i1, i2)) { stage_thread_dense_k0_one<M, BS>(a, co, i0, i1, i2); }
+}
+
 // marching kernel: grid = (segments along the sweep axis, z chunks, perpendicular axis)
 template<class P, int BS>
 GCMB_GLOBAL void GCMB_BOUNDS(ZT) k_stage_march(const StageArgs a, int seg) {
@@ -156,6 +168,24 @@ static void launch_dense(const StageArgs& a, cudaStream_t stream) {
 	GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a);
 }
 
+template<int M, int BS>
+static void launch_dense_k0(const StageArgs& a, cudaStream_t stream) {
+	if (a.n_tables == 1 && a.host_tables) {
+		const StageTable& T = a.host_tables[a.dir];
+		DenseParamCoef<M, BS> co;
+		for (int k = 0; k < M; k++) {
+			for (int j = 0; j < M; j++) { co.U[k * M + j] = T.U[k * M + j]; co.U1[k * M + j] = T.U1[k * M + j]; }
+			for (int i = 0; i < BS; i++) { co.F[k * BS + i] = T.F[k * MAXBS + i]; }
+			co.sd[k] = T.F[k * MAXBS] == 0.0 ? 0 : T.dir[k];
+		}
+		auto kernel = k_stage_dense_k0_one<M, BS>;
+		GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a, co);
+		return;
+	}
+	auto kernel = k_stage_dense_k0<M, BS>;
+	GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a);
+}
+
 #define GCMB_PATTERN(NAME, MM, SGN, UM, U1M, BASE, UNEG, U1NEG) \
 	{#NAME, MM, SGN, UM, U1M, BASE, UNEG, U1NEG, &launch_sparse<Pat_##NAME, 1>, &launch_sparse<Pat_##NAME, 2>},
 static const PatternInfo g_patterns[] = {
@@ -173,6 +203,19 @@ StageLauncher dense_launcher(int M) {
 		case 4: return &launch_dense<4>;
 		case 5: return &launch_dense<5>;
 		case 9: return &launch_dense<9>;
+		default: return nullptr;
+	}
+}
+
+// dense eigen-system with every foot in the first cell (the caller checks that): stencil held in registers
+StageLauncher dense_k0_launcher(int M, int bs) {
+	if (bs != 1 && bs != 2) { return nullptr; }
+	switch (M) {
+		case 2: return bs == 1 ? &launch_dense_k0<2, 1> : &launch_dense_k0<2, 2>;
+		case 3: return bs == 1 ? &launch_dense_k0<3, 1> : &launch_dense_k0<3, 2>;
+		case 4: return bs == 1 ? &launch_dense_k0<4, 1> : &launch_dense_k0<4, 2>;
+		case 5: return bs == 1 ? &launch_dense_k0<5, 1> : &launch_dense_k0<5, 2>;
+		case 9: return bs == 1 ? &launch_dense_k0<9, 1> : &launch_dense_k0<9, 2>;
 		default: return nullptr;
 	}
 }

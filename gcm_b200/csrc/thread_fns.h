@@ -213,6 +213,94 @@ GCMB_HD void gcm_node_dense(const StageTable* __restrict__ T, int bs, LOAD load,
 	}
 }
 
+// Dense eigen-system, all feet inside the first cell (k0 == 0 everywhere: Courant number <= 1) and a compile-time
+// border size: the kernel of rotated orthotropic materials and of any eigen-system no pattern covers.  The node's
+// stencil is read once; per side of the node the quantities that do not depend on the foot (first differences,
+// the bracket's minimum and maximum) are formed once per component and shared by every characteristic whose foot
+// lies on that side.  Every value is produced by the same operations, in the same order, as gcm_node_dense.
+// A foot at the node itself (q == 0: Newton factor F[0] == 0) takes the node's value, as in gcm_node_sparse.
+// coefficient sources: (1) the StageTable of the node's material in global memory
+template<int M>
+struct DenseTableCoef {
+	const StageTable* __restrict__ T;
+	GCMB_HD double u(int k, int j) const { return GCMB_LDG(&T->U[k * M + j]); }
+	GCMB_HD double u1(int i, int k) const { return GCMB_LDG(&T->U1[i * M + k]); }
+	GCMB_HD double f(int k, int i) const { return GCMB_LDG(&T->F[k * MAXBS + i]); }
+	GCMB_HD int side(int k) const { return f(k, 0) == 0.0 ? 0 : T->dir[k]; }
+};
+// (2) a body of ONE material: the coefficients travel as a kernel parameter, so that every one of them is a
+//     constant-bank operand of the arithmetic instruction that uses it (no load, no register)
+template<int M, int BS>
+struct DenseParamCoef {
+	double U[M * M], U1[M * M], F[M * BS];
+	int sd[M];
+	GCMB_HD double u(int k, int j) const { return U[k * M + j]; }
+	GCMB_HD double u1(int i, int k) const { return U1[i * M + k]; }
+	GCMB_HD double f(int k, int i) const { return F[k * BS + i]; }
+	GCMB_HD int side(int k) const { return sd[k]; }
+};
+
+template<int M, int BS, class COEF, class LOAD>
+GCMB_HD void gcm_node_dense_k0(const COEF& co, LOAD load, double (&out)[M]) {
+	static_assert(BS == 1 || BS == 2, "border sizes 1 and 2");
+	double c[M], r[M];
+#pragma unroll
+	for (int j = 0; j < M; j++) { c[j] = load(j, 0); }
+	int side[M];
+#pragma unroll
+	for (int k = 0; k < M; k++) { side[k] = co.side(k); }
+#pragma unroll
+	for (int k = 0; k < M; k++) {
+		if (side[k] == 0) {
+			double acc = co.u(k, 0) * c[0];
+#pragma unroll
+			for (int j = 1; j < M; j++) { acc += co.u(k, j) * c[j]; }
+			r[k] = acc;
+		}
+	}
+#pragma unroll
+	for (int sd = 1; sd >= -1; sd -= 2) {
+		double d0[M], d1[BS == 2 ? M : 1], mx[M], mn[M];
+#pragma unroll
+		for (int j = 0; j < M; j++) {
+			const double s1 = load(j, sd);
+			d0[j] = s1 - c[j];
+			if (BS == 2) { d1[j] = load(j, 2 * sd) - s1; }
+			const bool gt = c[j] > s1;
+			mx[j] = gt ? c[j] : s1;
+			mn[j] = gt ? s1 : c[j];
+		}
+#pragma unroll
+		for (int k = 0; k < M; k++) {
+			if (side[k] == sd) {
+				const double f0 = co.f(k, 0);
+				const double f1 = BS == 2 ? co.f(k, 1) : 0.0;
+				double acc = 0.0;
+#pragma unroll
+				for (int j = 0; j < M; j++) {
+					const double a0 = d0[j] * f0;
+					double ans = c[j] + a0;
+					if (BS == 2) {
+						const double a1 = d1[j] * f0;
+						ans += (a1 - a0) * f1;
+					}
+					if (ans > mx[j]) { ans = mx[j]; } else if (ans < mn[j]) { ans = mn[j]; }
+					const double t = co.u(k, j) * ans;
+					if (j == 0) { acc = t; } else { acc += t; }
+				}
+				r[k] = acc;
+			}
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < M; i++) {
+		double acc = co.u1(i, 0) * r[0];
+#pragma unroll
+		for (int k = 1; k < M; k++) { acc += co.u1(i, k) * r[k]; }
+		out[i] = acc;
+	}
+}
+
 // loader over the structure-of-arrays volumes: component j at `o` nodes along the sweep axis
 struct SoaLoad {
 	const double* __restrict__ base;  // cur + idx
@@ -238,6 +326,27 @@ GCMB_HD void stage_thread_dense(const StageArgs& a, int i0, int i1, int i2) {
 	SoaLoad ld{a.cur + idx, a.g.comp, a.g.stride(a.axis)};
 	double out[M];
 	gcm_node_dense<M>(T, a.g.bs, ld, out);
+	for (int c = 0; c < M; c++) { a.nxt[c * a.g.comp + idx] = out[c]; }
+}
+
+template<int M, int BS>
+GCMB_HD void stage_thread_dense_k0(const StageArgs& a, int i0, int i1, int i2) {
+	const long long idx = a.g.index(i0, i1, i2);
+	const DenseTableCoef<M> co{a.tables + ((int) a.node_table[idx] * a.g.D + a.dir)};
+	SoaLoad ld{a.cur + idx, a.g.comp, a.g.stride(a.axis)};
+	double out[M];
+	gcm_node_dense_k0<M, BS>(co, ld, out);
+#pragma unroll
+	for (int c = 0; c < M; c++) { a.nxt[c * a.g.comp + idx] = out[c]; }
+}
+
+template<int M, int BS>
+GCMB_HD void stage_thread_dense_k0_one(const StageArgs& a, const DenseParamCoef<M, BS>& co, int i0, int i1, int i2) {
+	const long long idx = a.g.index(i0, i1, i2);
+	SoaLoad ld{a.cur + idx, a.g.comp, a.g.stride(a.axis)};
+	double out[M];
+	gcm_node_dense_k0<M, BS>(co, ld, out);
+#pragma unroll
 	for (int c = 0; c < M; c++) { a.nxt[c * a.g.comp + idx] = out[c]; }
 }
 

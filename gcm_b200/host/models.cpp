@@ -692,6 +692,27 @@ void orthotropicRotated3D(const OrthotropicMaterial& material, GcmMatrices& g) {
 			for (int a = 0; a < 9; a++) { U1[a * 9 + n] = U1[a * 9 + n] / normalizer; }
 			for (int a = 0; a < 9; a++) { U[n * 9 + a] = (sign * U[n * 9 + a]) / normalizer; }
 		}
+		// GcmMatrix::checkDecomposition(1e-2) (util/math/GridCharacteristicMethod.hpp:60-69): the traces within eps,
+		// A*U1 ~ U1*L, U*A ~ L*U and U*U1 ~ I under Utils::approximatelyEqual (util/Utils.hpp:33-41) with
+		// tolerance eps*1000 -- loose enough to accept the eigenvectors of an averaged pair of close roots,
+		// tight enough to reject a sign error
+		const double tol = 1e-2 * 1000;
+		auto near = [tol](double f1, double f2) {
+			return 4 * (f1 - f2) * (f1 - f2) / ((f1 + f2) * (f1 + f2) + tol) < tol * tol;
+		};
+		double trL = 0;
+		for (int n = 0; n < 9; n++) { trL += L[n]; }
+		bool ok = std::fabs(0.0 - trL) <= 1e-2;   // trace(A) == 0: A has no diagonal entry
+		for (int a = 0; a < 9 && ok; a++) for (int b = 0; b < 9 && ok; b++) {
+			double au1 = A[a][0] * U1[b], ua = U[a * 9] * A[0][b], uu1 = U[a * 9] * U1[b];
+			for (int k = 1; k < 9; k++) {
+				au1 += A[a][k] * U1[k * 9 + b];
+				ua += U[a * 9 + k] * A[k][b];
+				uu1 += U[a * 9 + k] * U1[k * 9 + b];
+			}
+			ok = near(au1, U1[a * 9 + b] * L[b]) && near(ua, L[a] * U[a * 9 + b]) && near(uu1, a == b ? 1.0 : 0.0);
+		}
+		if (!ok) { throw Exception(GCMB_E_INVALID_OP, "eigen-system check failed for a rotated orthotropic material"); }
 	}
 }
 
@@ -749,7 +770,7 @@ GcmMatrices constructGcmMatrices(Models::T model, int D, const AbstractMaterial&
 		if (model != Models::T::ELASTIC) { throw Exception(GCMB_E_UNSUPPORTED, "Unknown or inappropriate model type"); }
 		const bool isRotated = ortho->anglesOfRotation[0] != 0 || ortho->anglesOfRotation[1] != 0 || ortho->anglesOfRotation[2] != 0;
 		if (isRotated && D != 3) { throw Exception(GCMB_E_UNSUPPORTED, "rotated orthotropic materials exist in 3-D only"); }
-		if (D == 3 && isRotated) { orthotropicRotated3D(*ortho, g); g.checkDecomposition(1e-2); }
+		if (D == 3 && isRotated) { orthotropicRotated3D(*ortho, g); }
 		else if (D == 3) { orthotropic3D(*ortho, g); }
 		else if (D == 2) { orthotropic2D(*ortho, g); g.checkDecomposition(1e-9 * 1000); }
 		else { throw Exception(GCMB_E_UNSUPPORTED, "OrthotropicMaterial in 1D is meaningless"); }

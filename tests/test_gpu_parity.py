@@ -36,7 +36,7 @@ def test_cuda_engine_matches_reference_bitwise(lib, name):
     eng.close()
 
 
-@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "5"},
+@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_FORCE_DENSE": "1", "GCMB_DENSE_LITERAL": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "5"},
                                  {"GCMB_MARCH_SEG": "0"}])
 def test_kernel_variants_match_reference(env):
     """dense / direct / marching-with-odd-segments kernels: every variant reproduces the reference bits."""
@@ -44,7 +44,7 @@ def test_kernel_variants_match_reference(env):
             "import gcm_b200\n"
             "from helpers import compare_with_golden\n"
             "from scenarios import SCENARIOS\n"
-            "for n in ('elastic3d_layers', 'ortho3d_contact', 'acoustic3d_free', 'elastic2d_ortho', 'acoustic2d_border1', 'maxwell3d'):\n"
+            "for n in ('elastic3d_layers', 'ortho3d_contact', 'acoustic3d_free', 'elastic2d_ortho', 'acoustic2d_border1', 'maxwell3d', 'ortho3d_rotated_plies', 'elastic3d_ortho_rotated'):\n"
             "    compare_with_golden(gcm_b200.library(), n, SCENARIOS[n])[0].close()\n"
             % (ROOT, os.path.join(ROOT, "tests")))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)

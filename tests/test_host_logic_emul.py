@@ -35,6 +35,7 @@ EXPECTED_KERNELS = {
     "elastic2d_pwave": ["sparse:elastic2d_iso_x/bs2", "sparse:elastic2d_iso_y/bs2"],
     "elastic2d_courant45": ["dense:M5", "dense:M5"],  # border size 5: no specialised kernel
     "elastic1d": ["sparse:elastic1d_iso_x/bs2"],
+    "elastic3d_ortho_rotated": ["dense:M9", "dense:M9", "dense:M9"],  # rotated axes: no zero of U is structural
 }
 
 
@@ -49,8 +50,8 @@ def test_sparsity_pattern_selection(lib, name):
         eng.close()
 
 
-@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "7"}])
-@pytest.mark.parametrize("name", ["elastic3d_layers", "ortho3d_contact", "acoustic2d_border1", "elastic2d_ortho"])
+@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_FORCE_DENSE": "1", "GCMB_DENSE_LITERAL": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "7"}])
+@pytest.mark.parametrize("name", ["elastic3d_layers", "ortho3d_contact", "acoustic2d_border1", "elastic2d_ortho", "ortho3d_rotated_plies"])
 def test_kernel_variants_agree(name, env):
     """dense kernel, direct kernel and short marching segments give the same bits (fresh process: the
     variant is read from the environment once)."""
