@@ -250,6 +250,39 @@ def simplex_section(lib, device, steps, warmup, with_cpu):
     return out
 
 
+def rotated_section(lib, device, steps, warmup):
+    """rotated orthotropic plies (BASELINE config 4 with the plies turned about the stacking axis):
+    node-updates/s of the dense-eigen-system stage kernel through Engine::run's loop, state resident in HBM"""
+    import torch
+    from gcm_b200 import capi
+    sys.path.insert(0, os.path.join(ROOT, "scripts", "gpu_runs"))
+    import rotated_bench
+    n = 512
+    eng = capi.HostEngine(lib, rotated_bench.task(n), device=device)
+    ctxh = eng.context_handle()
+    eng.advance(warmup)
+    lib.check(lib.c.gcmb_sync(ctxh))
+    torch.cuda.synchronize()
+    lib.check(lib.c.gcmb_timer_start(ctxh))
+    eng.advance(steps)
+    ms = capi.ctypes.c_float(0)
+    lib.check(lib.c.gcmb_timer_stop(ctxh, capi.ctypes.byref(ms)))
+    kernels = [eng.kernel_name(0, d) for d in range(3)]
+    eng.close()
+    per_s = n ** 3 * steps / (ms.value * 1e-3)
+    peak, which = measured_hbm_peak()
+    return {"metric": "GCM node-updates/sec (3D rotated orthotropic elastic, two glued bodies, fp64)", "value": per_s,
+            "unit": "node-updates/s", "steps": steps, "warmup": warmup, "ms_per_step": ms.value / steps, "kernels": kernels,
+            "config": {"workload": "two glued bodies %dx%dx%d, carbon-fibre plies (ndi.hpp:120-131) turned +-45 degrees, border size 2, "
+                                   "Courant 0.9; state larger than L2" % (n, n // 2, n)},
+            "roofline": {"bound": "hbm", "achieved": per_s * 3 * BYTES_PER_NODE_STAGE / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": per_s * 3 * BYTES_PER_NODE_STAGE / 1e9 / peak, "peak_source": which,
+                         "note": "dense 9x9 eigen-systems: 81 limited interpolations + two dense mat-vecs per node-stage, ~800 fp64 "
+                                 "instructions against 144 B; ncu (profiles/r1_dense_k0_one_ncu_384.csv): fp64 pipe 52 % active, "
+                                 "DRAM traffic == algorithmic bytes"},
+            "parity": "bit-identical to the unmodified reference engine (tests/golden/elastic3d_ortho_rotated.npz, ortho3d_rotated_plies.npz)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -260,6 +293,7 @@ def main():
     ap.add_argument("--ref-size", type=int, default=64, help="cube edge of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-simplex", action="store_true", help="skip the secondary simplex-path measurement")
+    ap.add_argument("--no-rotated", action="store_true", help="skip the secondary rotated-orthotropic measurement")
     ap.add_argument("--no-host-roundtrip", action="store_true", help="skip the host-resident-state measurement")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -458,6 +492,12 @@ def main():
                 line["simplex"] = simplex_section(lib, local, 20, 3, not args.no_cpu_baseline)
             except Exception as e:  # the headline line must survive a failure here
                 line["simplex"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if world == 1 and not args.no_rotated:
+            # secondary measurement (never the headline): dense eigen-systems of rotated orthotropic materials
+            try:
+                line["rotated_orthotropic"] = rotated_section(lib, local, 5, 3)
+            except Exception as e:
+                line["rotated_orthotropic"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -258,6 +258,8 @@ GCMB_HD void gcm_node_dense_k0(const COEF& co, LOAD load, double (&out)[M]) {
 			r[k] = acc;
 		}
 	}
+	// both sides unrolled: measured 33.1 ms/step against 34.8 ms with `#pragma unroll 1` (half the code, but 24 B of
+	// spills) on 2 x 512x256x512 rotated plies
 #pragma unroll
 	for (int sd = 1; sd >= -1; sd -= 2) {
 		double d0[M], d1[BS == 2 ? M : 1], mx[M], mn[M];
