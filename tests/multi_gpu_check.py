@@ -72,7 +72,7 @@ def main():
     os.chdir("/tmp")
 
     # (1) against the reference fixtures
-    for name in ("elastic3d_layers", "elastic3d_ortho", "acoustic3d_free", "ortho3d_contact", "maxwell3d"):
+    for name in ("elastic3d_layers", "elastic3d_ortho", "acoustic3d_free", "ortho3d_contact", "maxwell3d", "ortho3d_rotated_plies"):
         nx = int(SCENARIOS[name].split("sizes")[1].split()[0])
         if nx // world < 2:  # a slab must hold at least border_size planes (CubicGrid.hpp:186-199)
             continue
