@@ -219,6 +219,20 @@ GCMB_HD void gcm_node_dense(const StageTable* __restrict__ T, int bs, LOAD load,
 // the bracket's minimum and maximum) are formed once per component and shared by every characteristic whose foot
 // lies on that side.  Every value is produced by the same operations, in the same order, as gcm_node_dense.
 // A foot at the node itself (q == 0: Newton factor F[0] == 0) takes the node's value, as in gcm_node_sparse.
+// the limiter's clamp `if (ans > mx) ans = mx; else if (ans < mn) ans = mn;` (EqualDistanceLineInterpolator.hpp:30-35)
+// as two compare-and-select pairs: the same value for every input (mn <= mx, or a NaN that fails both comparisons), and
+// no divergent branch -- nvcc turns the if/else into BSSY/BRA/BSYNC plus six moves per clamp
+GCMB_HD double clamp_select(double ans, double mn, double mx) {
+#ifdef __CUDA_ARCH__
+	asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %0, %1;\n\tselp.f64 %0, %1, %0, p;\n\tsetp.lt.f64 p, %0, %2;\n\tselp.f64 %0, %2, %0, p;\n\t}"
+	    : "+d"(ans) : "d"(mx), "d"(mn));
+	return ans;
+#else
+	if (ans > mx) { ans = mx; } else if (ans < mn) { ans = mn; }
+	return ans;
+#endif
+}
+
 // coefficient sources: (1) the StageTable of the node's material in global memory
 template<int M>
 struct DenseTableCoef {
@@ -286,7 +300,7 @@ GCMB_HD void gcm_node_dense_k0(const COEF& co, LOAD load, double (&out)[M]) {
 						const double a1 = d1[j] * f0;
 						ans += (a1 - a0) * f1;
 					}
-					if (ans > mx[j]) { ans = mx[j]; } else if (ans < mn[j]) { ans = mn[j]; }
+					ans = clamp_select(ans, mn[j], mx[j]);
 					const double t = co.u(k, j) * ans;
 					if (j == 0) { acc = t; } else { acc += t; }
 				}
