@@ -278,7 +278,7 @@ def rotated_section(lib, device, steps, warmup):
             "roofline": {"bound": "hbm", "achieved": per_s * 3 * BYTES_PER_NODE_STAGE / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": per_s * 3 * BYTES_PER_NODE_STAGE / 1e9 / peak, "peak_source": which,
                          "note": "dense 9x9 eigen-systems: 81 limited interpolations + two dense mat-vecs per node-stage, ~800 fp64 "
-                                 "instructions against 144 B; ncu (profiles/r1_dense_k0_one_ncu_384.csv): fp64 pipe 52 % active, "
+                                 "instructions against 144 B; ncu (profiles/r1_dense_k0_one_ncu_384.csv): fp64 pipe 61 % active, "
                                  "DRAM traffic == algorithmic bytes"},
             "parity": "bit-identical to the unmodified reference engine (tests/golden/elastic3d_ortho_rotated.npz, ortho3d_rotated_plies.npz)"}
 
