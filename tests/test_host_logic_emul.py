@@ -106,6 +106,25 @@ def test_courant_above_border_size_is_rejected(lib):
     eng.close()
 
 
+def test_rotated_orthotropic_error_behaviour(lib):
+    """ElasticModel3D.cpp:151-283 through GslUtils.hpp:163-204: a characteristic cubic with complex roots is rejected
+    (the reference's fallback needs gsl_poly_complex_solve_cubic, which neither the oracle build nor the product
+    provides), and rotated axes exist in 3-D only -- the same on the product's host and in the oracle."""
+    import oracle_host as oh
+    from gcm_b200 import capi
+    from scenarios import elastic2d_ortho, elastic3d_ortho_rotated
+    complex_roots = elastic3d_ortho_rotated(8, 1).replace("orthotropic 4 360 70 70 180 70 90 10 20 30", "orthotropic 4 4 2 2 4 2 4 1 1 1")
+    assert complex_roots != elastic3d_ortho_rotated(8, 1)
+    flat = elastic2d_ortho()
+    line = [l for l in flat.splitlines() if l.startswith("material")][0]
+    flat = flat.replace(line, line + " angles 0.1 0 0")
+    for text in (complex_roots, flat):
+        with pytest.raises(capi.GcmError):
+            capi.HostEngine(lib, text)
+        with pytest.raises(ValueError):
+            oh.run_task_text(text)
+
+
 def test_random_state_single_stages_match_oracle(lib):
     """multi-chunk rows, ragged sizes, first-order border: stepping harness vs gcmo_stage, bitwise"""
     from helpers import random_stage_check
