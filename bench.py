@@ -90,7 +90,7 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference_cpu(n, steps):
+def run_reference_cpu(n, steps, text=None, what="layered elastic"):
     """The reference's own CPU engine (oracle/_ref/gcm_ref, unmodified sources) on a bounded sample."""
     exe = os.path.join(ROOT, "oracle", "_ref", "gcm_ref")
     kind = "reference"
@@ -99,13 +99,13 @@ def run_reference_cpu(n, steps):
     with tempfile.TemporaryDirectory() as tmp:
         tf = os.path.join(tmp, "task.txt")
         with open(tf, "w") as f:
-            f.write(task_text(n, n, n, steps, detector=False))
+            f.write(text if text is not None else task_text(n, n, n, steps, detector=False))
         subprocess.run([exe, tf, os.path.join(tmp, "out")], check=True, cwd=tmp)
         meta = dict(line.split()[:2] for line in open(os.path.join(tmp, "out.meta")) if not line.startswith("body"))
     seconds = float(meta["run_seconds"])
     done = int(float(meta["steps"]))
     return {"value": n ** 3 * done / seconds, "unit": "node-updates/s", "cores": 1, "kind": kind,
-            "sample": "%d^3 nodes x %d steps of the same layered elastic task, run() wall time %.2f s" % (n, done, seconds),
+            "sample": "%d^3 nodes x %d steps of the same %s task, run() wall time %.2f s" % (n, done, what, seconds),
             "seconds": seconds, "steps": done}
 
 
@@ -250,7 +250,7 @@ def simplex_section(lib, device, steps, warmup, with_cpu):
     return out
 
 
-def rotated_section(lib, device, steps, warmup):
+def rotated_section(lib, device, steps, warmup, with_cpu=True):
     """rotated orthotropic plies (BASELINE config 4 with the plies turned about the stacking axis):
     node-updates/s of the dense-eigen-system stage kernel through Engine::run's loop, state resident in HBM"""
     import torch
@@ -271,7 +271,13 @@ def rotated_section(lib, device, steps, warmup):
     eng.close()
     per_s = n ** 3 * steps / (ms.value * 1e-3)
     peak, which = measured_hbm_peak()
-    return {"metric": "GCM node-updates/sec (3D rotated orthotropic elastic, two glued bodies, fp64)", "value": per_s,
+    cpu = None
+    if with_cpu:
+        try:   # the unmodified reference engine (dense 9x9 products, 81 interpolations per node-stage) on a 40^3 sample
+            cpu = run_reference_cpu(40, 3, text=rotated_bench.task(40, 3), what="rotated-plies")
+        except Exception as e:
+            cpu = {"error": "%s: %s" % (type(e).__name__, e)}
+    return {"metric": "GCM node-updates/sec (3D rotated orthotropic elastic, two glued bodies, fp64)", "value": per_s, "cpu_baseline": cpu,
             "unit": "node-updates/s", "steps": steps, "warmup": warmup, "ms_per_step": ms.value / steps, "kernels": kernels,
             "config": {"workload": "two glued bodies %dx%dx%d, carbon-fibre plies (ndi.hpp:120-131) turned +-45 degrees, border size 2, "
                                    "Courant 0.9; state larger than L2" % (n, n // 2, n)},
@@ -495,7 +501,7 @@ def main():
         if world == 1 and not args.no_rotated:
             # secondary measurement (never the headline): dense eigen-systems of rotated orthotropic materials
             try:
-                line["rotated_orthotropic"] = rotated_section(lib, local, 5, 3)
+                line["rotated_orthotropic"] = rotated_section(lib, local, 5, 3, not args.no_cpu_baseline)
             except Exception as e:
                 line["rotated_orthotropic"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
