@@ -142,6 +142,9 @@ static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
 			// 2 planes in flight per thread, registers capped for 6 blocks = 24 warps per SM: the best of the
 			// variants measured on B200 (profiles/r1_variants.md)
 			auto kernel = k_stage_march_async<P, BS, MARCH_LEAD, 6>;
+			static const int carve = env_int("GCMB_MARCH_CARVEOUT", -1);
+			static const cudaError_t attr2 = carve >= 0 ? cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve) : cudaSuccess;
+			(void) attr2;
 			GCMB_LAUNCH_COOP(kernel, grid, MARCH_ZT, 0, stream, a, seg);
 		} else {
 			auto kernel = k_stage_march<P, BS>;
@@ -153,9 +156,19 @@ static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
 		                (unsigned) (a.x_end - a.x_begin));
 		typedef ZTileSmem<P::M, Packed<P, BS>::SIZE, ZLEAD> Smem;
 		auto kernel = k_stage_ztile<P, BS, ZLEAD>;
-		static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem));
+		// experiment knob: extra dynamic shared memory per block (lowers the number of resident blocks per SM)
+		static const int pad = env_int("GCMB_ZTILE_SMEM_PAD", 0);
+		static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem) + pad);
 		(void) attr;
-		GCMB_LAUNCH_COOP(kernel, grid, ZTILE, sizeof(Smem), stream, a, rows);
+		// shared-memory carve-out of the SM in percent of the maximum (the rest is L1); -1 = the driver's choice.
+		// The driver sizes it for the most blocks the registers allow (5 x 44 KB for the orthotropic patterns): the
+		// tiles arrive by cp.async through L1, and with 28 KB of it left the kernel is 2.5 ms slower per launch at
+		// 1024^3.  60 % = 3 tiles' worth: measured 98.2 -> 90.5 ms/step (orthotropic), 83.1 -> 82.8 (isotropic);
+		// anything <= 78 % is as good, >= 86 % is the slow mode (profiles/r1_carveout.md)
+		static const int carve = env_int("GCMB_ZTILE_CARVEOUT", 60);
+		static const cudaError_t attr2 = carve >= 0 ? cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve) : cudaSuccess;
+		(void) attr2;
+		GCMB_LAUNCH_COOP(kernel, grid, ZTILE, sizeof(Smem) + pad, stream, a, rows);
 	} else {
 		auto kernel = k_stage_direct<P, BS>;
 		GCMB_LAUNCH(kernel, node_blocks(a), ZT, stream, a);
