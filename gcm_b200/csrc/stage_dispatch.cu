@@ -22,6 +22,12 @@ namespace gcmb {
 
 constexpr int ZT = 128;  // threads per block, all along the contiguous axis
 
+// blocks per SM the marching kernel's registers are capped for (see launch_sparse)
+template<class P> struct MarchBlocks { static constexpr int value = 6; };
+template<> struct MarchBlocks<Pat_elastic3d_ortho_x> { static constexpr int value = 5; };
+template<> struct MarchBlocks<Pat_elastic3d_ortho_y> { static constexpr int value = 5; };
+template<> struct MarchBlocks<Pat_elastic3d_ortho_z> { static constexpr int value = 5; };
+
 // block -> node mapping: blockIdx.x runs along the sweep axis when it is strided, so that blocks
 // scheduled together share their halo planes in L2
 GCMB_DEV bool block_node(const StageArgs& a, int& i0, int& i1, int& i2) {
@@ -141,6 +147,16 @@ static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
 		if (impl == 2) {
 			// 2 planes in flight per thread, registers capped for 6 blocks = 24 warps per SM: the best of the
 			// variants measured on B200 (profiles/r1_variants.md)
+			// resident blocks per SM the registers are capped for: 6 (80 registers) is best for the isotropic patterns
+			// (profiles/r1_variants.md); the orthotropic ones spill 32-40 B at 80 registers and run 8 % faster at 5
+			// (96 registers, no spill): one body 1024^3, 90.9 -> 84.0 ms/step (isotropic: 82.8 -> 83.6)
+			static const int minb_env = env_int("GCMB_MARCH_MINB", -1);
+			const int minb = minb_env > 0 ? minb_env : MarchBlocks<P>::value;
+			if (P::M == 9 && minb == 5) {
+				auto kernel5 = k_stage_march_async<P, BS, MARCH_LEAD, 5>;
+				GCMB_LAUNCH_COOP(kernel5, grid, MARCH_ZT, 0, stream, a, seg);
+				return;
+			}
 			auto kernel = k_stage_march_async<P, BS, MARCH_LEAD, 6>;
 			static const int carve = env_int("GCMB_MARCH_CARVEOUT", -1);
 			static const cudaError_t attr2 = carve >= 0 ? cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve) : cudaSuccess;

@@ -36,7 +36,7 @@ def test_cuda_engine_matches_reference_bitwise(lib, name):
     eng.close()
 
 
-@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_FORCE_DENSE": "1", "GCMB_DENSE_LITERAL": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "5"},
+@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_FORCE_DENSE": "1", "GCMB_DENSE_LITERAL": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "5"}, {"GCMB_MARCH_MINB": "5"}, {"GCMB_MARCH_MINB": "6"},
                                  {"GCMB_MARCH_SEG": "0"}])
 def test_kernel_variants_match_reference(env):
     """dense / direct / marching-with-odd-segments kernels: every variant reproduces the reference bits."""
