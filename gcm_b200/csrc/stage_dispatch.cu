@@ -145,11 +145,10 @@ static void launch_sparse(const StageArgs& a, cudaStream_t stream) {
 		const int perp = a.axis == 0 ? a.g.n[1] : a.x_end - a.x_begin;
 		const dim3 grid((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZT - 1) / ZT), (unsigned) perp);
 		if (impl == 2) {
-			// 2 planes in flight per thread, registers capped for 6 blocks = 24 warps per SM: the best of the
-			// variants measured on B200 (profiles/r1_variants.md)
-			// resident blocks per SM the registers are capped for: 6 (80 registers) is best for the isotropic patterns
-			// (profiles/r1_variants.md); the orthotropic ones spill 32-40 B at 80 registers and run 8 % faster at 5
-			// (96 registers, no spill): one body 1024^3, 90.9 -> 84.0 ms/step (isotropic: 82.8 -> 83.6)
+			// 2 planes in flight per thread.  Resident blocks per SM the registers are capped for: 6 (80 registers,
+			// 24 warps) is the best of the variants measured for the isotropic patterns (profiles/r1_variants.md); the
+			// orthotropic ones spill 32-40 B at 80 registers and run 8 % faster at 5 (96 registers, no spill): one body
+			// 1024^3, 90.9 -> 84.0 ms/step (isotropic: 82.8 -> 83.6), profiles/r1_carveout.md
 			static const int minb_env = env_int("GCMB_MARCH_MINB", -1);
 			const int minb = minb_env > 0 ? minb_env : MarchBlocks<P>::value;
 			if (P::M == 9 && minb == 5) {
