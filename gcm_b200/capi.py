@@ -91,12 +91,22 @@ C_ABI = {
     "gcmb_simplex_contact_plain": (ctypes.c_int, [vp]),
     "gcmb_simplex_contact_correct": (ctypes.c_int, [vp]),
     "gcmb_cubic_stage_kernel_name": (ctypes.c_char_p, [vp, ctypes.c_int]),
+    "gcmb_real_bytes": (ctypes.c_int, [vp]),
+    "gcmb_set_fma": (ctypes.c_int, [vp, ctypes.c_int]),
+    "gcmb_cubic_download_box_begin": (ctypes.c_int, [vp, c_int_p, c_int_p, vp]),
+    "gcmb_cubic_download_box_end": (ctypes.c_int, [vp]),
+    "gcmb_cubic_stage_fill_next_border": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                                         c_double_p, c_int_p]),
+    "gcmb_cubic_seismo_at": (ctypes.c_int, [vp, c_double_p, c_ll_p, ctypes.c_int, c_double_p, ctypes.c_int, c_int_p]),
+    "gcmb_halo_exchange_bodies": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int]),
 }
 
 HOST_ABI = {
     "gcmb_host_last_error": (ctypes.c_char_p, []),
     "gcmb_host_engine_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
                                                ctypes.POINTER(vp)]),
+    "gcmb_host_engine_create2": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
+                                                ctypes.c_int, ctypes.POINTER(vp)]),
     "gcmb_host_engine_destroy": (None, [vp]),
     "gcmb_host_engine_run": (ctypes.c_int, [vp]),
     "gcmb_host_engine_advance": (ctypes.c_int, [vp, ctypes.c_int]),
@@ -174,6 +184,7 @@ class Context:
     def __init__(self, lib, device=0, real_bytes=8):
         self.lib = lib
         self.handle = vp()
+        self.real = np.float32 if real_bytes == 4 else np.float64
         lib.check(lib.c.gcmb_create(device, real_bytes, ctypes.byref(self.handle)))
 
     def close(self):
@@ -240,12 +251,12 @@ class CubicBody:
             self.handle = vp()
 
     def upload(self, array, with_ghosts):
-        a = np.ascontiguousarray(array, dtype=np.float64)
+        a = np.ascontiguousarray(array, dtype=self.ctx.real)
         self.lib.check(self.lib.c.gcmb_cubic_upload_state(self.handle, a.ctypes.data_as(vp), 1 if with_ghosts else 0))
 
     def download(self, with_ghosts=False):
         ext = self.sizes + (2 * self.bs if with_ghosts else 0)
-        out = np.empty(tuple(int(e) for e in ext) + (self.M,), dtype=np.float64)
+        out = np.empty(tuple(int(e) for e in ext) + (self.M,), dtype=self.ctx.real)
         self.lib.check(self.lib.c.gcmb_cubic_download_state(self.handle, out.ctypes.data_as(vp), 1 if with_ghosts else 0))
         return out
 
@@ -288,6 +299,23 @@ class CubicBody:
     def stage(self, direction, tau):
         self.lib.check(self.lib.c.gcmb_cubic_stage(self.handle, direction, tau))
 
+    def stage_fill_next_border(self, direction, tau, next_direction, values):
+        """stage + border fill of next_direction on the new layer; returns True when one kernel did both"""
+        v = np.array(values, dtype=np.float64)
+        fused = ctypes.c_int()
+        self.lib.check(self.lib.c.gcmb_cubic_stage_fill_next_border(self.handle, direction, tau, next_direction, len(v), dp(v),
+                                                                     ctypes.byref(fused)))
+        return bool(fused.value)
+
+    def download_box(self, box_min, extent):
+        """asynchronous read-back of a box of nodes (begin + end); [extent..., M]"""
+        lo = np.array(box_min, dtype=np.int32)
+        ext = np.array(extent, dtype=np.int32)
+        out = np.empty(tuple(int(e) for e in ext) + (self.M,), dtype=self.ctx.real)
+        self.lib.check(self.lib.c.gcmb_cubic_download_box_begin(self.handle, ip(lo), ip(ext), out.ctypes.data_as(vp)))
+        self.lib.check(self.lib.c.gcmb_cubic_download_box_end(self.handle))
+        return out
+
     def ode_maxwell(self, decay):
         d = np.array(decay, dtype=np.float64)
         self.lib.check(self.lib.c.gcmb_cubic_ode_maxwell(self.handle, dp(d)))
@@ -317,12 +345,12 @@ class CubicBody:
         return self.lib.c.gcmb_cubic_stage_kernel_name(self.handle, direction).decode()
 
     def halo_get(self, side):
-        buf = np.empty(self.lib.c.gcmb_cubic_halo_bytes(self.handle) // 8, dtype=np.float64)
+        buf = np.empty(self.lib.c.gcmb_cubic_halo_bytes(self.handle) // np.dtype(self.ctx.real).itemsize, dtype=self.ctx.real)
         self.lib.check(self.lib.c.gcmb_cubic_halo_get(self.handle, side, buf.ctypes.data_as(vp)))
         return buf
 
     def halo_put(self, side, buf):
-        buf = np.ascontiguousarray(buf, dtype=np.float64)
+        buf = np.ascontiguousarray(buf, dtype=self.ctx.real)
         assert buf.nbytes == self.lib.c.gcmb_cubic_halo_bytes(self.handle)
         self.lib.check(self.lib.c.gcmb_cubic_halo_put(self.handle, side, buf.ctypes.data_as(vp)))
 
@@ -330,16 +358,16 @@ class CubicBody:
 class HostEngine:
     """createEngine(task)->run() of the host layer, driven by a plain-text task (gcm_b200/host/task_file.cpp)."""
 
-    def __init__(self, lib, task_text, device=0, slab_rank=0, slab_count=1, nccl_id=None):
+    def __init__(self, lib, task_text, device=0, slab_rank=0, slab_count=1, nccl_id=None, real_bytes=8, fma=False):
         self.lib = lib
         self.handle = vp()
         idbuf = None
         if nccl_id is not None:
             idbuf = ctypes.create_string_buffer(bytes(nccl_id), 128)
         self._idbuf = idbuf
-        lib.hcheck(lib.h.gcmb_host_engine_create(task_text.encode(), device, slab_rank, slab_count,
-                                                 ctypes.cast(idbuf, vp) if idbuf is not None else None,
-                                                 ctypes.byref(self.handle)))
+        lib.hcheck(lib.h.gcmb_host_engine_create2(task_text.encode(), device, slab_rank, slab_count,
+                                                  ctypes.cast(idbuf, vp) if idbuf is not None else None,
+                                                  real_bytes, 1 if fma else 0, ctypes.byref(self.handle)))
 
     def close(self):
         if self.handle:

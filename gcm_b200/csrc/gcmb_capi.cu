@@ -4,14 +4,12 @@
 // enqueues hand-written kernels on the context's stream.  There is no host implementation of any
 // of the operations: without a device gcmb_create fails.
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <algorithm>
-#include <cmath>
 #include <cstring>
-#include <map>
 #include <memory>
 
+#include "capi_internal.cuh"
 #include "thread_fns.h"
 
 using namespace gcmb;
@@ -21,7 +19,8 @@ using namespace gcmb;
 // =============================================================================================
 namespace {
 
-GCMB_GLOBAL void k_border(BorderArgs b, long long n_face) {
+template<class R>
+GCMB_GLOBAL void k_border(BorderArgs<R> b, long long n_face) {
 	const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	if (b.axis == 2) {
 		// a face across the contiguous axis: the ghost layers of one face node share memory sectors with each
@@ -37,12 +36,14 @@ GCMB_GLOBAL void k_border(BorderArgs b, long long n_face) {
 	border_thread(b, f, a);
 }
 
-GCMB_GLOBAL void k_contact(ContactArgs c, long long n) {
+template<class R>
+GCMB_GLOBAL void k_contact(ContactArgs<R> c, long long n) {
 	const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	if (t < n) { contact_thread(c, t); }
 }
 
-GCMB_GLOBAL void k_ode_maxwell(Geom g, double* pde, const uint8_t* node_table, const double* decay) {
+template<class R>
+GCMB_GLOBAL void k_ode_maxwell(Geom g, R* pde, const uint8_t* node_table, const R* decay) {
 	const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i2 < g.n[2]) { ode_maxwell_thread(g, pde, node_table, decay, blockIdx.z, blockIdx.y, i2); }
 }
@@ -55,9 +56,10 @@ GCMB_GLOBAL void k_assign_table(Geom g, uint8_t* node_table, int table, AreaArgs
 	if (area_contains(area, x)) { node_table[g.index(blockIdx.z, blockIdx.y, i2)] = (uint8_t) table; }
 }
 
-struct VecArg { double v[MAXM]; };
+template<class R> struct VecArg { R v[MAXM]; };
 
-GCMB_GLOBAL void k_add_vector(Geom g, double* pde, VecArg vec, AreaArgs area) {
+template<class R>
+GCMB_GLOBAL void k_add_vector(Geom g, R* pde, VecArg<R> vec, AreaArgs area) {
 	const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i2 >= g.n[2]) { return; }
 	double x[3];
@@ -85,37 +87,37 @@ GCMB_GLOBAL void k_set_table_real_nodes(Geom g, uint8_t* node_table, const uint8
 	node_table[g.index(blockIdx.z, blockIdx.y, i2)] = ids ? ids[r] : 0;
 }
 
-GCMB_GLOBAL void k_xfer(XferArgs x, long long n, int to_device) {
+template<class R>
+GCMB_GLOBAL void k_xfer(XferArgs<R> x, long long n, int to_device) {
 	const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	if (t < n) { xfer_thread(x, t, to_device != 0); }
 }
 
-// deterministic block reduction: fixed tree over shared memory
+// deterministic block reduction: warp shuffles in a fixed butterfly, then a fixed tree over the warps' partials
 template<int THREADS>
 GCMB_DEV void block_sum(double& v, long long& c) {
 #ifdef GCMB_EMUL_BLOCK_SUM
 	GCMB_EMUL_BLOCK_SUM(v, c);
 	return;
-#endif
-	__shared__ double sv[THREADS];
-	__shared__ long long sc[THREADS];
-	sv[threadIdx.x] = v;
-	sc[threadIdx.x] = c;
-	__syncthreads();
-	for (int s = THREADS / 2; s > 0; s >>= 1) {
-		if ((int) threadIdx.x < s) {
-			sv[threadIdx.x] += sv[threadIdx.x + s];
-			sc[threadIdx.x] += sc[threadIdx.x + s];
-		}
-		__syncthreads();
+#else
+	__shared__ double sv[THREADS / 32];
+	__shared__ long long sc[THREADS / 32];
+	for (int o = 16; o > 0; o >>= 1) {
+		v += __shfl_down_sync(0xffffffffu, v, o);
+		c += __shfl_down_sync(0xffffffffu, c, o);
 	}
-	v = sv[0];
-	c = sc[0];
+	if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; sc[threadIdx.x >> 5] = c; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < THREADS / 32; w++) { v += sv[w]; c += sc[w]; }
+	}
+#endif
 }
 
 // detector: quantity summed over masked nodes of the right face of the last axis; one partial (sum, count)
 // per block in a fixed order => deterministic
-GCMB_GLOBAL void k_detector(Geom g, const double* pde, const uint8_t* mask, int code, double* out_sum,
+template<class R>
+GCMB_GLOBAL void k_detector(Geom g, const R* pde, const uint8_t* mask, int code, double* out_sum,
                            long long* out_count) {
 	const long long n_face = (long long) g.n[0] * g.n[1];
 	double sum = 0;
@@ -123,9 +125,9 @@ GCMB_GLOBAL void k_detector(Geom g, const double* pde, const uint8_t* mask, int 
 	for (long long f = (long long) blockIdx.x * blockDim.x + threadIdx.x; f < n_face; f += (long long) gridDim.x * blockDim.x) {
 		if (!mask[f]) { continue; }
 		const long long idx = g.index((int) (f / g.n[1]), (int) (f % g.n[1]), g.n[2] - 1);
-		double v[MAXM];
+		R v[MAXM];
 		for (int c = 0; c < g.M; c++) { v[c] = pde[c * g.comp + idx]; }
-		sum += get_quantity(g.D, code, v);
+		sum += (double) get_quantity(g.D, code, v);
 		count++;
 	}
 	block_sum<256>(sum, count);
@@ -133,7 +135,8 @@ GCMB_GLOBAL void k_detector(Geom g, const double* pde, const uint8_t* mask, int 
 }
 
 // checksum partials: sum_i (i+1) * u_i over real nodes, fixed grid => deterministic
-GCMB_GLOBAL void k_checksum(Geom g, const double* pde, double* partial) {
+template<class R>
+GCMB_GLOBAL void k_checksum(Geom g, const R* pde, double* partial) {
 	const long long n = (long long) g.n[0] * g.n[1] * g.n[2];
 	double sum = 0;
 	long long dummy = 0;
@@ -143,11 +146,24 @@ GCMB_GLOBAL void k_checksum(Geom g, const double* pde, double* partial) {
 		const int i0 = (int) (t / ((long long) g.n[2] * g.n[1]));
 		const long long idx = g.index(i0, i1, i2);
 		double acc = 0;
-		for (int c = 0; c < g.M; c++) { acc += (c + 1) * pde[c * g.comp + idx]; }
+		for (int c = 0; c < g.M; c++) { acc += (c + 1) * (double) pde[c * g.comp + idx]; }
 		sum += acc;
 	}
 	block_sum<256>(sum, dummy);
 	if (threadIdx.x == 0) { partial[blockIdx.x] = sum; }
+}
+
+// gather of a box of nodes into a dense array [component][box node] (asynchronous snapshots, thin-column checks)
+template<class R>
+GCMB_GLOBAL void k_gather_box(Geom g, const R* pde, R* out, int b0, int b1, int b2, int e0, int e1, int e2) {
+	const long long n = (long long) e0 * e1 * e2;
+	const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) { return; }
+	const int i2 = (int) (t % e2);
+	const int i1 = (int) ((t / e2) % e1);
+	const int i0 = (int) (t / ((long long) e2 * e1));
+	const long long idx = g.index(b0 + i0, b1 + i1, b2 + i2);
+	for (int c = 0; c < g.M; c++) { out[t * g.M + c] = pde[c * g.comp + idx]; }
 }
 
 }  // namespace
@@ -185,45 +201,7 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
-constexpr int N_CLASSES = 8;
-
-struct ProfileSpan {
-	int cls;
-	cudaEvent_t a, b;
-};
-
 }  // namespace gcmb
-
-struct gcmb_ctx {
-	int device = 0;
-	cudaStream_t own_stream = nullptr;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t timer_a = nullptr, timer_b = nullptr;
-	bool profiling = false;
-	std::vector<ProfileSpan> spans;
-	double class_ms[N_CLASSES] = {0};
-	long long class_launches[N_CLASSES] = {0};
-	long long launches = 0;
-	size_t bytes = 0;
-	std::vector<gcmb_body*> bodies;
-	ncclComm_t comm = nullptr;
-	int n_ranks = 1, rank = 0;
-	double* scratch = nullptr;  // small device scratch (reductions)
-	// halo exchange overlapped with the interior of the x stage: NCCL runs on comm_stream between ev_ready (state
-	// complete on `stream`) and ev_halo (ghost planes received); the next launch on `stream` waits for ev_halo
-	// unless it is the interior part of the x stage (halo_defer)
-	cudaStream_t comm_stream = nullptr;
-	cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
-	bool halo_pending = false, halo_defer = false;
-};
-
-// make `stream` wait for a halo exchange in flight (no-op when there is none)
-static void wait_halo(gcmb_ctx* ctx) {
-	if (ctx->halo_pending) {
-		cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0);
-		ctx->halo_pending = false;
-	}
-}
 
 struct BorderCond {
 	int cond = 0, dir = 0;
@@ -235,51 +213,39 @@ struct BorderCond {
 struct gcmb_body {
 	gcmb_ctx* ctx = nullptr;
 	Geom g;
-	double* buf[2] = {nullptr, nullptr};  // buf[cur], buf[1-cur]
+	void* buf[2] = {nullptr, nullptr};    // buf[cur], buf[1-cur]: R = double or float (ctx->real_bytes)
 	int cur = 0;
 	uint8_t* node_table = nullptr;
 	int n_tables = 0;
 	std::vector<double> U, U1, L;         // host copies [n][D][M*M] / [n][D][M]
-	StageTable* tables = nullptr;         // device [n*D]
-	std::vector<StageTable> host_tables;  // the same tables on the host
+	void* tables = nullptr;               // device StageTableT<R> [n*D]
+	std::vector<StageTable> host_tables;  // the tables in double
+	std::vector<unsigned char> host_tables_r;  // the tables as StageTableT<R> (what the device holds)
 	double tables_tau = NAN;
-	bool any_k0 = false;                  // some characteristic foot beyond the first cell (Courant > 1)
+	bool any_k0 = false;                  // some characteristic foot beyond the first cell (Courant >= 1)
+	int max_k0 = 0;
 	int pattern_of_dir[3] = {-1, -1, -1};
-	double* packed[3] = {nullptr, nullptr, nullptr};  // device: packed non-zero coefficients per direction
+	void* packed[3] = {nullptr, nullptr, nullptr};  // device: packed non-zero coefficients per direction
+	int packed_variant[3] = {-1, -1, -1};
 	std::string kernel_name[3];
 	std::map<int, BorderCond> borders;    // ordered by condition number
 	uint8_t* detector_mask = nullptr;
 	int detector_code = 0;
-	double* decay_dev = nullptr;
+	void* decay_dev = nullptr;
+	bool halo_inflight = false;           // my ghost x-planes are being received (ctx->halo_pending)
+	// ghost fill of the z faces handed to the next marching stage (gcmb_cubic_stage_fill_next_border)
+	bool zfill_armed = false;
+	ZFaceFill<double> zfill;
+	void* gather_dev = nullptr;           // staging of asynchronous box read-backs
+	size_t gather_bytes = 0;
 };
 
 namespace {
 
-struct Launch {
-	gcmb_ctx* ctx;
-	int cls;
-	ProfileSpan span;
-	Launch(gcmb_ctx* c, int cls_) : ctx(c), cls(cls_) {
-		if (ctx->halo_pending && !ctx->halo_defer) { wait_halo(ctx); }
-		if (ctx->profiling) {
-			span.cls = cls;
-			cudaEventCreate(&span.a);
-			cudaEventCreate(&span.b);
-			cudaEventRecord(span.a, ctx->stream);
-		}
-	}
-	~Launch() {
-		ctx->launches++;
-		if (ctx->profiling) {
-			cudaEventRecord(span.b, ctx->stream);
-			ctx->spans.push_back(span);
-		}
-	}
-};
-
 int flush_profile(gcmb_ctx* ctx) {
 	if (ctx->spans.empty()) { return GCMB_OK; }
 	GCMB_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (ctx->edge_stream) { GCMB_CUDA(cudaStreamSynchronize(ctx->edge_stream)); }
 	for (ProfileSpan& s : ctx->spans) {
 		float ms = 0;
 		cudaEventElapsedTime(&ms, s.a, s.b);
@@ -316,14 +282,36 @@ long long face_size(const Geom& g, int axis) {
 	return n;
 }
 
+int kernel_set(const gcmb_ctx* ctx) { return ctx->real_bytes == 4 ? SET_F32 : (ctx->fma ? SET_F64_FMA : SET_F64_EXACT); }
+
+// variant of the specialised kernels that serves this body at the current time step (-1: none)
+int sparse_variant(const gcmb_body* b) {
+	switch (b->g.bs) {
+		case 1: return VAR_BS1;
+		case 2: return b->any_k0 ? VAR_BS2 : VAR_BS2_K0;
+		case 3: return VAR_BS3;
+		default: return -1;
+	}
+}
+
+template<class R>
+void convert_table(const StageTable& s, StageTableT<R>& d) {
+	for (int i = 0; i < MAXM * MAXM; i++) { d.U[i] = (R) s.U[i]; d.U1[i] = (R) s.U1[i]; }
+	for (int i = 0; i < MAXM * MAXBS; i++) { d.F[i] = (R) s.F[i]; }
+	for (int i = 0; i < MAXM; i++) { d.k0[i] = s.k0[i]; d.dir[i] = s.dir[i]; }
+}
+
 // Newton factors, foot cells and sides of every (table, direction) for time step tau
 // (reference engine/cubic/GridCharacteristicMethod.hpp:56-59,78-84 + EqualDistanceLineInterpolator.hpp:20,63)
+template<class R>
 int build_tables(gcmb_body* b, double tau) {
 	const Geom& g = b->g;
 	const int M = g.M, D = g.D;
+	b->tables_tau = NAN;  // a failure below must not leave half-built tables marked as current
 	std::vector<StageTable>& host = b->host_tables;
 	host.assign((size_t) b->n_tables * D, StageTable());
 	b->any_k0 = false;
+	b->max_k0 = 0;
 	for (int t = 0; t < b->n_tables; t++) {
 		for (int s = 0; s < D; s++) {
 			StageTable& T = host[(size_t) t * D + s];
@@ -344,31 +332,39 @@ int build_tables(gcmb_body* b, double tau) {
 				}
 				T.k0[k] = (int) k0;
 				if (k0 != 0) { b->any_k0 = true; }
+				b->max_k0 = std::max(b->max_k0, (int) k0);
 				for (int i = 1; i <= g.bs; i++) { T.F[k * MAXBS + i - 1] = (q - i + 1) / i; }
 			}
 		}
 	}
-	GCMB_CUDA(cudaMemcpyAsync(b->tables, host.data(), host.size() * sizeof(StageTable), cudaMemcpyHostToDevice, b->ctx->stream));
+	b->host_tables_r.resize(host.size() * sizeof(StageTableT<R>));
+	StageTableT<R>* hr = reinterpret_cast<StageTableT<R>*>(b->host_tables_r.data());
+	for (size_t i = 0; i < host.size(); i++) { convert_table(host[i], hr[i]); }
+	GCMB_CUDA(cudaMemcpyAsync(b->tables, hr, host.size() * sizeof(StageTableT<R>), cudaMemcpyHostToDevice, b->ctx->stream));
 	// packed copies of the structurally non-zero coefficients for the specialised kernels
-	std::vector<double> pk;
+	const int variant = sparse_variant(b);
+	std::vector<R> pk;
 	for (int s = 0; s < D; s++) {
 		cudaFree(b->packed[s]);
 		b->packed[s] = nullptr;
-		if (b->pattern_of_dir[s] < 0) { continue; }
+		b->packed_variant[s] = -1;
+		if (b->pattern_of_dir[s] < 0 || variant < 0) { continue; }
 		const PatternInfo& P = pattern(b->pattern_of_dir[s]);
-		pk.assign((size_t) b->n_tables * (MAXM * MAXM * 2 + MAXM * MAXBS), 0.0);
+		const bool k0rt = variant_k0rt(variant);
+		pk.assign((size_t) b->n_tables * (MAXM * MAXM * 2 + MAXM * (MAXBS + 1)), R(0));
 		int size = 0;
 		bool shares = true;
 		for (int t = 0; t < b->n_tables; t++) {
-			double one[MAXM * MAXM * 2 + MAXM * MAXBS];
-			size = pack_table(P, g.bs, host[(size_t) t * D + s], one);
-			std::memcpy(pk.data() + (size_t) t * size, one, (size_t) size * sizeof(double));
-			shares = shares && table_shares_as_pattern(P, g.bs, host[(size_t) t * D + s]);
+			R one[MAXM * MAXM * 2 + MAXM * (MAXBS + 1)];
+			size = pack_table(P, g.bs, k0rt, hr[(size_t) t * D + s], one);
+			std::memcpy(pk.data() + (size_t) t * size, one, (size_t) size * sizeof(R));
+			shares = shares && table_shares_as_pattern(P, g.bs, hr[(size_t) t * D + s]);
 		}
-		if (!shares) { continue; }  // no packed table: the stage falls back to the full-table kernels
-		GCMB_CUDA(cudaMalloc(&b->packed[s], (size_t) b->n_tables * size * sizeof(double)));
-		GCMB_CUDA(cudaMemcpyAsync(b->packed[s], pk.data(), (size_t) b->n_tables * size * sizeof(double), cudaMemcpyHostToDevice, b->ctx->stream));
+		if (!shares) { continue; }  // no packed table: the stage falls back to the dense kernels
+		GCMB_CUDA(cudaMalloc(&b->packed[s], (size_t) b->n_tables * size * sizeof(R)));
+		GCMB_CUDA(cudaMemcpyAsync(b->packed[s], pk.data(), (size_t) b->n_tables * size * sizeof(R), cudaMemcpyHostToDevice, b->ctx->stream));
 		GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+		b->packed_variant[s] = variant;
 	}
 	GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));
 	b->tables_tau = tau;
@@ -398,10 +394,10 @@ void choose_patterns(gcmb_body* b) {
 			}
 		}
 		int chosen = -1;
-		if (sgn_ok && (g.bs == 1 || g.bs == 2) && !getenv("GCMB_FORCE_DENSE")) {
+		if (sgn_ok && g.bs <= 3 && !getenv("GCMB_FORCE_DENSE")) {
 			for (int p = 0; p < pattern_count() && chosen < 0; p++) {
 				const PatternInfo& P = pattern(p);
-				if (P.M != M) { continue; }
+				if (P.M != M || P.axis != s + g.shift) { continue; }
 				bool ok = true;
 				for (int k = 0; k < M && ok; k++) {
 					ok = P.sgn[k] == sgn[k] && (um[k] & ~P.um[k]) == 0 && (u1m[k] & ~P.u1m[k]) == 0;
@@ -410,24 +406,56 @@ void choose_patterns(gcmb_body* b) {
 			}
 		}
 		b->pattern_of_dir[s] = chosen;
-		b->kernel_name[s] = chosen >= 0 ? std::string("sparse:") + pattern(chosen).name + "/bs" + std::to_string(g.bs)
-		                                : std::string("dense:M") + std::to_string(M);
+		b->kernel_name[s] = "unset";
 	}
+}
+
+template<class R> R* layer(gcmb_body* b, int which) { return static_cast<R*>(b->buf[which]); }
+
+// what gcmb_cubic_stage launches for `dir` at the current tables; fills kernel_name
+StageLauncher pick_launcher(gcmb_body* b, int dir) {
+	const int set = kernel_set(b->ctx);
+	const int M = b->g.M, bs = b->g.bs;
+	const int p = b->pattern_of_dir[dir];
+	const int variant = sparse_variant(b);
+	static const char* const set_name[N_SETS] = {"", "+fma", "/f32"};
+	if (p >= 0 && variant >= 0 && b->packed[dir] && b->packed_variant[dir] == variant) {
+		StageLauncher f = sparse_launcher(set, p, variant);
+		if (f) {
+			static const char* const var_name[N_VARIANTS] = {"/bs1", "/bs2", "/bs2+k0", "/bs3+k0"};
+			b->kernel_name[dir] = std::string("sparse:") + pattern(p).name + var_name[variant] + set_name[set];
+			return f;
+		}
+	}
+	static const bool literal_dense = std::getenv("GCMB_DENSE_LITERAL") != nullptr;
+	if (!literal_dense && bs <= 2 && b->max_k0 <= 1) {
+		StageLauncher f = dense_k0_launcher(set, M, bs, b->any_k0);
+		if (f) {
+			b->kernel_name[dir] = std::string(b->n_tables == 1 ? "dense_k0_one:M" : "dense_k0:M") + std::to_string(M) + "/bs" + std::to_string(bs) +
+			                      (b->any_k0 ? "+k0" : "") + set_name[set];
+			return f;
+		}
+	}
+	StageLauncher f = dense_launcher(set, M);
+	b->kernel_name[dir] = std::string("dense:M") + std::to_string(M) + set_name[set];
+	return f;
 }
 
 }  // namespace
 
+#define GCMB_BY_REAL(ctx, call_double, call_float) ((ctx)->real_bytes == 4 ? (call_float) : (call_double))
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
-extern "C" {
+// (every entry point below is declared extern "C" by include/gcm_b200.h)
 
 const char* gcmb_last_error(void) { return g_error.c_str(); }
-const char* gcmb_version(void) { return "gcm_b200 0.1 (sm_100a, fp64)"; }
+const char* gcmb_version(void) { return "gcm_b200 0.2 (sm_100a, fp64 / fp32)"; }
 
 int gcmb_create(int device, int real_bytes, gcmb_ctx** out) {
 	if (!out) { GCMB_FAIL(GCMB_E_INVALID_ARG, "out is null"); }
-	if (real_bytes != 8) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "only real_bytes == 8 (fp64) is implemented"); }
+	if (real_bytes != 8 && real_bytes != 4) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "real_bytes must be 8 (fp64) or 4 (fp32)"); }
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
 		cudaGetLastError();
@@ -437,12 +465,27 @@ int gcmb_create(int device, int real_bytes, gcmb_ctx** out) {
 	GCMB_CUDA(cudaSetDevice(device));
 	std::unique_ptr<gcmb_ctx> ctx(new gcmb_ctx);
 	ctx->device = device;
+	ctx->real_bytes = real_bytes;
+	const char* fma = std::getenv("GCMB_FMA");
+	ctx->fma = fma && fma[0] == '1';
 	GCMB_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
 	ctx->stream = ctx->own_stream;
 	GCMB_CUDA(cudaEventCreate(&ctx->timer_a));
 	GCMB_CUDA(cudaEventCreate(&ctx->timer_b));
 	GCMB_CUDA(cudaMalloc(&ctx->scratch, 4096 * sizeof(double)));
 	*out = ctx.release();
+	return GCMB_OK;
+}
+
+int gcmb_real_bytes(gcmb_ctx* ctx) { return ctx ? ctx->real_bytes : 0; }
+
+int gcmb_set_fma(gcmb_ctx* ctx, int on) {
+	if (!ctx) { GCMB_FAIL(GCMB_E_INVALID_ARG, "ctx is null"); }
+	if (on && ctx->real_bytes == 8 && !dense_launcher(SET_F64_FMA, 9)) {
+		GCMB_FAIL(GCMB_E_UNSUPPORTED, "this build of libgcm_b200.so holds no FMA-contracted fp64 kernels");
+	}
+	ctx->fma = on != 0;
+	for (gcmb_body* b : ctx->bodies) { b->tables_tau = NAN; }
 	return GCMB_OK;
 }
 
@@ -453,8 +496,16 @@ void gcmb_destroy(gcmb_ctx* ctx) {
 	while (!ctx->bodies.empty()) { gcmb_cubic_body_destroy(ctx->bodies.back()); }
 	for (ProfileSpan& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
 	if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); }
+	if (ctx->edge_stream) { cudaStreamSynchronize(ctx->edge_stream); }
 	if (ctx->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->comm); }
-	if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_halo); }
+	if (ctx->comm_stream) {
+		cudaStreamDestroy(ctx->comm_stream); cudaStreamDestroy(ctx->edge_stream);
+		cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_halo); cudaEventDestroy(ctx->ev_edge);
+	}
+	if (ctx->copy_stream) {
+		cudaStreamSynchronize(ctx->copy_stream);
+		cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy_ready); cudaEventDestroy(ctx->ev_copy_done);
+	}
 	cudaFree(ctx->scratch);
 	cudaEventDestroy(ctx->timer_a);
 	cudaEventDestroy(ctx->timer_b);
@@ -464,6 +515,7 @@ void gcmb_destroy(gcmb_ctx* ctx) {
 
 int gcmb_set_stream(gcmb_ctx* ctx, void* cuda_stream) {
 	if (!ctx) { GCMB_FAIL(GCMB_E_INVALID_ARG, "ctx is null"); }
+	wait_halo(ctx);
 	GCMB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
 	return GCMB_OK;
@@ -473,10 +525,12 @@ int gcmb_sync(gcmb_ctx* ctx) {
 	GCMB_CUDA(cudaSetDevice(ctx->device));
 	wait_halo(ctx);
 	GCMB_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (ctx->copy_stream) { GCMB_CUDA(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
 	return GCMB_OK;
 }
 
 int gcmb_timer_start(gcmb_ctx* ctx) {
+	wait_halo(ctx);
 	GCMB_CUDA(cudaEventRecord(ctx->timer_a, ctx->stream));
 	return GCMB_OK;
 }
@@ -530,11 +584,13 @@ int gcmb_cubic_body_create(gcmb_ctx* ctx, int D, int M, const int* sizes, const 
 		const int a = i + g.shift;
 		g.n[a] = sizes[i]; g.g[a] = border_size; g.start[a] = start[i]; g.h[a] = h[i];
 	}
-	g.zoff = 16;  // >= MAXBS, multiple of 16 doubles (128 B)
+	g.zoff = 16;  // >= MAXBS, multiple of 16 elements (128 B of doubles)
 	g.pitch = ((g.zoff + g.n[2] + g.g[2]) + 15) / 16 * 16;
 	g.plane = (long long) (g.n[1] + 2 * g.g[1]) * g.pitch;
 	g.comp = ((long long) (g.n[0] + 2 * g.g[0]) * g.plane + 31) / 32 * 32;
-	const size_t bytes = (size_t) g.comp * M * sizeof(double);
+	// slack behind the last component: the bulk-copy kernels fetch whole 128/256-node row segments
+	const size_t slack = 512;
+	const size_t bytes = ((size_t) g.comp * M + slack) * (size_t) ctx->real_bytes;
 	for (int i = 0; i < 2; i++) {
 		if (cudaMalloc(&b->buf[i], bytes) != cudaSuccess) {
 			cudaGetLastError();
@@ -543,8 +599,8 @@ int gcmb_cubic_body_create(gcmb_ctx* ctx, int D, int M, const int* sizes, const 
 		}
 		GCMB_CUDA(cudaMemsetAsync(b->buf[i], 0, bytes, ctx->stream));
 	}
-	GCMB_CUDA(cudaMalloc(&b->node_table, (size_t) g.comp + 64));  // slack: 4-byte id copies of the z-tile kernel
-	GCMB_CUDA(cudaMemsetAsync(b->node_table, 0, (size_t) g.comp, ctx->stream));
+	GCMB_CUDA(cudaMalloc(&b->node_table, (size_t) g.comp + slack));  // slack: id copies of the tile kernels
+	GCMB_CUDA(cudaMemsetAsync(b->node_table, 0, (size_t) g.comp + slack, ctx->stream));
 	GCMB_CUDA(cudaMalloc(&b->decay_dev, 256 * sizeof(double)));
 	ctx->bytes += 2 * bytes + (size_t) g.comp;
 	ctx->bodies.push_back(b.get());
@@ -556,8 +612,10 @@ void gcmb_cubic_body_destroy(gcmb_body* b) {
 	if (!b) { return; }
 	gcmb_ctx* ctx = b->ctx;
 	cudaSetDevice(ctx->device);
+	wait_halo(ctx);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->bytes -= 2 * (size_t) b->g.comp * b->g.M * sizeof(double) + (size_t) b->g.comp;
+	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); }
+	ctx->bytes -= 2 * ((size_t) b->g.comp * b->g.M + 512) * (size_t) ctx->real_bytes + (size_t) b->g.comp;
 	cudaFree(b->buf[0]);
 	cudaFree(b->buf[1]);
 	cudaFree(b->node_table);
@@ -565,41 +623,42 @@ void gcmb_cubic_body_destroy(gcmb_body* b) {
 	for (int s = 0; s < 3; s++) { cudaFree(b->packed[s]); }
 	cudaFree(b->decay_dev);
 	cudaFree(b->detector_mask);
+	cudaFree(b->gather_dev);
 	for (auto& kv : b->borders) { cudaFree(kv.second.mask[0]); cudaFree(kv.second.mask[1]); }
 	ctx->bodies.erase(std::remove(ctx->bodies.begin(), ctx->bodies.end(), b), ctx->bodies.end());
 	delete b;
 }
 
+template<class R>
 static int transfer(gcmb_body* b, void* host, int with_ghosts, bool to_device) {
-	if (!b || !host) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
 	gcmb_ctx* ctx = b->ctx;
 	const Geom& g = b->g;
 	GCMB_CUDA(cudaSetDevice(ctx->device));
 	const int e0 = with_ghosts ? g.n[0] + 2 * g.g[0] : g.n[0];
 	const long long e12 = (long long) (with_ghosts ? g.n[1] + 2 * g.g[1] : g.n[1]) * (with_ghosts ? g.n[2] + 2 * g.g[2] : g.n[2]);
-	const long long per_plane = e12 * g.M;  // doubles per slice of internal axis 0
+	const long long per_plane = e12 * g.M;  // reals per slice of internal axis 0
 	int chunk = (int) std::max<long long>(1, (64LL << 20) / std::max<long long>(1, per_plane));
 	chunk = std::min(chunk, e0);
-	double* stage = nullptr;
-	GCMB_CUDA(cudaMalloc(&stage, (size_t) chunk * per_plane * sizeof(double)));
+	R* stage = nullptr;
+	GCMB_CUDA(cudaMalloc(&stage, (size_t) chunk * per_plane * sizeof(R)));
 	int rc = GCMB_OK;
 	for (int x0 = 0; x0 < e0 && rc == GCMB_OK; x0 += chunk) {
 		const int x1 = std::min(e0, x0 + chunk);
 		const long long n = (long long) (x1 - x0) * e12;
-		double* hp = static_cast<double*>(host) + (long long) x0 * per_plane;
-		XferArgs x;
-		x.soa = b->buf[b->cur]; x.aos = stage; x.g = g; x.with_ghosts = with_ghosts; x.x_begin = x0; x.x_end = x1;
+		R* hp = static_cast<R*>(host) + (long long) x0 * per_plane;
+		XferArgs<R> x;
+		x.soa = layer<R>(b, b->cur); x.aos = stage; x.g = g; x.with_ghosts = with_ghosts; x.x_begin = x0; x.x_end = x1;
 		cudaError_t e = cudaSuccess;
 		if (to_device) {
-			e = cudaMemcpyAsync(stage, hp, (size_t) n * g.M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+			e = cudaMemcpyAsync(stage, hp, (size_t) n * g.M * sizeof(R), cudaMemcpyHostToDevice, ctx->stream);
 		}
 		if (e == cudaSuccess) {
 			Launch l(ctx, 6);
-			GCMB_LAUNCH(k_xfer, (unsigned) ((n + 255) / 256), 256, ctx->stream, x, n, to_device ? 1 : 0);
+			GCMB_LAUNCH(k_xfer<R>, (unsigned) ((n + 255) / 256), 256, ctx->stream, x, n, to_device ? 1 : 0);
 			e = cudaGetLastError();
 		}
 		if (e == cudaSuccess && !to_device) {
-			e = cudaMemcpyAsync(hp, stage, (size_t) n * g.M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+			e = cudaMemcpyAsync(hp, stage, (size_t) n * g.M * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream);
 		}
 		if (e == cudaSuccess) { e = cudaStreamSynchronize(ctx->stream); }
 		if (e != cudaSuccess) { set_error(std::string("state transfer: ") + cudaGetErrorString(e)); rc = GCMB_E_CUDA; }
@@ -609,11 +668,70 @@ static int transfer(gcmb_body* b, void* host, int with_ghosts, bool to_device) {
 }
 
 int gcmb_cubic_upload_state(gcmb_body* body, const void* aos_pde, int with_ghosts) {
-	return transfer(body, const_cast<void*>(aos_pde), with_ghosts, true);
+	if (!body || !aos_pde) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	return GCMB_BY_REAL(body->ctx, transfer<double>(body, const_cast<void*>(aos_pde), with_ghosts, true),
+	                    transfer<float>(body, const_cast<void*>(aos_pde), with_ghosts, true));
 }
 
 int gcmb_cubic_download_state(gcmb_body* body, void* aos_pde, int with_ghosts) {
-	return transfer(body, aos_pde, with_ghosts, false);
+	if (!body || !aos_pde) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	return GCMB_BY_REAL(body->ctx, transfer<double>(body, aos_pde, with_ghosts, false), transfer<float>(body, aos_pde, with_ghosts, false));
+}
+
+// ---- asynchronous read-back of a box of real nodes (snapshots that do not stall the time loop) ----
+template<class R>
+static int box_begin(gcmb_body* b, const int* box_min, const int* extent, void* pinned_host) {
+	gcmb_ctx* ctx = b->ctx;
+	const Geom& g = b->g;
+	int lo[3] = {0, 0, 0}, ext[3] = {1, 1, 1};
+	long long n = 1;
+	for (int i = 0; i < g.D; i++) {
+		const int a = i + g.shift;
+		lo[a] = box_min[i]; ext[a] = extent[i];
+		if (extent[i] < 1 || box_min[i] < -g.g[a] || box_min[i] + extent[i] > g.n[a] + g.g[a]) { GCMB_FAIL(GCMB_E_INVALID_ARG, "box leaves the grid"); }
+		n *= extent[i];
+	}
+	GCMB_CUDA(cudaSetDevice(ctx->device));
+	if (!ctx->copy_stream) {
+		GCMB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+		GCMB_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy_ready, cudaEventDisableTiming));
+		GCMB_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming));
+	}
+	const size_t bytes = (size_t) n * g.M * sizeof(R);
+	if (b->gather_bytes < bytes) {
+		GCMB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+		cudaFree(b->gather_dev);
+		b->gather_dev = nullptr;
+		b->gather_bytes = 0;
+		GCMB_CUDA(cudaMalloc(&b->gather_dev, bytes));
+		b->gather_bytes = bytes;
+	}
+	// the gather runs on the copy stream behind everything enqueued so far; later kernels that overwrite the
+	// layer wait for it (Launch -> wait_copy), the PCIe transfer itself overlaps them
+	wait_halo(ctx);
+	GCMB_CUDA(cudaEventRecord(ctx->ev_copy_ready, ctx->stream));
+	GCMB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_ready, 0));
+	GCMB_LAUNCH(k_gather_box<R>, (unsigned) ((n + 255) / 256), 256, ctx->copy_stream, g, (const R*) layer<R>(b, b->cur),
+	            static_cast<R*>(b->gather_dev), lo[0], lo[1], lo[2], ext[0], ext[1], ext[2]);
+	ctx->launches++;
+	GCMB_CUDA(cudaGetLastError());
+	GCMB_CUDA(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+	ctx->copy_pending = true;
+	GCMB_CUDA(cudaMemcpyAsync(pinned_host, b->gather_dev, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+	return GCMB_OK;
+}
+
+int gcmb_cubic_download_box_begin(gcmb_body* body, const int* box_min, const int* extent, void* host) {
+	if (!body || !box_min || !extent || !host) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	return GCMB_BY_REAL(body->ctx, box_begin<double>(body, box_min, extent, host), box_begin<float>(body, box_min, extent, host));
+}
+
+int gcmb_cubic_download_box_end(gcmb_body* body) {
+	if (!body) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	gcmb_ctx* ctx = body->ctx;
+	GCMB_CUDA(cudaSetDevice(ctx->device));
+	if (ctx->copy_stream) { GCMB_CUDA(cudaStreamSynchronize(ctx->copy_stream)); }
+	return GCMB_OK;
 }
 
 int gcmb_cubic_download_tables(gcmb_body* b, uint8_t* node_table_id) {
@@ -642,6 +760,8 @@ int gcmb_cubic_set_materials(gcmb_body* b, int n_tables, const double* U, const 
 	b->U.assign(U, U + mm);
 	b->U1.assign(U1, U1 + mm);
 	b->L.assign(L, L + lm);
+	wait_halo(ctx);
+	GCMB_CUDA(cudaStreamSynchronize(ctx->stream));  // stages in flight may still read the old tables
 	cudaFree(b->tables);
 	b->tables = nullptr;
 	GCMB_CUDA(cudaMalloc(&b->tables, (size_t) n_tables * g.D * sizeof(StageTable)));
@@ -679,19 +799,24 @@ int gcmb_cubic_assign_table_in_area(gcmb_body* b, int table_id, int area_kind, c
 	return GCMB_OK;
 }
 
+template<class R>
+static int add_vector(gcmb_body* b, const double* vector_M, int area_kind, const double* params) {
+	VecArg<R> v;
+	std::memset(&v, 0, sizeof v);
+	for (int c = 0; c < b->g.M; c++) { v.v[c] = (R) vector_M[c]; }
+	{
+		Launch l(b->ctx, 6);
+		GCMB_LAUNCH(k_add_vector<R>, node_grid(b->g, 128), 128, b->ctx->stream, b->g, layer<R>(b, b->cur), v, make_area(area_kind, params));
+	}
+	GCMB_CUDA(cudaGetLastError());
+	return GCMB_OK;
+}
+
 int gcmb_cubic_add_vector_in_area(gcmb_body* b, const double* vector_M, int area_kind, const double* params) {
 	if (!b || !vector_M) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
 	if (area_kind < 0 || area_kind > 3) { GCMB_FAIL(GCMB_E_INVALID_ARG, "unknown area kind"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
-	VecArg v;
-	std::memset(&v, 0, sizeof v);
-	for (int c = 0; c < b->g.M; c++) { v.v[c] = vector_M[c]; }
-	{
-		Launch l(b->ctx, 6);
-		GCMB_LAUNCH(k_add_vector, node_grid(b->g, 128), 128, b->ctx->stream, b->g, b->buf[b->cur], v, make_area(area_kind, params));
-	}
-	GCMB_CUDA(cudaGetLastError());
-	return GCMB_OK;
+	return GCMB_BY_REAL(b->ctx, add_vector<double>(b, vector_M, area_kind, params), add_vector<float>(b, vector_M, area_kind, params));
 }
 
 // ---- borders ---------------------------------------------------------------------------------
@@ -755,12 +880,15 @@ int gcmb_cubic_border_set_area(gcmb_body* b, int cond, int dir, int sides, int a
 	return GCMB_OK;
 }
 
-int gcmb_cubic_border_apply(gcmb_body* b, int dir, int n_values, const double* values) {
-	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
-	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+static int border_values_check(gcmb_body* b, int dir, int n_values, const double* values) {
 	int need = 0;
 	for (auto& kv : b->borders) { if (kv.second.dir == dir) { need += (int) kv.second.q.size(); } }
 	if (need != n_values || (need > 0 && !values)) { GCMB_FAIL(GCMB_E_INVALID_ARG, "wrong number of border values"); }
+	return GCMB_OK;
+}
+
+template<class R>
+static int border_apply(gcmb_body* b, int dir, const double* values) {
 	const Geom& g = b->g;
 	const int axis = dir + g.shift;
 	const long long nf = face_size(g, axis);
@@ -770,14 +898,14 @@ int gcmb_cubic_border_apply(gcmb_body* b, int dir, int n_values, const double* v
 		if (c.dir != dir) { continue; }
 		for (int s = 0; s < 2; s++) {
 			if (!c.side_on[s]) { continue; }
-			BorderArgs a;
+			BorderArgs<R> a;
 			std::memset(&a, 0, sizeof a);
-			a.pde = b->buf[b->cur]; a.mask = c.mask[s]; a.g = g; a.axis = axis; a.side = s;
+			a.pde = layer<R>(b, b->cur); a.mask = c.mask[s]; a.g = g; a.axis = axis; a.side = s;
 			a.nq = (int) c.q.size();
-			for (int i = 0; i < a.nq; i++) { a.q[i] = c.q[(size_t) i]; a.val[i] = values[used + i]; }
+			for (int i = 0; i < a.nq; i++) { a.q[i] = c.q[(size_t) i]; a.val[i] = (R) values[used + i]; }
 			const long long n = axis == 2 ? nf : nf * g.bs;
 			Launch l(b->ctx, 3);
-			GCMB_LAUNCH(k_border, (unsigned) ((n + 127) / 128), 128, b->ctx->stream, a, nf);
+			GCMB_LAUNCH(k_border<R>, (unsigned) ((n + 127) / 128), 128, b->ctx->stream, a, nf);
 		}
 		used += (int) c.q.size();
 	}
@@ -785,15 +913,53 @@ int gcmb_cubic_border_apply(gcmb_body* b, int dir, int n_values, const double* v
 	return GCMB_OK;
 }
 
+int gcmb_cubic_border_apply(gcmb_body* b, int dir, int n_values, const double* values) {
+	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	const int rc = border_values_check(b, dir, n_values, values);
+	if (rc) { return rc; }
+	return GCMB_BY_REAL(b->ctx, border_apply<double>(b, dir, values), border_apply<float>(b, dir, values));
+}
+
+// Can the ghost fill of direction `dir` ride on the marching stage that writes the layer?  Yes when the direction
+// is the contiguous axis, the row length allows whole-warp sector stores, and on every face the LAST registered
+// condition (the one whose values survive, BorderConditions.hpp:81-95) covers the whole face with plain components.
+static bool zfill_possible(gcmb_body* b, int dir, const double* values, ZFaceFill<double>& zf) {
+#ifdef GCMB_EMUL
+	return false;
+#else
+	static const bool off = std::getenv("GCMB_NO_FUSED_BORDER") != nullptr;
+	const Geom& g = b->g;
+	if (off || dir != g.D - 1 || g.D < 2 || g.n[2] % 32 != 0 || g.n[2] < 64 || g.bs > 4) { return false; }
+	std::memset(&zf, 0, sizeof zf);
+	int used = 0;
+	for (auto& kv : b->borders) {
+		const BorderCond& c = kv.second;
+		if (c.dir != dir) { continue; }
+		for (int s = 0; s < 2; s++) {
+			if (!c.side_on[s]) { continue; }
+			if (c.mask[s]) { return false; }
+			zf.on[s] = 1;
+			zf.set[s] = 0;
+			for (size_t i = 0; i < c.q.size(); i++) {
+				if (c.q[i] < 0) { return false; }
+				// a later Set of the same component wins, as in the reference's loop over the condition's values
+				zf.set[s] |= 1u << c.q[i];
+				zf.add[s][c.q[i]] = 2 * values[used + (int) i];
+			}
+		}
+		used += (int) c.q.size();
+	}
+	return zf.on[0] || zf.on[1];
+#endif
+}
+
 // ---- contacts --------------------------------------------------------------------------------
-int gcmb_cubic_contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_min,
-                             const int* boxB_min, const int* extent) {
-	if (!a || !b || !boxA_min || !boxB_min || !extent) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
-	if (a->g.D != b->g.D || a->g.M != b->g.M || a->g.bs != b->g.bs) { GCMB_FAIL(GCMB_E_INVALID_ARG, "bodies are not compatible"); }
-	GCMB_CUDA(cudaSetDevice(a->ctx->device));
-	ContactArgs c;
+template<class R>
+static int contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_min, const int* boxB_min, const int* extent) {
+	ContactArgs<R> c;
 	std::memset(&c, 0, sizeof c);
-	c.a = a->buf[a->cur]; c.b = b->buf[b->cur]; c.ga = a->g; c.gb = b->g;
+	c.a = layer<R>(a, a->cur); c.b = static_cast<const R*>(b->buf[b->cur]); c.ga = a->g; c.gb = b->g;
 	long long n = 1;
 	for (int ax = 0; ax < 3; ax++) { c.amin[ax] = c.bmin[ax] = 0; c.ext[ax] = 1; }
 	for (int i = 0; i < a->g.D; i++) {
@@ -808,70 +974,117 @@ int gcmb_cubic_contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_m
 	}
 	{
 		Launch l(a->ctx, 4);
-		GCMB_LAUNCH(k_contact, (unsigned) ((n + 127) / 128), 128, a->ctx->stream, c, n);
+		GCMB_LAUNCH(k_contact<R>, (unsigned) ((n + 127) / 128), 128, a->ctx->stream, c, n);
 	}
 	GCMB_CUDA(cudaGetLastError());
 	return GCMB_OK;
 }
 
+int gcmb_cubic_contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_min,
+                             const int* boxB_min, const int* extent) {
+	if (!a || !b || !boxA_min || !boxB_min || !extent) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	if (a->ctx != b->ctx) { GCMB_FAIL(GCMB_E_INVALID_ARG, "bodies belong to different contexts"); }
+	if (a->g.D != b->g.D || a->g.M != b->g.M || a->g.bs != b->g.bs) { GCMB_FAIL(GCMB_E_INVALID_ARG, "bodies are not compatible"); }
+	GCMB_CUDA(cudaSetDevice(a->ctx->device));
+	return GCMB_BY_REAL(a->ctx, contact_apply<double>(a, b, boxA_min, boxB_min, extent), contact_apply<float>(a, b, boxA_min, boxB_min, extent));
+}
+
 // ---- stage -----------------------------------------------------------------------------------
-int gcmb_cubic_stage(gcmb_body* b, int dir, double tau) {
-	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
-	if (dir < 0 || dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "direction out of range"); }
-	if (!b->tables) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
-	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+template<class R>
+static int stage_impl(gcmb_body* b, int dir, double tau) {
 	if (!(b->tables_tau == tau)) {
-		const int rc = build_tables(b, tau);
+		const int rc = build_tables<R>(b, tau);
 		if (rc) { return rc; }
 	}
-	StageArgs a;
-	a.cur = b->buf[b->cur];
-	a.nxt = b->buf[1 - b->cur];
+	StageArgsT<R> a;
+	std::memset(&a, 0, sizeof a);
+	a.cur = layer<R>(b, b->cur);
+	a.nxt = layer<R>(b, 1 - b->cur);
 	a.node_table = b->node_table;
-	a.tables = b->tables;
-	a.packed = b->packed[dir];
+	a.tables = static_cast<const StageTableT<R>*>(b->tables);
+	a.packed = static_cast<const R*>(b->packed[dir]);
 	a.n_tables = b->n_tables;
 	a.g = b->g;
 	a.axis = dir + b->g.shift;
 	a.dir = dir;
 	a.x_begin = 0;
 	a.x_end = b->g.n[0];
-	a.host_tables = b->host_tables.data();
-	StageLauncher launch = nullptr;
-	const int p = b->pattern_of_dir[dir];
-	if (p >= 0 && !b->any_k0) {
-		launch = b->g.bs == 1 ? pattern(p).launch_bs1 : pattern(p).launch_bs2;
-	}
-	static const bool literal_dense = std::getenv("GCMB_DENSE_LITERAL") != nullptr;
-	if (!launch && !b->any_k0 && !literal_dense) {
-		launch = dense_k0_launcher(b->g.M, b->g.bs);
-		if (launch && p < 0) {
-			b->kernel_name[dir] = std::string(b->n_tables == 1 ? "dense_k0_one:M" : "dense_k0:M") + std::to_string(b->g.M) + "/bs" + std::to_string(b->g.bs);
+	a.host_tables = reinterpret_cast<const StageTableT<R>*>(b->host_tables_r.data());
+	StageLauncher launch = pick_launcher(b, dir);
+	if (!launch) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "no stage kernel for this PDE size / arithmetic type in this build"); }
+	if (b->zfill_armed) {
+		b->zfill_armed = false;
+		// only the marching kernels of the specialised patterns carry the fused ghost fill
+		if (a.axis != 1 || b->kernel_name[dir].compare(0, 7, "sparse:") != 0) { GCMB_FAIL(GCMB_E_INVALID_OP, "fused border fill is not available for this stage"); }
+		a.zfill = 1;
+		for (int s = 0; s < 2; s++) {
+			a.zf.on[s] = b->zfill.on[s];
+			a.zf.set[s] = b->zfill.set[s];
+			for (int c = 0; c < MAXM; c++) { a.zf.add[s][c] = (R) b->zfill.add[s][c]; }
 		}
 	}
-	if (!launch) { launch = dense_launcher(b->g.M); }
-	if (!launch) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "no stage kernel for this PDE size"); }
 	gcmb_ctx* ctx = b->ctx;
 	const int bs = b->g.g[0];
-	if (ctx->halo_pending && a.axis == 0 && bs > 0 && b->g.n[0] > 2 * bs) {
+	if (b->halo_inflight && ctx->halo_pending && a.axis == 0 && bs > 0 && b->g.n[0] > 2 * bs) {
 		// the nodes at least `bs` planes away from both slab faces read no ghost plane: they go first, while the
-		// halo exchange is still in flight; the two boundary strips follow once the ghost planes have arrived
-		StageArgs part = a;
+		// halo exchange is still in flight; the two boundary strips run on a stream of their own behind the
+		// exchange, so that the interiors of the context's other bodies are not held back either
+		StageArgsT<R> part = a;
 		part.x_begin = bs; part.x_end = b->g.n[0] - bs;
 		ctx->halo_defer = true;
-		{ Launch l(ctx, a.axis); launch(part, ctx->stream); }
-		ctx->halo_defer = false;
+		{ Launch l(ctx, a.axis); launch(&part, ctx->stream); }
+		if (!ctx->edge_waits_halo) {
+			GCMB_CUDA(cudaStreamWaitEvent(ctx->edge_stream, ctx->ev_halo, 0));
+			ctx->edge_waits_halo = true;
+		}
 		part.x_begin = 0; part.x_end = bs;
-		{ Launch l(ctx, a.axis); launch(part, ctx->stream); }
+		{ Launch l(ctx, a.axis, ctx->edge_stream); launch(&part, ctx->edge_stream); }
 		part.x_begin = b->g.n[0] - bs; part.x_end = b->g.n[0];
-		{ Launch l(ctx, a.axis); launch(part, ctx->stream); }
+		{ Launch l(ctx, a.axis, ctx->edge_stream); launch(&part, ctx->edge_stream); }
+		ctx->halo_defer = false;
+		GCMB_CUDA(cudaEventRecord(ctx->ev_edge, ctx->edge_stream));
+		ctx->edge_pending = true;
 	} else {
 		Launch l(ctx, a.axis);
-		launch(a, ctx->stream);
+		launch(&a, ctx->stream);
 	}
+	b->halo_inflight = false;
 	GCMB_CUDA(cudaGetLastError());
 	b->cur = 1 - b->cur;  // swapCurrAndNextPdeTimeLayer
 	return GCMB_OK;
+}
+
+int gcmb_cubic_stage(gcmb_body* b, int dir, double tau) {
+	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	if (dir < 0 || dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "direction out of range"); }
+	if (!b->tables) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	return GCMB_BY_REAL(b->ctx, stage_impl<double>(b, dir, tau), stage_impl<float>(b, dir, tau));
+}
+
+int gcmb_cubic_stage_fill_next_border(gcmb_body* b, int dir, double tau, int next_dir, int n_values, const double* values, int* fused) {
+	if (!b || !fused) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	if (dir < 0 || dir >= b->g.D || next_dir < 0 || next_dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "direction out of range"); }
+	if (!b->tables) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	int rc = border_values_check(b, next_dir, n_values, values);
+	if (rc) { return rc; }
+	*fused = 0;
+	ZFaceFill<double> zf;
+	if (dir != next_dir && dir + b->g.shift == 1 && zfill_possible(b, next_dir, values, zf)) {
+		// the tables must be current before the launcher is known
+		if (!(b->tables_tau == tau)) {
+			rc = GCMB_BY_REAL(b->ctx, build_tables<double>(b, tau), build_tables<float>(b, tau));
+			if (rc) { return rc; }
+		}
+		pick_launcher(b, dir);
+		if (b->kernel_name[dir].compare(0, 7, "sparse:") == 0) {
+			b->zfill = zf;
+			b->zfill_armed = true;
+			*fused = 1;
+		}
+	}
+	return gcmb_cubic_stage(b, dir, tau);
 }
 
 const char* gcmb_cubic_stage_kernel_name(gcmb_body* b, int dir) {
@@ -880,18 +1093,25 @@ const char* gcmb_cubic_stage_kernel_name(gcmb_body* b, int dir) {
 }
 
 // ---- ode -------------------------------------------------------------------------------------
+template<class R>
+static int ode_maxwell(gcmb_body* b, const double* decay_per_table) {
+	std::vector<R> d((size_t) b->n_tables);
+	for (int i = 0; i < b->n_tables; i++) { d[(size_t) i] = (R) decay_per_table[i]; }
+	GCMB_CUDA(cudaMemcpyAsync(b->decay_dev, d.data(), d.size() * sizeof(R), cudaMemcpyHostToDevice, b->ctx->stream));
+	GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));  // the host array is a temporary
+	{
+		Launch l(b->ctx, 5);
+		GCMB_LAUNCH(k_ode_maxwell<R>, node_grid(b->g, 128), 128, b->ctx->stream, b->g, layer<R>(b, b->cur), b->node_table, static_cast<const R*>(b->decay_dev));
+	}
+	GCMB_CUDA(cudaGetLastError());
+	return GCMB_OK;
+}
+
 int gcmb_cubic_ode_maxwell(gcmb_body* b, const double* decay_per_table) {
 	if (!b || !decay_per_table) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
 	if (b->n_tables < 1) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
-	GCMB_CUDA(cudaMemcpyAsync(b->decay_dev, decay_per_table, (size_t) b->n_tables * sizeof(double), cudaMemcpyHostToDevice, b->ctx->stream));
-	GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));  // the host array may be a temporary
-	{
-		Launch l(b->ctx, 5);
-		GCMB_LAUNCH(k_ode_maxwell, node_grid(b->g, 128), 128, b->ctx->stream, b->g, b->buf[b->cur], b->node_table, b->decay_dev);
-	}
-	GCMB_CUDA(cudaGetLastError());
-	return GCMB_OK;
+	return GCMB_BY_REAL(b->ctx, ode_maxwell<double>(b, decay_per_table), ode_maxwell<float>(b, decay_per_table));
 }
 
 // ---- seismogram taps ---------------------------------------------------------------------------
@@ -927,11 +1147,10 @@ int gcmb_cubic_detector_set_area(gcmb_body* b, int q_code, int area_kind, const 
 	return GCMB_OK;
 }
 
-int gcmb_cubic_seismo(gcmb_body* b, double* sum, long long* count, int line_comp, double* line, int n_line) {
-	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+template<class R>
+static int seismo(gcmb_body* b, double* sum, long long* count, int line_comp, double* line, int n_line, int line_i0, int line_i1) {
 	gcmb_ctx* ctx = b->ctx;
 	const Geom& g = b->g;
-	GCMB_CUDA(cudaSetDevice(ctx->device));
 	if (sum || count) {
 		if (!b->detector_mask) { GCMB_FAIL(GCMB_E_INVALID_OP, "detector is not set"); }
 		const long long nf = (long long) g.n[0] * g.n[1];
@@ -940,7 +1159,7 @@ int gcmb_cubic_seismo(gcmb_body* b, double* sum, long long* count, int line_comp
 		long long* d_count = reinterpret_cast<long long*>(ctx->scratch + 1024);
 		{
 			Launch l(ctx, 7);
-			GCMB_LAUNCH(k_detector, blocks, 256, ctx->stream, g, b->buf[b->cur], b->detector_mask, b->detector_code, d_sum, d_count);
+			GCMB_LAUNCH(k_detector<R>, blocks, 256, ctx->stream, g, (const R*) layer<R>(b, b->cur), b->detector_mask, b->detector_code, d_sum, d_count);
 		}
 		GCMB_CUDA(cudaGetLastError());
 		std::vector<double> ps((size_t) blocks);
@@ -957,21 +1176,42 @@ int gcmb_cubic_seismo(gcmb_body* b, double* sum, long long* count, int line_comp
 	if (line) {
 		if (line_comp < 0 || line_comp >= g.M) { GCMB_FAIL(GCMB_E_INVALID_ARG, "line component out of range"); }
 		if (n_line != g.n[2]) { GCMB_FAIL(GCMB_E_INVALID_ARG, "n_line must equal the size of the last axis"); }
-		const double* src = b->buf[b->cur] + (long long) line_comp * g.comp + g.index(g.n[0] / 2, g.n[1] / 2, 0);
-		GCMB_CUDA(cudaMemcpyAsync(line, src, (size_t) n_line * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		if (line_i0 < 0 || line_i0 >= g.n[0] || line_i1 < 0 || line_i1 >= g.n[1]) { GCMB_FAIL(GCMB_E_INVALID_ARG, "line position is outside the body"); }
+		wait_halo(ctx);
+		const R* src = layer<R>(b, b->cur) + (long long) line_comp * g.comp + g.index(line_i0, line_i1, 0);
+		std::vector<R> tmp((size_t) n_line);
+		GCMB_CUDA(cudaMemcpyAsync(tmp.data(), src, (size_t) n_line * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
 		GCMB_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (int i = 0; i < n_line; i++) { line[i] = (double) tmp[(size_t) i]; }
 	}
 	return GCMB_OK;
 }
 
-int gcmb_cubic_checksum(gcmb_body* b, double* out) {
-	if (!b || !out) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+int gcmb_cubic_seismo(gcmb_body* b, double* sum, long long* count, int line_comp, double* line, int n_line) {
+	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	const int i0 = b->g.n[0] / 2, i1 = b->g.n[1] / 2;
+	return GCMB_BY_REAL(b->ctx, seismo<double>(b, sum, count, line_comp, line, n_line, i0, i1), seismo<float>(b, sum, count, line_comp, line, n_line, i0, i1));
+}
+
+int gcmb_cubic_seismo_at(gcmb_body* b, double* sum, long long* count, int line_comp, double* line, int n_line, const int* line_node) {
+	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	int it[3] = {0, 0, 0};
+	if (line) {
+		if (!line_node) { GCMB_FAIL(GCMB_E_INVALID_ARG, "line_node is null"); }
+		for (int i = 0; i < b->g.D - 1; i++) { it[i + b->g.shift] = line_node[i]; }
+	}
+	return GCMB_BY_REAL(b->ctx, seismo<double>(b, sum, count, line_comp, line, n_line, it[0], it[1]), seismo<float>(b, sum, count, line_comp, line, n_line, it[0], it[1]));
+}
+
+template<class R>
+static int checksum(gcmb_body* b, double* out) {
 	gcmb_ctx* ctx = b->ctx;
-	GCMB_CUDA(cudaSetDevice(ctx->device));
 	const int blocks = 1024;
 	{
 		Launch l(ctx, 7);
-		GCMB_LAUNCH(k_checksum, blocks, 256, ctx->stream, b->g, b->buf[b->cur], ctx->scratch);
+		GCMB_LAUNCH(k_checksum<R>, blocks, 256, ctx->stream, b->g, (const R*) layer<R>(b, b->cur), ctx->scratch);
 	}
 	GCMB_CUDA(cudaGetLastError());
 	std::vector<double> partial((size_t) blocks);
@@ -981,6 +1221,12 @@ int gcmb_cubic_checksum(gcmb_body* b, double* out) {
 	for (double p : partial) { s += p; }
 	*out = s;
 	return GCMB_OK;
+}
+
+int gcmb_cubic_checksum(gcmb_body* b, double* out) {
+	if (!b || !out) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	return GCMB_BY_REAL(b->ctx, checksum<double>(b, out), checksum<float>(b, out));
 }
 
 // ---- multi-GPU ---------------------------------------------------------------------------------
@@ -1016,25 +1262,27 @@ int gcmb_comm_init(gcmb_ctx* ctx, int n_ranks, int rank, const void* id128) {
 	return GCMB_OK;
 }
 
-int gcmb_cubic_halo_exchange(gcmb_body* b) {
-	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
-	gcmb_ctx* ctx = b->ctx;
+int gcmb_halo_exchange_bodies(gcmb_body* const* bodies, int n) {
+	if (!bodies || n < 1) { GCMB_FAIL(GCMB_E_INVALID_ARG, "no bodies"); }
+	for (int i = 0; i < n; i++) {
+		if (!bodies[i] || bodies[i]->ctx != bodies[0]->ctx) { GCMB_FAIL(GCMB_E_INVALID_ARG, "the bodies must belong to one context"); }
+	}
+	gcmb_ctx* ctx = bodies[0]->ctx;
 	if (!ctx->comm || ctx->n_ranks == 1) { return GCMB_OK; }
-	const Geom& g = b->g;
-	if (g.D != 3 && g.g[0] == 0) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "slab decomposition needs the x axis to be the slowest internal axis (3-D grids)"); }
+	for (int i = 0; i < n; i++) {
+		if (bodies[i]->g.g[0] == 0) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "slab decomposition needs the x axis to be the slowest internal axis (3-D grids)"); }
+	}
 	GCMB_CUDA(cudaSetDevice(ctx->device));
-	// x-planes are contiguous inside every component volume: ghost planes [0,bs) and [n0+bs, n0+2bs),
-	// outermost real planes [bs, 2bs) and [n0, n0+bs)
-	const size_t count = (size_t) g.g[0] * (size_t) g.plane;
-	double* base = b->buf[b->cur];
 	// on a stream of its own, so that the interior of the following x stage (which reads no ghost plane) overlaps it
 	static const bool overlap = !std::getenv("GCMB_NO_HALO_OVERLAP");
 	if (overlap && !ctx->comm_stream) {
 		int least = 0, greatest = 0;
 		GCMB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
 		GCMB_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, greatest));
+		GCMB_CUDA(cudaStreamCreateWithPriority(&ctx->edge_stream, cudaStreamNonBlocking, greatest));
 		GCMB_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
 		GCMB_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+		GCMB_CUDA(cudaEventCreateWithFlags(&ctx->ev_edge, cudaEventDisableTiming));
 	}
 	wait_halo(ctx);
 	cudaStream_t comm_stream = overlap ? ctx->comm_stream : ctx->stream;
@@ -1042,29 +1290,55 @@ int gcmb_cubic_halo_exchange(gcmb_body* b) {
 		GCMB_CUDA(cudaEventRecord(ctx->ev_ready, ctx->stream));
 		GCMB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0));
 	}
+	// x-planes are contiguous inside every component volume: ghost planes [0,bs) and [n0+bs, n0+2bs),
+	// outermost real planes [bs, 2bs) and [n0, n0+bs).  One group for all bodies: one NCCL launch per step.
+	const ncclDataType_t type = ctx->real_bytes == 4 ? ncclFloat : ncclDouble;
+	const size_t rb = (size_t) ctx->real_bytes;
+	ncclResult_t failed = ncclSuccess;
+	const char* what = "";
+#define GCMB_NCCL_IN_GROUP(call) do { if (failed == ncclSuccess) { failed = (call); if (failed != ncclSuccess) { what = #call; } } } while (0)
 	GCMB_NCCL(g_nccl.GroupStart());
-	for (int c = 0; c < g.M; c++) {
-		double* v = base + (long long) c * g.comp;
-		if (ctx->rank > 0) {
-			GCMB_NCCL(g_nccl.Send(v + (long long) g.g[0] * g.plane, count, ncclDouble, ctx->rank - 1, ctx->comm, comm_stream));
-			GCMB_NCCL(g_nccl.Recv(v, count, ncclDouble, ctx->rank - 1, ctx->comm, comm_stream));
-		}
-		if (ctx->rank < ctx->n_ranks - 1) {
-			GCMB_NCCL(g_nccl.Send(v + (long long) g.n[0] * g.plane, count, ncclDouble, ctx->rank + 1, ctx->comm, comm_stream));
-			GCMB_NCCL(g_nccl.Recv(v + (long long) (g.n[0] + g.g[0]) * g.plane, count, ncclDouble, ctx->rank + 1, ctx->comm, comm_stream));
+	for (int i = 0; i < n; i++) {
+		gcmb_body* b = bodies[i];
+		const Geom& g = b->g;
+		const size_t count = (size_t) g.g[0] * (size_t) g.plane;
+		char* base = static_cast<char*>(b->buf[b->cur]);
+		for (int c = 0; c < g.M; c++) {
+			char* v = base + (size_t) c * (size_t) g.comp * rb;
+			if (ctx->rank > 0) {
+				GCMB_NCCL_IN_GROUP(g_nccl.Send(v + (size_t) g.g[0] * g.plane * rb, count, type, ctx->rank - 1, ctx->comm, comm_stream));
+				GCMB_NCCL_IN_GROUP(g_nccl.Recv(v, count, type, ctx->rank - 1, ctx->comm, comm_stream));
+			}
+			if (ctx->rank < ctx->n_ranks - 1) {
+				GCMB_NCCL_IN_GROUP(g_nccl.Send(v + (size_t) g.n[0] * g.plane * rb, count, type, ctx->rank + 1, ctx->comm, comm_stream));
+				GCMB_NCCL_IN_GROUP(g_nccl.Recv(v + (size_t) (g.n[0] + g.g[0]) * g.plane * rb, count, type, ctx->rank + 1, ctx->comm, comm_stream));
+			}
 		}
 	}
-	GCMB_NCCL(g_nccl.GroupEnd());
+	const ncclResult_t ended = g_nccl.GroupEnd();  // always closed, also after a failed call inside
+#undef GCMB_NCCL_IN_GROUP
+	if (failed != ncclSuccess || ended != ncclSuccess) {
+		set_error(std::string(failed != ncclSuccess ? what : "ncclGroupEnd") + " -> " +
+		          (g_nccl.GetErrorString ? g_nccl.GetErrorString(failed != ncclSuccess ? failed : ended) : "nccl error"));
+		return GCMB_E_NCCL;
+	}
 	if (overlap) {
 		GCMB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
 		ctx->halo_pending = true;
+		ctx->edge_waits_halo = false;
+		for (int i = 0; i < n; i++) { bodies[i]->halo_inflight = true; }
 	}
 	ctx->launches++;
 	return GCMB_OK;
 }
 
+int gcmb_cubic_halo_exchange(gcmb_body* b) {
+	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	return gcmb_halo_exchange_bodies(&b, 1);
+}
+
 size_t gcmb_cubic_halo_bytes(gcmb_body* b) {
-	return b ? (size_t) b->g.M * (size_t) b->g.g[0] * (size_t) b->g.plane * sizeof(double) : 0;
+	return b ? (size_t) b->g.M * (size_t) b->g.g[0] * (size_t) b->g.plane * (size_t) b->ctx->real_bytes : 0;
 }
 
 static int halo_host(gcmb_body* b, int side, void* host, bool get) {
@@ -1074,14 +1348,15 @@ static int halo_host(gcmb_body* b, int side, void* host, bool get) {
 	if (g.g[0] == 0) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "slab decomposition needs the x axis to be the slowest internal axis (3-D grids)"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
 	wait_halo(b->ctx);
+	const size_t rb = (size_t) b->ctx->real_bytes;
 	const size_t count = (size_t) g.g[0] * (size_t) g.plane;
 	// real planes next to the face: [bs, 2bs) left, [n0, n0+bs) right; ghost planes: [0, bs) / [n0+bs, n0+2bs)
 	const long long first = get ? (side == 0 ? g.g[0] : g.n[0]) : (side == 0 ? 0 : g.n[0] + g.g[0]);
 	for (int c = 0; c < g.M; c++) {
-		double* dev = b->buf[b->cur] + (long long) c * g.comp + first * g.plane;
-		double* h = static_cast<double*>(host) + (size_t) c * count;
-		if (get) { GCMB_CUDA(cudaMemcpyAsync(h, dev, count * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream)); }
-		else { GCMB_CUDA(cudaMemcpyAsync(dev, h, count * sizeof(double), cudaMemcpyHostToDevice, b->ctx->stream)); }
+		char* dev = static_cast<char*>(b->buf[b->cur]) + ((size_t) c * (size_t) g.comp + (size_t) first * g.plane) * rb;
+		char* h = static_cast<char*>(host) + (size_t) c * count * rb;
+		if (get) { GCMB_CUDA(cudaMemcpyAsync(h, dev, count * rb, cudaMemcpyDeviceToHost, b->ctx->stream)); }
+		else { GCMB_CUDA(cudaMemcpyAsync(dev, h, count * rb, cudaMemcpyHostToDevice, b->ctx->stream)); }
 	}
 	GCMB_CUDA(cudaStreamSynchronize(b->ctx->stream));
 	return GCMB_OK;
@@ -1096,6 +1371,7 @@ int gcmb_comm_allreduce_sum(gcmb_ctx* ctx, double* host_values, int n) {
 	if (!ctx || !host_values || n < 1 || n > 2048) { GCMB_FAIL(GCMB_E_INVALID_ARG, "bad argument"); }
 	if (!ctx->comm || ctx->n_ranks == 1) { return GCMB_OK; }
 	GCMB_CUDA(cudaSetDevice(ctx->device));
+	wait_halo(ctx);  // one communicator: the reduction is ordered behind a halo exchange in flight on every rank
 	double* d = ctx->scratch + 2048;
 	GCMB_CUDA(cudaMemcpyAsync(d, host_values, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	GCMB_NCCL(g_nccl.AllReduce(d, d, (size_t) n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
@@ -1104,6 +1380,3 @@ int gcmb_comm_allreduce_sum(gcmb_ctx* ctx, double* host_values, int n) {
 	return GCMB_OK;
 }
 
-}  // extern "C"
-
-#include "simplex_capi.inc"

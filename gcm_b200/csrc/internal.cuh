@@ -20,9 +20,9 @@
 // kernels with block barriers: written as phases over GCMB_BLOCK_THREADS (a single pass on the device)
 #define GCMB_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define GCMB_BLOCK_THREADS(tid) for (int tid = threadIdx.x, gcmb_once_ = 1; gcmb_once_; gcmb_once_ = 0)
-#define GCMB_DYN_SMEM(type, name)                                  \
-	extern __shared__ __align__(16) unsigned char gcmb_dyn_smem_[]; \
-	type& name = *reinterpret_cast<type*>(gcmb_dyn_smem_)
+#define GCMB_DYN_SMEM_RAW(name)                                      \
+	extern __shared__ __align__(128) unsigned char gcmb_dyn_smem_[]; \
+	unsigned char* name = gcmb_dyn_smem_
 #endif
 #ifdef __CUDACC__
 #define GCMB_HD __host__ __device__ __forceinline__
@@ -60,50 +60,87 @@ struct Geom {
 	}
 };
 
-// One eigen-system prepared for the stage kernels: per (material table, reference direction).
-struct StageTable {
-	double U[MAXM * MAXM];   // row-major, row k = left eigenvector k
-	double U1[MAXM * MAXM];  // row-major
-	double F[MAXM * MAXBS];  // F[k*MAXBS + i-1] = (q_k - i + 1) / i, i = 1..bs  (Newton factors)
-	int k0[MAXM];            // (size_t) q_k : cell containing the characteristic foot
-	int dir[MAXM];           // +1 / -1 : side the foot lies on (dx_k > 0 ? +1 : -1)
+// One eigen-system prepared for the stage kernels: per (material table, reference direction), in the
+// arithmetic type R of the body (double, or float for gcmb_create(..., 4)).
+template<class R>
+struct StageTableT {
+	R U[MAXM * MAXM];   // row-major, row k = left eigenvector k
+	R U1[MAXM * MAXM];  // row-major
+	R F[MAXM * MAXBS];  // F[k*MAXBS + i-1] = (q_k - i + 1) / i, i = 1..bs  (Newton factors)
+	int k0[MAXM];       // (size_t) q_k : cell containing the characteristic foot
+	int dir[MAXM];      // +1 / -1 : side the foot lies on (dx_k > 0 ? +1 : -1)
+};
+typedef StageTableT<double> StageTable;
+
+// ghost fill of the two faces across the contiguous axis, done by the marching stage kernel that writes the
+// layer (reference engine/cubic/BorderConditions.hpp:97-114 for conditions over the whole face with plain
+// component quantities): ghost(-a) = inner(+a), components in `flip` negated and shifted by add[c] = 2 b_c(t)
+template<class R>
+struct ZFaceFill {
+	int on[2];        // left / right face
+	unsigned set[2];  // bit c: component c is Set by some condition of the face
+	R add[2][MAXM];   // 2 * b_c(t_n) of the LAST condition that sets component c
 };
 
-struct StageArgs {
-	const double* cur;
-	double* nxt;
+template<class R>
+struct StageArgsT {
+	const R* cur;
+	R* nxt;
 	const uint8_t* node_table;
-	const StageTable* tables; // indexed [table * D + dir]
-	const double* packed;     // this direction's packed coefficient tables [table][Packed::SIZE] or null
+	const StageTableT<R>* tables; // indexed [table * D + dir]
+	const R* packed;          // this direction's packed coefficient tables [table][Packed::SIZE] or null
 	int n_tables;
 	Geom g;
 	int axis;                 // internal axis of the sweep
 	int dir;                  // reference direction
 	int x_begin, x_end;       // range of internal axis 0 to process (slab sub-ranges for overlap)
-	const StageTable* host_tables; // HOST copy of `tables` (launchers only: coefficients passed as kernel parameters)
+	const StageTableT<R>* host_tables; // HOST copy of `tables` (launchers only: coefficients passed as kernel parameters)
+	int zfill;                // != 0: also fill the z ghosts of the written layer (zf)
+	ZFaceFill<R> zf;
 };
+typedef StageArgsT<double> StageArgs;
 
-typedef void (*StageLauncher)(const StageArgs&, cudaStream_t);
+// type-erased launcher: `args` points to the StageArgsT<R> of the kernel set the launcher belongs to
+typedef void (*StageLauncher)(const void* args, cudaStream_t);
+
+// kernel sets: arithmetic type x floating-point contraction
+enum { SET_F64_EXACT = 0,  // double, no FMA contraction: bit-identical to the reference CPU engine
+       SET_F64_FMA = 1,    // double, contraction allowed (gcmb_set_fma): within 1e-12 of the reference, not bit-identical
+       SET_F32 = 2,        // float (gcmb_create(..., 4)), contraction allowed
+       N_SETS = 3 };
+// variants of the specialised kernels: border size x where the characteristic feet may lie
+enum { VAR_BS1 = 0,        // border size 1, foot cell read from the table
+       VAR_BS2_K0 = 1,     // border size 2, every foot inside the first cell (Courant number < 1)
+       VAR_BS2 = 2,        // border size 2, foot cell read from the table (Courant number up to 2)
+       VAR_BS3 = 3,        // border size 3, foot cell read from the table
+       N_VARIANTS = 4 };
+constexpr int variant_bs(int v) { return v == VAR_BS1 ? 1 : (v == VAR_BS3 ? 3 : 2); }
+constexpr bool variant_k0rt(int v) { return v != VAR_BS2_K0; }
 
 struct PatternInfo {
 	const char* name;
+	int group;             // translation unit the kernels of the pattern are compiled in (build.py)
 	int M;
+	int axis;              // internal axis of the pattern's direction (2 = contiguous)
 	int sgn[MAXM];
 	unsigned um[MAXM];
 	unsigned u1m[MAXM];
 	int base[MAXM];        // row/column whose coefficients row/column k shares (k itself when none)
 	unsigned uneg[MAXM];   // bit j: U(k,j) == -U(base,j)
 	unsigned u1neg[MAXM];  // bit i: U1(i,k) == -U1(i,base)
-	StageLauncher launch_bs1;
-	StageLauncher launch_bs2;
 };
 
-// host side of thread_fns.h Packed<P,BS>: the non-zero coefficients of one table in kernel order, the
-// rows/columns that share their coefficients with a base row stored once
-inline int pack_table(const PatternInfo& p, int bs, const StageTable& T, double* out) {
+// host side of thread_fns.h Packed<P,BS,K0RT>: the non-zero coefficients of one table in kernel order, the
+// rows/columns that share their coefficients with a base row stored once; with k0rt the foot cell of every
+// interpolated base row follows its Newton factors
+template<class R>
+inline int pack_table(const PatternInfo& p, int bs, bool k0rt, const StageTableT<R>& T, R* out) {
 	int n = 0;
 	for (int k = 0; k < p.M; k++) {
-		if (p.sgn[k] != 0 && p.base[k] == k) { for (int i = 0; i < bs; i++) { out[n++] = T.F[k * MAXBS + i]; } }
+		if (p.sgn[k] != 0 && p.base[k] == k) {
+			for (int i = 0; i < bs; i++) { out[n++] = T.F[k * MAXBS + i]; }
+			if (k0rt) { out[n++] = (R) T.k0[k]; }
+		}
 	}
 	for (int k = 0; k < p.M; k++) {
 		if (p.base[k] != k) { continue; }
@@ -116,26 +153,30 @@ inline int pack_table(const PatternInfo& p, int bs, const StageTable& T, double*
 }
 
 // true when the table really has the sharing structure the pattern assumes (checked bit for bit)
-inline bool table_shares_as_pattern(const PatternInfo& p, int bs, const StageTable& T) {
+template<class R>
+inline bool table_shares_as_pattern(const PatternInfo& p, int bs, const StageTableT<R>& T) {
 	for (int k = 0; k < p.M; k++) {
 		const int b = p.base[k];
 		if (b == k) { continue; }
+		if (T.k0[k] != T.k0[b]) { return false; }
 		for (int i = 0; i < bs; i++) { if (T.F[k * MAXBS + i] != T.F[b * MAXBS + i]) { return false; } }
 		for (int j = 0; j < p.M; j++) {
-			const double want = ((p.uneg[k] >> j) & 1u) ? -T.U[b * p.M + j] : T.U[b * p.M + j];
+			const R want = ((p.uneg[k] >> j) & 1u) ? -T.U[b * p.M + j] : T.U[b * p.M + j];
 			if (T.U[k * p.M + j] != want) { return false; }
-			const double want1 = ((p.u1neg[k] >> j) & 1u) ? -T.U1[j * p.M + b] : T.U1[j * p.M + b];
+			const R want1 = ((p.u1neg[k] >> j) & 1u) ? -T.U1[j * p.M + b] : T.U1[j * p.M + b];
 			if (T.U1[j * p.M + k] != want1) { return false; }
 		}
 	}
 	return true;
 }
 
-// stage_dispatch.cu
+// stage_dispatch.cu: registry of the stage kernels compiled in stage_inst.cu (one translation unit per
+// kernel set and pattern group)
 int pattern_count();
 const PatternInfo& pattern(int i);
-StageLauncher dense_launcher(int M);
-StageLauncher dense_k0_launcher(int M, int bs);
+StageLauncher sparse_launcher(int set, int pattern, int variant);  // null when the set was not built
+StageLauncher dense_launcher(int set, int M);                       // literal restatement, any border size / foot cell
+StageLauncher dense_k0_launcher(int set, int M, int bs, bool k0rt); // feet within the first two cells, bs 1..2
 
 // error handling ------------------------------------------------------------------------------
 void set_error(const std::string& msg);

@@ -15,30 +15,21 @@
 
 namespace gcmb {
 
-#if defined(__CUDA_ARCH__)
-GCMB_DEV void cp_async_b32(void* smem_dst, const void* gmem_src) {
-	const unsigned dst = (unsigned) __cvta_generic_to_shared(smem_dst);
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(dst), "l"(gmem_src) : "memory");
-}
-#else
-inline void cp_async_b32(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 4); }
-#endif
-
 constexpr int ZTILE = 256;             // threads per block = nodes per tile
 constexpr int ZLEAD = 1;               // tiles in flight ahead of the one being computed
-constexpr int ZHALO = 2;               // largest border size served by this kernel
+constexpr int ZHALO = 4;               // largest border size served by this kernel
 constexpr int ZROW = ZTILE + 2 * ZHALO;
 
-template<int M, int TABLE_SIZE, int LEAD>
+// followed in dynamic shared memory by the packed coefficient tables of all materials
+template<class R, int M, int LEAD>
 struct ZTileSmem {
-	double v[LEAD + 1][M][ZROW];
-	double tab[SMEM_TABLES * TABLE_SIZE];
+	R v[LEAD + 1][M][ZROW];
 	uint8_t id[LEAD + 1][ZTILE];
 };
 
 // phase A, one thread: start the copies of row `i1` (tile slot `slot`); rows past the end copy nothing
-template<class P, int BS, int LEAD>
-GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M, Packed<P, BS>::SIZE, LEAD>& sm, int slot, int tid, int i0, int i1, int z0, int i1_end) {
+template<class R, class P, int BS, int LEAD>
+GCMB_HD void ztile_issue(const StageArgsT<R>& a, ZTileSmem<R, P::M, LEAD>& sm, int slot, int tid, int i0, int i1, int z0, int i1_end) {
 	constexpr int M = P::M;
 	constexpr unsigned IC = PatternSets<P>::interp();
 	constexpr unsigned CC = PatternSets<P>::center();
@@ -49,7 +40,7 @@ GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M, Packed<P, BS>::SIZE
 		if (z < g.n[2] + BS) {
 #pragma unroll
 			for (int j = 0; j < M; j++) {
-				if (((IC | CC) >> j) & 1u) { cp_async_f64(&sm.v[slot][j][tid + ZHALO], a.cur + j * g.comp + row + z); }
+				if (((IC | CC) >> j) & 1u) { cp_async_real(&sm.v[slot][j][tid + ZHALO], a.cur + j * g.comp + row + z); }
 			}
 		}
 		// halo: BS values on each side of the chunk, copied by the first 2*BS threads
@@ -59,28 +50,28 @@ GCMB_HD void ztile_issue(const StageArgs& a, ZTileSmem<P::M, Packed<P, BS>::SIZE
 			if (zh < g.n[2] + BS) {
 #pragma unroll
 				for (int j = 0; j < M; j++) {
-					if ((IC >> j) & 1u) { cp_async_f64(&sm.v[slot][j][e + ZHALO], a.cur + j * g.comp + row + zh); }
+					if ((IC >> j) & 1u) { cp_async_real(&sm.v[slot][j][e + ZHALO], a.cur + j * g.comp + row + zh); }
 				}
 			}
 		}
-		if ((tid & 3) == 0 && z < g.n[2]) { cp_async_b32(&sm.id[slot][tid], a.node_table + row + z); }
+		if ((tid & 3) == 0 && z < g.n[2]) { cp_async_bytes<4>(&sm.id[slot][tid], a.node_table + row + z); }
 	}
 	cp_async_commit();
 }
 
 // phase B, one thread: one node of the tile from shared memory
-template<class P, int BS, int LEAD>
-GCMB_HD void ztile_compute(const StageArgs& a, const ZTileSmem<P::M, Packed<P, BS>::SIZE, LEAD>& sm, int slot, int tid, int i0, int i1, int z0) {
+template<class R, class P, int BS, bool K0RT, int LEAD>
+GCMB_HD void ztile_compute(const StageArgsT<R>& a, const ZTileSmem<R, P::M, LEAD>& sm, const R* tabs, int slot, int tid, int i0, int i1, int z0) {
 	constexpr int M = P::M;
 	const Geom& g = a.g;
 	const int z = z0 + tid;
 	if (z >= g.n[2]) { return; }
 	const long long idx = g.index(i0, i1, z);
-	const double* tab = sm.tab + (int) sm.id[slot][tid] * Packed<P, BS>::SIZE;
-	const double (*v)[ZROW] = sm.v[slot];
-	auto load = [&](int j, int o) -> double { return v[j][tid + ZHALO + o]; };
-	double out[M];
-	gcm_node_sparse<P, BS>(PackedCoef<P, BS>{tab}, load, out);
+	const R* tab = tabs + (int) sm.id[slot][tid] * Packed<P, BS, K0RT>::SIZE;
+	const R (*v)[ZROW] = sm.v[slot];
+	auto load = [&](int j, int o) -> R { return v[j][tid + ZHALO + o]; };
+	R out[M];
+	gcm_node_sparse<R, P, BS, K0RT>(PackedCoef<R, P, BS, K0RT>{tab}, load, out);
 #pragma unroll
 	for (int c = 0; c < M; c++) { a.nxt[c * g.comp + idx] = out[c]; }
 }

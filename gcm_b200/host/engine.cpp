@@ -86,7 +86,14 @@ real Mesh::getMinimalSpatialStep() const {
 const std::vector<real>& Mesh::pdeRealNodes() const {
 	if (!hostValid) {
 		host.resize(sizeOfRealNodes() * (size_t) M);
-		check(gcmb_cubic_download_state(body, host.data(), 0));
+		if (realBytes == 4) {
+			// an fp32 context keeps floats (the reference's `real` with LIBGCM_DOUBLE_PRECISION off)
+			std::vector<float> tmp(host.size());
+			check(gcmb_cubic_download_state(body, tmp.data(), 0));
+			for (size_t i = 0; i < tmp.size(); i++) { host[i] = tmp[i]; }
+		} else {
+			check(gcmb_cubic_download_state(body, host.data(), 0));
+		}
 		hostValid = true;
 	}
 	return host;
@@ -117,7 +124,8 @@ EngineBase::EngineBase(const Task& task, int dimensionality) :
 	}
 	slabRank = task.device.slabRank;
 	slabCount = task.device.slabCount;
-	check(gcmb_create(task.device.device, 8, &ctx));
+	check(gcmb_create(task.device.device, task.device.realBytes, &ctx));
+	if (task.device.fma) { check(gcmb_set_fma(ctx, 1)); }
 	if (slabCount > 1) {
 		if (!task.device.ncclUniqueId) { throw Exception(GCMB_E_INVALID_ARG, "slab decomposition needs the NCCL id"); }
 		check(gcmb_comm_init(ctx, slabCount, slabRank, task.device.ncclUniqueId));
@@ -200,6 +208,28 @@ void EngineBase::createGridsAndContacts(const Task& task) {
 	}
 
 	const int bs = task.cubicGrid.borderSize;
+	if (slabCount > 1) {
+		// Every body is cut along x by slab, so a contact NORMAL to x between two bodies would join planes that live on
+		// different processes: the local boxes below would not find it and the facing ghost planes would silently stay
+		// empty.  Such tasks are detected on the undecomposed cubes and refused.
+		for (const Body& body : bodies) {
+			for (const Body& other : bodies) {
+				if (other.mesh->id == body.mesh->id) { continue; }
+				const Mesh& a = *body.mesh;
+				const Mesh& b = *other.mesh;
+				int width[3], axis = 0;
+				for (int i = 0; i < D; i++) {
+					width[i] = std::min(a.globalStart[i] + a.globalSizes[i] - 1, b.globalStart[i] + b.globalSizes[i] - 1) -
+					           std::max(a.globalStart[i], b.globalStart[i]);
+				}
+				for (int i = 1; i < D; i++) { if (width[i] < width[axis]) { axis = i; } }
+				if (width[axis] == -1 && axis == 0) {
+					throw Exception(GCMB_E_UNSUPPORTED, "slab decomposition along x cannot hold a contact normal to x (bodies " +
+							std::to_string(a.id) + " and " + std::to_string(b.id) + "): stack the bodies along y or z");
+				}
+			}
+		}
+	}
 	for (Body& body : bodies) {
 		for (const Body& other : bodies) {
 			if (other.mesh->id == body.mesh->id) { continue; }
@@ -344,13 +374,21 @@ void EngineBase::setUpBorders(const Task& task, Body& body) {
 
 /// reference engine/cubic/Engine.cpp:92-121
 void EngineBase::nextTimeStep() {
+	auto borderValues = [&](const Body& body, int direction) {
+		std::vector<double> values;
+		for (const Border& b : body.borders) {
+			if (b.direction != direction) { continue; }
+			for (const auto& f : b.values) { values.push_back(f(Clock::Time())); }
+		}
+		return values;
+	};
 	for (int stage = 0; stage < D; stage++) {
 		for (Body& body : bodies) {
-			std::vector<double> values;
-			for (const Border& b : body.borders) {
-				if (b.direction != stage) { continue; }
-				for (const auto& f : b.values) { values.push_back(f(Clock::Time())); }
+			if (body.borderFilledByStage) {  // the previous stage's kernel has written these ghost nodes already
+				body.borderFilledByStage = false;
+				continue;
 			}
+			const std::vector<double> values = borderValues(body, stage);
 			if (!values.empty() || !body.borders.empty()) {
 				check(gcmb_cubic_border_apply(body.mesh->body, stage, (int) values.size(), values.data()));
 			}
@@ -364,10 +402,23 @@ void EngineBase::nextTimeStep() {
 			}
 		}
 		if (stage == 0 && slabCount > 1) {
-			for (Body& body : bodies) { check(gcmb_cubic_halo_exchange(body.mesh->body)); }
+			// one exchange for all bodies; the interior of every body's x stage overlaps it
+			std::vector<gcmb_body*> all;
+			for (Body& body : bodies) { all.push_back(body.mesh->body); }
+			check(gcmb_halo_exchange_bodies(all.data(), (int) all.size()));
 		}
 		for (Body& body : bodies) {
-			check(gcmb_cubic_stage(body.mesh->body, stage, Clock::TimeStep()));
+			if (stage + 1 == D - 1 && !body.borders.empty()) {
+				// the stage before the last one can write the ghost nodes of the last direction's faces with the rows
+				// it produces (the border values are those of the same time, BorderConditions.hpp:81-95)
+				const std::vector<double> values = borderValues(body, D - 1);
+				int fused = 0;
+				check(gcmb_cubic_stage_fill_next_border(body.mesh->body, stage, Clock::TimeStep(), D - 1,
+						(int) values.size(), values.data(), &fused));
+				body.borderFilledByStage = fused != 0;
+			} else {
+				check(gcmb_cubic_stage(body.mesh->body, stage, Clock::TimeStep()));
+			}
 		}
 	}
 	for (Body& body : bodies) {
@@ -422,19 +473,27 @@ void EngineBase::sliceSnapshot(const int step_) {
 		std::vector<double> line((size_t) m.sizes[last]);
 		double sum = 0;
 		long long count = 0;
-		check(gcmb_cubic_seismo(m.body, isDetectorBody ? &sum : nullptr, isDetectorBody ? &count : nullptr,
-				last /* velocity along the last axis */, line.data(), m.sizes[last]));
+		// the line runs through the centre of the WHOLE body (SliceSnapshotter.hpp:44-58: sizes / 2): of a decomposed
+		// body only the slab that holds that node has it
+		int lineNode[3] = {0, 0, 0};
+		bool holdsLine = true;
+		for (int i = 0; i < last; i++) {
+			lineNode[i] = m.globalStart[(size_t) i] + m.globalSizes[(size_t) i] / 2 - m.start[(size_t) i];
+			if (lineNode[i] < 0 || lineNode[i] >= m.sizes[(size_t) i]) { holdsLine = false; }
+		}
+		check(gcmb_cubic_seismo_at(m.body, isDetectorBody ? &sum : nullptr, isDetectorBody ? &count : nullptr,
+				last /* velocity along the last axis */, holdsLine ? line.data() : nullptr, m.sizes[last], lineNode));
 		if (isDetectorBody && slabCount > 1) {
 			double both[2] = {sum, (double) count};
 			check(gcmb_comm_allreduce_sum(ctx, both, 2));
 			sum = both[0];
 			count = (long long) both[1];
 		}
-		const bool writer = slabRank == slabCount / 2;  // every slab records the seismogram, one writes files
+		const bool writer = holdsLine;  // every slab records the seismogram, the one with the centre line writes the files
 		const std::string name = "mesh" + std::to_string(m.id) + "core" + padded(slabRank, 2) + "snap" + padded(step_, 4) + ".txt";
 		if (writer) {
 			std::ofstream f(dir + "/zaxis/" + name);
-			Mesh::Iterator it = {{m.sizes[0] / 2, m.sizes[1] / 2, m.sizes[2] / 2}};
+			Mesh::Iterator it = {{lineNode[0], lineNode[1], lineNode[2]}};
 			for (int k = 0; k < m.sizes[last]; k++) {
 				it[(size_t) last] = k;
 				f << m.coords(it)[(size_t) last] << "\t" << line[(size_t) k] << "\t" << std::endl;

@@ -288,6 +288,8 @@ struct Task {
 		int device = 0;
 		int slabRank = 0, slabCount = 1;   ///< this process owns slab slabRank of slabCount
 		const void* ncclUniqueId = nullptr; ///< 128 bytes shared by all slabs when slabCount > 1
+		int realBytes = 8;                  ///< 8: double (reference default), 4: float (LIBGCM_DOUBLE_PRECISION off)
+		bool fma = false;                   ///< fp64 stage kernels with FMA contraction (<= 1e-12 of the reference, not bitwise)
 	} device;
 };
 
@@ -335,6 +337,9 @@ public:
 	GridId id = 0;
 	int D = 0, M = 0, borderSize = 0;
 	std::array<int, 3> sizes = {{1, 1, 1}}, start = {{0, 0, 0}};
+	/// the whole body when this process holds a slab of it (== sizes / start otherwise)
+	std::array<int, 3> globalSizes = {{1, 1, 1}}, globalStart = {{0, 0, 0}};
+	int realBytes = 8;
 	std::array<real, 3> h = {{1, 1, 1}};
 	Models::T modelType = Models::T::ELASTIC;
 	Materials::T materialType = Materials::T::ISOTROPIC;
@@ -390,6 +395,7 @@ private:
 		std::vector<Contact> contacts;
 		std::vector<Border> borders;
 		std::vector<Odes::T> odes;
+		bool borderFilledByStage = false;  ///< the last direction's ghost nodes were written by the previous stage kernel
 	};
 	int D;
 	gcmb_ctx* ctx = nullptr;

@@ -1,5 +1,6 @@
 // C entry points of the host layer, for bindings (Python ctypes in gcm_b200/capi.py, tests, bench).
 #include <cstring>
+#include <memory>
 
 #include "gcmb_host.hpp"
 
@@ -12,6 +13,11 @@ struct Handle {
 	cubic::EngineBase* base = nullptr;
 	simplex::Engine* sx = nullptr;
 };
+cubic::EngineBase& cubicOf(void* handle) {
+	cubic::EngineBase* e = static_cast<Handle*>(handle)->base;
+	if (!e) { throw Exception(GCMB_E_INVALID_OP, "not a cubic engine"); }
+	return *e;
+}
 simplex::Engine& simplexOf(void* handle) {
 	simplex::Engine* e = static_cast<Handle*>(handle)->sx;
 	if (!e) { throw Exception(GCMB_E_INVALID_OP, "not a simplex engine"); }
@@ -28,21 +34,30 @@ extern "C" {
 
 const char* gcmb_host_last_error(void) { return hostError.c_str(); }
 
-/// createEngine(parseTaskText(text)); slab_count > 1 decomposes every body along x across processes
-int gcmb_host_engine_create(const char* task_text, int device, int slab_rank, int slab_count,
-		const void* nccl_id128, void** out) {
+/// createEngine(parseTaskText(text)); slab_count > 1 decomposes every body along x across processes;
+/// real_bytes 8 | 4 = the arithmetic type of the cubic engines (the reference's compile-time `real`);
+/// flags: bit 0 = fp64 stage kernels with FMA contraction
+int gcmb_host_engine_create2(const char* task_text, int device, int slab_rank, int slab_count,
+		const void* nccl_id128, int real_bytes, int flags, void** out) {
 	return guarded([&] {
 		Task task = parseTaskText(task_text);
 		task.device.device = device;
 		task.device.slabRank = slab_rank;
 		task.device.slabCount = slab_count;
 		task.device.ncclUniqueId = nccl_id128;
-		auto* h = new Handle;
+		task.device.realBytes = real_bytes;
+		task.device.fma = (flags & 1) != 0;
+		std::unique_ptr<Handle> h(new Handle);
 		h->engine = createEngine(task);
 		h->base = dynamic_cast<cubic::EngineBase*>(h->engine.get());
 		h->sx = dynamic_cast<simplex::Engine*>(h->engine.get());
-		*out = h;
+		*out = h.release();
 	});
+}
+
+int gcmb_host_engine_create(const char* task_text, int device, int slab_rank, int slab_count,
+		const void* nccl_id128, void** out) {
+	return gcmb_host_engine_create2(task_text, device, slab_rank, slab_count, nccl_id128, 8, 0, out);
 }
 
 void gcmb_host_engine_destroy(void* handle) { delete static_cast<Handle*>(handle); }
@@ -66,7 +81,7 @@ int gcmb_host_engine_info(void* handle, int* steps_done, double* time, double* t
 /// D, M, sizes[3] of a body (sizes of THIS process' slab when decomposed)
 int gcmb_host_engine_body_info(void* handle, size_t id, int* D, int* M, int* sizes, int* start) {
 	return guarded([&] {
-		auto mesh = static_cast<Handle*>(handle)->base->getMesh(id);
+		auto mesh = cubicOf(handle).getMesh(id);
 		*D = mesh->D;
 		*M = mesh->M;
 		for (int i = 0; i < 3; i++) { sizes[i] = mesh->sizes[(size_t) i]; start[i] = mesh->start[(size_t) i]; }
@@ -76,15 +91,16 @@ int gcmb_host_engine_body_info(void* handle, size_t id, int* D, int* M, int* siz
 /// real nodes of the current time layer, x slowest, M per node
 int gcmb_host_engine_body_pde(void* handle, size_t id, double* out) {
 	return guarded([&] {
-		auto mesh = static_cast<Handle*>(handle)->base->getMesh(id);
+		auto mesh = cubicOf(handle).getMesh(id);
 		const auto& v = mesh->pdeRealNodes();
 		std::memcpy(out, v.data(), v.size() * sizeof(double));
 	});
 }
 
 void* gcmb_host_engine_body_handle(void* handle, size_t id) {
-	try { return static_cast<Handle*>(handle)->base->getMesh(id)->handle(); }
-	catch (...) { return nullptr; }
+	void* ans = nullptr;
+	guarded([&] { ans = cubicOf(handle).getMesh(id)->handle(); });
+	return ans;
 }
 
 void* gcmb_host_engine_context(void* handle) {
@@ -169,7 +185,7 @@ int gcmb_host_simplex_errors(void* handle, int* count) {
 /// eigen-systems of every material table of a body: U,U1 [tables][D][M][M], L [tables][D][M]
 int gcmb_host_engine_body_matrices(void* handle, size_t id, int* n_tables, double* U, double* U1, double* L) {
 	return guarded([&] {
-		auto mesh = static_cast<Handle*>(handle)->base->getMesh(id);
+		auto mesh = cubicOf(handle).getMesh(id);
 		const auto& ms = mesh->tableMatrices();
 		*n_tables = (int) ms.size();
 		size_t a = 0, b = 0;
@@ -185,9 +201,13 @@ int gcmb_host_engine_body_matrices(void* handle, size_t id, int* n_tables, doubl
 
 /// seismogram recorded so far; returns the number of samples (copies at most `capacity`)
 int gcmb_host_engine_seismogram(void* handle, double* times, float* values, int capacity) {
-	const auto& s = static_cast<Handle*>(handle)->base->seismogram();
-	for (int i = 0; i < (int) s.size() && i < capacity; i++) { times[i] = s[(size_t) i].first; values[i] = s[(size_t) i].second; }
-	return (int) s.size();
+	int n = -1;
+	guarded([&] {
+		const auto& s = cubicOf(handle).seismogram();
+		for (int i = 0; i < (int) s.size() && i < capacity; i++) { times[i] = s[(size_t) i].first; values[i] = s[(size_t) i].second; }
+		n = (int) s.size();
+	});
+	return n;
 }
 
 /// Model::constructGcmMatrices for one material.  model: 0 elastic, 1 acoustic.  material_kind:

@@ -53,8 +53,18 @@ const char* gcmb_last_error(void);
 const char* gcmb_version(void);
 
 /* ---- context ------------------------------------------------------------------------------- */
-/* real_bytes: 8 (fp64, the reference's `real`, util/infrastructure/Types.hpp:8-14).  4 is reserved. */
+/* real_bytes: 8 = fp64 or 4 = fp32 -- the reference's compile-time `real` (util/infrastructure/Types.hpp:8-14,
+ * LIBGCM_DOUBLE_PRECISION) chosen per context.  With 4 the grid state, the eigen-system tables and all stage
+ * arithmetic are float; `void*` state arrays of gcmb_cubic_upload/download_state, download_box and halo_get/put hold
+ * floats; everything typed `double` in this header (tables, tau, border values, sums) stays double and is rounded
+ * on the way in.  The simplex entry points need real_bytes == 8. */
 int gcmb_create(int device, int real_bytes, gcmb_ctx** out);
+int gcmb_real_bytes(gcmb_ctx* ctx);
+/* fp64 contexts: on != 0 selects the stage kernels compiled WITH floating-point contraction (FMA).  Their results
+ * agree with the reference to <= 1e-12 relative (north_star's fp64 tolerance) but not bit for bit; the default
+ * (off, or environment GCMB_FMA=1 to switch it on at gcmb_create) is the bit-exact set, built like the reference
+ * without contraction (CMakeLists.txt:6-7).  fp32 contexts always contract. */
+int gcmb_set_fma(gcmb_ctx* ctx, int on);
 void gcmb_destroy(gcmb_ctx* ctx);
 /* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the own stream */
 int gcmb_set_stream(gcmb_ctx* ctx, void* cuda_stream);
@@ -84,6 +94,14 @@ void gcmb_cubic_body_destroy(gcmb_body* body);
  * prod(sizes+2*border) nodes; 0: real nodes only (prod(sizes)).  Both sync. */
 int gcmb_cubic_upload_state(gcmb_body* body, const void* aos_pde, int with_ghosts);
 int gcmb_cubic_download_state(gcmb_body* body, void* aos_pde, int with_ghosts);
+/* Asynchronous read-back of a box of nodes of the current layer (snapshots that do not stall the time loop,
+ * util/snapshot/VtkSnapshotter.hpp:20-61): begin enqueues a gather + device-to-host copy on a side stream behind the
+ * work enqueued so far and returns at once; kernels enqueued later that overwrite the layer wait for the gather only,
+ * the PCIe transfer overlaps them.  host: pinned memory of prod(extent)*M reals, x slowest, M per node (the layout of
+ * download_state over the box); valid after end (sync).  box_min/extent: D entries, local node indices (ghosts allowed).
+ * One read-back in flight per body. */
+int gcmb_cubic_download_box_begin(gcmb_body* body, const int* box_min, const int* extent, void* host);
+int gcmb_cubic_download_box_end(gcmb_body* body);
 /* material table id of every REAL node, x slowest (DefaultMesh::material(it), engine/cubic/DefaultMesh.hpp:96-110;
  * read by VtkSnapshotter for its material_index field, util/snapshot/VtkSnapshotter.hpp:49-56). sync */
 int gcmb_cubic_download_tables(gcmb_body* body, uint8_t* node_table_id);
@@ -130,6 +148,14 @@ int gcmb_cubic_contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_m
  * layers, like cubic/Engine.cpp:110-111 */
 int gcmb_cubic_stage(gcmb_body* body, int dir, double tau);
 
+/* gcmb_cubic_stage(body, dir, tau) followed by gcmb_cubic_border_apply(body, next_dir, n_values, values) on the new
+ * layer, as ONE kernel when it can be (*fused = 1): next_dir is the contiguous axis, on each of its faces the last
+ * registered condition covers the whole face with plain components, and dir's stage is a marching kernel -- the rows it
+ * writes then leave with their ghost nodes, and the caller must NOT call border_apply for next_dir on this layer.
+ * With *fused = 0 only the stage was done and the caller applies the border as usual (cubic/Engine.cpp:94-98). */
+int gcmb_cubic_stage_fill_next_border(gcmb_body* body, int dir, double tau, int next_dir, int n_values,
+                                      const double* values, int* fused);
+
 /* ---- Maxwell viscosity (rheology/ode/Ode.hpp:28-38): sigma *= decay[table of the node];
  * decay = exp(-tau/tau0) is evaluated by the caller with the host libm, like the reference ------- */
 int gcmb_cubic_ode_maxwell(gcmb_body* body, const double* decay_per_table);
@@ -143,6 +169,10 @@ int gcmb_cubic_detector_set_mask(gcmb_body* body, int q_code, const uint8_t* fac
  * -> line (may be NULL).  sync. */
 int gcmb_cubic_seismo(gcmb_body* body, double* sum, long long* count, int line_comp, double* line,
                       int n_line);
+/* the same with the line through the given LOCAL node (D-1 entries: all axes but the last) -- slabs of a decomposed
+ * grid pass the global centre translated into their own indices */
+int gcmb_cubic_seismo_at(gcmb_body* body, double* sum, long long* count, int line_comp, double* line,
+                         int n_line, const int* line_node);
 
 /* ---- multi-GPU: slab decomposition along x (the slowest axis), one process per GPU ------------- */
 /* NCCL communicator shared by all slabs: rank 0 makes the id (128 bytes), the launcher distributes it */
@@ -152,6 +182,9 @@ int gcmb_comm_init(gcmb_ctx* ctx, int n_ranks, int rank, const void* id128);
  * none at the ends): my ghost planes <- neighbour's outermost real planes.  Equivalent to two
  * ContactCopiers between neighbouring slabs; call before the direction-0 stage. */
 int gcmb_cubic_halo_exchange(gcmb_body* body);
+/* the same for several bodies of one context (a decomposed multi-body task) in ONE NCCL group: one exchange in flight
+ * for all of them, overlapped with the interior of every body's direction-0 stage */
+int gcmb_halo_exchange_bodies(gcmb_body* const* bodies, int n);
 /* Host-staged variant for transports that are not GPU-aware (the reference's own MPI_Sendrecv of raw
  * PdeVector bytes, src/test/TestMPI.cpp:31-51): get copies the outermost `border_size` REAL x-planes of
  * side (0 left, 1 right) into a host buffer of gcmb_cubic_halo_bytes(body) bytes, put writes such a buffer
@@ -248,7 +281,9 @@ int gcmb_simplex_gradient(gcmb_sbody* body, const double* values, double* grad);
 /* ---- checksum of the current layer over real nodes: sum_nodes sum_i (i+1)*u_i (sync) ---------- */
 int gcmb_cubic_checksum(gcmb_body* body, double* out);
 
-/* description of the stage kernel chosen for a direction (for logs/tests), e.g. "sparse:elastic3d_iso_x/bs2" */
+/* description of the stage kernel LAST LAUNCHED for a direction (for logs/tests), e.g. "sparse:elastic3d_iso_x/bs2",
+ * "sparse:acoustic2d_x/bs2+k0" (foot cells read from the table: Courant number >= 1), "dense_k0_one:M9/bs2";
+ * "unset" before the first stage of that direction */
 const char* gcmb_cubic_stage_kernel_name(gcmb_body* body, int dir);
 
 #ifdef __cplusplus

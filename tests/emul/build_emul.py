@@ -13,14 +13,32 @@ def _fresh(out, deps):
 
 
 def build_emul():
-    """The product's CUDA sources compiled for the host; kernels are stepped thread by thread."""
+    """The product's CUDA sources compiled for the host; kernels are stepped thread by thread.  Every translation
+    unit of gcm_b200/csrc is compiled by g++ with emul_prelude.h force-included; the stage kernels of the bit-exact
+    fp64 set (0) and of the fp32 set (2) are built (set 1 differs from set 0 only by nvcc's FMA contraction)."""
     out = os.path.join(HERE, "libgcm_b200_emul.so")
-    src = os.path.join(HERE, "emul_all.cpp")
-    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc"))]
-    if not _fresh(out, deps):
-        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
-                        "-Wl,-Bsymbolic", "-I" + cuda_inc, src, "-o", out, "-ldl"], check=True)
+    prelude = os.path.join(HERE, "emul_prelude.h")
+    deps = [prelude, os.path.abspath(__file__)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc"))]
+    if _fresh(out, deps):
+        return out
+    from concurrent.futures import ThreadPoolExecutor
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    objdir = os.path.join(ROOT, "build", "emul")
+    os.makedirs(objdir, exist_ok=True)
+    units = [("gcmb_capi.cu", "gcmb_capi.o", []), ("simplex_capi.cu", "simplex_capi.o", []), ("stage_dispatch.cu", "stage_dispatch.o", [])]
+    for s in (0, 2):
+        for g in (0, 1, 2, 3, 100):
+            units.append(("stage_inst.cu", "stage_s%d_g%d.o" % (s, g), ["-DGCMB_SET=%d" % s, "-DGCMB_GROUP=%d" % g]))
+
+    def compile_one(u):
+        src, obj, flags = u
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-x", "c++", "-include", prelude,
+                        "-I" + cuda_inc, "-c", os.path.join(CSRC, src), "-o", os.path.join(objdir, obj)] + flags, check=True)
+        return os.path.join(objdir, obj)
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        objs = list(ex.map(compile_one, units))
+    subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", out] + objs + ["-ldl"], check=True)
     return out
 
 

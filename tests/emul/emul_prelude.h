@@ -1,5 +1,8 @@
 // Stepping harness: the product's CUDA sources compiled for the host, kernels run thread by thread.
-// TEST INFRASTRUCTURE ONLY (see README.md).
+// TEST INFRASTRUCTURE ONLY (see README.md).  Force-included (-include) in front of every translation unit of
+// gcm_b200/csrc by build_emul.py.
+#pragma once
+#define GCMB_EMUL 1
 #include <cuda_runtime.h>  // types only; every runtime call is redirected below
 
 #include <algorithm>
@@ -9,10 +12,10 @@
 #include <functional>
 
 namespace gcmb_emul {
-thread_local uint3 t_blockIdx, t_threadIdx;
-thread_local dim3 t_blockDim, t_gridDim;
-thread_local double acc_v;
-thread_local long long acc_c;
+inline thread_local uint3 t_blockIdx, t_threadIdx;
+inline thread_local dim3 t_blockDim, t_gridDim;
+inline thread_local double acc_v;
+inline thread_local long long acc_c;
 
 template<typename F>
 void launch(dim3 grid, dim3 block, F body) {
@@ -99,12 +102,11 @@ using std::max;
 #define GCMB_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
 	gcmb_emul::launch_blocks(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); })
 #define GCMB_BLOCK_THREADS(tid) for (int tid = 0; tid < (int) gcmb_emul::t_blockDim.x; tid++)
-#define GCMB_DYN_SMEM(type, name)            \
-	static thread_local type name##_storage_; \
-	type& name = name##_storage_
+#define GCMB_DYN_SMEM_RAW(name)                                                       \
+	alignas(128) static thread_local unsigned char name##_storage_[256 * 1024];        \
+	unsigned char* name = name##_storage_
 #define cudaFuncSetAttribute(k, a, v) cudaSuccess
+#define cudaGetDevice(p) (*(p) = 0, cudaSuccess)
 #define GCMB_EMUL_BLOCK_SUM(v, c) \
 	do { gcmb_emul::acc_v += (v); gcmb_emul::acc_c += (c); (v) = gcmb_emul::acc_v; (c) = gcmb_emul::acc_c; } while (0)
 
-#include "../../gcm_b200/csrc/gcmb_capi.cu"
-#include "../../gcm_b200/csrc/stage_dispatch.cu"

@@ -35,7 +35,8 @@ EXPECTED_KERNELS = {
     "elastic2d_pwave": ["sparse:elastic2d_iso_x/bs2", "sparse:elastic2d_iso_y/bs2"],
     "elastic2d_courant45": ["dense:M5", "dense:M5"],  # border size 5: no specialised kernel
     "elastic1d": ["sparse:elastic1d_iso_x/bs2"],
-    "elastic3d_ortho_rotated": ["dense:M9", "dense:M9", "dense:M9"],  # rotated axes: no zero of U is structural
+    # rotated axes: no zero of U is structural; one material: the coefficients travel as kernel parameters
+    "elastic3d_ortho_rotated": ["dense_k0_one:M9/bs2", "dense_k0_one:M9/bs2", "dense_k0_one:M9/bs2"],
 }
 
 
@@ -45,12 +46,14 @@ def test_sparsity_pattern_selection(lib, name):
     eng = capi.HostEngine(lib, SCENARIOS[name])
     try:
         D = eng.body_info(0)[0]
+        assert [eng.kernel_name(0, d) for d in range(D)] == ["unset"] * D
+        eng.advance(1)  # the name is that of the kernel actually launched
         assert [eng.kernel_name(0, d) for d in range(D)] == EXPECTED_KERNELS[name]
     finally:
         eng.close()
 
 
-@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_FORCE_DENSE": "1", "GCMB_DENSE_LITERAL": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "7"}])
+@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_FORCE_DENSE": "1", "GCMB_DENSE_LITERAL": "1"}, {"GCMB_MARCH_SEG": "7"}, {"GCMB_ZTILE_ROWS": "5"}])
 @pytest.mark.parametrize("name", ["elastic3d_layers", "ortho3d_contact", "acoustic2d_border1", "elastic2d_ortho", "ortho3d_rotated_plies"])
 def test_kernel_variants_agree(name, env):
     """dense kernel, direct kernel and short marching segments give the same bits (fresh process: the
