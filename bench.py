@@ -169,28 +169,31 @@ simplex_box {nx} {ny} {nz} 0 0 0 {h!r} jitter 0.3 seed 1
 cavity box {c0!r} {c0!r} {c1!r} {c2!r} {c2!r} {c3!r}
 body 0 elastic isotropic
 material body 0 isotropic 7800 1.2e11 8.0e10
-basis 1 0 0 0 1 0 0 0 1
+basis {basis}
 border_condition infinite fixed_force const 0 const 0 const 0
 initial quantity PRESSURE 1 sphere {r!r} {sx!r} {sx!r} {sz!r}
 """
 
 
-def simplex_task(nx, ny, nz, h, steps=1000000):
+def simplex_task(nx, ny, nz, h, steps=1000000, basis="identity"):
     """a 4:4:1 plate of tetrahedra with an inner cavity (the geometry of
     meshes/layers_with_fracture.off, meshed by our box mesher), isotropic elastic, fixed identity calculation
     basis, zero fixed force on every border, pressure-sphere source"""
     lx, lz = nx * h, nz * h
     return SIMPLEX_TASK.format(steps=steps, nx=nx, ny=ny, nz=nz, h=h, c0=0.4 * lx, c2=0.6 * lx, c1=0.35 * lz, c3=0.65 * lz,
-                               r=0.08 * lx, sx=0.3 * lx, sz=0.5 * lz)
+                               r=0.08 * lx, sx=0.3 * lx, sz=0.5 * lz, basis="1 0 0 0 1 0 0 0 1" if basis == "identity" else "random 1")
 
 
-def simplex_section(lib, device, steps, warmup, with_cpu):
-    """the simplex (tetrahedral) path, SURVEY.md §8 rows a13-a21: vertex-updates/s through simplex::Engine"""
+def simplex_section(lib, device, steps, warmup, with_cpu, basis="random"):
+    """the simplex (tetrahedral) path, SURVEY.md §8 rows a13-a21: vertex-updates/s through simplex::Engine.
+    basis = "random": a new random calculation basis every time step, the reference's default
+    (engine/simplex/Engine.hpp:190-206) -- every characteristic foot is located afresh each step;
+    basis = "identity": a fixed basis, where the located feet repeat and are cached from the third step on."""
     import numpy as np
     from gcm_b200 import capi
     nx, ny, nz = (int(x) for x in os.environ.get("GCMB_BENCH_SIMPLEX_CUBES", "160,160,40").split(","))
     h = 0.16 / nx
-    eng = capi.SimplexHostEngine(lib, simplex_task(nx, ny, nz, h), device=device)
+    eng = capi.SimplexHostEngine(lib, simplex_task(nx, ny, nz, h, basis=basis), device=device)
     info = eng.simplex_body_info(0)
     ctxh = eng.context_handle()
     eng.advance(warmup)
@@ -210,7 +213,9 @@ def simplex_section(lib, device, steps, warmup, with_cpu):
                    "what": "simplex::Engine::run loop incl. border functors on the host and the final state read-back"},
            "gpu_launches": int(lib.c.gcmb_launch_count(ctxh) - launches0),
            "config": {"workload": "%dx%dx%d cubes of edge %g cut into 6 tetrahedra each, jitter 0.3, inner cavity: %d vertices; "
-                                  "identity calculation basis, fixed zero force on all borders, Courant 0.7" % (nx, ny, nz, h, info["n_local"])},
+                                  "%s, fixed zero force on all borders, Courant 0.7" % (
+                                      nx, ny, nz, h, info["n_local"], "a new random calculation basis every step (the reference's default: no foot can be cached)"
+                                      if basis == "random" else "fixed identity calculation basis (located feet are cached from the third step on)")},
            "parity": "bit-identical to the unmodified reference simplex engine built against a CGAL stand-in (tests/golden/simplex_*.npz)"}
     eng.close()
     if with_cpu:
@@ -218,7 +223,7 @@ def simplex_section(lib, device, steps, warmup, with_cpu):
         # (oracle/_ref/gcm_ref_simplex, built against a CGAL stand-in) when it was built, else the C port
         sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
         cpu_steps = 10
-        text = simplex_task(24, 24, 6, 0.16 / 24, steps=cpu_steps)
+        text = simplex_task(24, 24, 6, 0.16 / 24, steps=cpu_steps, basis="identity")
         small = capi.SimplexHostEngine(lib, text, device=device)
         i2 = small.simplex_body_info(0)
         tri = small.triangulation()
@@ -289,6 +294,99 @@ def rotated_section(lib, device, steps, warmup, with_cpu=True):
             "parity": "bit-identical to the unmodified reference engine (tests/golden/elastic3d_ortho_rotated.npz, ortho3d_rotated_plies.npz)"}
 
 
+def make_engine(lib, text, local, rank, world, nccl_id_fn, **kw):
+    from gcm_b200 import capi
+    return capi.HostEngine(lib, text, device=local, slab_rank=rank, slab_count=world,
+                           nccl_id=nccl_id_fn() if world > 1 else None, **kw)
+
+
+def timed_engine_loop(lib, eng, K, W, barrier):
+    """W warm-up steps, then K steps of Engine::run's loop timed on the device (CUDA events on the engine's stream) and by the
+    host clock; per-kernel-class device times from the library's own event pairs"""
+    import numpy as np
+    from gcm_b200 import capi
+    ctxh = eng.context_handle()
+    eng.advance(W)
+    barrier(ctxh)
+    lib.check(lib.c.gcmb_profile_enable(ctxh, 1))
+    launches0 = lib.c.gcmb_launch_count(ctxh)
+    lib.check(lib.c.gcmb_timer_start(ctxh))
+    t0 = time.perf_counter()
+    eng.advance(K)
+    ms = capi.ctypes.c_float()
+    lib.check(lib.c.gcmb_timer_stop(ctxh, capi.ctypes.byref(ms)))
+    barrier(ctxh)
+    wall = time.perf_counter() - t0
+    prof_ms = np.zeros(8)
+    prof_n = np.zeros(8, dtype=np.int64)
+    lib.check(lib.c.gcmb_profile_get(ctxh, 8, capi.dp(prof_ms), prof_n.ctypes.data_as(capi.c_ll_p)))
+    lib.check(lib.c.gcmb_profile_enable(ctxh, 0))
+    return {"dev_ms": float(ms.value), "wall_s": wall, "launches": int(lib.c.gcmb_launch_count(ctxh) - launches0),
+            "class_ms": [float(x) / K for x in prof_ms], "class_launches": [int(x) // K for x in prof_n]}
+
+
+def section(lib, text, nodes_per_gpu, bytes_per_node_update, K, W, local, rank, world, nccl_id_fn, barrier, reduce_max, what, **kw):
+    """one secondary configuration measured like the headline: node-updates/s of the engine's time loop, device-timed"""
+    eng = make_engine(lib, text, local, rank, world, nccl_id_fn, **kw)
+    r = timed_engine_loop(lib, eng, K, W, barrier)
+    n_bodies = 0
+    while True:
+        try:
+            eng.body_info(n_bodies)
+            n_bodies += 1
+        except Exception:
+            break
+    kernels = [[eng.kernel_name(b, d) for d in range(3)] for b in range(min(2, n_bodies))]
+    eng.close()
+    dev_ms, wall = reduce_max(r["dev_ms"], r["wall_s"])
+    peak, src = measured_hbm_peak()
+    per_s = nodes_per_gpu * world * K / (dev_ms * 1e-3)
+    return {"workload": what, "value": per_s, "unit": "node-updates/s", "ms_per_step": dev_ms / K, "steps": K, "warmup": W,
+            "e2e": {"value": nodes_per_gpu * world * K / wall, "unit": "node-updates/s"},
+            "kernels": kernels, "gpu_launches": r["launches"], "bytes_per_node_update": bytes_per_node_update,
+            "roofline": {"bound": "hbm", "achieved": per_s / world * bytes_per_node_update / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": per_s / world * bytes_per_node_update / 1e9 / peak, "peak_source": src},
+            "per_class_ms": dict(zip(("stage_x", "stage_y", "stage_z", "border", "contact", "ode", "transfer", "seismo"), r["class_ms"]))}
+
+
+def c2_text(n):
+    """BASELINE config 2: 3-D acoustic, point source, PRESSURE -> 0 on all six faces"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from scenarios import acoustic3d_free
+    return acoustic3d_free(n, 10 ** 6).replace("sphere 0.2 0.5 0.5 0.5", "sphere 0.05 0.5 0.5 0.5")
+
+
+def c4_text(nx, ny, nz):
+    """BASELINE config 4: four stacked bodies nx x ny/4 x nz along y, the carbon-fibre composite of
+    launcher/ndi.hpp:120-131 alternating with titanium written as an orthotropic material (ndi.hpp:136-159), automatic
+    ADHESION contacts, fixed normal velocity on a disc of the top face; nx is the GLOBAL x extent"""
+    sys.path.insert(0, os.path.join(ROOT, "scripts", "gpu_runs"))
+    import c4_bench
+    t = c4_bench.task(nz)
+    q = ny // 4
+    h = 1.0 / (nz - 1)
+    lx = (nx - 1) * h
+    out = []
+    for line in t.splitlines():
+        if line.startswith("body "):
+            f = line.split()
+            b = int(f[1])
+            line = "body %d elastic orthotropic sizes %d %d %d start 0 %d 0" % (b, nx, q, nz, b * q)
+        elif line.startswith("initial "):
+            line = "initial quantity PRESSURE 1 sphere 0.2 %r 0.5 0.5" % (lx / 2)
+        elif line.startswith("border "):
+            line = "border 3 1 sphere 0.3 %r 1.0 0.5 Vy sin 1.0 5.0" % (lx / 2)
+        out.append(line)
+    return "\n".join(out) + "\n"
+
+
+def multi_gpu_parity(lib, rank, world, local):
+    """bitwise comparison of decomposed runs with the reference's fixtures (tests/golden), inside the bench"""
+    sys.path[:0] = [os.path.join(ROOT, "tests")]
+    import multi_gpu_check as mg
+    return mg.check_fixtures(lib, rank, world, local, verbose=False)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,6 +399,7 @@ def main():
     ap.add_argument("--no-simplex", action="store_true", help="skip the secondary simplex-path measurement")
     ap.add_argument("--no-rotated", action="store_true", help="skip the secondary rotated-orthotropic measurement")
     ap.add_argument("--no-host-roundtrip", action="store_true", help="skip the host-resident-state measurement")
+    ap.add_argument("--no-sections", action="store_true", help="headline only (kernel experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -317,19 +416,41 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist = None
-    nccl_id = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = gcm_b200.library()
-    if world > 1:
+
+    def nccl_id_fn():
+        """a fresh NCCL id for every engine (an id initialises exactly one communicator)"""
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             raw = (capi.ctypes.c_ubyte * 128)()
             lib.check(lib.c.gcmb_comm_unique_id(capi.ctypes.cast(raw, capi.vp)))
             buf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
         dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().tolist())
+        return bytes(buf.cpu().tolist())
+
+    def barrier(ctxh=None):
+        if ctxh is not None:
+            lib.check(lib.c.gcmb_sync(ctxh))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def reduce_max(*values):
+        if world == 1:
+            return values
+        t = torch.tensor(list(values), device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(x) for x in t.tolist())
+
+    os.chdir(tempfile.mkdtemp(prefix="gcmb_bench_"))  # snapshots/ of the SliceSnapshotter land here
+
+    # ---- multi-GPU: the decomposed engine reproduces the reference's fixtures bit for bit, checked in this very run ----
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity(lib, rank, world, local)
 
     free, total = torch.cuda.mem_get_info()
     n = pick_size(free, args.size)
@@ -341,41 +462,43 @@ def main():
     nodes_per_gpu = n ** 3
     text = task_text(n * world, n, n, steps=10 ** 6, detector=True)
 
-    os.chdir(tempfile.mkdtemp(prefix="gcmb_bench_"))  # snapshots/ of the SliceSnapshotter land here
-    eng = capi.HostEngine(lib, text, device=local, slab_rank=rank, slab_count=world, nccl_id=nccl_id)
+    t_create = time.perf_counter()
+    eng = make_engine(lib, text, local, rank, world, nccl_id_fn)
     ctxh = eng.context_handle()
+    barrier(ctxh)
+    create_s = time.perf_counter() - t_create
     body = eng.body_handle(0)
-    kernels = [lib.c.gcmb_cubic_stage_kernel_name(body, d).decode() for d in range(3)]
     tau = eng.info()[2]
-
-    def barrier():
-        lib.check(lib.c.gcmb_sync(ctxh))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
 
     # ---- warm-up through the public API -------------------------------------------------------
     eng.advance(W)
-    barrier()
+    barrier(ctxh)
+    kernels = [lib.c.gcmb_cubic_stage_kernel_name(body, d).decode() for d in range(3)]
 
-    # ---- (1) device-timed region: K steps of the hot path, state resident in HBM -----------------
+    # ---- (1) device-timed region: K steps of the hot path through the C ABI, state resident in HBM -----------------
     sampler = ClockSampler(local)
     sampler.start()
     lib.check(lib.c.gcmb_profile_enable(ctxh, 1))
     launches0 = lib.c.gcmb_launch_count(ctxh)
     zeros3 = np.zeros(3)
-    barrier()
+    fused = capi.ctypes.c_int(0)
+    fused_steps = 0
+    barrier(ctxh)
     lib.check(lib.c.gcmb_timer_start(ctxh))
     for _ in range(K):
-        for d in range(3):
-            if d == 2:
-                lib.check(lib.c.gcmb_cubic_border_apply(body, 2, 3, capi.dp(zeros3)))
-            if d == 0 and world > 1:
-                lib.check(lib.c.gcmb_cubic_halo_exchange(body))
-            lib.check(lib.c.gcmb_cubic_stage(body, d, tau))
+        # cubic::Engine::nextTimeStep (engine/cubic/Engine.cpp:92-121) for this task: [halo] stage x; stage y, which also
+        # writes the ghost nodes of the free surface when the library can fuse that (else border fill); stage z
+        if world > 1:
+            lib.check(lib.c.gcmb_cubic_halo_exchange(body))
+        lib.check(lib.c.gcmb_cubic_stage(body, 0, tau))
+        lib.check(lib.c.gcmb_cubic_stage_fill_next_border(body, 1, tau, 2, 3, capi.dp(zeros3), capi.ctypes.byref(fused)))
+        if not fused.value:
+            lib.check(lib.c.gcmb_cubic_border_apply(body, 2, 3, capi.dp(zeros3)))
+        fused_steps += fused.value
+        lib.check(lib.c.gcmb_cubic_stage(body, 2, tau))
     ms = capi.ctypes.c_float()
     lib.check(lib.c.gcmb_timer_stop(ctxh, capi.ctypes.byref(ms)))
-    barrier()
+    barrier(ctxh)
     dev_ms = float(ms.value)
     launches = lib.c.gcmb_launch_count(ctxh) - launches0
     prof_ms = np.zeros(8)
@@ -385,21 +508,33 @@ def main():
 
     # ---- (2) end to end through the reference-facing API: Engine loop with border functors evaluated on
     #          the host every stage and the surface seismogram read back (and written) every step --------
-    barrier()
+    barrier(ctxh)
     t0 = time.perf_counter()
     eng.advance(K)
-    barrier()
+    barrier(ctxh)
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag.set()
     sampler.join()
     times, values = eng.seismogram()
     assert len(values) >= K and np.all(np.isfinite(values)), "seismogram is not finite"
+    # ---- (3) the whole run a user of the reference launcher sees: engine construction (grid state built on the device from
+    #          the Task) + the K steps above + the final state read back to pinned host memory -------------------------------
+    t0 = time.perf_counter()
+    final_bytes = 0
+    if world == 1:
+        host = torch.empty(n * n * 9, dtype=torch.float64, pin_memory=True)   # one x-plane at a time through the box read-back
+        lo = np.zeros(3, dtype=np.int32)
+        ext = np.array([1, n, n], dtype=np.int32)
+        for x in range(0, n, max(1, n // 8)):      # a bounded sample of planes: the figure is extrapolated, and says so
+            lo[0] = x
+            lib.check(lib.c.gcmb_cubic_download_box_begin(body, capi.ip(lo), capi.ip(ext), capi.ctypes.c_void_p(host.data_ptr())))
+            lib.check(lib.c.gcmb_cubic_download_box_end(body))
+            final_bytes += host.numel() * 8
+        assert bool(torch.isfinite(host[::4097]).all())
+    sample_s = time.perf_counter() - t0
+    download_s = sample_s * (n ** 3 * 72 / final_bytes) if final_bytes else None
 
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0].item()), float(t[1].item())
-
+    dev_ms, e2e_s = reduce_max(dev_ms, e2e_s)
     total_nodes = nodes_per_gpu * world
     value = total_nodes * K / (dev_ms * 1e-3)
     e2e = total_nodes * K / e2e_s
@@ -414,18 +549,21 @@ def main():
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "per_stage_ms": {kernels[a]: stage_ms[a] for a in range(3)},
                 "per_stage_gbs": {kernels[a]: bytes_per_launch / (stage_ms[a] * 1e-3) / 1e9 for a in range(3)},
+                "border_fill_ms": prof_ms[3] / K, "border_fill_fused_into_stage_y": bool(fused_steps == K),
                 "whole_step_frac": value * 3 * BYTES_PER_NODE_STAGE / world / 1e9 / peak}
     traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(traffic_file):
         try:
             t = json.load(open(traffic_file))
-            # dram__bytes_read+write of one launch from the ncu --set full capture (taken at 512^3), scaled
-            # to this run's launch by the node count
-            roofline["traffic"] = t["ratio_to_algorithmic"] * bytes_per_launch
-            roofline["traffic_source"] = t["source"]
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this size, from the committed
+            # `ncu --set full` capture named in traffic_source (the bench itself is never run under a profiler)
+            if t.get("nodes_per_launch") == nodes_per_gpu:
+                roofline["traffic"] = t["dram_bytes_per_launch"]
+                roofline["traffic_source"] = t["source"]
         except Exception:
             pass
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "node-updates/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -447,15 +585,22 @@ def main():
                             "read back and written to the SliceSnapshotter text files every step; the grid state is "
                             "created on the device from the Task's analytic areas, like the reference builds it from "
                             "the Task (no state array crosses PCIe)"},
+            "e2e_full_run": {"construction_s": create_s, "steps_s": e2e_s, "final_download_s": download_s,
+                             "value": total_nodes * K / (create_s + e2e_s + (download_s or 0.0)), "unit": "node-updates/s",
+                             "what": "createEngine(task) (allocation, materials, initial state and masks built on the device) + %d "
+                                     "steps + read-back of the whole final state to pinned host memory (extrapolated from every "
+                                     "%d-th x-plane); a run of this length is dominated by set-up, the reference's is not" % (K, max(1, n // 8))},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "device_bytes": int(lib.c.gcmb_device_bytes(ctxh)),
         }
+        if parity is not None:
+            line["parity_check"] = parity
         if not args.no_cpu_baseline:
             base = cpu_baseline(args.ref_size, 5)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     eng.close()
-    if rank == 0 and world == 1 and not args.no_host_roundtrip:
+    if rank == 0 and world == 1 and not args.no_host_roundtrip and not args.no_sections:
         # ---- (3) the pessimistic bound of a drop-in that keeps the reference's HOST-resident mesh: the whole state
         #          (reference AoS layout with ghost nodes) goes up from pinned host memory before EVERY step and comes
         #          back after it.  Measured on a 512^3 body (9.8 GB each way) so that the pinned buffer fits any host.
@@ -491,14 +636,54 @@ def main():
             del host
         except Exception as e:
             line["e2e_host_state_every_step"] = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    # ---- secondary configurations (never the headline), every one through the same engine loop ----------------------------
+    def run_section(name, fn):
+        try:
+            out = fn()
+        except Exception as e:  # the headline line must survive a failure here
+            out = {"error": "%s: %s" % (type(e).__name__, e)}
+        if rank == 0:
+            line[name] = out
+
+    common = dict(local=local, rank=rank, world=world, nccl_id_fn=nccl_id_fn, barrier=barrier, reduce_max=reduce_max)
+    if not args.no_sections:
+        # BASELINE config 4 (configs[3]): four glued orthotropic bodies per GPU, x-slabs, all four halo exchanges in one group
+        n4 = n
+        run_section("config4", lambda: section(
+            lib, c4_text(n4 * world, n4, n4), n4 ** 3, 432, 5, 3,
+            what="BASELINE config 4: four glued bodies %dx%dx%d per GPU (x-slabs over %d GPUs), composite / titanium-as-orthotropic, "
+                 "ADHESION contacts, velocity disc, fp64, border size 2" % (n4, n4 // 4, n4, world), **common))
+    if world == 1 and not args.no_sections:
+        run_section("config2", lambda: section(
+            lib, c2_text(512), 512 ** 3, 192, 10, 3,
+            what="BASELINE config 2: 3-D acoustic 512^3, PRESSURE -> 0 on six faces, fp64, border size 2 (2.1 GB per layer: larger than L2)", **common))
+        run_section("fp32", lambda: dict(section(
+            lib, task_text(n, n, n, steps=10 ** 6, detector=True), n ** 3, 216, 10, 3,
+            what="the headline task in fp32 (gcmb_create(..., 4); reference: LIBGCM_DOUBLE_PRECISION off, Types.hpp:8-14): "
+                 "216 B per node-update", real_bytes=4, **common),
+            parity="max|g-r|/max|r| against the fp64 run after 1 / 10 / 100 steps: tests/test_gpu_parity.py::test_fp32_variant_bound_over_steps"))
+        run_section("fma", lambda: dict(section(
+            lib, task_text(n, n, n, steps=10 ** 6, detector=True), n ** 3, 432, 5, 3,
+            what="the headline task with the FMA-contracted fp64 kernels (gcmb_set_fma): <= 1e-12 of the reference, not bit-identical",
+            fma=True, **common)))
+        m1 = min(n, 512)
+        run_section("courant1", lambda: section(
+            lib, task_text(m1, m1, m1, steps=10 ** 6, detector=True).replace("courant 0.9", "courant 1.0"), m1 ** 3, 432, 10, 3,
+            what="the headline medium at %d^3 with the reference launcher's Courant number 1 (src/launcher/main.cpp:82,197,...): feet in "
+                 "the second cell, specialised kernels with run-time foot cells" % m1, **common))
+        run_section("courant09_same_size", lambda: section(
+            lib, task_text(m1, m1, m1, steps=10 ** 6, detector=True), m1 ** 3, 432, 10, 3,
+            what="the headline medium at %d^3, Courant 0.9 (the comparison for courant1)" % m1, **common))
     if rank == 0:
-        if world == 1 and not args.no_simplex:
+        if world == 1 and not args.no_simplex and not args.no_sections:
             # secondary measurement (never the headline): the tetrahedral path of SURVEY.md §8 a13-a21
-            try:
-                line["simplex"] = simplex_section(lib, local, 20, 3, not args.no_cpu_baseline)
-            except Exception as e:  # the headline line must survive a failure here
-                line["simplex"] = {"error": "%s: %s" % (type(e).__name__, e)}
-        if world == 1 and not args.no_rotated:
+            for key, basis in (("simplex", "random"), ("simplex_fixed_basis", "identity")):
+                try:
+                    line[key] = simplex_section(lib, local, 20, 3, (not args.no_cpu_baseline) and basis == "random", basis=basis)
+                except Exception as e:  # the headline line must survive a failure here
+                    line[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if world == 1 and not args.no_rotated and not args.no_sections:
             # secondary measurement (never the headline): dense eigen-systems of rotated orthotropic materials
             try:
                 line["rotated_orthotropic"] = rotated_section(lib, local, 5, 3, not args.no_cpu_baseline)

@@ -19,7 +19,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 BUILD = os.path.join(ROOT, "build")
 
-NVCC_BASE = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3"]
+# GCMB_NVCC_EXTRA: extra definitions for experiments, e.g. -DGCMB_TMA_ALL_MODES (all bulk-copy pipeline layouts)
+NVCC_BASE = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3"] + os.environ.get("GCMB_NVCC_EXTRA", "").split()
 # the reference is built without FMA contraction (CMakeLists.txt:6-7); bit-exact parity needs the same
 NVCC_EXACT = NVCC_BASE + ["-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off"]
 NVCC_FMA = NVCC_BASE + ["-fmad=true", "-Xcompiler", "-fPIC,-ffp-contract=off"]

@@ -928,7 +928,12 @@ static bool zfill_possible(gcmb_body* b, int dir, const double* values, ZFaceFil
 #ifdef GCMB_EMUL
 	return false;
 #else
-	static const bool off = std::getenv("GCMB_NO_FUSED_BORDER") != nullptr;
+	// Off unless GCMB_FUSED_BORDER=1.  Measured at 1024^3 (profiles/r2_variants.md): the 2 x 9 sector stores per row cost the
+	// marching kernel as much as the separate fill kernel takes (bulk-copy variant: y stage 30.3 -> 32.6 ms against 2.7 ms
+	// of k_border; the LDGSTS variant collapses to 80 ms), because the ghost sector lies in a 128-byte line of its own:
+	// the partial-line write is what costs, whoever issues it.
+	static const bool on = std::getenv("GCMB_FUSED_BORDER") != nullptr && std::getenv("GCMB_FUSED_BORDER")[0] == '1';
+	const bool off = !on;
 	const Geom& g = b->g;
 	if (off || dir != g.D - 1 || g.D < 2 || g.n[2] % 32 != 0 || g.n[2] < 64 || g.bs > 4) { return false; }
 	std::memset(&zf, 0, sizeof zf);

@@ -13,9 +13,6 @@
 #include "tma_pipe.h"
 #endif
 
-#ifndef GCMB_DEFAULT_STAGE_IMPL
-#define GCMB_DEFAULT_STAGE_IMPL 2
-#endif
 #ifndef GCMB_SET
 #error "GCMB_SET is not defined"
 #endif
@@ -267,24 +264,28 @@ void launch_march(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes
 	constexpr int MINB = MarchBlocks<P, BS, K0RT>::value;
 #ifndef GCMB_EMUL
 	if (impl == 3) {
+		// the bulk-copy marching kernels are compiled for at most 5 blocks per SM (96 registers, no spills): the
+		// 80-register build of the fp64 3-D elastic patterns spilled and gave wrong values in the lanes that do not issue
+		// the copies (gpurun_out of round 2, scripts/gpu_runs/r2_debug_tma.py); at 5 blocks every variant is bit-exact
+		constexpr int TMINB = MINB > 5 ? 5 : MINB;
 		// GCMB_TMA_MARCH: 0 = a pipeline per warp (256-byte copies, no coupling between warps);
 		// 1 = one ring per block, refilled by lane 0 of warp 0; 2 = one ring per block, producer warp
 		static const int mode = env_int("GCMB_TMA_MARCH", 0);
 		static unsigned long long done[3] = {0, 0, 0};
 		constexpr int NST = 3;
 		if (mode == 0) {
-			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 1, false, MINB, ZF>;
+			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 1, false, TMINB, ZF>;
 			const size_t smem = sizeof(MarchTmaSmem<Real, P::M, NST, 32, 4>) + tab_bytes;
 			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024, done[0]);
 			kernel<<<grid, MARCH_ZT, smem, stream>>>(a, seg);
 #ifdef GCMB_TMA_ALL_MODES
 		} else if (mode == 1) {
-			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 4, false, MINB, ZF>;
+			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 4, false, TMINB, ZF>;
 			const size_t smem = sizeof(MarchTmaSmem<Real, P::M, NST, 128, 1>) + tab_bytes;
 			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024, done[1]);
 			kernel<<<grid, MARCH_ZT, smem, stream>>>(a, seg);
 		} else {
-			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 4, true, (MINB > 5 ? 5 : MINB), ZF>;
+			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 4, true, TMINB, ZF>;
 			const size_t smem = sizeof(MarchTmaSmem<Real, P::M, NST, 128, 1>) + tab_bytes;
 			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024, done[2]);
 			kernel<<<grid, MARCH_ZT + 32, smem, stream>>>(a, seg);
@@ -305,7 +306,9 @@ void launch_march(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes
 // launch of the tile kernel of a pattern whose direction runs along the contiguous axis
 template<class P, int BS, bool K0RT>
 void launch_ztile(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes) {
-	static const int rows = env_int("GCMB_ZTILE_ROWS", 32);
+	static const int rows_env = env_int("GCMB_ZTILE_ROWS", 0);
+	// rows per block: 32 for the LDGSTS tiles (round 1), 16 for the bulk-copy tiles (25.0 ms against 25.9 at 32 and 27.4 at 64)
+	const int rows = rows_env > 0 ? rows_env : (impl == 3 ? 16 : 32);
 #ifndef GCMB_EMUL
 	if (impl == 3) {
 		// GCMB_TMA_ZTILE: 0 = a pipeline per warp; 1 = one ring per block of 8 warps
@@ -361,8 +364,12 @@ void launch_ztile(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes
 template<class P, int BS, bool K0RT>
 void launch_sparse(const void* args, cudaStream_t stream) {
 	const Args& a = *static_cast<const Args*>(args);
-	// GCMB_STAGE_IMPL: 2 = cp.async (LDGSTS) rings; 3 = bulk copies (TMA) + mbarriers
-	static const int impl = env_int("GCMB_STAGE_IMPL", GCMB_DEFAULT_STAGE_IMPL);
+	// GCMB_STAGE_IMPL: 2 = cp.async (LDGSTS) rings everywhere; 3 = bulk copies (TMA) + mbarriers everywhere; default: the
+	// faster of the two per kernel as measured at 1024^3 (profiles/r2_variants.md) -- bulk copies for the fp64 tile
+	// kernel of the contiguous axis (25.0 against 26.8 ms), LDGSTS rings for the marching kernels (28.2 against 28.3 ms
+	// at equal occupancy) and for fp32 (17.6 against 18.5 ms)
+	static const int impl_env = env_int("GCMB_STAGE_IMPL", 0);
+	const int impl = impl_env ? impl_env : ((P::axis == 2 && sizeof(Real) == 8) ? 3 : 2);
 	const size_t tab_bytes = (size_t) a.n_tables * Packed<P, BS, K0RT>::SIZE * sizeof(Real);
 	if (a.axis != P::axis) { return; }  // (the caller matched the pattern by axis)
 	if constexpr (P::axis == 2) {

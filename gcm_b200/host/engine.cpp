@@ -124,6 +124,26 @@ EngineBase::EngineBase(const Task& task, int dimensionality) :
 	}
 	slabRank = task.device.slabRank;
 	slabCount = task.device.slabCount;
+	if (slabCount > 1) {
+		// Every body is cut along x by slab, so a contact NORMAL to x between two bodies would join planes that live on
+		// different processes: the local contact boxes would not find it and the facing ghost planes would silently stay
+		// empty.  Such tasks are detected on the undecomposed cubes and refused before anything is created.
+		for (const auto& a : task.cubicGrid.cubics) {
+			for (const auto& b : task.cubicGrid.cubics) {
+				if (a.first == b.first || (int) a.second.sizes.size() != D || (int) b.second.sizes.size() != D) { continue; }
+				int width[3], axis = 0;
+				for (int i = 0; i < D; i++) {
+					width[i] = std::min(a.second.start[i] + a.second.sizes[i] - 1, b.second.start[i] + b.second.sizes[i] - 1) -
+					           std::max(a.second.start[i], b.second.start[i]);
+				}
+				for (int i = 1; i < D; i++) { if (width[i] < width[axis]) { axis = i; } }
+				if (width[axis] == -1 && axis == 0) {
+					throw Exception(GCMB_E_UNSUPPORTED, "slab decomposition along x cannot hold a contact normal to x (bodies " +
+							std::to_string(a.first) + " and " + std::to_string(b.first) + "): stack the bodies along y or z");
+				}
+			}
+		}
+	}
 	check(gcmb_create(task.device.device, task.device.realBytes, &ctx));
 	if (task.device.fma) { check(gcmb_set_fma(ctx, 1)); }
 	if (slabCount > 1) {
@@ -190,11 +210,14 @@ void EngineBase::createGridsAndContacts(const Task& task) {
 		m.modelType = taskBody.second.modelId;
 		m.materialType = taskBody.second.materialId;
 		m.M = pdeSize(m.modelType, D);
+		m.realBytes = task.device.realBytes;
 		for (int i = 0; i < D; i++) {
 			m.sizes[i] = cube.sizes[i];
 			m.start[i] = cube.start[i];
 			m.h[i] = task.cubicGrid.h[i];
 		}
+		m.globalSizes = m.sizes;
+		m.globalStart = m.start;
 		if (slabCount > 1) {
 			// slab decomposition along x: this process keeps planes [lo, hi) of the body
 			const int nx = m.sizes[0];
@@ -208,28 +231,6 @@ void EngineBase::createGridsAndContacts(const Task& task) {
 	}
 
 	const int bs = task.cubicGrid.borderSize;
-	if (slabCount > 1) {
-		// Every body is cut along x by slab, so a contact NORMAL to x between two bodies would join planes that live on
-		// different processes: the local boxes below would not find it and the facing ghost planes would silently stay
-		// empty.  Such tasks are detected on the undecomposed cubes and refused.
-		for (const Body& body : bodies) {
-			for (const Body& other : bodies) {
-				if (other.mesh->id == body.mesh->id) { continue; }
-				const Mesh& a = *body.mesh;
-				const Mesh& b = *other.mesh;
-				int width[3], axis = 0;
-				for (int i = 0; i < D; i++) {
-					width[i] = std::min(a.globalStart[i] + a.globalSizes[i] - 1, b.globalStart[i] + b.globalSizes[i] - 1) -
-					           std::max(a.globalStart[i], b.globalStart[i]);
-				}
-				for (int i = 1; i < D; i++) { if (width[i] < width[axis]) { axis = i; } }
-				if (width[axis] == -1 && axis == 0) {
-					throw Exception(GCMB_E_UNSUPPORTED, "slab decomposition along x cannot hold a contact normal to x (bodies " +
-							std::to_string(a.id) + " and " + std::to_string(b.id) + "): stack the bodies along y or z");
-				}
-			}
-		}
-	}
 	for (Body& body : bodies) {
 		for (const Body& other : bodies) {
 			if (other.mesh->id == body.mesh->id) { continue; }

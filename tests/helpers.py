@@ -56,20 +56,21 @@ def compare_with_golden(lib, name, task_text, exact=True):
             t, v = eng.seismogram()
             det = g["detector"]
             assert len(t) == det.shape[0]
-            assert np.allclose(t, det[:, 0], rtol=2e-6, atol=1e-30)
-            assert np.allclose(v, det[:, 1], rtol=2e-6, atol=1e-30)
+            assert np.allclose(t, det[:, 0], rtol=5e-6, atol=1e-30)
+            assert np.allclose(v, det[:, 1], rtol=5e-6, atol=1e-30)
         return eng, worst
     except Exception:
         eng.close()
         raise
 
 
-def random_stage_check(lib, cases, seed=7):
-    """C-ABI level: random state with ghosts, random material map, every direction, bitwise vs gcmo_stage."""
+def random_stage_check(lib, cases, seed=7, real_bytes=8):
+    """C-ABI level: random state with ghosts, random material map, every direction, bitwise vs gcmo_stage
+    (real_bytes=4: the fp32 kernels, within single-precision rounding of the fp64 oracle)."""
     import oracle_host as oh
     L = oh.lib()
     rng = np.random.default_rng(seed)
-    ctx = capi.Context(lib)
+    ctx = capi.Context(lib, real_bytes=real_bytes)
     for (D, sizes, model, bs) in cases:
         mats = [{"kind": "isotropic", "rho": rng.uniform(1, 5), "lambda": rng.uniform(1, 5), "mu": rng.uniform(0.5, 3)}
                 for _ in range(3)]
@@ -95,10 +96,60 @@ def random_stage_check(lib, cases, seed=7):
             rc = L.gcmo_stage(D, M, oh._ip(sz), bs, oh._dp(h), s, tau, 3, oh._dp(U), oh._dp(U1), oh._dp(Lm),
                               oh._bp(table_full), oh._dp(state), oh._dp(nxt))
             assert rc == 0
+            if real_bytes == 4:
+                assert np.abs(nxt[real] - got).max() <= 2e-5 * np.abs(nxt[real]).max(), (D, sizes, model, bs, s, body.kernel_name(s))
+                continue
             assert np.array_equal(nxt[real], got), (D, sizes, model, bs, s, body.kernel_name(s),
                                                     np.abs(nxt[real] - got).max())
         body.close()
     ctx.close()
+
+
+def fused_border_check(lib, seed=11):
+    """gcmb_cubic_stage_fill_next_border == gcmb_cubic_stage + gcmb_cubic_border_apply, ghost nodes included, bit for bit;
+    returns the number of cases that took the fused path"""
+    rng = np.random.default_rng(seed)
+    ctx = capi.Context(lib)
+    fused_cases = 0
+    # (D, sizes, model, border size, conditions of the last direction: (quantity codes, which sides))
+    cases = ((3, (6, 37, 64), "elastic", 2, [((5, 7, 8), 3)]), (3, (5, 9, 128), "elastic", 2, [((2,), 1), ((5, 7, 8), 2)]),
+             (3, (4, 300, 96), "acoustic", 2, [((3,), 3)]), (2, (45, 160), "elastic", 2, [((3, 4), 3)]),
+             (3, (5, 7, 64), "elastic", 3, [((5, 7, 8), 3), ((0, 8), 3)]), (3, (5, 7, 64), "elastic", 1, [((8,), 2)]),
+             (3, (6, 37, 50), "elastic", 2, [((5, 7, 8), 3)]))
+    for (D, sizes, model, bs, conds) in cases:
+        mats = [("isotropic", rng.uniform(1, 5), rng.uniform(1, 5), rng.uniform(0.5, 3) if model == "elastic" else 0.0) for _ in range(3)]
+        ms = [capi.host_matrices(lib, model, D, m) for m in mats]
+        U, U1, Lm = (np.ascontiguousarray(np.stack([m[i] for m in ms])) for i in range(3))
+        M = U.shape[-1]
+        h = rng.uniform(0.5, 1.5, D)
+        full = tuple(s + 2 * bs for s in sizes)
+        state = rng.normal(size=full + (M,))
+        table = rng.integers(0, 3, size=sizes).astype(np.uint8)
+        tau = 0.4 * h.min() / np.abs(Lm).max()
+        last, prev = D - 1, D - 2
+        results = []
+        for fused_call in (True, False):
+            body = capi.CubicBody(ctx, D, M, sizes, [0] * D, h, bs)
+            body.set_materials(U, U1, Lm, table)
+            values = []
+            for i, (codes, sides) in enumerate(conds):
+                body.border_set_area(i, last, ("infinite",), list(codes), sides=sides)
+                values += [0.25 * (i + 1) + 0.1 * c for c in codes]
+            body.upload(state, with_ghosts=True)
+            if fused_call:
+                took = body.stage_fill_next_border(prev, tau, last, values)
+                fused_cases += int(took)
+                if not took:
+                    body.border_apply(last, values)
+            else:
+                body.stage(prev, tau)
+                body.border_apply(last, values)
+            results.append(body.download(with_ghosts=True))
+            body.close()
+        real = tuple(slice(bs, bs + s) for s in sizes[:-1])  # real nodes of every axis but the last, whole rows
+        assert np.array_equal(results[0][real], results[1][real]), (D, sizes, model, bs, np.abs(results[0][real] - results[1][real]).max())
+    ctx.close()
+    return fused_cases
 
 
 def read_vtk_appended(path):

@@ -62,6 +62,39 @@ def run_slabs(lib, text, rank, world, local, nccl_id=None):
     return out, (t, v)
 
 
+def check_fixtures(lib, rank, world, local, verbose=True):
+    """decomposed runs against the reference fixtures; returns {"bitwise": bool, "cases": [...]} (rank 0 decides)"""
+    cases, ok = [], True
+    for name in ("elastic3d_layers", "elastic3d_ortho", "acoustic3d_free", "ortho3d_contact", "maxwell3d", "ortho3d_rotated_plies",
+                 "elastic3d_layers_courant1", "ortho3d_contact_courant1"):
+        nx = int(SCENARIOS[name].split("sizes")[1].split()[0])
+        bs = int(SCENARIOS[name].split("border_size")[1].split()[0])
+        if nx // world < bs:  # a slab must hold at least border_size planes (CubicGrid.hpp:186-199)
+            continue
+        got, seis = run_slabs(lib, SCENARIOS[name], rank, world, local)
+        if rank == 0:
+            g = golden(name)
+            same = all(np.array_equal(arr, g["body%d" % bid]) for bid, arr in got.items())
+            if "detector" in g.files:
+                same = same and bool(np.allclose(seis[1], g["detector"][:, 1], rtol=5e-6, atol=1e-30))
+            ok = ok and same
+            cases.append({"task": name, "gpus": world, "bitwise_equal_to_reference": bool(same)})
+            if verbose:
+                print("multi-gpu == reference (bitwise):", name, "on", world, "GPUs", same, flush=True)
+    # a contact normal to x cannot be decomposed along x: the engine must refuse it, not drop it silently
+    text = SCENARIOS["ortho3d_contact"].replace("start 0 8 0", "start 16 0 0").replace("sizes 16 8 16", "sizes 16 16 16")
+    refused = False
+    try:
+        eng = capi.HostEngine(lib, text, device=local, slab_rank=rank, slab_count=world, nccl_id=new_nccl_id(lib, rank))
+        eng.close()
+    except capi.GcmError as e:
+        refused = e.code == -1
+    if rank == 0:
+        cases.append({"task": "two bodies in contact across x", "gpus": world, "refused_as_unsupported": refused})
+        ok = ok and refused
+    return {"bitwise": bool(ok), "cases": cases}
+
+
 def main():
     dist.init_process_group("nccl")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -72,19 +105,9 @@ def main():
     os.chdir("/tmp")
 
     # (1) against the reference fixtures
-    for name in ("elastic3d_layers", "elastic3d_ortho", "acoustic3d_free", "ortho3d_contact", "maxwell3d", "ortho3d_rotated_plies"):
-        nx = int(SCENARIOS[name].split("sizes")[1].split()[0])
-        if nx // world < 2:  # a slab must hold at least border_size planes (CubicGrid.hpp:186-199)
-            continue
-        got, seis = run_slabs(lib, SCENARIOS[name], rank, world, local, nccl_id)
-        if rank == 0:
-            g = golden(name)
-            for bid, arr in got.items():
-                ref = g["body%d" % bid]
-                assert np.array_equal(arr, ref), (name, bid, np.abs(arr - ref).max())
-            if "detector" in g.files:
-                assert np.allclose(seis[1], g["detector"][:, 1], rtol=2e-6, atol=1e-30)
-            print("multi-gpu == reference (bitwise):", name, "on", world, "GPUs", flush=True)
+    res = check_fixtures(lib, rank, world, local)
+    if rank == 0:
+        assert res["bitwise"], res
 
     # (2) against one GPU at a larger size (uneven slabs when world does not divide 100)
     text = elastic3d_layers(n=100, steps=12)

@@ -24,13 +24,13 @@ initial quantity PRESSURE 1 sphere 0.3 0.5 0.5 0.5
 """
 
 
-def acoustic3d_free(n=20, steps=5):
+def acoustic3d_free(n=20, steps=5, courant=0.9, bs=2):
     # BASELINE config 2 at reduced size: point source, PRESSURE -> 0 on all six faces
     h = _h(n)
     return f"""
 dimensionality 3
-courant 0.9
-border_size 2
+courant {courant}
+border_size {bs}
 h {h} {h} {h}
 steps {steps}
 body 0 acoustic isotropic sizes {n} {n} {n} start 0 0 0
@@ -42,13 +42,13 @@ border 0 2 infinite PRESSURE const 0
 """
 
 
-def elastic3d_layers(n=20, steps=5):
+def elastic3d_layers(n=20, steps=5, courant=0.9, bs=2):
     # BASELINE config 3 at reduced size: y-layered medium, free surface on top (z right), detector disc
     h = _h(n)
     return f"""
 dimensionality 3
-courant 0.9
-border_size 2
+courant {courant}
+border_size {bs}
 h {h} {h} {h}
 steps {steps}
 body 0 elastic isotropic sizes {n} {n} {n} start 0 0 0
@@ -76,12 +76,12 @@ initial quantity PRESSURE 1 sphere 0.3 0.5 0.5 0.5
 """
 
 
-def elastic3d_ortho_rotated(n=14, steps=4):
+def elastic3d_ortho_rotated(n=14, steps=4, courant=0.9):
     # rotated axes of the material (ElasticModel3D.cpp:151-283): dense eigen-systems from the cubic's roots
     h = _h(n)
     return f"""
 dimensionality 3
-courant 0.9
+courant {courant}
 border_size 2
 h {h} {h} {h}
 steps {steps}
@@ -91,14 +91,14 @@ initial quantity PRESSURE 1 sphere 0.3 0.5 0.5 0.5
 """
 
 
-def ortho3d_contact(n=16, steps=5):
+def ortho3d_contact(n=16, steps=5, courant=0.9, bs=2):
     # BASELINE config 4 at reduced size: two orthotropic bodies glued along y + fixed velocity on a disc
     h = _h(n)
     half = n // 2
     return f"""
 dimensionality 3
-courant 0.9
-border_size 2
+courant {courant}
+border_size {bs}
 h {h} {h} {h}
 steps {steps}
 body 0 elastic orthotropic sizes {n} {half} {n} start 0 0 0
@@ -131,13 +131,13 @@ border 1 1 sphere 0.3 0.5 1.0 0.5 Vy sin 1.0 5.0
 """
 
 
-def elastic2d_pwave(n=40, steps=8):
+def elastic2d_pwave(n=40, steps=8, courant=0.9, bs=2):
     # BASELINE config 1 (200x200, 20 steps) at reduced size
     h = repr(4.0 / (n - 1))
     return f"""
 dimensionality 2
-courant 0.9
-border_size 2
+courant {courant}
+border_size {bs}
 h {h} {h}
 steps {steps}
 body 0 elastic isotropic sizes {n} {n} start 0 0
@@ -270,6 +270,25 @@ initial wave P_FORWARD 1 PRESSURE 1 box -10 0.4 -10 10 1.6 10
     return two, one
 
 
+def elastic2d_bs3(n=26, steps=6, courant=1.5):
+    # the border size of the reference's engine tests (test/sequence/TestEngine.cpp:105,168,247) with feet in the
+    # second cell: two materials, a border condition on each direction
+    h = _h(n)
+    return f"""
+dimensionality 2
+courant {courant}
+border_size 3
+h {h} {h}
+steps {steps}
+body 0 elastic isotropic sizes {n} {n + 3} start 0 0
+material default isotropic 4 2 1
+material area box -10 0.5 -10 10 10 10 isotropic 1 3 0.5
+initial quantity PRESSURE 1 sphere 0.25 0.5 0.5 0
+border 0 0 infinite Sxx const 0 Sxy const 0
+border 0 1 box 0.2 -10 -10 0.8 10 10 Vy const 0.5
+"""
+
+
 SCENARIOS = {
     "elastic3d_iso": elastic3d_iso(),
     "elastic3d_iso_bs1": elastic3d_iso(14, 4, bs=1, courant=0.8),
@@ -288,4 +307,17 @@ SCENARIOS = {
     "maxwell3d": maxwell3d(),
     "adhesion2d_two": adhesion2d()[0],
     "adhesion2d_one": adhesion2d()[1],
+    # Courant number 1, the value the reference launcher uses almost everywhere (src/launcher/main.cpp:82,197,272,395,
+    # 438,477,580): the fastest wave's foot lies exactly one cell away (foot cell 1)
+    "elastic3d_layers_courant1": elastic3d_layers(16, 4, courant=1.0),
+    "acoustic3d_courant1": acoustic3d_free(16, 4, courant=1.0),
+    "elastic2d_courant1": elastic2d_pwave(32, 6, courant=1.0),
+    "ortho3d_contact_courant1": ortho3d_contact(12, 4, courant=1.0),
+    "elastic3d_ortho_rotated_courant1": elastic3d_ortho_rotated(12, 3, courant=1.0),
+    "elastic3d_layers_courant17": elastic3d_layers(14, 3, courant=1.7),
+    # border size 3 (test/sequence/TestEngine.cpp:105,168,247)
+    "elastic3d_iso_bs3": elastic3d_iso(14, 3, bs=3, courant=0.9),
+    "elastic3d_layers_bs3_courant25": elastic3d_layers(14, 3, courant=2.5, bs=3),
+    "acoustic3d_bs3_courant1": acoustic3d_free(14, 3, courant=1.0, bs=3),
+    "elastic2d_bs3_courant15": elastic2d_bs3(),
 }

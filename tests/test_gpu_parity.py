@@ -36,19 +36,162 @@ def test_cuda_engine_matches_reference_bitwise(lib, name):
     eng.close()
 
 
-@pytest.mark.parametrize("env", [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_FORCE_DENSE": "1", "GCMB_DENSE_LITERAL": "1"}, {"GCMB_STAGE_IMPL": "0"}, {"GCMB_STAGE_IMPL": "1"}, {"GCMB_MARCH_SEG": "5"}, {"GCMB_MARCH_MINB": "5"}, {"GCMB_MARCH_MINB": "6"},
-                                 {"GCMB_MARCH_SEG": "0"}])
+VARIANT_ENVS = [{"GCMB_FORCE_DENSE": "1"}, {"GCMB_FORCE_DENSE": "1", "GCMB_DENSE_LITERAL": "1"}, {"GCMB_MARCH_SEG": "5"}, {"GCMB_MARCH_SEG": "0"},
+                {"GCMB_ZTILE_ROWS": "7"}, {"GCMB_STAGE_IMPL": "2"}, {"GCMB_STAGE_IMPL": "3"}, {"GCMB_STAGE_IMPL": "3", "GCMB_MARCH_SEG": "5", "GCMB_ZTILE_ROWS": "3"},
+                {"GCMB_FUSED_BORDER": "1"}, {"GCMB_FUSED_BORDER": "1", "GCMB_STAGE_IMPL": "3"}]
+
+
+@pytest.mark.parametrize("env", VARIANT_ENVS)
 def test_kernel_variants_match_reference(env):
-    """dense / direct / marching-with-odd-segments kernels: every variant reproduces the reference bits."""
-    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+    """dense kernels, cp.async (LDGSTS) and bulk-copy (TMA) pipelines, odd marching segments and row counts, fused and
+    separate ghost fill: every variant reproduces the reference bits -- on the fixtures and, for sizes with full warps
+    and several z chunks, on random states against the oracle."""
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]\n"
             "import gcm_b200\n"
-            "from helpers import compare_with_golden\n"
+            "from helpers import compare_with_golden, random_stage_check, fused_border_check\n"
             "from scenarios import SCENARIOS\n"
-            "for n in ('elastic3d_layers', 'ortho3d_contact', 'acoustic3d_free', 'elastic2d_ortho', 'acoustic2d_border1', 'maxwell3d', 'ortho3d_rotated_plies', 'elastic3d_ortho_rotated'):\n"
-            "    compare_with_golden(gcm_b200.library(), n, SCENARIOS[n])[0].close()\n"
-            % (ROOT, os.path.join(ROOT, "tests")))
+            "lib = gcm_b200.library()\n"
+            "for n in ('elastic3d_layers', 'ortho3d_contact', 'acoustic3d_free', 'elastic2d_ortho', 'acoustic2d_border1', 'maxwell3d', 'ortho3d_rotated_plies',\n"
+            "          'elastic3d_ortho_rotated', 'elastic3d_layers_courant1', 'acoustic3d_courant1', 'elastic2d_courant1', 'ortho3d_contact_courant1',\n"
+            "          'elastic3d_ortho_rotated_courant1', 'elastic3d_layers_bs3_courant25', 'elastic2d_bs3_courant15', 'acoustic1d'):\n"
+            "    compare_with_golden(lib, n, SCENARIOS[n])[0].close()\n"
+            "random_stage_check(lib, ((3, (19, 13, 37), 'elastic', 2), (3, (7, 9, 300), 'acoustic', 2), (3, (5, 40, 700), 'elastic', 2),\n"
+            "                         (2, (23, 131), 'elastic', 2), (2, (70, 515), 'acoustic', 1), (3, (6, 11, 130), 'elastic', 3), (1, (1000,), 'acoustic', 2)))\n"
+            "fused_border_check(lib)\n"
+            % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_kernel_names_report_what_was_launched(lib):
+    """the Courant number of the reference launcher (1) and border size 3 run the specialised kernels, and
+    gcmb_cubic_stage_kernel_name says so"""
+    for name, want in (("elastic3d_layers_courant1", "sparse:elastic3d_iso_%s/bs2+k0"), ("acoustic3d_courant1", "sparse:acoustic3d_%s/bs2+k0"),
+                       ("elastic3d_iso_bs3", "sparse:elastic3d_iso_%s/bs3+k0"), ("elastic3d_layers", "sparse:elastic3d_iso_%s/bs2"),
+                       ("elastic3d_ortho_rotated_courant1", "dense_k0_one:M9/bs2+k0")):
+        eng = capi.HostEngine(lib, SCENARIOS[name])
+        assert [eng.kernel_name(0, d) for d in range(3)] == ["unset"] * 3
+        eng.advance(1)
+        assert [eng.kernel_name(0, d) for d in range(3)] == [want % c if "%s" in want else want for c in "xyz"]
+        eng.close()
+
+
+def test_fused_border_fill_equals_separate_fill():
+    """GCMB_FUSED_BORDER=1 (off by default: it does not pay): the marching stage writes the z ghosts itself"""
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]\n"
+            "import gcm_b200\n"
+            "from helpers import fused_border_check\n"
+            "n = fused_border_check(gcm_b200.library())\n"
+            "assert n >= 4, n\n" % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")))
+    for impl in ("2", "3"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GCMB_FUSED_BORDER="1", GCMB_STAGE_IMPL=impl), capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_fma_kernels_within_stated_tolerance(lib, name):
+    """gcmb_set_fma: the stage kernels compiled WITH contraction agree with the reference to north_star's 1e-12 (relative to
+    the largest value of the field); bit-exactness is the default mode's property, not this one's"""
+    from helpers import golden
+    g = golden(name)
+    eng = capi.HostEngine(lib, SCENARIOS[name], fma=True).run()
+    assert eng.info()[0] == int(g["steps"])
+    bid = 0
+    while "body%d" % bid in g.files:
+        ref, got = g["body%d" % bid], eng.body_pde(bid)
+        assert np.abs(ref - got).max() <= 1e-12 * np.abs(ref).max(), (name, np.abs(ref - got).max() / np.abs(ref).max())
+        bid += 1
+    assert all("+fma" in eng.kernel_name(0, d) for d in range(eng.body_info(0)[0]))
+    eng.close()
+
+
+@pytest.mark.parametrize("maker,kw", [(elastic3d_layers, dict(n=48)), (acoustic3d_free, dict(n=48))])
+def test_fp32_variant_bound_over_steps(lib, maker, kw):
+    """gcmb_create(..., 4): max|g - r| / max|r| against the fp64 run (== the reference, bitwise) after 1, 10 and 100 steps
+    (SURVEY.md 8d parity protocol; the reference's own fp32 tolerance is 1e-3, util/infrastructure/Types.hpp:13)."""
+    f64 = capi.HostEngine(lib, maker(steps=1000, **kw))
+    f32 = capi.HostEngine(lib, maker(steps=1000, **kw), real_bytes=4)
+    assert f32.info()[2] == f64.info()[2]  # the same time step
+    done, bounds = 0, {}
+    for n in (1, 10, 100):
+        f64.advance(n - done)
+        f32.advance(n - done)
+        done = n
+        r, g = f64.body_pde(0), f32.body_pde(0)
+        bounds[n] = float(np.abs(g - r).max() / np.abs(r).max())
+    print("fp32 bound", maker.__name__, bounds)
+    assert bounds[1] <= 2e-6 and bounds[10] <= 1e-5 and bounds[100] <= 1e-4, bounds
+    assert "/f32" in f32.kernel_name(0, 0)
+    f64.close()
+    f32.close()
+
+
+def test_fp32_random_state_single_stages_close_to_oracle(lib):
+    from helpers import random_stage_check
+    random_stage_check(lib, ((3, (19, 13, 37), "elastic", 2), (3, (5, 40, 300), "acoustic", 2), (2, (23, 131), "elastic", 1),
+                             (3, (6, 11, 130), "elastic", 3)), real_bytes=4)
+
+
+def test_async_box_download_matches_state(lib):
+    ctx = capi.Context(lib)
+    rng = np.random.default_rng(5)
+    body = capi.CubicBody(ctx, 3, 9, (33, 20, 70), [0, 0, 0], [0.1, 0.1, 0.1], 2)
+    full = rng.normal(size=(37, 24, 74, 9))
+    body.upload(full, with_ghosts=True)
+    assert np.array_equal(body.download_box((3, -2, 10), (7, 24, 33)), full[5:12, 0:24, 12:45])
+    assert np.array_equal(body.download_box((0, 0, 0), (33, 20, 70)), full[2:-2, 2:-2, 2:-2])
+    body.close()
+    ctx.close()
+
+
+def test_full_size_anchor_1024(lib):
+    """The BASELINE headline task at its full size (1024^3, offsets beyond 2^33 bytes) against thin bodies cut out of the
+    same medium: after 3 steps every value depends on initial data at most 3 * border_size nodes away along each axis, so
+    the centre line of a 17-node-thick body placed inside the big one must reproduce the big run BIT FOR BIT, and the thin
+    bodies are small enough for the CPU oracle (pinned to the reference), which they must equal as well."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    import oracle_host as oh
+    free, _ = torch.cuda.mem_get_info()
+    n = bench.pick_size(free, 1024)
+    if n < 1024:
+        pytest.skip("needs a GPU with room for the 1024^3 state (%d fits)" % n)
+    steps = 3
+    big = capi.HostEngine(lib, bench.task_text(n, n, n, steps, detector=False)).run()
+    ctxh, bodyh = big.context_handle(), big.body_handle(0)
+
+    def column(lo, ext):
+        out = np.empty(tuple(ext) + (9,))
+        lo_a, ext_a = np.array(lo, dtype=np.int32), np.array(ext, dtype=np.int32)
+        lib.check(lib.c.gcmb_cubic_download_box_begin(bodyh, capi.ip(lo_a), capi.ip(ext_a), out.ctypes.data_as(capi.vp)))
+        lib.check(lib.c.gcmb_cubic_download_box_end(bodyh))
+        return out
+
+    try:
+        # thin bodies: 17 x 17 x n along z (crossing the pulse and the free surface), 17 x n x 17 along y (crossing all four
+        # material layers), n x 17 x 17 along x -- placed away from the big body's faces except along their long axis
+        for sizes, start in (((17, 17, n), (600, 300, 0)), ((17, n, 17), (900, 0, 400)), ((n, 17, 17), (0, 700, 500))):
+            text = bench.task_text(n, n, n, steps, detector=False).replace(
+                "sizes %d %d %d start 0 0 0" % (n, n, n), "sizes %d %d %d start %d %d %d" % (sizes + start))
+            assert "start %d" % start[0] in text
+            thin = capi.HostEngine(lib, text).run()
+            got = thin.body_pde(0).reshape(sizes + (9,))
+            ora = oh.run_task_text(text)
+            assert thin.info()[0] == ora.steps_done == steps
+            assert np.array_equal(got, ora.real_nodes(0).reshape(sizes + (9,))), "thin body differs from the CPU oracle"
+            long_axis = int(np.argmax(sizes))
+            lo = [start[i] + (8 if i != long_axis else 0) for i in range(3)]
+            ext = [1 if i != long_axis else n for i in range(3)]
+            line_big = column(lo, ext).reshape(n, 9)
+            sel = [8, 8, 8]
+            sel[long_axis] = slice(None)
+            line_thin = got[tuple(sel)]
+            assert np.abs(line_thin).max() > 0
+            assert np.array_equal(line_big, line_thin), (sizes, np.abs(line_big - line_thin).max())
+            thin.close()
+    finally:
+        big.close()
 
 
 def _oracle_engine(text):

@@ -37,7 +37,48 @@ EXPECTED_KERNELS = {
     "elastic1d": ["sparse:elastic1d_iso_x/bs2"],
     # rotated axes: no zero of U is structural; one material: the coefficients travel as kernel parameters
     "elastic3d_ortho_rotated": ["dense_k0_one:M9/bs2", "dense_k0_one:M9/bs2", "dense_k0_one:M9/bs2"],
+    # Courant number 1 (feet in the second cell) and border size 3 stay on the specialised kernels
+    "elastic3d_layers_courant1": ["sparse:elastic3d_iso_x/bs2+k0", "sparse:elastic3d_iso_y/bs2+k0", "sparse:elastic3d_iso_z/bs2+k0"],
+    "acoustic3d_courant1": ["sparse:acoustic3d_x/bs2+k0", "sparse:acoustic3d_y/bs2+k0", "sparse:acoustic3d_z/bs2+k0"],
+    "elastic2d_courant1": ["sparse:elastic2d_iso_x/bs2+k0", "sparse:elastic2d_iso_y/bs2+k0"],
+    "ortho3d_contact_courant1": ["sparse:elastic3d_ortho_x/bs2+k0", "sparse:elastic3d_ortho_y/bs2+k0", "sparse:elastic3d_ortho_z/bs2+k0"],
+    "elastic3d_ortho_rotated_courant1": ["dense_k0_one:M9/bs2+k0", "dense_k0_one:M9/bs2+k0", "dense_k0_one:M9/bs2+k0"],
+    "elastic3d_iso_bs3": ["sparse:elastic3d_iso_x/bs3+k0", "sparse:elastic3d_iso_y/bs3+k0", "sparse:elastic3d_iso_z/bs3+k0"],
+    "elastic2d_bs3_courant15": ["sparse:elastic2d_iso_x/bs3+k0", "sparse:elastic2d_iso_y/bs3+k0"],
 }
+
+
+@pytest.mark.parametrize("name", ["elastic3d_layers", "acoustic3d_free", "elastic2d_pwave", "ortho3d_contact", "elastic3d_layers_courant1",
+                                  "elastic2d_bs3_courant15", "elastic3d_ortho_rotated", "acoustic2d_border1", "maxwell3d", "elastic1d"])
+def test_fp32_engine_close_to_reference(lib, name):
+    """real_bytes = 4 (the reference's `real` = float build, util/infrastructure/Types.hpp:8-14): the same engine in
+    single precision stays within a few float roundings of the fp64 reference over these short runs"""
+    g = golden(name)
+    eng = capi.HostEngine(lib, SCENARIOS[name], real_bytes=4).run()
+    try:
+        assert eng.info()[0] == int(g["steps"]) and eng.info()[2] == float(g["tau"])
+        bid = 0
+        while "body%d" % bid in g.files:
+            ref, got = g["body%d" % bid], eng.body_pde(bid)
+            assert np.abs(ref - got).max() <= 5e-5 * np.abs(ref).max()
+            bid += 1
+        assert all(eng.kernel_name(0, d).endswith("/f32") for d in range(eng.body_info(0)[0]))
+    finally:
+        eng.close()
+
+
+def test_async_box_download(lib):
+    ctx = capi.Context(lib)
+    rng = np.random.default_rng(5)
+    for real_bytes in (8, 4):
+        c = capi.Context(lib, real_bytes=real_bytes)
+        body = capi.CubicBody(c, 3, 9, (9, 6, 20), [0, 0, 0], [0.1, 0.1, 0.1], 2)
+        full = rng.normal(size=(13, 10, 24, 9)).astype(c.real)
+        body.upload(full, with_ghosts=True)
+        assert np.array_equal(body.download_box((3, -2, 10), (5, 10, 7)), full[5:10, 0:10, 12:19])
+        body.close()
+        c.close()
+    ctx.close()
 
 
 @pytest.mark.parametrize("name", sorted(EXPECTED_KERNELS))
@@ -327,3 +368,12 @@ def test_simplex_cell_location_matches_reference(lib):
 @pytest.mark.parametrize("name", _sx.GOLDEN_SIMPLEX[:5])   # the fixtures made before the host had its own clean-up
 def test_simplex_mesh_cleanup_matches_reference(lib, name):
     _sx.check_mesh_cleanup_against_reference(lib, name)
+
+
+def test_slabs_refuse_contact_across_x(lib):
+    """two bodies touching across x cannot be cut into x-slabs; the engine says so instead of dropping the contact"""
+    text = SCENARIOS["ortho3d_contact"].replace("start 0 8 0", "start 16 0 0")
+    with pytest.raises(capi.GcmError) as e:
+        capi.HostEngine(lib, text, slab_rank=0, slab_count=2, nccl_id=bytes(128))
+    assert e.value.code == -1 and "contact normal to x" in str(e.value)
+    capi.HostEngine(lib, text).advance(1).close()  # undecomposed: fine
