@@ -199,6 +199,7 @@ def simplex_section(lib, device, steps, warmup, with_cpu, basis="random"):
     eng.advance(warmup)
     lib.check(lib.c.gcmb_sync(ctxh))
     launches0 = lib.c.gcmb_launch_count(ctxh)
+    lib.check(lib.c.gcmb_profile_enable(ctxh, 1))
     lib.check(lib.c.gcmb_timer_start(ctxh))
     t0 = time.perf_counter()
     eng.advance(steps)
@@ -206,12 +207,18 @@ def simplex_section(lib, device, steps, warmup, with_cpu, basis="random"):
     lib.check(lib.c.gcmb_timer_stop(ctxh, capi.ctypes.byref(ms)))
     state = eng.simplex_pde(0)
     wall = time.perf_counter() - t0
+    prof_ms = np.zeros(8)
+    prof_n = np.zeros(8, dtype=np.int64)
+    lib.check(lib.c.gcmb_profile_get(ctxh, 8, capi.dp(prof_ms), prof_n.ctypes.data_as(capi.c_ll_p)))
+    lib.check(lib.c.gcmb_profile_enable(ctxh, 0))
     assert eng.errors() == 0 and np.isfinite(state).all() and np.abs(state).max() > 0
     out = {"metric": "simplex GCM vertex-updates/s (3-D isotropic elastic tetrahedra, SURVEY.md §8d C5)",
            "value": info["n_local"] * steps / (ms.value * 1e-3), "unit": "vertex-updates/s", "ms_per_step": ms.value / steps,
            "e2e": {"value": info["n_local"] * steps / wall, "unit": "vertex-updates/s", "d2h_bytes_per_step": info["n_local"] * 72 // steps,
                    "what": "simplex::Engine::run loop incl. border functors on the host and the final state read-back"},
            "gpu_launches": int(lib.c.gcmb_launch_count(ctxh) - launches0),
+           "per_class_ms": dict(zip(("riemann_transforms", "gradient", "border_nodes", "border_correct", "contact", "inner_nodes", "setup", "ode"),
+                                    (float(x) / steps for x in prof_ms))),
            "config": {"workload": "%dx%dx%d cubes of edge %g cut into 6 tetrahedra each, jitter 0.3, inner cavity: %d vertices; "
                                   "%s, fixed zero force on all borders, Courant 0.7" % (
                                       nx, ny, nz, h, info["n_local"], "a new random calculation basis every step (the reference's default: no foot can be cached)"

@@ -95,6 +95,8 @@ C_ABI = {
     "gcmb_set_fma": (ctypes.c_int, [vp, ctypes.c_int]),
     "gcmb_cubic_download_box_begin": (ctypes.c_int, [vp, c_int_p, c_int_p, vp]),
     "gcmb_cubic_download_box_end": (ctypes.c_int, [vp]),
+    "gcmb_host_alloc_pinned": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "gcmb_host_free_pinned": (None, [vp]),
     "gcmb_cubic_stage_fill_next_border": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                                          c_double_p, c_int_p]),
     "gcmb_cubic_seismo_at": (ctypes.c_int, [vp, c_double_p, c_ll_p, ctypes.c_int, c_double_p, ctypes.c_int, c_int_p]),

@@ -734,6 +734,16 @@ int gcmb_cubic_download_box_end(gcmb_body* body) {
 	return GCMB_OK;
 }
 
+int gcmb_host_alloc_pinned(size_t bytes, void** out) {
+	if (!out) { GCMB_FAIL(GCMB_E_INVALID_ARG, "out is null"); }
+	GCMB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+	return GCMB_OK;
+}
+
+void gcmb_host_free_pinned(void* p) {
+	if (p) { cudaFreeHost(p); }
+}
+
 int gcmb_cubic_download_tables(gcmb_body* b, uint8_t* node_table_id) {
 	if (!b || !node_table_id) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
 	const Geom& g = b->g;

@@ -369,7 +369,9 @@ void launch_sparse(const void* args, cudaStream_t stream) {
 	// kernel of the contiguous axis (25.0 against 26.8 ms), LDGSTS rings for the marching kernels (28.2 against 28.3 ms
 	// at equal occupancy) and for fp32 (17.6 against 18.5 ms)
 	static const int impl_env = env_int("GCMB_STAGE_IMPL", 0);
-	const int impl = impl_env ? impl_env : ((P::axis == 2 && sizeof(Real) == 8) ? 3 : 2);
+	// ... and, for fp64, bulk copies for the marching kernels that read the foot cell from the table as well: they need
+	// 96 registers either way, and there the bulk-copy kernel has no spills (28.2 / 27.7 against 29.0 / 29.1 ms at Courant 1)
+	const int impl = impl_env ? impl_env : ((sizeof(Real) == 8 && (P::axis == 2 || K0RT)) ? 3 : 2);
 	const size_t tab_bytes = (size_t) a.n_tables * Packed<P, BS, K0RT>::SIZE * sizeof(Real);
 	if (a.axis != P::axis) { return; }  // (the caller matched the pattern by axis)
 	if constexpr (P::axis == 2) {

@@ -29,14 +29,26 @@ AbstractEngine::AbstractEngine(const Task& task) :
 	Clock::setZero();
 }
 
+void AbstractEngine::activateClock() const {
+	Clock::time = time;
+	Clock::timeStep = timeStep;
+}
+
+void AbstractEngine::storeClock() {
+	time = Clock::time;
+	timeStep = Clock::timeStep;
+}
+
 void AbstractEngine::afterConstruction(const Task& task) {
 	Clock::timeStep = estimateTimeStep();
+	storeClock();
 	requiredTime = Clock::TimeStep() * task.globalSettings.numberOfSnaps * task.globalSettings.stepsPerSnap;
 	if (task.globalSettings.numberOfSnaps <= 0) { requiredTime = task.globalSettings.requiredTime; }
 	if (!(requiredTime > 0)) { throw Exception(GCMB_E_INVALID_ARG, "required time must be positive"); }
 }
 
 void AbstractEngine::run() {
+	activateClock();
 	step = 0;
 	writeSnapshots(step);
 	// the step count is decided by the same floating-point accumulation as in the reference
@@ -48,18 +60,23 @@ void AbstractEngine::run() {
 		nextTimeStep();
 		step++;
 		Clock::tickTack();
+		storeClock();
 		writeSnapshots(step);
 	}
+	finishRun();
 }
 
 void AbstractEngine::advance(int n) {
+	activateClock();
 	for (int i = 0; i < n; i++) {
 		Clock::timeStep = estimateTimeStep();
 		nextTimeStep();
 		step++;
 		Clock::tickTack();
+		storeClock();
 		writeSnapshots(step);
 	}
+	finishRun();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,6 +190,8 @@ EngineBase::EngineBase(const Task& task, int dimensionality) :
 }
 
 EngineBase::~EngineBase() {
+	try { finishPendingSnapshots(); } catch (...) { }
+	for (void* p : pinned) { gcmb_host_free_pinned(p); }
 	bodies.clear();
 	if (ctx) { gcmb_destroy(ctx); }
 }
@@ -519,13 +538,49 @@ void EngineBase::writeSnapshots(const int step_) {
 	}
 }
 
-/// VtkSnapshotter::snapshotImpl (util/snapshot/VtkSnapshotter.hpp:20-61) for every body of this process
+/// VtkSnapshotter::snapshotImpl (util/snapshot/VtkSnapshotter.hpp:20-61) for every body of this process.  The state is read
+/// back ASYNCHRONOUSLY: a gather + device-to-host copy is enqueued on a side stream into page-locked memory and the time
+/// loop goes on; the file is written when the copy has landed -- at the next snapshot or at the end of run()/advance().
+/// Bodies whose state does not fit the device-side staging (ASYNC_LIMIT) are read back in chunks, synchronously.
 void EngineBase::vtkSnapshot(const int step_) {
+	finishPendingSnapshots();
+	static const size_t ASYNC_LIMIT = (size_t) 1 << 30;
+	for (size_t i = 0; i < bodies.size(); i++) {
+		const Mesh& m = *bodies[i].mesh;
+		const size_t bytes = m.sizeOfRealNodes() * (size_t) m.M * (size_t) m.realBytes;
+		PendingSnapshot p;
+		p.step = step_;
+		p.body = i;
+		if (bytes <= ASYNC_LIMIT) {
+			if (pinned.size() <= i) { pinned.resize(bodies.size(), nullptr); }
+			if (!pinned[i]) { check(gcmb_host_alloc_pinned(bytes, &pinned[i])); }
+			const int lo[3] = {0, 0, 0};
+			check(gcmb_cubic_download_box_begin(m.body, lo, m.sizes.data(), pinned[i]));
+			p.async = true;
+		} else {
+			p.values = m.pdeRealNodes();  // chunked, synchronous
+			p.async = false;
+		}
+		pending.push_back(std::move(p));
+	}
+}
+
+void EngineBase::finishPendingSnapshots() {
 	const Task& task = taskCopy;
-	for (Body& body : bodies) {
-		const Mesh& m = *body.mesh;
-		const int n[3] = {m.sizes[0], m.sizes[1], m.sizes[2]};   // unused axes have size 1
+	for (PendingSnapshot& p : pending) {
+		const Mesh& m = *bodies[p.body].mesh;
 		const size_t total = m.sizeOfRealNodes();
+		if (p.async) {
+			check(gcmb_cubic_download_box_end(m.body));
+			p.values.resize(total * (size_t) m.M);
+			if (m.realBytes == 4) {
+				const float* src = static_cast<const float*>(pinned[p.body]);
+				for (size_t i = 0; i < p.values.size(); i++) { p.values[i] = src[i]; }
+			} else {
+				std::memcpy(p.values.data(), pinned[p.body], p.values.size() * sizeof(real));
+			}
+		}
+		const int n[3] = {m.sizes[0], m.sizes[1], m.sizes[2]};   // unused axes have size 1
 		std::vector<uint8_t> tables(total);
 		check(gcmb_cubic_download_tables(m.body, tables.data()));
 		// VTK point order: x fastest (linal::SlowZFastX); ours: x slowest
@@ -539,11 +594,14 @@ void EngineBase::vtkSnapshot(const int step_) {
 			for (size_t d = 0; d < 3; d++) { points[3 * i + d] = (float) c[d]; }
 			material[i] = (float) m.materials[tables[order[i]]]->materialNumber;
 		}
-		const auto fields = vtk::snapshotFields(m.modelType, D, m.M, m.pdeRealNodes(), order, task.vtkSnapshotter.quantitiesToSnap, material);
-		vtk::writeStructuredGrid(vtk::snapshotFileName(task.globalSettings.outputDirectory, "vtk", m.id, slabRank, step_, "vts"),
+		const auto fields = vtk::snapshotFields(m.modelType, D, m.M, p.values, order, task.vtkSnapshotter.quantitiesToSnap, material);
+		vtk::writeStructuredGrid(vtk::snapshotFileName(task.globalSettings.outputDirectory, "vtk", m.id, slabRank, p.step, "vts"),
 				n, points, fields);
 	}
+	pending.clear();
 }
+
+void EngineBase::finishRun() { finishPendingSnapshots(); }
 
 }  // namespace cubic
 

@@ -294,7 +294,9 @@ struct Task {
 };
 
 // ---- engine ---------------------------------------------------------------------------------
-/// time and step of the running engine (reference engine/GlobalVariables.hpp:16-40)
+/// time and step of the RUNNING engine (reference engine/GlobalVariables.hpp:16-40).  The reference keeps them in
+/// process-wide statics; here every engine owns its clock (AbstractEngine::time / timeStep) and publishes it through this
+/// interface while one of its methods runs, so that several engines can live in one process.
 struct Clock {
 	static real Time() { return time; }
 	static real TimeStep() { return timeStep; }
@@ -317,7 +319,14 @@ public:
 	void advance(int n);
 	/// steps performed by run() so far
 	int stepsDone() const { return step; }
+	/// this engine's own clock (what Clock::Time() / Clock::TimeStep() show while it runs)
+	real currentTime() const { return time; }
+	real currentTimeStep() const { return timeStep; }
 protected:
+	real time = 0, timeStep = 0;
+	/// publish / take back this engine's clock around everything that reads the global Clock
+	void activateClock() const;
+	void storeClock();
 	const real CourantNumber = 0;
 	real requiredTime = 0;
 	bool verboseTimeSteps = true;
@@ -326,6 +335,8 @@ protected:
 	virtual void nextTimeStep() = 0;
 	virtual real estimateTimeStep() = 0;
 	virtual void writeSnapshots(const int step) = 0;
+	/// end of run() / advance(): snapshots still in flight are written, deferred error checks are made
+	virtual void finishRun() { }
 };
 
 namespace cubic {
@@ -411,6 +422,17 @@ private:
 	void setUpBorders(const Task& task, Body& body);
 	void sliceSnapshot(const int step);
 	void vtkSnapshot(const int step);
+	/// VTK snapshots whose read-back is still in flight (gcmb_cubic_download_box_begin) or waiting to be written
+	struct PendingSnapshot {
+		int step = 0;
+		size_t body = 0;
+		bool async = false;
+		std::vector<real> values;
+	};
+	std::vector<PendingSnapshot> pending;
+	std::vector<void*> pinned;   ///< page-locked read-back buffer per body
+	void finishPendingSnapshots();
+	void finishRun() override;
 };
 
 template<int Dimensionality>
@@ -496,11 +518,18 @@ public:
 	void contactNodes(const GridsPair& pair, std::vector<int>& first, std::vector<int>& second, std::vector<real>& normals) const;
 	size_t numberOfBorderConditions(const GridId id) const { return getBody(id).borders.size(); }
 	const real* calculationBasis() const { return basis; }
+	/// Where the reference throws in the middle of a step (a characteristic foot on a mesh edge, interpolation weights
+	/// outside the cell, a failed least-squares fit, ...), the kernels count the event and go on; run() / advance() and
+	/// every snapshot then throw BAD_MESH here, so that a run the reference would have aborted never ends with rc 0.
+	/// false: keep going and leave the count to errorCount() (benchmarks on deliberately rough meshes).
+	bool throwOnNodeErrors = true;
 protected:
 	void nextTimeStep() override;
 	real estimateTimeStep() override;
 	void writeSnapshots(const int step) override;
+	void finishRun() override;
 private:
+	void checkNodeErrors() const;
 	Task::VtkSnapshotter vtkSettings;
 	std::vector<Snapshotters::T> snapshotters;
 	std::string outputDirectory;

@@ -73,8 +73,8 @@ int gcmb_host_engine_advance(void* handle, int n) {
 int gcmb_host_engine_info(void* handle, int* steps_done, double* time, double* tau) {
 	return guarded([&] {
 		*steps_done = static_cast<Handle*>(handle)->engine->stepsDone();
-		*time = Clock::Time();
-		*tau = Clock::TimeStep();
+		*time = static_cast<Handle*>(handle)->engine->currentTime();
+		*tau = static_cast<Handle*>(handle)->engine->currentTimeStep();
 	});
 }
 

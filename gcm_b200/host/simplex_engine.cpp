@@ -562,6 +562,7 @@ void Engine::writeSnapshots(const int step_) {
 	if (step_ % stepsPerSnap != 0) { return; }
 	for (const Snapshotters::T s : snapshotters) {
 		if (s != Snapshotters::T::VTK) { continue; }
+		checkNodeErrors();  // never write a snapshot of a state the reference would not have reached
 		for (const Body& body : bodies) {
 			const Mesh& m = *body.mesh;
 			const size_t n = m.sizeOfRealNodes();
@@ -582,6 +583,17 @@ void Engine::writeSnapshots(const int step_) {
 		}
 	}
 }
+
+void Engine::checkNodeErrors() const {
+	if (!throwOnNodeErrors) { return; }
+	const int n = errorCount();
+	if (n > 0) {
+		throw Exception(GCMB_E_BAD_MESH, std::to_string(n) + " node computations hit a case on which the reference engine throws "
+				"(degenerate cell location, interpolation outside the cell or failed least squares): the results are not valid");
+	}
+}
+
+void Engine::finishRun() { checkNodeErrors(); }
 
 int Engine::errorCount() const {
 	int total = 0;

@@ -102,6 +102,9 @@ int gcmb_cubic_download_state(gcmb_body* body, void* aos_pde, int with_ghosts);
  * One read-back in flight per body. */
 int gcmb_cubic_download_box_begin(gcmb_body* body, const int* box_min, const int* extent, void* host);
 int gcmb_cubic_download_box_end(gcmb_body* body);
+/* page-locked host memory for the asynchronous read-backs (cudaHostAlloc / cudaFreeHost) */
+int gcmb_host_alloc_pinned(size_t bytes, void** out);
+void gcmb_host_free_pinned(void* p);
 /* material table id of every REAL node, x slowest (DefaultMesh::material(it), engine/cubic/DefaultMesh.hpp:96-110;
  * read by VtkSnapshotter for its material_index field, util/snapshot/VtkSnapshotter.hpp:49-56). sync */
 int gcmb_cubic_download_tables(gcmb_body* body, uint8_t* node_table_id);

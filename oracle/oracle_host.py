@@ -540,9 +540,10 @@ def run_task_text(text):
     return OracleEngine(parse_task(text)).run()
 
 
-def run_reference(task_text, workdir, matrices=False):
-    """Run the UNMODIFIED reference (oracle/_ref/gcm_ref) on a task; returns dict body id -> array."""
-    exe = os.path.join(HERE, "_ref", "gcm_ref")
+def run_reference(task_text, workdir, matrices=False, exe_name="gcm_ref"):
+    """Run the UNMODIFIED reference (oracle/_ref/gcm_ref) on a task; returns dict body id -> array.
+    exe_name="gcm_ref_gpu": the same unmodified engine with gcm_b200 plugged in as its backend (integration/)."""
+    exe = os.path.join(HERE, "_ref", exe_name)
     os.makedirs(workdir, exist_ok=True)
     tf = os.path.join(workdir, "task.txt")
     with open(tf, "w") as f:

@@ -235,6 +235,10 @@ void dumpBody(const cubic::Engine<D>& engine, const size_t id,
 	typedef cubic::DefaultMesh<Model, CubicGrid<D>, Material> Mesh;
 	auto mesh = std::dynamic_pointer_cast<const Mesh>(engine.getMesh(id));
 	assert_true(mesh);
+#ifdef GCMB_GPU_BACKEND
+	// gcm_ref_gpu: the state lives on the device; DefaultMesh is its host mirror
+	dynamic_cast<const cubic::gpu::GpuMeshBase&>(*mesh).downloadToHost();
+#endif
 	const int M = Mesh::PdeVector::M;
 	std::vector<double> data;
 	data.reserve(mesh->sizeOfRealNodes() * (size_t) M);

@@ -87,6 +87,8 @@ using std::max;
 #define cudaEventDestroy(e) gcmb_emul::ev_destroy(e)
 #define cudaMalloc(p, n) gcmb_emul::e_malloc((void**) (p), n)
 #define cudaFree(p) gcmb_emul::e_free(p)
+#define cudaHostAlloc(p, n, f) gcmb_emul::e_malloc((void**) (p), n)
+#define cudaFreeHost(p) gcmb_emul::e_free(p)
 #define cudaMemsetAsync(d, v, n, s) gcmb_emul::e_memset(d, v, n)
 #define cudaMemcpyAsync(d, s, n, k, st) gcmb_emul::e_memcpy(d, s, n)
 #define cudaMemcpy(d, s, n, k) gcmb_emul::e_memcpy(d, s, n)

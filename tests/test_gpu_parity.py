@@ -63,6 +63,28 @@ def test_kernel_variants_match_reference(env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_reference_engine_with_gpu_backend_matches_reference_bitwise(name, tmp_path):
+    """The drop-in, run: oracle/_ref/gcm_ref_gpu is the UNMODIFIED reference cubic::Engine<D> (Engine.cpp, AbstractEngine.cpp,
+    models, materials, snapshotters compiled where they lie) whose factory hands out the GPU-backed mesh / GCM / border /
+    contact / ODE objects of integration/GpuBackend.hpp.  Its results must equal those of the all-CPU reference build
+    (tests/golden, made by oracle/_ref/gcm_ref) bit for bit: states of every body, time step, step count, seismogram."""
+    import oracle_host as oh
+    from helpers import golden
+    exe = os.path.join(ROOT, "oracle", "_ref", "gcm_ref_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gcm_ref_gpu is built where /root/reference exists (make -C oracle ref_gpu)")
+    g = golden(name)
+    out = oh.run_reference(SCENARIOS[name], str(tmp_path), exe_name="gcm_ref_gpu")
+    assert out["meta"]["tau"] == float(g["tau"]) and out["meta"]["time"] == float(g["time"]) and int(out["meta"]["steps"]) == int(g["steps"])
+    bid = 0
+    while "body%d" % bid in g.files:
+        assert np.array_equal(out[bid], g["body%d" % bid]), (name, bid, np.abs(out[bid] - g["body%d" % bid]).max())
+        bid += 1
+    if "detector" in g.files:
+        assert np.array_equal(out["detector"], g["detector"])  # both written by the reference's own SliceSnapshotter
+
+
 def test_kernel_names_report_what_was_launched(lib):
     """the Courant number of the reference launcher (1) and border size 3 run the specialised kernels, and
     gcmb_cubic_stage_kernel_name says so"""
@@ -142,6 +164,38 @@ def test_async_box_download_matches_state(lib):
     assert np.array_equal(body.download_box((0, 0, 0), (33, 20, 70)), full[2:-2, 2:-2, 2:-2])
     body.close()
     ctx.close()
+
+
+def test_vtk_snapshots_on_gpu_match_reference_fields(lib, tmp_path, monkeypatch):
+    """VtkSnapshotter (util/snapshot/VtkSnapshotter.hpp:20-61) on the GPU engine, read back asynchronously while the time
+    loop goes on: every .vts of the run is parsed and its float32 fields are compared with (a) the state the engine held at
+    that step and (b) the values the reference's snapshotter writes, i.e. float32 of the reference's own state at that step
+    (fixtures of the unmodified engine stopped at each snapshot step)."""
+    from helpers import golden, read_vtk_appended
+    monkeypatch.chdir(tmp_path)
+    base = SCENARIOS["elastic3d_layers"]          # 20^3, 5 steps in the fixture
+    g = golden("elastic3d_layers")
+    text = base + "vtk every 1 PRESSURE Sxy\noutput vtkrun\n"
+    eng = capi.HostEngine(lib, text)
+    D, M, sizes, _ = eng.body_info(0)
+    states = {0: eng.body_pde(0).copy()}
+    for step in range(1, 6):
+        eng.advance(1)                            # writes snapshot `step` asynchronously ...
+        states[step] = eng.body_pde(0).copy()     # ... while we already use the engine again
+    eng.close()                                   # the last snapshot is written when the engine ends
+    files = sorted(os.listdir(tmp_path / "snapshots" / "vtkrun" / "vtk"))
+    assert files == ["mesh0core00snap%04d.vts" % s for s in range(1, 6)], files
+    nx, ny, nz = (int(s) for s in sizes)
+    for step in range(1, 6):
+        v = read_vtk_appended(tmp_path / "snapshots" / "vtkrun" / "vtk" / ("mesh0core00snap%04d.vts" % step))
+        u = states[step].reshape(nx, ny, nz, M).transpose(2, 1, 0, 3).reshape(-1, M)   # VTK order: x fastest
+        assert np.array_equal(v["Velocity"], u[:, :3].astype(np.float32))
+        assert np.array_equal(v["Sxy"], u[:, 4].astype(np.float32))
+        assert np.array_equal(v["pressure"], (-(u[:, 3] + u[:, 6] + u[:, 8]) / 3).astype(np.float32))
+    # the last step is the reference fixture's final state: the file holds float32 of the REFERENCE's values
+    ref = g["body0"].reshape(nx, ny, nz, M).transpose(2, 1, 0, 3).reshape(-1, M)
+    assert np.array_equal(v["Velocity"], ref[:, :3].astype(np.float32))
+    assert np.array_equal(v["pressure"], (-(ref[:, 3] + ref[:, 6] + ref[:, 8]) / 3).astype(np.float32))
 
 
 def test_full_size_anchor_1024(lib):
