@@ -132,6 +132,7 @@ HOST_ABI = {
                                                        c_int_p, c_double_p]),
     "gcmb_host_simplex_errors": (ctypes.c_int, [vp, c_int_p]),
     "gcmb_host_simplex_save_inm": (ctypes.c_int, [vp, ctypes.c_char_p]),
+    "gcmb_host_inm_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_double, c_int_p, c_double_p, c_int_p, c_int_p]),
 }
 
 
@@ -489,6 +490,17 @@ class SimplexHostEngine(HostEngine):
         c = ctypes.c_int()
         self.lib.hcheck(self.lib.h.gcmb_host_simplex_errors(self.handle, ctypes.byref(c)))
         return c.value
+
+
+def inm_read(lib, path, scale=1.0):
+    """InmMeshLoader::readFromFile: (points [nV][3], cells [nC][4] 0-based, materials [nC])"""
+    sizes = np.zeros(2, dtype=np.int32)
+    lib.hcheck(lib.h.gcmb_host_inm_read(str(path).encode(), scale, ip(sizes), None, None, None))
+    xyz = np.zeros((int(sizes[0]), 3))
+    cells = np.zeros((int(sizes[1]), 4), dtype=np.int32)
+    mats = np.zeros(int(sizes[1]), dtype=np.int32)
+    lib.hcheck(lib.h.gcmb_host_inm_read(str(path).encode(), scale, ip(sizes), dp(xyz), ip(cells), ip(mats)))
+    return xyz, cells, mats
 
 
 def host_matrices(lib, model, D, material):

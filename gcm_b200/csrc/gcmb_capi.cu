@@ -20,6 +20,12 @@ using namespace gcmb;
 namespace {
 
 template<class R>
+GCMB_GLOBAL void k_border_zsector(BorderArgs<R> b, long long n_face) {
+	const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < n_face) { border_thread_zsector(b, t); }
+}
+
+template<class R>
 GCMB_GLOBAL void k_border(BorderArgs<R> b, long long n_face) {
 	const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	if (b.axis == 2) {
@@ -915,6 +921,13 @@ static int border_apply(gcmb_body* b, int dir, const double* values) {
 			for (int i = 0; i < a.nq; i++) { a.q[i] = c.q[(size_t) i]; a.val[i] = (R) values[used + i]; }
 			const long long n = axis == 2 ? nf : nf * g.bs;
 			Launch l(b->ctx, 3);
+			// z faces: whole-sector ghost writes where the row layout allows (see border_thread_zsector)
+			constexpr int SECT = 32 / (int) sizeof(R);
+			static const bool no_sector = std::getenv("GCMB_BORDER_LAYERWISE") != nullptr;
+			if (axis == 2 && !no_sector && g.bs <= SECT && g.zoff % SECT == 0 && g.zoff >= SECT && g.n[2] > g.bs && (s == 0 || g.n[2] % SECT == 0)) {
+				GCMB_LAUNCH(k_border_zsector<R>, (unsigned) ((nf + 127) / 128), 128, b->ctx->stream, a, nf);
+				continue;
+			}
 			GCMB_LAUNCH(k_border<R>, (unsigned) ((n + 127) / 128), 128, b->ctx->stream, a, nf);
 		}
 		used += (int) c.q.size();

@@ -178,6 +178,19 @@ int gcmb_host_simplex_save_inm(void* handle, const char* file_name) {
 	return guarded([&] { simplex::saveInmMesh(simplexOf(handle).getTriangulation(), file_name); });
 }
 
+/// InmMeshLoader::readFromFile (reference grid/simplex/mesh_loaders/InmMeshLoader.hpp:96-168): points [nV][3], cells
+/// [nC][4] (0-based vertex ids) and the material number of every cell.  sizes_out = {nV, nC}; arrays may be null to query
+/// the sizes only
+int gcmb_host_inm_read(const char* file_name, double scale, int* sizes_out, double* xyz, int* cell_v, int* cell_material) {
+	return guarded([&] {
+		const simplex::FlatTriangulation t = simplex::loadInmMesh(file_name, scale);
+		sizes_out[0] = t.nV; sizes_out[1] = t.nC;
+		if (xyz) { std::memcpy(xyz, t.xyz.data(), t.xyz.size() * sizeof(double)); }
+		if (cell_v) { std::memcpy(cell_v, t.cellV.data(), t.cellV.size() * sizeof(int)); }
+		if (cell_material) { std::memcpy(cell_material, t.cellGrid.data(), t.cellGrid.size() * sizeof(int)); }
+	});
+}
+
 int gcmb_host_simplex_errors(void* handle, int* count) {
 	return guarded([&] { *count = simplexOf(handle).errorCount(); });
 }

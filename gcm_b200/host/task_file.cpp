@@ -101,6 +101,10 @@ Task::TimeDependency timeDependency(Words& t) {
 		const real amp = t.num(), omega = t.num();
 		return [amp, omega](real time) { return amp * std::sin(omega * time); };
 	}
+	if (kind == "gauss") {  // amp * exp(-(t - t0)^2 / (2 tau^2)): the pulse of the reference's ndi tasks (src/launcher/ndi.hpp:200-203)
+		const real amp = t.num(), t0 = t.num(), tau = t.num();
+		return [amp, t0, tau](real time) { time -= t0; return amp * std::exp(-time * time / (2 * tau * tau)); };
+	}
 	throw Exception(GCMB_E_INVALID_ARG, "task text: unknown time dependency " + kind);
 }
 

@@ -115,6 +115,10 @@ Task::TimeDependency parseTimeDependency(Tokens& tk) {
 		real amp = tk.num(), omega = tk.num();
 		return [amp, omega](real t) { return amp * sin(omega * t); };
 	}
+	if (kind == "gauss") {
+		real amp = tk.num(), t0 = tk.num(), tau = tk.num();
+		return [amp, t0, tau](real t) { t -= t0; return amp * exp(-t * t / (2 * tau * tau)); };
+	}
 	THROW_INVALID_ARG("task file: unknown time dependency " + kind);
 }
 

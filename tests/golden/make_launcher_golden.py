@@ -13,13 +13,20 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import oracle_host as oh  # noqa: E402
 
-out = {}
-for name in ("cubic2d", "cubic3d", "acoustic"):
+path = os.path.join(HERE, "launcher_tasks.json")
+out = json.load(open(path)) if os.path.exists(path) else {}
+# main.cpp:332-467 (cubic2d, cubic3d, acoustic) and ndi.hpp:162-317 (ndi_empty, ndi, titan)
+for name in sys.argv[1:] or ("cubic2d", "cubic3d", "acoustic", "ndi_empty", "ndi", "titan"):
     text = open(os.path.join(ROOT, "gcm_b200", "tasks", name + ".task")).read()
     r = oh.run_reference(text, tempfile.mkdtemp())
-    u = r[0]
+    bodies = sorted(k for k in r if isinstance(k, int))
+    first = bodies[0]
+    u = r[first]
     weights = np.arange(1, u.shape[1] + 1, dtype=np.float64)
-    out[name] = {"steps": int(r["meta"]["steps"]), "time": r["meta"]["time"], "checksum": float((u * weights).sum()),
-                 "abs_sum": float(np.abs(u).sum()), "nodes": int(u.shape[0])}
+    out[name] = {"steps": int(r["meta"]["steps"]), "time": r["meta"]["time"], "body": first, "checksum": float((u * weights).sum()),
+                 "abs_sum": float(np.abs(u).sum()), "nodes": int(u.shape[0]),
+                 "bodies": {str(b): {"checksum": float((r[b] * weights).sum()), "abs_sum": float(np.abs(r[b]).sum())} for b in bodies}}
+    if "detector" in r:
+        out[name]["detector_last"] = [float(x) for x in r["detector"][-1]]
     print(name, out[name])
-json.dump(out, open(os.path.join(HERE, "launcher_tasks.json"), "w"), indent=1)
+json.dump(out, open(path, "w"), indent=1)

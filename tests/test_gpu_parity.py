@@ -413,10 +413,10 @@ def test_simplex_pde_vectors_gpu(lib, model):
     simplex_cases.check_engine(lib, model, bodies=2, basis="random", cavity=True, steps=3, gcm_type=1)
 
 
-@pytest.mark.parametrize("task", ["cubic2d", "cubic3d", "acoustic"])
+@pytest.mark.parametrize("task", ["cubic2d", "cubic3d", "acoustic", "ndi_empty", "ndi", "titan"])
 def test_launcher_gpu(task, tmp_path):
     """gcm_b200/gcmb_exe --task <id>: the reference launcher's cubic demo tasks (src/launcher/main.cpp:332-467) on
-    the GPU against the unmodified reference's step count, end time and checksum"""
+    and of ndi.hpp:162-317 on the GPU against the unmodified reference's step count, end time and the checksum of every body"""
     import json
     import re
     exe = os.path.join(ROOT, "gcm_b200", "gcmb_exe")
@@ -425,8 +425,9 @@ def test_launcher_gpu(task, tmp_path):
     assert out.returncode == 0, out.stderr
     steps, time = re.search(r"steps = (\d+), time = (\S+)", out.stdout).groups()
     assert int(steps) == gold["steps"] and float(time) == gold["time"]
-    checksum = float(re.search(r"body 0 checksum = (\S+)", out.stdout).group(1))
-    assert abs(checksum - gold["checksum"]) <= 1e-10 * gold["abs_sum"]
+    for body, want in gold.get("bodies", {"0": gold}).items():
+        checksum = float(re.search(r"body %s checksum = (\S+)" % body, out.stdout).group(1))
+        assert abs(checksum - want["checksum"]) <= 1e-10 * want["abs_sum"], (task, body)
 
 
 def test_launcher_simplex_plate_gpu(tmp_path):

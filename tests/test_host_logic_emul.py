@@ -14,6 +14,8 @@ from gcm_b200 import capi
 from helpers import compare_with_golden, emul_library, golden, run_engine
 from scenarios import SCENARIOS
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 @pytest.fixture(scope="module")
 def lib():
@@ -250,7 +252,7 @@ def test_simplex_pde_vectors_engine(lib):
     simplex_cases.check_engine(lib, 0, bodies=2, basis="rotated", steps=4, gcm_type=1)
 
 
-@pytest.mark.parametrize("task", ["cubic2d", "acoustic"])
+@pytest.mark.parametrize("task", ["cubic2d", "acoustic", "ndi_empty", "ndi"])
 def test_launcher_command_line(task, tmp_path):
     """gcmb_exe --task <id> (src/launcher/main.cpp:22-71) on the shipped demo tasks: step count, end time and state
     checksum against the unmodified reference's (tests/golden/launcher_tasks.json)"""
@@ -267,8 +269,9 @@ def test_launcher_command_line(task, tmp_path):
     assert out.returncode == 0, out.stderr
     steps, time = re.search(r"steps = (\d+), time = (\S+)", out.stdout).groups()
     assert int(steps) == gold["steps"] and float(time) == gold["time"]
-    checksum = float(re.search(r"body 0 checksum = (\S+)", out.stdout).group(1))
-    assert abs(checksum - gold["checksum"]) <= 1e-10 * gold["abs_sum"]
+    for body, want in gold.get("bodies", {"0": gold}).items():
+        checksum = float(re.search(r"body %s checksum = (\S+)" % body, out.stdout).group(1))
+        assert abs(checksum - want["checksum"]) <= 1e-10 * want["abs_sum"], (task, body)
     bad = subprocess.run([exe, "--task", "no_such_task"], capture_output=True, text=True)
     assert bad.returncode != 0 and "Invalid task file" in bad.stderr
 
@@ -377,3 +380,50 @@ def test_slabs_refuse_contact_across_x(lib):
         capi.HostEngine(lib, text, slab_rank=0, slab_count=2, nccl_id=bytes(128))
     assert e.value.code == -1 and "contact normal to x" in str(e.value)
     capi.HostEngine(lib, text).advance(1).close()  # undecomposed: fine
+
+
+def test_inm_loader_reads_the_reference_fixture(lib):
+    """src/test/sequence/TestInmMeshLoader.cpp:19-68 on our loader: the same file (tests/golden/testInmLoader.out is a byte copy of
+    /root/reference/meshes/testInmLoader.out, compared here when the reference tree is present), the same assertions"""
+    fixture = os.path.join(ROOT, "tests", "golden", "testInmLoader.out")
+    original = "/root/reference/meshes/testInmLoader.out"
+    if os.path.exists(original):
+        assert open(original, "rb").read() == open(fixture, "rb").read()
+    points, cells, materials = capi.inm_read(lib, fixture)
+    assert len(points) == 12 and len(cells) == 3
+    x = {3: -2.583210754394531250e+01, 4: 2.400143432617187500e+01, 5: 2.306465148925781250e+01, 6: 2.364865112304687500e+01,
+         7: 2.377413177490234375e+01, 8: -7.073544311523437500e+01, 9: -6.941218566894531250e+01, 10: -6.654748535156250000e+01,
+         11: -6.843022155761718750e+01}
+    y = [4.283624267578125000e+01, 4.416368865966796875e+01, 4.302170562744140625e+01, 4.141203308105468750e+01, 1.096292877197265625e+01,
+         1.127018737792968750e+01, 1.141680145263671875e+01, 1.079985809326171875e+01, 3.833699035644531250e+01, 4.111538696289062500e+01,
+         4.088376617431640625e+01, 3.788503265380859375e+01]
+    z = [1.406894775390625000e+03, 1.404953125000000000e+03, 1.405088378906250000e+03, 1.405093261718750000e+03, 1.388465698242187500e+03,
+         1.388329711914062500e+03, 1.388676269531250000e+03, 1.387921020507812500e+03, 1.369011962890625000e+03, 1.365369384765625000e+03,
+         1.370376220703125000e+03, 1.366383422851562500e+03]
+    for i, v in x.items():
+        assert points[i, 0] == v
+    assert list(points[:, 1]) == y and list(points[:, 2]) == z
+    # InmMeshLoader::Cell holds the file's 1-based vertex numbers: {1,2,3,4} -> 4, {5,6,7,8} -> 5, {9,10,11,12} -> 1
+    got = {tuple(sorted(int(v) + 1 for v in c)): int(m) for c, m in zip(cells, materials)}
+    assert got == {(1, 2, 3, 4): 4, (5, 6, 7, 8): 5, (9, 10, 11, 12): 1}
+    # the denominator of Task::SimplexGrid::scale is applied to the points
+    half, _, _ = capi.inm_read(lib, fixture, scale=2.0)
+    assert np.array_equal(half, points / 2.0)
+
+
+def test_ndi_task_as_written_is_refused_like_the_reference_does(lib):
+    """src/launcher/ndi.hpp:241-242 starts the sample one node inside the prism; cubic::Engine throws "Bodies must not intersect"
+    (engine/cubic/Engine.cpp:57) and so does ours -- the shipped ndi.task moves the sample one node down"""
+    text = open(os.path.join(ROOT, "gcm_b200", "tasks", "ndi.task")).read().replace("start 0 -31", "start 0 -30")
+    with pytest.raises(capi.GcmError) as e:
+        capi.HostEngine(lib, text)
+    assert e.value.code == 4 and "Bodies must not intersect" in str(e.value)  # gcm::Exception::BAD_MESH
+    import oracle_host as oh
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "gcm_ref")):
+        import subprocess
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            open(os.path.join(tmp, "t.txt"), "w").write(text)
+            r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "gcm_ref"), os.path.join(tmp, "t.txt"), os.path.join(tmp, "out")],
+                               capture_output=True, text=True, cwd=tmp)
+        assert r.returncode != 0 and "Bodies must not intersect" in r.stderr + r.stdout
