@@ -282,6 +282,23 @@ def rotated_section(lib, device, steps, warmup, with_cpu=True):
     kernels = [eng.kernel_name(0, d) for d in range(3)]
     eng.close()
     per_s = n ** 3 * steps / (ms.value * 1e-3)
+    # the same with the FMA-contracted kernels (gcmb_set_fma): this stage is fp64-issue-bound, where contraction can pay
+    fma = None
+    try:
+        eng = capi.HostEngine(lib, rotated_bench.task(n), device=device, fma=True)
+        ctxh = eng.context_handle()
+        eng.advance(warmup)
+        lib.check(lib.c.gcmb_sync(ctxh))
+        lib.check(lib.c.gcmb_timer_start(ctxh))
+        eng.advance(steps)
+        ms2 = capi.ctypes.c_float(0)
+        lib.check(lib.c.gcmb_timer_stop(ctxh, capi.ctypes.byref(ms2)))
+        fma = {"value": n ** 3 * steps / (ms2.value * 1e-3), "unit": "node-updates/s", "ms_per_step": ms2.value / steps,
+               "kernels": [eng.kernel_name(0, d) for d in range(3)],
+               "note": "within 1e-12 of the reference, not bit-identical (tests/test_gpu_parity.py::test_fma_kernels_within_stated_tolerance)"}
+        eng.close()
+    except Exception as e:
+        fma = {"error": "%s: %s" % (type(e).__name__, e)}
     peak, which = measured_hbm_peak()
     cpu = None
     if with_cpu:
@@ -289,7 +306,7 @@ def rotated_section(lib, device, steps, warmup, with_cpu=True):
             cpu = run_reference_cpu(40, 3, text=rotated_bench.task(40, 3), what="rotated-plies")
         except Exception as e:
             cpu = {"error": "%s: %s" % (type(e).__name__, e)}
-    return {"metric": "GCM node-updates/sec (3D rotated orthotropic elastic, two glued bodies, fp64)", "value": per_s, "cpu_baseline": cpu,
+    return {"metric": "GCM node-updates/sec (3D rotated orthotropic elastic, two glued bodies, fp64)", "value": per_s, "cpu_baseline": cpu, "fma": fma,
             "unit": "node-updates/s", "steps": steps, "warmup": warmup, "ms_per_step": ms.value / steps, "kernels": kernels,
             "config": {"workload": "two glued bodies %dx%dx%d, carbon-fibre plies (ndi.hpp:120-131) turned +-45 degrees, border size 2, "
                                    "Courant 0.9; state larger than L2" % (n, n // 2, n)},

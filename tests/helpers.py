@@ -64,7 +64,7 @@ def compare_with_golden(lib, name, task_text, exact=True):
         raise
 
 
-def random_stage_check(lib, cases, seed=7, real_bytes=8):
+def random_stage_check(lib, cases, seed=7, real_bytes=8, n_materials=3):
     """C-ABI level: random state with ghosts, random material map, every direction, bitwise vs gcmo_stage
     (real_bytes=4: the fp32 kernels, within single-precision rounding of the fp64 oracle)."""
     import oracle_host as oh
@@ -73,7 +73,7 @@ def random_stage_check(lib, cases, seed=7, real_bytes=8):
     ctx = capi.Context(lib, real_bytes=real_bytes)
     for (D, sizes, model, bs) in cases:
         mats = [{"kind": "isotropic", "rho": rng.uniform(1, 5), "lambda": rng.uniform(1, 5), "mu": rng.uniform(0.5, 3)}
-                for _ in range(3)]
+                for _ in range(n_materials)]
         ms = [oh.matrices_for(model, D, m) for m in mats]
         U = np.ascontiguousarray(np.stack([m[0] for m in ms]))
         U1 = np.ascontiguousarray(np.stack([m[1] for m in ms]))
@@ -82,7 +82,7 @@ def random_stage_check(lib, cases, seed=7, real_bytes=8):
         h = rng.uniform(0.5, 1.5, D)
         full = tuple(s + 2 * bs for s in sizes)
         state = rng.normal(size=full + (M,))
-        table_full = rng.integers(0, 3, size=full).astype(np.uint8)
+        table_full = rng.integers(0, n_materials, size=full).astype(np.uint8)
         real = tuple(slice(bs, bs + s) for s in sizes)
         body = capi.CubicBody(ctx, D, M, sizes, [0] * D, h, bs)
         body.set_materials(U, U1, Lm, np.ascontiguousarray(table_full[real]))
@@ -93,7 +93,7 @@ def random_stage_check(lib, cases, seed=7, real_bytes=8):
             body.stage(s, tau)
             got = body.download(with_ghosts=False)
             nxt = np.zeros_like(state)
-            rc = L.gcmo_stage(D, M, oh._ip(sz), bs, oh._dp(h), s, tau, 3, oh._dp(U), oh._dp(U1), oh._dp(Lm),
+            rc = L.gcmo_stage(D, M, oh._ip(sz), bs, oh._dp(h), s, tau, n_materials, oh._dp(U), oh._dp(U1), oh._dp(Lm),
                               oh._bp(table_full), oh._dp(state), oh._dp(nxt))
             assert rc == 0
             if real_bytes == 4:

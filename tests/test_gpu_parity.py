@@ -276,6 +276,13 @@ def test_random_state_single_stages_match_oracle(lib):
                              (1, (300,), "elastic", 2), (1, (1000,), "acoustic", 2)))
 
 
+def test_many_materials_stay_on_the_specialised_kernels(lib):
+    """255 materials in one body: the packed tables of all of them sit in dynamic shared memory of the same kernels"""
+    from helpers import random_stage_check
+    random_stage_check(lib, ((3, (19, 13, 300), "elastic", 2), (3, (9, 40, 130), "acoustic", 2), (2, (23, 515), "elastic", 2)), n_materials=255)
+    random_stage_check(lib, ((3, (19, 13, 300), "elastic", 2),), n_materials=40)
+
+
 def test_ghost_layers_roundtrip_and_checksum(lib):
     ctx = capi.Context(lib)
     rng = np.random.default_rng(3)

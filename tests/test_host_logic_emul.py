@@ -427,3 +427,10 @@ def test_ndi_task_as_written_is_refused_like_the_reference_does(lib):
             r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "gcm_ref"), os.path.join(tmp, "t.txt"), os.path.join(tmp, "out")],
                                capture_output=True, text=True, cwd=tmp)
         assert r.returncode != 0 and "Bodies must not intersect" in r.stderr + r.stdout
+
+
+def test_many_materials_stay_on_the_specialised_kernels(lib):
+    """the coefficient tables of ALL materials of a body live in dynamic shared memory: a body with 60 materials (round 1 switched
+    to a slower kernel beyond 16) runs the same kernels and reproduces the oracle bit for bit"""
+    from helpers import random_stage_check
+    random_stage_check(lib, ((3, (7, 6, 40), "elastic", 2), (2, (9, 70), "acoustic", 2)), n_materials=60)
