@@ -101,6 +101,8 @@ C_ABI = {
                                                          c_double_p, c_int_p]),
     "gcmb_cubic_seismo_at": (ctypes.c_int, [vp, c_double_p, c_ll_p, ctypes.c_int, c_double_p, ctypes.c_int, c_int_p]),
     "gcmb_halo_exchange_bodies": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int]),
+    "gcmb_cubic_seismo_begin": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_int_p]),
+    "gcmb_cubic_seismo_end": (ctypes.c_int, [vp, c_double_p, c_ll_p, c_double_p, ctypes.c_int]),
 }
 
 HOST_ABI = {

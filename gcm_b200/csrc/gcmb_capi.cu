@@ -159,6 +159,22 @@ GCMB_GLOBAL void k_checksum(Geom g, const R* pde, double* partial) {
 	if (threadIdx.x == 0) { partial[blockIdx.x] = sum; }
 }
 
+// final reduction of the detector partials in index order (the order the host used to sum them in), and the z-axis line
+// as doubles: results of gcmb_cubic_seismo_begin, fetched by one asynchronous copy
+GCMB_GLOBAL void k_detector_final(const double* part_sum, const long long* part_count, int blocks, double* out2) {
+	double s = 0;
+	long long c = 0;
+	for (int i = 0; i < blocks; i++) { s += part_sum[i]; c += part_count[i]; }
+	out2[0] = s;
+	out2[1] = (double) c;
+}
+
+template<class R>
+GCMB_GLOBAL void k_line_to_double(const R* src, double* dst, int n) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { dst[i] = (double) src[i]; }
+}
+
 // gather of a box of nodes into a dense array [component][box node] (asynchronous snapshots, thin-column checks)
 template<class R>
 GCMB_GLOBAL void k_gather_box(Geom g, const R* pde, R* out, int b0, int b1, int b2, int e0, int e1, int e2) {
@@ -244,6 +260,12 @@ struct gcmb_body {
 	ZFaceFill<double> zfill;
 	void* gather_dev = nullptr;           // staging of asynchronous box read-backs
 	size_t gather_bytes = 0;
+	// asynchronous seismogram taps (gcmb_cubic_seismo_begin/end): {sum, count, line...} on the device and in pinned memory
+	double* seis_dev = nullptr;
+	double* seis_host = nullptr;
+	cudaEvent_t ev_seis = nullptr;
+	bool seis_pending = false, seis_detector = false;
+	int seis_line = 0;
 };
 
 namespace {
@@ -630,6 +652,9 @@ void gcmb_cubic_body_destroy(gcmb_body* b) {
 	cudaFree(b->decay_dev);
 	cudaFree(b->detector_mask);
 	cudaFree(b->gather_dev);
+	cudaFree(b->seis_dev);
+	if (b->seis_host) { cudaFreeHost(b->seis_host); }
+	if (b->ev_seis) { cudaEventDestroy(b->ev_seis); }
 	for (auto& kv : b->borders) { cudaFree(kv.second.mask[0]); cudaFree(kv.second.mask[1]); }
 	ctx->bodies.erase(std::remove(ctx->bodies.begin(), ctx->bodies.end(), b), ctx->bodies.end());
 	delete b;
@@ -1231,6 +1256,80 @@ int gcmb_cubic_seismo_at(gcmb_body* b, double* sum, long long* count, int line_c
 		for (int i = 0; i < b->g.D - 1; i++) { it[i + b->g.shift] = line_node[i]; }
 	}
 	return GCMB_BY_REAL(b->ctx, seismo<double>(b, sum, count, line_comp, line, n_line, it[0], it[1]), seismo<float>(b, sum, count, line_comp, line, n_line, it[0], it[1]));
+}
+
+template<class R>
+static int seismo_begin(gcmb_body* b, int with_detector, int line_comp, const int* line_node) {
+	gcmb_ctx* ctx = b->ctx;
+	const Geom& g = b->g;
+	const int n_line = line_node ? g.n[2] : 0;
+	if (b->seis_pending) { GCMB_FAIL(GCMB_E_INVALID_OP, "a seismogram read-back is already in flight: call gcmb_cubic_seismo_end first"); }
+	if (!b->seis_dev) {
+		GCMB_CUDA(cudaMalloc(&b->seis_dev, (size_t) (2 + g.n[2]) * sizeof(double)));
+		GCMB_CUDA(cudaHostAlloc(&b->seis_host, (size_t) (2 + g.n[2]) * sizeof(double), cudaHostAllocDefault));
+		GCMB_CUDA(cudaEventCreateWithFlags(&b->ev_seis, cudaEventDisableTiming));
+	}
+	if (with_detector) {
+		if (!b->detector_mask) { GCMB_FAIL(GCMB_E_INVALID_OP, "detector is not set"); }
+		const long long nf = (long long) g.n[0] * g.n[1];
+		const int blocks = (int) std::max<long long>(1, std::min<long long>(1024, (nf + 255) / 256));
+		double* d_sum = ctx->scratch;
+		long long* d_count = reinterpret_cast<long long*>(ctx->scratch + 1024);
+		{
+			Launch l(ctx, 7);
+			GCMB_LAUNCH(k_detector<R>, blocks, 256, ctx->stream, g, (const R*) layer<R>(b, b->cur), b->detector_mask, b->detector_code, d_sum, d_count);
+		}
+		{
+			Launch l(ctx, 7);
+			GCMB_LAUNCH(k_detector_final, 1, 1, ctx->stream, (const double*) d_sum, (const long long*) d_count, blocks, b->seis_dev);
+		}
+		GCMB_CUDA(cudaGetLastError());
+		if (ctx->comm && ctx->n_ranks > 1) {
+			// slabs of a decomposed body: the detector sums of all ranks, still on the stream (no host round trip)
+			const ncclResult_t r = g_nccl.AllReduce(b->seis_dev, b->seis_dev, 2, ncclDouble, ncclSum, ctx->comm, ctx->stream);
+			if (r != ncclSuccess) { GCMB_FAIL(GCMB_E_NCCL, std::string("ncclAllReduce -> ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error")); }
+		}
+	}
+	if (n_line) {
+		if (line_comp < 0 || line_comp >= g.M) { GCMB_FAIL(GCMB_E_INVALID_ARG, "line component out of range"); }
+		int it[3] = {0, 0, 0};
+		for (int i = 0; i < g.D - 1; i++) { it[i + g.shift] = line_node[i]; }
+		if (it[0] < 0 || it[0] >= g.n[0] || it[1] < 0 || it[1] >= g.n[1]) { GCMB_FAIL(GCMB_E_INVALID_ARG, "line position is outside the body"); }
+		const R* src = layer<R>(b, b->cur) + (long long) line_comp * g.comp + g.index(it[0], it[1], 0);
+		Launch l(ctx, 7);
+		GCMB_LAUNCH(k_line_to_double<R>, (unsigned) ((n_line + 255) / 256), 256, ctx->stream, src, b->seis_dev + 2, n_line);
+		GCMB_CUDA(cudaGetLastError());
+	}
+	wait_halo(ctx);
+	GCMB_CUDA(cudaMemcpyAsync(b->seis_host, b->seis_dev, (size_t) (2 + n_line) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	GCMB_CUDA(cudaEventRecord(b->ev_seis, ctx->stream));
+	b->seis_pending = true;
+	b->seis_detector = with_detector != 0;
+	b->seis_line = n_line;
+	return GCMB_OK;
+}
+
+int gcmb_cubic_seismo_begin(gcmb_body* b, int with_detector, int line_comp, const int* line_node) {
+	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	return GCMB_BY_REAL(b->ctx, seismo_begin<double>(b, with_detector, line_comp, line_node), seismo_begin<float>(b, with_detector, line_comp, line_node));
+}
+
+int gcmb_cubic_seismo_end(gcmb_body* b, double* sum, long long* count, double* line, int n_line) {
+	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	if (!b->seis_pending) { GCMB_FAIL(GCMB_E_INVALID_OP, "no seismogram read-back in flight"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	GCMB_CUDA(cudaEventSynchronize(b->ev_seis));
+	b->seis_pending = false;
+	if (b->seis_detector) {
+		if (sum) { *sum = b->seis_host[0]; }
+		if (count) { *count = (long long) b->seis_host[1]; }
+	}
+	if (line) {
+		if (n_line != b->seis_line) { GCMB_FAIL(GCMB_E_INVALID_ARG, "n_line does not match the line requested by gcmb_cubic_seismo_begin"); }
+		std::memcpy(line, b->seis_host + 2, (size_t) n_line * sizeof(double));
+	}
+	return GCMB_OK;
 }
 
 template<class R>

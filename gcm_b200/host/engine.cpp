@@ -190,7 +190,7 @@ EngineBase::EngineBase(const Task& task, int dimensionality) :
 }
 
 EngineBase::~EngineBase() {
-	try { finishPendingSnapshots(); } catch (...) { }
+	try { finishPendingSeismo(); finishPendingSnapshots(); } catch (...) { }
 	for (void* p : pinned) { gcmb_host_free_pinned(p); }
 	bodies.clear();
 	if (ctx) { gcmb_destroy(ctx); }
@@ -475,11 +475,39 @@ static std::string padded(int v, int digits) {
 	return buf;
 }
 
-/// reference util/snapshot/SliceSnapshotter.hpp:36-82 (file names: Snapshotter.hpp:53-68)
+/// reference util/snapshot/SliceSnapshotter.hpp:36-82 (file names: Snapshotter.hpp:53-68).  The taps are read back
+/// asynchronously: the detector reduction and the z-axis line of this step are enqueued behind the step's kernels and the
+/// time loop goes on; the values are collected, and the step's files written, at the next snapshot or at the end of
+/// run() / advance() -- the per-step host synchronisation of a synchronous read-back cost 1 % of a 1024^3 step.
 void EngineBase::sliceSnapshot(const int step_) {
+	finishPendingSeismo();
+	const int last = D - 1;
+	pendingSeismoStep = step_;
+	pendingSeismoTime = Clock::Time();
+	for (Body& body : bodies) {
+		const Mesh& m = *body.mesh;
+		const bool isDetectorBody = m.id == taskCopy.detector.gridId;
+		// the line runs through the centre of the WHOLE body (SliceSnapshotter.hpp:44-58: sizes / 2): of a decomposed
+		// body only the slab that holds that node has it
+		int lineNode[3] = {0, 0, 0};
+		bool holdsLine = true;
+		for (int i = 0; i < last; i++) {
+			lineNode[i] = m.globalStart[(size_t) i] + m.globalSizes[(size_t) i] / 2 - m.start[(size_t) i];
+			if (lineNode[i] < 0 || lineNode[i] >= m.sizes[(size_t) i]) { holdsLine = false; }
+		}
+		// detector sums of a decomposed body are all-reduced on the stream
+		check(gcmb_cubic_seismo_begin(m.body, isDetectorBody ? 1 : 0, last /* velocity along the last axis */, holdsLine ? lineNode : nullptr));
+	}
+	seismoPending = true;
+}
+
+void EngineBase::finishPendingSeismo() {
+	if (!seismoPending) { return; }
+	seismoPending = false;
 	const Task& task = taskCopy;
+	const int step_ = pendingSeismoStep;
 	// the reference insists on an odd number of processes and lets the middle one write; with slabs the
-	// detector value is reduced over all of them and slab slabCount/2 writes, for any count
+	// detector value is reduced over all of them and the slab that holds the centre line writes, for any count
 	std::string dir = "snapshots";
 	if (!task.globalSettings.outputDirectory.empty()) { dir += "/" + task.globalSettings.outputDirectory; }
 	mkdir("snapshots", 0777);
@@ -493,22 +521,14 @@ void EngineBase::sliceSnapshot(const int step_) {
 		std::vector<double> line((size_t) m.sizes[last]);
 		double sum = 0;
 		long long count = 0;
-		// the line runs through the centre of the WHOLE body (SliceSnapshotter.hpp:44-58: sizes / 2): of a decomposed
-		// body only the slab that holds that node has it
 		int lineNode[3] = {0, 0, 0};
 		bool holdsLine = true;
 		for (int i = 0; i < last; i++) {
 			lineNode[i] = m.globalStart[(size_t) i] + m.globalSizes[(size_t) i] / 2 - m.start[(size_t) i];
 			if (lineNode[i] < 0 || lineNode[i] >= m.sizes[(size_t) i]) { holdsLine = false; }
 		}
-		check(gcmb_cubic_seismo_at(m.body, isDetectorBody ? &sum : nullptr, isDetectorBody ? &count : nullptr,
-				last /* velocity along the last axis */, holdsLine ? line.data() : nullptr, m.sizes[last], lineNode));
-		if (isDetectorBody && slabCount > 1) {
-			double both[2] = {sum, (double) count};
-			check(gcmb_comm_allreduce_sum(ctx, both, 2));
-			sum = both[0];
-			count = (long long) both[1];
-		}
+		check(gcmb_cubic_seismo_end(m.body, isDetectorBody ? &sum : nullptr, isDetectorBody ? &count : nullptr,
+				holdsLine ? line.data() : nullptr, holdsLine ? m.sizes[last] : 0));
 		const bool writer = holdsLine;  // every slab records the seismogram, the one with the centre line writes the files
 		const std::string name = "mesh" + std::to_string(m.id) + "core" + padded(slabRank, 2) + "snap" + padded(step_, 4) + ".txt";
 		if (writer) {
@@ -522,7 +542,7 @@ void EngineBase::sliceSnapshot(const int step_) {
 		if (!isDetectorBody) { continue; }
 		if (count < 1) { throw Exception(GCMB_E_INVALID_ARG, "the detector area holds no node"); }
 		const real value = sum / (real) count;
-		seismo.push_back({Clock::Time(), (float) value});
+		seismo.push_back({pendingSeismoTime, (float) value});
 		if (!writer) { continue; }
 		std::ofstream f(dir + "/detector/" + name);
 		for (const auto& s : seismo) { f << s.first << "\t" << (real) s.second << "\t" << std::endl; }
@@ -601,7 +621,10 @@ void EngineBase::finishPendingSnapshots() {
 	pending.clear();
 }
 
-void EngineBase::finishRun() { finishPendingSnapshots(); }
+void EngineBase::finishRun() {
+	finishPendingSeismo();
+	finishPendingSnapshots();
+}
 
 }  // namespace cubic
 

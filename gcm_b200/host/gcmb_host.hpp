@@ -432,6 +432,11 @@ private:
 	std::vector<PendingSnapshot> pending;
 	std::vector<void*> pinned;   ///< page-locked read-back buffer per body
 	void finishPendingSnapshots();
+	/// seismogram taps of a snapshot step whose read-back is in flight (gcmb_cubic_seismo_begin)
+	bool seismoPending = false;
+	int pendingSeismoStep = 0;
+	real pendingSeismoTime = 0;
+	void finishPendingSeismo();
 	void finishRun() override;
 };
 

@@ -177,6 +177,12 @@ int gcmb_cubic_seismo(gcmb_body* body, double* sum, long long* count, int line_c
 int gcmb_cubic_seismo_at(gcmb_body* body, double* sum, long long* count, int line_comp, double* line,
                          int n_line, const int* line_node);
 
+/* The same taps without stalling the time loop: begin enqueues the detector reduction (over all slabs of a decomposed body:
+ * an all-reduce on the stream), the line gather and ONE asynchronous copy into page-locked memory, and returns at once;
+ * end (sync on that copy only) hands out the values.  line_node: D-1 local indices or NULL for no line; one in flight per body. */
+int gcmb_cubic_seismo_begin(gcmb_body* body, int with_detector, int line_comp, const int* line_node);
+int gcmb_cubic_seismo_end(gcmb_body* body, double* sum, long long* count, double* line, int n_line);
+
 /* ---- multi-GPU: slab decomposition along x (the slowest axis), one process per GPU ------------- */
 /* NCCL communicator shared by all slabs: rank 0 makes the id (128 bytes), the launcher distributes it */
 int gcmb_comm_unique_id(void* id128);
