@@ -38,6 +38,7 @@ typedef StageArgsT<Real> Args;
 
 constexpr int ZT = 128;  // threads per block, all along the contiguous axis
 
+#if GCMB_GROUP == 100
 // block -> node mapping of the one-thread-per-node kernels: blockIdx.x runs along the sweep axis when it is
 // strided, so that blocks scheduled together share their halo planes in L2
 GCMB_DEV bool block_node(const Args& a, int& i0, int& i1, int& i2) {
@@ -57,23 +58,6 @@ dim3 node_blocks(const Args& a) {
 	return dim3(zc, (unsigned) a.g.n[1], nx);
 }
 
-int env_int(const char* name, int dflt) {
-	const char* v = getenv(name);
-	return v ? atoi(v) : dflt;
-}
-
-// cudaFuncSetAttribute once per (kernel, device)
-template<class K>
-void func_attr_once(K kernel, cudaFuncAttribute attr, int value, unsigned long long& done_mask) {
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (!((done_mask >> (dev & 63)) & 1ull)) {
-		cudaFuncSetAttribute(kernel, attr, value);
-		done_mask |= 1ull << (dev & 63);
-	}
-}
-
-#if GCMB_GROUP == 100
 // ------------------------------------------------------------------------------------------------
 // dense eigen-systems
 // ------------------------------------------------------------------------------------------------
@@ -143,6 +127,22 @@ struct Registrar {
 const Registrar g_registrar;
 
 #else
+int env_int(const char* name, int dflt) {
+	const char* v = getenv(name);
+	return v ? atoi(v) : dflt;
+}
+
+// cudaFuncSetAttribute once per (kernel, device)
+template<class K>
+void func_attr_once(K kernel, cudaFuncAttribute attr, int value, unsigned long long& done_mask) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!((done_mask >> (dev & 63)) & 1ull)) {
+		cudaFuncSetAttribute(kernel, attr, value);
+		done_mask |= 1ull << (dev & 63);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // sparse eigen-systems: the patterns of this group
 // ------------------------------------------------------------------------------------------------
