@@ -601,6 +601,19 @@ GCMB_HD Found locateFoot(const StageS& a, int it, V3 shift, long long slot, int&
 	return f;
 }
 
+// Cell location of ONE foot of a vertex, stored in the cache of feet and nothing else: the first of the two passes of a
+// stage whose feet are not cached yet (a new calculation basis every step, the reference's default).  The pass that
+// follows interpolates from the stored cells (cacheMode 2).  Split like this, the location runs without the
+// interpolation's registers (the fused kernel spills 0.9-1.2 KB per thread at 128 registers), and the results are the
+// same bits: the stored cell and barycentric coordinates are exactly what the fused pass would have computed.
+// A location that raised an error is stored as "not cached" and recomputed -- and counted -- by the second pass.
+GCMB_HD void locateFootOnly(const StageS& a, int it, int foot, long long slot) {
+	const double dx = -a.tau * a.footLambda[foot];
+	if (dx == 0) { return; }
+	int err = 0;
+	locateFoot(a, it, vertexDirection(a, it) * dx, slot, err);
+}
+
 // interpolateValuesAround (…InRiemannInvariants.hpp:146-198) for the characteristics `same` of vertex `it`
 // that share the eigenvalue lambda, hence the foot x0 - tau*lambda*direction: the cell location and the
 // interpolation geometry are computed once per distinct foot (the reference recomputes them identically for
