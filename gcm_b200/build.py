@@ -29,7 +29,7 @@ CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall"]
 STAGE_SETS = (0, 1, 2)
 STAGE_GROUPS = (0, 1, 2, 3, 100)   # pattern groups of csrc/patterns.inc; 100 = dense kernels
 CUDA_HEADERS = ["csrc/internal.cuh", "csrc/capi_internal.cuh", "csrc/thread_fns.h", "csrc/march_async.h", "csrc/ztile.h",
-                "csrc/tma_pipe.h", "csrc/patterns.inc", "csrc/simplex_fns.h", "csrc/simplex_capi.inc", "../include/gcm_b200.h"]
+                "csrc/tma_pipe.h", "csrc/triangle_fns.h", "csrc/patterns.inc", "csrc/simplex_fns.h", "csrc/simplex_capi.inc", "../include/gcm_b200.h"]
 HOST_SOURCES = ["host/models.cpp", "host/engine.cpp", "host/task_file.cpp", "host/host_capi.cpp", "host/simplex_mesh.cpp", "host/simplex_engine.cpp", "host/vtk_writer.cpp"]
 HOST_HEADERS = ["host/gcmb_host.hpp", "../include/gcm_b200.h"]
 

@@ -101,6 +101,7 @@ C_ABI = {
                                                          c_double_p, c_int_p]),
     "gcmb_cubic_seismo_at": (ctypes.c_int, [vp, c_double_p, c_ll_p, ctypes.c_int, c_double_p, ctypes.c_int, c_int_p]),
     "gcmb_halo_exchange_bodies": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int]),
+    "gcmb_triangle_interpolate": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
     "gcmb_cubic_seismo_begin": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_int_p]),
     "gcmb_cubic_seismo_end": (ctypes.c_int, [vp, c_double_p, c_ll_p, c_double_p, ctypes.c_int]),
 }
@@ -492,6 +493,19 @@ class SimplexHostEngine(HostEngine):
         c = ctypes.c_int()
         self.lib.hcheck(self.lib.h.gcmb_host_simplex_errors(self.handle, ctypes.byref(c)))
         return c.value
+
+
+def triangle_interpolate(ctx, mode, points, values, gradients, queries):
+    """gcmb_triangle_interpolate: (out [n], status [n])"""
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    queries = np.ascontiguousarray(queries, dtype=np.float64)
+    grads = None if gradients is None else np.ascontiguousarray(gradients, dtype=np.float64)
+    n = len(queries)
+    out = np.zeros(n)
+    status = np.zeros(n, dtype=np.int32)
+    ctx.lib.check(ctx.lib.c.gcmb_triangle_interpolate(ctx.handle, mode, n, dp(points), dp(values), dp(grads), dp(queries), dp(out), ip(status)))
+    return out, status
 
 
 def inm_read(lib, path, scale=1.0):

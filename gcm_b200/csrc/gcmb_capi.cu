@@ -11,6 +11,7 @@
 
 #include "capi_internal.cuh"
 #include "thread_fns.h"
+#include "triangle_fns.h"
 
 using namespace gcmb;
 
@@ -173,6 +174,12 @@ template<class R>
 GCMB_GLOBAL void k_line_to_double(const R* src, double* dst, int n) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) { dst[i] = (double) src[i]; }
+}
+
+GCMB_GLOBAL void k_triangle_interpolate(int mode, long long n, const double* points, const double* values, const double* grads,
+                                        const double* queries, double* out, int* status) {
+	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { tri2::query_thread(mode, i, points, values, grads, queries, out, status); }
 }
 
 // gather of a box of nodes into a dense array [component][box node] (asynchronous snapshots, thin-column checks)
@@ -763,6 +770,43 @@ int gcmb_cubic_download_box_end(gcmb_body* body) {
 	GCMB_CUDA(cudaSetDevice(ctx->device));
 	if (ctx->copy_stream) { GCMB_CUDA(cudaStreamSynchronize(ctx->copy_stream)); }
 	return GCMB_OK;
+}
+
+int gcmb_triangle_interpolate(gcmb_ctx* ctx, int mode, int n, const double* points, const double* values, const double* gradients,
+                              const double* queries, double* out, int* status) {
+	if (!ctx || !points || !values || !queries || !out || !status) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	if (mode < 0 || mode > 4 || n < 1) { GCMB_FAIL(GCMB_E_INVALID_ARG, "mode must be 0..4 and n positive"); }
+	if (mode >= 1 && mode <= 3 && !gradients) { GCMB_FAIL(GCMB_E_INVALID_ARG, "the quadratic interpolants need the gradients"); }
+	GCMB_CUDA(cudaSetDevice(ctx->device));
+	const int np = mode == 4 ? 4 : 3;
+	const size_t nn = (size_t) n;
+	double *d_p = nullptr, *d_v = nullptr, *d_g = nullptr, *d_q = nullptr, *d_o = nullptr;
+	int* d_s = nullptr;
+	int rc = GCMB_OK;
+	auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == GCMB_OK) { set_error(std::string("gcmb_triangle_interpolate: ") + cudaGetErrorString(e)); rc = GCMB_E_CUDA; } };
+	fail(cudaMalloc(&d_p, nn * np * 2 * sizeof(double)));
+	fail(cudaMalloc(&d_v, nn * np * sizeof(double)));
+	fail(cudaMalloc(&d_g, nn * 3 * 2 * sizeof(double)));
+	fail(cudaMalloc(&d_q, nn * 2 * sizeof(double)));
+	fail(cudaMalloc(&d_o, nn * sizeof(double)));
+	fail(cudaMalloc(&d_s, nn * sizeof(int)));
+	if (rc == GCMB_OK) {
+		fail(cudaMemcpyAsync(d_p, points, nn * np * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		fail(cudaMemcpyAsync(d_v, values, nn * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		if (gradients && mode != 4) { fail(cudaMemcpyAsync(d_g, gradients, nn * 3 * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); }
+		fail(cudaMemcpyAsync(d_q, queries, nn * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		{
+			Launch l(ctx, 7);
+			GCMB_LAUNCH(k_triangle_interpolate, (unsigned) ((n + 127) / 128), 128, ctx->stream, mode, (long long) n, (const double*) d_p, (const double*) d_v,
+			            (const double*) d_g, (const double*) d_q, d_o, d_s);
+		}
+		fail(cudaGetLastError());
+		fail(cudaMemcpyAsync(out, d_o, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		fail(cudaMemcpyAsync(status, d_s, nn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		fail(cudaStreamSynchronize(ctx->stream));
+	}
+	cudaFree(d_p); cudaFree(d_v); cudaFree(d_g); cudaFree(d_q); cudaFree(d_o); cudaFree(d_s);
+	return rc;
 }
 
 int gcmb_host_alloc_pinned(size_t bytes, void** out) {

@@ -287,6 +287,14 @@ int gcmb_simplex_contact_correct(gcmb_scontact* contact);
 /* Differentiation::estimateGradient of a host field [n_local][M] -> [n_local][3][M] (test hook). sync */
 int gcmb_simplex_gradient(gcmb_sbody* body, const double* values, double* grad);
 
+/* ---- TriangleInterpolator (util/math/interpolation/TriangleInterpolator.hpp:8-130), the 2-D member of the simplex
+ * interpolators, for n independent scalar queries on the GPU (test hook; the 2-D simplex engine itself is not built).
+ * mode 0: interpolate, linear (points [n][3][2], values [n][3]); 1: interpolate, quadratic (+ gradients [n][3][2]);
+ * 2: minMaxInterpolate; 3: hybridInterpolate; 4: interpolateInOwner (points [n][4][2], values [n][4], no gradients).
+ * queries [n][2] -> out [n]; status[n]: 0, or 1 where the reference throws (degenerate triangle, query outside). sync */
+int gcmb_triangle_interpolate(gcmb_ctx* ctx, int mode, int n, const double* points, const double* values,
+                              const double* gradients, const double* queries, double* out, int* status);
+
 /* ---- checksum of the current layer over real nodes: sum_nodes sum_i (i+1)*u_i (sync) ---------- */
 int gcmb_cubic_checksum(gcmb_body* body, double* out);
 

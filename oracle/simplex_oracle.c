@@ -1291,3 +1291,69 @@ static void nodes_pde_vectors(gcmo_sstage* h, int pass) {
 		if (pass == 0) { h->waves[it] = outers; }
 	}
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * TriangleInterpolator (util/math/interpolation/TriangleInterpolator.hpp:8-130): the 2-D member of the simplex
+ * interpolators.  Pinned bit for bit to the reference's own class (oracle/_ref/gcm_ref_interp, tests/golden/
+ * triangle_interpolator.npz) and to the known answers of src/test/sequence/TestInterpolator.cpp:129-189,267-274.
+ * ------------------------------------------------------------------------------------------------------------------- */
+/* linal::barycentricCoordinates(a, b, c, q) (linal/geometry.hpp:108-116) through solveLinearSystem 2x2
+ * (linal/linearSystems.hpp:60-88) and determinant 2x2 (linal/determinants.hpp:20-35); 0 = "SLE determinant is zero" */
+static int tri2_barycentric(const double* a, const double* b, const double* c, const double* q, double* l) {
+	const double T00 = a[0] - c[0], T01 = b[0] - c[0];
+	const double T10 = a[1] - c[1], T11 = b[1] - c[1];
+	const double r0 = q[0] - c[0], r1 = q[1] - c[1];
+	const double det = T00 * T11 - T01 * T10;
+	if (det == 0) { return 0; }
+	l[0] = (r0 * T11 - T01 * r1) / det;
+	l[1] = (T00 * r1 - r0 * T10) / det;
+	l[2] = 1 - l[0] - l[1];
+	return 1;
+}
+static int tri2_is_interpolation(const double* l) { return l[0] > -1e-9 && l[1] > -1e-9 && l[2] > -1e-9; }   /* :14-18 */
+static double tri2_min(double a, double b) { return b < a ? b : a; }   /* std::min, folded left (linal/functions.hpp:560-598) */
+static double tri2_max(double a, double b) { return a < b ? b : a; }
+
+void gcmo_triangle_interpolate(int mode, int n, const double* points, const double* values, const double* grads,
+                               const double* queries, double* out, int* status) {
+	for (int i = 0; i < n; i++) {
+		const double* q = queries + 2 * (size_t) i;
+		out[i] = 0;
+		status[i] = 1;
+		if (mode == 4) {   /* interpolateInOwner :108-129 */
+			static const int T[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+			const double* c = points + 8 * (size_t) i;
+			const double* v = values + 4 * (size_t) i;
+			for (int k = 0; k < 4; k++) {
+				double l[3];
+				if (!tri2_barycentric(c + 2 * T[k][0], c + 2 * T[k][1], c + 2 * T[k][2], q, l)) { break; }
+				if (tri2_is_interpolation(l)) {
+					out[i] = l[0] * v[T[k][0]] + l[1] * v[T[k][1]] + l[2] * v[T[k][2]];
+					status[i] = 0;
+					break;
+				}
+			}
+			continue;
+		}
+		const double* c = points + 6 * (size_t) i;
+		const double* v = values + 3 * (size_t) i;
+		double l[3];
+		if (!tri2_barycentric(c, c + 2, c + 4, q, l) || !tri2_is_interpolation(l)) { continue; }
+		const double linear = l[0] * v[0] + l[1] * v[1] + l[2] * v[2];   /* :27-36 */
+		status[i] = 0;
+		if (mode == 0) { out[i] = linear; continue; }
+		const double* g = grads + 6 * (size_t) i;
+		double quadratic = 0;   /* :47-58 */
+		for (int k = 0; k < 3; k++) {
+			double dot = g[2 * k] * (q[0] - c[2 * k]);
+			dot += g[2 * k + 1] * (q[1] - c[2 * k + 1]);
+			const double term = l[k] * (v[k] + dot / 2.0);
+			quadratic = k == 0 ? term : quadratic + term;
+		}
+		if (mode == 1) { out[i] = quadratic; continue; }
+		const double lo = tri2_min(tri2_min(v[0], v[1]), v[2]), hi = tri2_max(tri2_max(v[0], v[1]), v[2]);
+		const double limited = tri2_min(tri2_max(quadratic, lo), hi);   /* limiterMinMax, linal/functions.hpp:676-679 */
+		out[i] = mode == 2 ? limited : (quadratic == limited ? quadratic : linear);   /* :69-78, :91-101 */
+	}
+}

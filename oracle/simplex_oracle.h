@@ -123,4 +123,11 @@ void gcmo_simplex_plain_border(int model, int M, int n_border, const int* border
 #ifdef __cplusplus
 }
 #endif
+/* TriangleInterpolator<real> (util/math/interpolation/TriangleInterpolator.hpp:8-130) for n independent queries.
+ * mode 0 interpolate (linear), 1 interpolate (quadratic), 2 minMaxInterpolate, 3 hybridInterpolate: points [n][3][2],
+ * values [n][3], grads [n][3][2] (modes 1-3); mode 4 interpolateInOwner: points [n][4][2], values [n][4].
+ * queries [n][2] -> out [n], status [n] (1 where the reference throws). */
+void gcmo_triangle_interpolate(int mode, int n, const double* points, const double* values, const double* grads,
+                               const double* queries, double* out, int* status);
+
 #endif
