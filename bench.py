@@ -514,16 +514,15 @@ def main():
     barrier(ctxh)
     lib.check(lib.c.gcmb_timer_start(ctxh))
     for _ in range(K):
-        # cubic::Engine::nextTimeStep (engine/cubic/Engine.cpp:92-121) for this task: [halo] stage x; stage y, which also
-        # writes the ghost nodes of the free surface when the library can fuse that (else border fill); stage z
+        # cubic::Engine::nextTimeStep (engine/cubic/Engine.cpp:92-121) for this task: [halo] stage x; stage y; free-surface
+        # ghost fill + stage z
         if world > 1:
             lib.check(lib.c.gcmb_cubic_halo_exchange(body))
         lib.check(lib.c.gcmb_cubic_stage(body, 0, tau))
-        lib.check(lib.c.gcmb_cubic_stage_fill_next_border(body, 1, tau, 2, 3, capi.dp(zeros3), capi.ctypes.byref(fused)))
-        if not fused.value:
-            lib.check(lib.c.gcmb_cubic_border_apply(body, 2, 3, capi.dp(zeros3)))
+        lib.check(lib.c.gcmb_cubic_stage(body, 1, tau))
+        # free surface + stage z in one call: the tile kernel mirrors the ghost nodes inside its shared-memory rows
+        lib.check(lib.c.gcmb_cubic_stage_with_border(body, 2, tau, 3, capi.dp(zeros3), capi.ctypes.byref(fused)))
         fused_steps += fused.value
-        lib.check(lib.c.gcmb_cubic_stage(body, 2, tau))
     ms = capi.ctypes.c_float()
     lib.check(lib.c.gcmb_timer_stop(ctxh, capi.ctypes.byref(ms)))
     barrier(ctxh)
@@ -580,7 +579,7 @@ def main():
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "per_stage_ms": {kernels[a]: stage_ms[a] for a in range(3)},
                 "per_stage_gbs": {kernels[a]: bytes_per_launch / (stage_ms[a] * 1e-3) / 1e9 for a in range(3)},
-                "border_fill_ms": prof_ms[3] / K, "border_fill_fused_into_stage_y": bool(fused_steps == K),
+                "border_fill_ms": prof_ms[3] / K, "border_fill_inside_stage_z": bool(fused_steps == K),
                 "whole_step_frac": value * 3 * BYTES_PER_NODE_STAGE / world / 1e9 / peak}
     traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(traffic_file):

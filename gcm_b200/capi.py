@@ -99,6 +99,7 @@ C_ABI = {
     "gcmb_host_free_pinned": (None, [vp]),
     "gcmb_cubic_stage_fill_next_border": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                                          c_double_p, c_int_p]),
+    "gcmb_cubic_stage_with_border": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_double_p, c_int_p]),
     "gcmb_cubic_seismo_at": (ctypes.c_int, [vp, c_double_p, c_ll_p, ctypes.c_int, c_double_p, ctypes.c_int, c_int_p]),
     "gcmb_halo_exchange_bodies": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int]),
     "gcmb_triangle_interpolate": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
@@ -311,6 +312,13 @@ class CubicBody:
         fused = ctypes.c_int()
         self.lib.check(self.lib.c.gcmb_cubic_stage_fill_next_border(self.handle, direction, tau, next_direction, len(v), dp(v),
                                                                      ctypes.byref(fused)))
+        return bool(fused.value)
+
+    def stage_with_border(self, direction, tau, values):
+        """border fill of `direction` + its stage; returns True when the stage kernel produced the ghost nodes itself"""
+        v = np.array(values, dtype=np.float64)
+        fused = ctypes.c_int()
+        self.lib.check(self.lib.c.gcmb_cubic_stage_with_border(self.handle, direction, tau, len(v), dp(v), ctypes.byref(fused)))
         return bool(fused.value)
 
     def download_box(self, box_min, extent):

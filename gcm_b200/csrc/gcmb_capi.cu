@@ -1013,21 +1013,10 @@ int gcmb_cubic_border_apply(gcmb_body* b, int dir, int n_values, const double* v
 	return GCMB_BY_REAL(b->ctx, border_apply<double>(b, dir, values), border_apply<float>(b, dir, values));
 }
 
-// Can the ghost fill of direction `dir` ride on the marching stage that writes the layer?  Yes when the direction
-// is the contiguous axis, the row length allows whole-warp sector stores, and on every face the LAST registered
-// condition (the one whose values survive, BorderConditions.hpp:81-95) covers the whole face with plain components.
-static bool zfill_possible(gcmb_body* b, int dir, const double* values, ZFaceFill<double>& zf) {
-#ifdef GCMB_EMUL
-	return false;
-#else
-	// Off unless GCMB_FUSED_BORDER=1.  Measured at 1024^3 (profiles/r2_variants.md): the 2 x 9 sector stores per row cost the
-	// marching kernel as much as the separate fill kernel takes (bulk-copy variant: y stage 30.3 -> 32.6 ms against 2.7 ms
-	// of k_border; the LDGSTS variant collapses to 80 ms), because the ghost sector lies in a 128-byte line of its own:
-	// the partial-line write is what costs, whoever issues it.
-	static const bool on = std::getenv("GCMB_FUSED_BORDER") != nullptr && std::getenv("GCMB_FUSED_BORDER")[0] == '1';
-	const bool off = !on;
-	const Geom& g = b->g;
-	if (off || dir != g.D - 1 || g.D < 2 || g.n[2] % 32 != 0 || g.n[2] < 64 || g.bs > 4) { return false; }
+// The ghost fill of the faces across direction `dir` as data for a stage kernel: possible when, on every face, the LAST
+// registered condition (the one whose values survive, BorderConditions.hpp:81-95) covers the whole face with plain
+// components.
+static bool zface_conditions(gcmb_body* b, int dir, const double* values, ZFaceFill<double>& zf) {
 	std::memset(&zf, 0, sizeof zf);
 	int used = 0;
 	for (auto& kv : b->borders) {
@@ -1048,6 +1037,22 @@ static bool zfill_possible(gcmb_body* b, int dir, const double* values, ZFaceFil
 		used += (int) c.q.size();
 	}
 	return zf.on[0] || zf.on[1];
+}
+
+// Can the ghost fill of direction `dir` ride on the marching stage that WRITES the layer (whole-warp sector stores)?
+static bool zfill_possible(gcmb_body* b, int dir, const double* values, ZFaceFill<double>& zf) {
+#ifdef GCMB_EMUL
+	return false;
+#else
+	// Off unless GCMB_FUSED_BORDER=1.  Measured at 1024^3 (profiles/r2_variants.md): the 2 x 9 sector stores per row cost the
+	// marching kernel as much as the separate fill kernel takes (bulk-copy variant: y stage 30.3 -> 32.6 ms against 2.7 ms
+	// of k_border; the LDGSTS variant collapses to 80 ms), because the ghost sector lies in a 128-byte line of its own:
+	// the partial-line write is what costs, whoever issues it.  The contiguous-axis stage fills the ghosts of the rows it
+	// has staged in shared memory instead (gcmb_cubic_stage_with_border), which costs no HBM traffic at all.
+	static const bool on = std::getenv("GCMB_FUSED_BORDER") != nullptr && std::getenv("GCMB_FUSED_BORDER")[0] == '1';
+	const Geom& g = b->g;
+	if (!on || dir != g.D - 1 || g.D < 2 || g.n[2] % 32 != 0 || g.n[2] < 64 || g.bs > 4) { return false; }
+	return zface_conditions(b, dir, values, zf);
 #endif
 }
 
@@ -1111,8 +1116,9 @@ static int stage_impl(gcmb_body* b, int dir, double tau) {
 	if (!launch) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "no stage kernel for this PDE size / arithmetic type in this build"); }
 	if (b->zfill_armed) {
 		b->zfill_armed = false;
-		// only the marching kernels of the specialised patterns carry the fused ghost fill
-		if (a.axis != 1 || b->kernel_name[dir].compare(0, 7, "sparse:") != 0) { GCMB_FAIL(GCMB_E_INVALID_OP, "fused border fill is not available for this stage"); }
+		// only the kernels of the specialised patterns carry a ghost fill: the row-writing marching kernel (axis 1) for
+		// the NEXT stage's faces, the tile kernel of the contiguous axis (axis 2) for its own
+		if (a.axis == 0 || b->kernel_name[dir].compare(0, 7, "sparse:") != 0) { GCMB_FAIL(GCMB_E_INVALID_OP, "fused border fill is not available for this stage"); }
 		a.zfill = 1;
 		for (int s = 0; s < 2; s++) {
 			a.zf.on[s] = b->zfill.on[s];
@@ -1180,6 +1186,36 @@ int gcmb_cubic_stage_fill_next_border(gcmb_body* b, int dir, double tau, int nex
 			b->zfill_armed = true;
 			*fused = 1;
 		}
+	}
+	return gcmb_cubic_stage(b, dir, tau);
+}
+
+int gcmb_cubic_stage_with_border(gcmb_body* b, int dir, double tau, int n_values, const double* values, int* fused) {
+	if (!b || !fused) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	if (dir < 0 || dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "direction out of range"); }
+	if (!b->tables) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
+	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	int rc = border_values_check(b, dir, n_values, values);
+	if (rc) { return rc; }
+	*fused = 0;
+	// GCMB_ZTILE_BORDER=0: always the separate fill kernel (measurements)
+	static const bool off = std::getenv("GCMB_ZTILE_BORDER") != nullptr && std::getenv("GCMB_ZTILE_BORDER")[0] == '0';
+	ZFaceFill<double> zf;
+	if (!off && dir == b->g.D - 1 && b->g.n[2] > b->g.bs && zface_conditions(b, dir, values, zf)) {
+		if (!(b->tables_tau == tau)) {  // the tables must be current before the launcher is known
+			rc = GCMB_BY_REAL(b->ctx, build_tables<double>(b, tau), build_tables<float>(b, tau));
+			if (rc) { return rc; }
+		}
+		pick_launcher(b, dir);
+		if (b->kernel_name[dir].compare(0, 7, "sparse:") == 0) {
+			b->zfill = zf;
+			b->zfill_armed = true;
+			*fused = 1;
+		}
+	}
+	if (!*fused) {
+		rc = GCMB_BY_REAL(b->ctx, border_apply<double>(b, dir, values), border_apply<float>(b, dir, values));
+		if (rc) { return rc; }
 	}
 	return gcmb_cubic_stage(b, dir, tau);
 }

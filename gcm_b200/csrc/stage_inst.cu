@@ -247,6 +247,12 @@ GCMB_GLOBAL void GCMB_BOUNDS(ZTILE) k_stage_ztile(const Args a, int rows) {
 		GCMB_BLOCK_THREADS(tid) { ztile_issue<Real, P, BS, ZLEAD>(a, sm, (it + ZLEAD) % ZRING, tid, i0, r + ZLEAD, z0, r1); }
 		cp_async_wait<ZLEAD>();
 		__syncthreads();
+		if (a.zfill && (z0 == 0 || z0 + ZTILE + BS > a.g.n[2])) {  // (the same for all threads of the block)
+			GCMB_BLOCK_THREADS(tid) {
+				if (tid < BS) { zface_mirror_tile<Real, PatternSets<P>::interp(), P::M, BS, ZROW>(a, sm.v[it % ZRING], ZHALO, z0, ZTILE, tid); }
+			}
+			__syncthreads();
+		}
 		GCMB_BLOCK_THREADS(tid) { ztile_compute<Real, P, BS, K0RT, ZLEAD>(a, sm, tab, it % ZRING, tid, i0, r, z0); }
 		__syncthreads();
 	}

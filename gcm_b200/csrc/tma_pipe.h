@@ -21,6 +21,7 @@ GCMB_DEV unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_
 GCMB_DEV void mbar_init(unsigned long long* bar, unsigned count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
+GCMB_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 GCMB_DEV void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 GCMB_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -209,10 +210,12 @@ __global__ void __launch_bounds__(NWARP * 32) k_stage_ztile_tma(const StageArgsT
 	const int i2 = zb + tid;
 	const bool live = i2 < g.n[2];
 	const bool issuer = zl == 0;
+	const int seg = zb + gi * ZW;  // first node of the group's part of the row
+	static_assert(GW == 1 || NG == 1, "the in-tile ghost fill synchronises a warp or the whole block");
 
 	auto issue = [&](int it) {
 		const int slot = it % NSTAGE;
-		const long long row = g.index(i0, r0 + it, zb + gi * ZW);
+		const long long row = g.index(i0, r0 + it, seg);
 		constexpr unsigned wide = (ZW + 2 * HALO) * (unsigned) sizeof(R);
 		constexpr unsigned bytes = (unsigned) popcount_u(IC | CC) * wide + ZW;
 		unsigned long long* bar = &sm.full[gi][slot];
@@ -235,6 +238,15 @@ __global__ void __launch_bounds__(NWARP * 32) k_stage_ztile_tma(const StageArgsT
 			issue(nit);
 		}
 		mbar_wait(&sm.full[gi][slot], (unsigned) ((it / NSTAGE) & 1));
+		if (a.zfill && (seg == 0 || seg + ZW + BS > g.n[2])) {  // (the same for all threads of the group)
+			// border condition of the z faces: ghost nodes of the staged row from its own inner nodes (ztile.h)
+			if (zl < BS) {
+				zface_mirror_tile<R, IC, M, BS, ZW + 2 * HALO>(a, sm.v[gi][slot], HALO, seg, ZW, zl);
+				// generic-proxy writes into a buffer that the next bulk copy (async proxy) of this slot overwrites
+				fence_proxy_async_smem();
+			}
+			if (GW == 1) { __syncwarp(); } else { __syncthreads(); }
+		}
 		if (live) {
 			const long long idx = g.index(i0, r0 + it, i2);
 			const R* tb = tab + (int) sm.id[gi][slot][zl] * Packed<P, BS, K0RT>::SIZE;

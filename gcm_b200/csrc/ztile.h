@@ -59,6 +59,38 @@ GCMB_HD void ztile_issue(const StageArgsT<R>& a, ZTileSmem<R, P::M, LEAD>& sm, i
 	cp_async_commit();
 }
 
+// In-tile ghost fill of the faces across the contiguous axis (a.zfill on a contiguous-axis stage): the ghost nodes of the
+// staged row are overwritten IN SHARED MEMORY by the mirrored inner values of the same row, so the border condition
+// costs no pass over the faces in HBM at all (reference engine/cubic/BorderConditions.hpp:97-114 for conditions over
+// the whole face with plain component quantities; the ghost nodes of these faces in HBM are then never read).
+// `row` = the staged components, `base` = index of node z = `seg` in a staged row, `width` = nodes of the row that
+// this tile owns, t = 0..BS-1 (one caller per ghost layer).  Reads real nodes only, writes ghost nodes only.  The
+// right face's ghost nodes can also lie in the halo of the tile BEFORE the one that holds the last node (when that
+// one holds fewer than BS nodes): every tile whose nodes read them fills them.
+template<class R, unsigned IC, int M, int BS, int ROWW>
+GCMB_HD void zface_mirror_tile(const StageArgsT<R>& a, R (*row)[ROWW], int base, int seg, int width, int t) {
+	const int d = t + 1;
+	if (a.zf.on[0] && seg == 0) {
+#pragma unroll
+		for (int j = 0; j < M; j++) {
+			if (!((IC >> j) & 1u)) { continue; }
+			R x = row[j][base + d];
+			if ((a.zf.set[0] >> j) & 1u) { x = -x + a.zf.add[0][j]; }
+			row[j][base - d] = x;
+		}
+	}
+	const int last = a.g.n[2] - 1 - seg;
+	if (a.zf.on[1] && last >= 0 && last + d < width + BS) {
+#pragma unroll
+		for (int j = 0; j < M; j++) {
+			if (!((IC >> j) & 1u)) { continue; }
+			R x = row[j][base + last - d];
+			if ((a.zf.set[1] >> j) & 1u) { x = -x + a.zf.add[1][j]; }
+			row[j][base + last + d] = x;
+		}
+	}
+}
+
 // phase B, one thread: one node of the tile from shared memory
 template<class R, class P, int BS, bool K0RT, int LEAD>
 GCMB_HD void ztile_compute(const StageArgsT<R>& a, const ZTileSmem<R, P::M, LEAD>& sm, const R* tabs, int slot, int tid, int i0, int i1, int z0) {

@@ -159,6 +159,16 @@ int gcmb_cubic_stage(gcmb_body* body, int dir, double tau);
 int gcmb_cubic_stage_fill_next_border(gcmb_body* body, int dir, double tau, int next_dir, int n_values,
                                       const double* values, int* fused);
 
+/* gcmb_cubic_border_apply(body, dir, n_values, values) followed by gcmb_cubic_stage(body, dir, tau) -- the reference's
+ * order for one direction of one body (cubic/Engine.cpp:94-111).  When dir is the contiguous (last) axis, on each of its
+ * faces the last registered condition covers the whole face with plain components, and the stage has a specialised
+ * tile kernel, the ghost nodes are produced inside the stage kernel, in the shared-memory copy of every row, from that
+ * row's own inner nodes (*fused = 1): no pass over the faces in HBM; the ghost nodes of these two faces in HBM are then
+ * NOT refreshed (nothing reads them: the other directions' stages touch real nodes only).  Otherwise (*fused = 0) the two
+ * calls are made one after the other.  The caller must have no contact of direction `dir` on this body (a contact copy
+ * comes between the two in the reference and overwrites part of the ghost nodes). */
+int gcmb_cubic_stage_with_border(gcmb_body* body, int dir, double tau, int n_values, const double* values, int* fused);
+
 /* ---- Maxwell viscosity (rheology/ode/Ode.hpp:28-38): sigma *= decay[table of the node];
  * decay = exp(-tau/tau0) is evaluated by the caller with the host libm, like the reference ------- */
 int gcmb_cubic_ode_maxwell(gcmb_body* body, const double* decay_per_table);

@@ -14,6 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 VARIANTS = {
     # name: (environment, real_bytes, fma, courant)
     "default": ({}, 8, False, 0.9),
+    "separate_z_border_kernel": ({"GCMB_ZTILE_BORDER": "0"}, 8, False, 0.9),
+    "fp32_default": ({}, 4, False, 0.9),
+    "fp32_separate_z_border_kernel": ({"GCMB_ZTILE_BORDER": "0"}, 4, False, 0.9),
     "ldgsts_separate_border": ({"GCMB_STAGE_IMPL": "2"}, 8, False, 0.9),
     "ldgsts_fused_border": ({"GCMB_STAGE_IMPL": "2", "GCMB_FUSED_BORDER": "1"}, 8, False, 0.9),
     "tma_warp_pipes": ({"GCMB_STAGE_IMPL": "3", "GCMB_FUSED_BORDER": "1"}, 8, False, 0.9),

@@ -152,6 +152,54 @@ def fused_border_check(lib, seed=11):
     return fused_cases
 
 
+def tile_border_check(lib, real_bytes=8, seed=12):
+    """gcmb_cubic_stage_with_border == gcmb_cubic_border_apply + gcmb_cubic_stage on all real nodes, bit for bit, at row lengths
+    around the tile and warp boundaries (ghost nodes in the halo of the tile before the last one, one-sided conditions,
+    several conditions per face, rows shorter than a warp); returns the number of cases that took the in-tile path"""
+    rng = np.random.default_rng(seed)
+    ctx = capi.Context(lib, real_bytes=real_bytes)
+    fused_cases = 0
+    el = (5, 7, 8)
+    cases = ((3, (3, 5, 33), "elastic", 2, [(el, 3)]), (3, (3, 4, 34), "elastic", 2, [(el, 3)]), (3, (3, 5, 65), "elastic", 3, [(el, 3)]),
+             (3, (2, 3, 257), "elastic", 2, [(el, 3)]), (3, (2, 3, 258), "acoustic", 2, [((3,), 3)]), (3, (2, 3, 257), "elastic", 1, [((2,), 3)]),
+             (3, (2, 3, 256), "elastic", 2, [(el, 2)]), (3, (3, 3, 255), "elastic", 3, [((0, 1, 2), 1), (el, 2)]),
+             (2, (5, 513), "elastic", 2, [((3, 4), 1)]), (2, (5, 64), "elastic", 2, [((3, 4), 3), ((0, 1), 3)]),
+             (1, (1000,), "acoustic", 1, [((1,), 3)]), (1, (31,), "acoustic", 2, [((0,), 3)]),
+             (3, (4, 6, 3), "elastic", 2, [(el, 3)]), (3, (3, 3, 2), "elastic", 2, [(el, 3)]), (3, (2, 40, 96), "elastic", 2, [(el, 3)]))
+    for (D, sizes, model, bs, conds) in cases:
+        mats = [("isotropic", rng.uniform(1, 5), rng.uniform(1, 5), rng.uniform(0.5, 3) if model == "elastic" else 0.0) for _ in range(3)]
+        ms = [capi.host_matrices(lib, model, D, m) for m in mats]
+        U, U1, Lm = (np.ascontiguousarray(np.stack([m[i] for m in ms])) for i in range(3))
+        M = U.shape[-1]
+        h = rng.uniform(0.5, 1.5, D)
+        full = tuple(s + 2 * bs for s in sizes)
+        state = rng.normal(size=full + (M,))
+        table = rng.integers(0, 3, size=sizes).astype(np.uint8)
+        tau = 0.4 * h.min() / np.abs(Lm).max()
+        last = D - 1
+        results = []
+        for one_call in (True, False):
+            body = capi.CubicBody(ctx, D, M, sizes, [0] * D, h, bs)
+            body.set_materials(U, U1, Lm, table)
+            values = []
+            for i, (codes, sides) in enumerate(conds):
+                body.border_set_area(i, last, ("infinite",), list(codes), sides=sides)
+                values += [0.25 * (i + 1) + 0.1 * c for c in codes]
+            body.upload(state, with_ghosts=True)
+            if one_call:
+                took = body.stage_with_border(last, tau, values)
+                assert took == (sizes[-1] > bs), (D, sizes, model, bs, body.kernel_name(last))
+                fused_cases += int(took)
+            else:
+                body.border_apply(last, values)
+                body.stage(last, tau)
+            results.append(body.download())
+            body.close()
+        assert np.array_equal(results[0], results[1]), (D, sizes, model, bs, np.abs(results[0] - results[1]).max())
+    ctx.close()
+    return fused_cases
+
+
 def read_vtk_appended(path):
     """arrays of a VTK XML file written with one raw appended block (gcm_b200/host/vtk_writer.cpp)"""
     import re

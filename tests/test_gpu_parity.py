@@ -110,6 +110,32 @@ def test_fused_border_fill_equals_separate_fill():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("impl", ["0", "2", "3"])
+def test_border_inside_contiguous_stage_equals_separate_fill(impl):
+    """gcmb_cubic_stage_with_border: the tile kernels of the contiguous axis (LDGSTS and bulk-copy pipelines, fp64 and fp32)
+    mirror the ghost nodes inside their shared-memory rows; real nodes equal border fill + stage bit for bit"""
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]\n"
+            "import gcm_b200\n"
+            "from helpers import tile_border_check\n"
+            "lib = gcm_b200.library()\n"
+            "assert tile_border_check(lib, 8) == 14 and tile_border_check(lib, 4) == 14\n" % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GCMB_STAGE_IMPL=impl), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_separate_border_fill_still_matches_reference():
+    """GCMB_ZTILE_BORDER=0: the sector-wide fill kernel of the z faces (the path bodies with a contact across z take)"""
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]\n"
+            "import gcm_b200\n"
+            "from helpers import compare_with_golden\n"
+            "from scenarios import SCENARIOS\n"
+            "lib = gcm_b200.library()\n"
+            "for n in ('elastic3d_layers', 'acoustic3d_free', 'elastic3d_layers_courant1', 'elastic3d_layers_bs3_courant25', 'acoustic1d'):\n"
+            "    compare_with_golden(lib, n, SCENARIOS[n])[0].close()\n" % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GCMB_ZTILE_BORDER="0"), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 @pytest.mark.parametrize("name", sorted(SCENARIOS))
 def test_fma_kernels_within_stated_tolerance(lib, name):
     """gcmb_set_fma: the stage kernels compiled WITH contraction agree with the reference to north_star's 1e-12 (relative to

@@ -113,6 +113,14 @@ def test_kernel_variants_agree(name, env):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("real_bytes", [8, 4])
+def test_border_inside_contiguous_stage_equals_separate_fill(lib, real_bytes):
+    """gcmb_cubic_stage_with_border == border fill + stage on the real nodes, bit for bit (row lengths around the tile and warp
+    boundaries, one-sided and repeated conditions)"""
+    from helpers import tile_border_check
+    assert tile_border_check(lib, real_bytes) == 14
+
+
 def test_adhesion_contact_equals_single_body(lib):
     """test/sequence/TestEngine.cpp:27-87 through our engine: two glued bodies == one body, bitwise."""
     two = run_engine(lib, SCENARIOS["adhesion2d_two"])
