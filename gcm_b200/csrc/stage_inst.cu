@@ -270,9 +270,10 @@ void launch_march(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes
 	constexpr int MINB = MarchBlocks<P, BS, K0RT>::value;
 #ifndef GCMB_EMUL
 	if (impl == 3) {
-		// the bulk-copy marching kernels are compiled for at most 5 blocks per SM (96 registers, no spills): the
-		// 80-register build of the fp64 3-D elastic patterns spilled and gave wrong values in the lanes that do not issue
-		// the copies (gpurun_out of round 2, scripts/gpu_runs/r2_debug_tma.py); at 5 blocks every variant is bit-exact
+		// the bulk-copy marching kernels are compiled for at most 5 blocks per SM (96 registers, no spills): 6 or 7 blocks
+		// are no faster (29.7-30.5 ms per launch at 1024^3 at 5, 6 and 7 blocks, profiles/r2_variants.md).  (The wrong values
+		// the first 80-register builds gave came from the uninitialised register window, see tma_pipe.h; with that fixed
+		// every occupancy is bit-exact.)
 		constexpr int TMINB = MINB > 5 ? 5 : MINB;
 		// GCMB_TMA_MARCH: 0 = a pipeline per warp (256-byte copies, no coupling between warps);
 		// 1 = one ring per block, refilled by lane 0 of warp 0; 2 = one ring per block, producer warp

@@ -127,6 +127,15 @@ __global__ void __launch_bounds__(MARCH_ZT + (PRODUCER ? 32 : 0), MINB) k_stage_
 	}
 	R w[M][W];
 	R cv[M];
+	// The warm-up iterations rotate the window before it is full: it must hold DEFINED values.  With the window left
+	// uninitialised ptxas kept its oldest plane in UNIFORM registers whenever the register cap was tight (R2UR of a
+	// per-lane value, then DADD/FSEL with the UR operand: every lane computed with lane 0's plane) -- the wrong results
+	// of the 80-register builds in profiles/r2_debug_tma.log; found in the SASS, profiles/r2_variants.md "Call 12-15".
+#pragma unroll
+	for (int j = 0; j < M; j++) {
+#pragma unroll
+		for (int o = 0; o < W; o++) { w[j][o] = R(0); }
+	}
 	const long long idx_first = a.axis == 0 ? g.index(s_begin, perp, i2) : g.index(perp, s_begin, i2);
 	for (int it = 0; it < n_it; it++) {
 		const int slot = it % NSTAGE;

@@ -16,6 +16,24 @@ VARIANTS = {
     "default": ({}, 8, False, 0.9),
     "separate_z_border_kernel": ({"GCMB_ZTILE_BORDER": "0"}, 8, False, 0.9),
     "fp32_default": ({}, 4, False, 0.9),
+    # experiment builds (scripts/exp_build.py): bulk-copy marching kernels, blocks per SM x window layout
+    "exp_tma6_slot_plane": ({"GCMB_EXP_LIB_DIR": "b6", "GCMB_STAGE_IMPL": "3", "GCMB_TMA_WINDOW": "1"}, 8, False, 0.9),
+    "exp_tma6_register_window": ({"GCMB_EXP_LIB_DIR": "b6", "GCMB_STAGE_IMPL": "3", "GCMB_TMA_WINDOW": "0"}, 8, False, 0.9),
+    "exp_ldgsts6_register_window": ({"GCMB_EXP_LIB_DIR": "b6", "GCMB_STAGE_IMPL": "2"}, 8, False, 0.9),
+    "exp_tma7_slot_plane": ({"GCMB_EXP_LIB_DIR": "b7", "GCMB_STAGE_IMPL": "3", "GCMB_TMA_WINDOW": "1"}, 8, False, 0.9),
+    "exp_tma7_register_window": ({"GCMB_EXP_LIB_DIR": "b7", "GCMB_STAGE_IMPL": "3", "GCMB_TMA_WINDOW": "0"}, 8, False, 0.9),
+    "exp_ldgsts7_slot_plane": ({"GCMB_EXP_LIB_DIR": "b7s", "GCMB_STAGE_IMPL": "2"}, 8, False, 0.9),
+    "exp_tma6_zt256": ({"GCMB_EXP_LIB_DIR": "zt256", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma6_order1": ({"GCMB_EXP_LIB_DIR": "ord1", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma6_order1_seg128": ({"GCMB_EXP_LIB_DIR": "ord1", "GCMB_STAGE_IMPL": "3", "GCMB_MARCH_SEG": "128"}, 8, False, 0.9),
+    "exp_tma6_order1_seg1024": ({"GCMB_EXP_LIB_DIR": "ord1", "GCMB_STAGE_IMPL": "3", "GCMB_MARCH_SEG": "1024"}, 8, False, 0.9),
+    "exp_tma6_order1_zt256": ({"GCMB_EXP_LIB_DIR": "ord1zt256", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma6_order1_zt256_seg1024": ({"GCMB_EXP_LIB_DIR": "ord1zt256", "GCMB_STAGE_IMPL": "3", "GCMB_MARCH_SEG": "1024"}, 8, False, 0.9),
+    "exp_ldgsts_base": ({"GCMB_EXP_LIB_DIR": "base"}, 8, False, 0.9),
+    "exp_ldgsts_regwin_idring": ({"GCMB_EXP_LIB_DIR": "regwin_idring"}, 8, False, 0.9),
+    "exp_ldgsts_slot_idring": ({"GCMB_EXP_LIB_DIR": "slot_idring"}, 8, False, 0.9),
+    "exp_ldgsts_slot_idring7": ({"GCMB_EXP_LIB_DIR": "slot_idring7"}, 8, False, 0.9),
+    "exp_tma5_slot_plane": ({"GCMB_EXP_LIB_DIR": "b5", "GCMB_STAGE_IMPL": "3", "GCMB_TMA_WINDOW": "1"}, 8, False, 0.9),
     "fp32_separate_z_border_kernel": ({"GCMB_ZTILE_BORDER": "0"}, 4, False, 0.9),
     "ldgsts_separate_border": ({"GCMB_STAGE_IMPL": "2"}, 8, False, 0.9),
     "ldgsts_fused_border": ({"GCMB_STAGE_IMPL": "2", "GCMB_FUSED_BORDER": "1"}, 8, False, 0.9),
@@ -42,7 +60,12 @@ def child(args):
     import gcm_b200
     from gcm_b200 import capi
     import bench
-    lib = gcm_b200.library()
+    if os.environ.get("GCMB_EXP_LIB_DIR"):   # an experiment build of scripts/exp_build.py (loaded INSTEAD of the product's: same soname)
+        d = os.path.join(ROOT, "exp_libs", os.environ["GCMB_EXP_LIB_DIR"])
+        lib = capi.Library(os.path.join(d, "libgcm_b200.so"), os.path.join(d, "libgcm_b200_host.so"))
+        gcm_b200._LIB = lib
+    else:
+        lib = gcm_b200.library()
     n = args.size
     text = bench.task_text(n, n, n, steps=10 ** 6, detector=False).replace("courant 0.9", "courant %r" % args.courant)
     os.chdir("/tmp")

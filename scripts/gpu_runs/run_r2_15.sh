@@ -1,0 +1,12 @@
+#!/bin/bash
+# round 2, GPU call 15: cp.async marching kernels: material ids through the ring instead of a global load per thread; window layouts
+cd "$GRAFT_REPO_ROOT" || exit 1
+timeout 1500 python scripts/gpu_runs/r2_variants.py --only exp_ldgsts_base,exp_ldgsts_regwin_idring,exp_ldgsts_slot_idring,exp_ldgsts_slot_idring7 > gpurun_out/r2_15_variants.jsonl 2>&1
+python - <<'PY'
+import json
+for line in open("gpurun_out/r2_15_variants.jsonl"):
+    if not line.startswith("VARIANT "): print(line[:300]); continue
+    d = json.loads(line[8:])
+    if "error" in d: print(d["variant"], "ERROR", d["error"][-300:]); continue
+    print("%-32s %.2f ms/step  x %.2f y %.2f z %.2f  whole %.3f  checksum %.6f" % (d["variant"], d["ms_per_step"], *d["stage_ms"], d["whole_step_frac"], d["checksum"]))
+PY
