@@ -265,6 +265,13 @@ struct gcmb_body {
 	// ghost fill of the z faces handed to the next marching stage (gcmb_cubic_stage_fill_next_border)
 	bool zfill_armed = false;
 	ZFaceFill<double> zfill;
+	// border condition of the contiguous axis' faces that gcmb_cubic_border_apply has DEFERRED to the stage of that
+	// direction (the tile kernel produces the ghost nodes in shared memory); anything else that could see or overwrite
+	// these ghost nodes first makes the fill kernel run after all (flush_deferred_border)
+	bool border_deferred = false;
+	int border_deferred_dir = 0;
+	std::vector<double> border_deferred_values;
+	bool border_in_tile = false;          // the last gcmb_cubic_stage consumed a deferred condition inside its kernel
 	void* gather_dev = nullptr;           // staging of asynchronous box read-backs
 	size_t gather_bytes = 0;
 	// asynchronous seismogram taps (gcmb_cubic_seismo_begin/end): {sum, count, line...} on the device and in pinned memory
@@ -598,6 +605,9 @@ long long gcmb_launch_count(gcmb_ctx* ctx) { return ctx->launches; }
 size_t gcmb_device_bytes(gcmb_ctx* ctx) { return ctx->bytes; }
 
 // ---- body ------------------------------------------------------------------------------------
+static int flush_deferred_border(gcmb_body* b);
+#define GCMB_FLUSH_BORDER(body) do { const int rc_flush_ = flush_deferred_border(body); if (rc_flush_) { return rc_flush_; } } while (0)
+
 int gcmb_cubic_body_create(gcmb_ctx* ctx, int D, int M, const int* sizes, const int* start,
                            const double* h, int border_size, gcmb_body** out) {
 	if (!ctx || !sizes || !start || !h || !out) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
@@ -672,6 +682,7 @@ static int transfer(gcmb_body* b, void* host, int with_ghosts, bool to_device) {
 	gcmb_ctx* ctx = b->ctx;
 	const Geom& g = b->g;
 	GCMB_CUDA(cudaSetDevice(ctx->device));
+	GCMB_FLUSH_BORDER(b);
 	const int e0 = with_ghosts ? g.n[0] + 2 * g.g[0] : g.n[0];
 	const long long e12 = (long long) (with_ghosts ? g.n[1] + 2 * g.g[1] : g.n[1]) * (with_ghosts ? g.n[2] + 2 * g.g[2] : g.n[2]);
 	const long long per_plane = e12 * g.M;  // reals per slice of internal axis 0
@@ -707,12 +718,14 @@ static int transfer(gcmb_body* b, void* host, int with_ghosts, bool to_device) {
 
 int gcmb_cubic_upload_state(gcmb_body* body, const void* aos_pde, int with_ghosts) {
 	if (!body || !aos_pde) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	GCMB_FLUSH_BORDER(body);
 	return GCMB_BY_REAL(body->ctx, transfer<double>(body, const_cast<void*>(aos_pde), with_ghosts, true),
 	                    transfer<float>(body, const_cast<void*>(aos_pde), with_ghosts, true));
 }
 
 int gcmb_cubic_download_state(gcmb_body* body, void* aos_pde, int with_ghosts) {
 	if (!body || !aos_pde) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	if (with_ghosts) { GCMB_FLUSH_BORDER(body); }
 	return GCMB_BY_REAL(body->ctx, transfer<double>(body, aos_pde, with_ghosts, false), transfer<float>(body, aos_pde, with_ghosts, false));
 }
 
@@ -761,6 +774,7 @@ static int box_begin(gcmb_body* b, const int* box_min, const int* extent, void* 
 
 int gcmb_cubic_download_box_begin(gcmb_body* body, const int* box_min, const int* extent, void* host) {
 	if (!body || !box_min || !extent || !host) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
+	GCMB_FLUSH_BORDER(body);
 	return GCMB_BY_REAL(body->ctx, box_begin<double>(body, box_min, extent, host), box_begin<float>(body, box_min, extent, host));
 }
 
@@ -901,12 +915,14 @@ int gcmb_cubic_add_vector_in_area(gcmb_body* b, const double* vector_M, int area
 	if (!b || !vector_M) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
 	if (area_kind < 0 || area_kind > 3) { GCMB_FAIL(GCMB_E_INVALID_ARG, "unknown area kind"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	GCMB_FLUSH_BORDER(b);
 	return GCMB_BY_REAL(b->ctx, add_vector<double>(b, vector_M, area_kind, params), add_vector<float>(b, vector_M, area_kind, params));
 }
 
 // ---- borders ---------------------------------------------------------------------------------
 static int border_register(gcmb_body* b, int cond, int dir, int n_q, const int* q_codes, BorderCond** out) {
 	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
+	GCMB_FLUSH_BORDER(b);  // (a deferred fill belongs to the conditions registered when it was requested)
 	if (dir < 0 || dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "direction out of range"); }
 	if (n_q < 0 || n_q > MAXM + 1 || (n_q > 0 && !q_codes)) { GCMB_FAIL(GCMB_E_INVALID_ARG, "bad quantity list"); }
 	for (int i = 0; i < n_q; i++) {
@@ -1005,11 +1021,37 @@ static int border_apply(gcmb_body* b, int dir, const double* values) {
 	return GCMB_OK;
 }
 
+// The deferred border condition, if any, applied by the fill kernel now.  Called by every entry point that reads or
+// writes ghost nodes of the current layer, or that computes a stage the deferred fill does not ride on.
+static int flush_deferred_border(gcmb_body* b) {
+	if (!b->border_deferred) { return GCMB_OK; }
+	b->border_deferred = false;
+	const double* values = b->border_deferred_values.data();
+	return GCMB_BY_REAL(b->ctx, border_apply<double>(b, b->border_deferred_dir, values), border_apply<float>(b, b->border_deferred_dir, values));
+}
+
+static bool zface_conditions(gcmb_body* b, int dir, const double* values, ZFaceFill<double>& zf);
+
 int gcmb_cubic_border_apply(gcmb_body* b, int dir, int n_values, const double* values) {
 	if (!b) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null body"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
-	const int rc = border_values_check(b, dir, n_values, values);
+	int rc = border_values_check(b, dir, n_values, values);
 	if (rc) { return rc; }
+	rc = flush_deferred_border(b);
+	if (rc) { return rc; }
+	// Faces across the contiguous axis, whole-face conditions on plain components: nothing is launched here.  The stage of
+	// this direction -- the next call on this body in the reference's time step (cubic/Engine.cpp:94-111), unless a
+	// contact copy comes between -- mirrors the ghost nodes inside the shared-memory rows it stages anyway, so the
+	// condition costs no pass over the faces in HBM (1.8 ms of an 83 ms step at 1024^3, profiles/r2_variants.md call 11).
+	// GCMB_ZTILE_BORDER=0: always the fill kernel (measurements).
+	static const bool off = std::getenv("GCMB_ZTILE_BORDER") != nullptr && std::getenv("GCMB_ZTILE_BORDER")[0] == '0';
+	ZFaceFill<double> zf;
+	if (!off && dir == b->g.D - 1 && b->g.n[2] > b->g.bs && b->tables && zface_conditions(b, dir, values, zf)) {
+		b->border_deferred = true;
+		b->border_deferred_dir = dir;
+		b->border_deferred_values.assign(values, values + n_values);
+		return GCMB_OK;
+	}
 	return GCMB_BY_REAL(b->ctx, border_apply<double>(b, dir, values), border_apply<float>(b, dir, values));
 }
 
@@ -1088,6 +1130,9 @@ int gcmb_cubic_contact_apply(gcmb_body* a, const gcmb_body* b, const int* boxA_m
 	if (a->ctx != b->ctx) { GCMB_FAIL(GCMB_E_INVALID_ARG, "bodies belong to different contexts"); }
 	if (a->g.D != b->g.D || a->g.M != b->g.M || a->g.bs != b->g.bs) { GCMB_FAIL(GCMB_E_INVALID_ARG, "bodies are not compatible"); }
 	GCMB_CUDA(cudaSetDevice(a->ctx->device));
+	// the reference's order is border conditions, contact copies, stage: a deferred border fill must not come after the copy
+	GCMB_FLUSH_BORDER(a);
+	GCMB_FLUSH_BORDER(const_cast<gcmb_body*>(b));
 	return GCMB_BY_REAL(a->ctx, contact_apply<double>(a, b, boxA_min, boxB_min, extent), contact_apply<float>(a, b, boxA_min, boxB_min, extent));
 }
 
@@ -1162,6 +1207,28 @@ int gcmb_cubic_stage(gcmb_body* b, int dir, double tau) {
 	if (dir < 0 || dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "direction out of range"); }
 	if (!b->tables) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	b->border_in_tile = false;
+	if (b->border_deferred) {
+		bool in_tile = false;
+		ZFaceFill<double> zf;
+		if (dir == b->border_deferred_dir && !b->zfill_armed && zface_conditions(b, dir, b->border_deferred_values.data(), zf)) {
+			if (!(b->tables_tau == tau)) {  // the tables must be current before the launcher is known
+				const int rc = GCMB_BY_REAL(b->ctx, build_tables<double>(b, tau), build_tables<float>(b, tau));
+				if (rc) { return rc; }
+			}
+			pick_launcher(b, dir);
+			in_tile = b->kernel_name[dir].compare(0, 7, "sparse:") == 0;
+		}
+		if (in_tile) {
+			b->border_deferred = false;
+			b->border_in_tile = true;
+			b->zfill = zf;
+			b->zfill_armed = true;
+		} else {
+			const int rc = flush_deferred_border(b);
+			if (rc) { return rc; }
+		}
+	}
 	return GCMB_BY_REAL(b->ctx, stage_impl<double>(b, dir, tau), stage_impl<float>(b, dir, tau));
 }
 
@@ -1194,30 +1261,12 @@ int gcmb_cubic_stage_with_border(gcmb_body* b, int dir, double tau, int n_values
 	if (!b || !fused) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
 	if (dir < 0 || dir >= b->g.D) { GCMB_FAIL(GCMB_E_INVALID_ARG, "direction out of range"); }
 	if (!b->tables) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
-	GCMB_CUDA(cudaSetDevice(b->ctx->device));
-	int rc = border_values_check(b, dir, n_values, values);
-	if (rc) { return rc; }
 	*fused = 0;
-	// GCMB_ZTILE_BORDER=0: always the separate fill kernel (measurements)
-	static const bool off = std::getenv("GCMB_ZTILE_BORDER") != nullptr && std::getenv("GCMB_ZTILE_BORDER")[0] == '0';
-	ZFaceFill<double> zf;
-	if (!off && dir == b->g.D - 1 && b->g.n[2] > b->g.bs && zface_conditions(b, dir, values, zf)) {
-		if (!(b->tables_tau == tau)) {  // the tables must be current before the launcher is known
-			rc = GCMB_BY_REAL(b->ctx, build_tables<double>(b, tau), build_tables<float>(b, tau));
-			if (rc) { return rc; }
-		}
-		pick_launcher(b, dir);
-		if (b->kernel_name[dir].compare(0, 7, "sparse:") == 0) {
-			b->zfill = zf;
-			b->zfill_armed = true;
-			*fused = 1;
-		}
-	}
-	if (!*fused) {
-		rc = GCMB_BY_REAL(b->ctx, border_apply<double>(b, dir, values), border_apply<float>(b, dir, values));
-		if (rc) { return rc; }
-	}
-	return gcmb_cubic_stage(b, dir, tau);
+	int rc = gcmb_cubic_border_apply(b, dir, n_values, values);
+	if (rc) { return rc; }
+	rc = gcmb_cubic_stage(b, dir, tau);
+	*fused = (rc == GCMB_OK && b->border_in_tile) ? 1 : 0;
+	return rc;
 }
 
 const char* gcmb_cubic_stage_kernel_name(gcmb_body* b, int dir) {
@@ -1244,6 +1293,7 @@ int gcmb_cubic_ode_maxwell(gcmb_body* b, const double* decay_per_table) {
 	if (!b || !decay_per_table) { GCMB_FAIL(GCMB_E_INVALID_ARG, "null argument"); }
 	if (b->n_tables < 1) { GCMB_FAIL(GCMB_E_INVALID_OP, "materials are not set"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	GCMB_FLUSH_BORDER(b);
 	return GCMB_BY_REAL(b->ctx, ode_maxwell<double>(b, decay_per_table), ode_maxwell<float>(b, decay_per_table));
 }
 
@@ -1480,6 +1530,7 @@ int gcmb_halo_exchange_bodies(gcmb_body* const* bodies, int n) {
 		if (bodies[i]->g.g[0] == 0) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "slab decomposition needs the x axis to be the slowest internal axis (3-D grids)"); }
 	}
 	GCMB_CUDA(cudaSetDevice(ctx->device));
+	for (int i = 0; i < n; i++) { GCMB_FLUSH_BORDER(bodies[i]); }
 	// on a stream of its own, so that the interior of the following x stage (which reads no ghost plane) overlaps it
 	static const bool overlap = !std::getenv("GCMB_NO_HALO_OVERLAP");
 	if (overlap && !ctx->comm_stream) {
@@ -1554,6 +1605,7 @@ static int halo_host(gcmb_body* b, int side, void* host, bool get) {
 	const Geom& g = b->g;
 	if (g.g[0] == 0) { GCMB_FAIL(GCMB_E_UNSUPPORTED, "slab decomposition needs the x axis to be the slowest internal axis (3-D grids)"); }
 	GCMB_CUDA(cudaSetDevice(b->ctx->device));
+	GCMB_FLUSH_BORDER(b);
 	wait_halo(b->ctx);
 	const size_t rb = (size_t) b->ctx->real_bytes;
 	const size_t count = (size_t) g.g[0] * (size_t) g.plane;

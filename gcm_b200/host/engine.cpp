@@ -402,26 +402,14 @@ void EngineBase::nextTimeStep() {
 		}
 		return values;
 	};
-	// a body without contacts across the last direction gets that direction's border condition from the stage call
-	// itself (the tile kernel mirrors the ghost nodes inside its shared-memory rows); with such a contact the reference's
-	// order border -> contact copy -> stage (cubic/Engine.cpp:94-111) needs the three separate calls
-	auto borderWithStage = [&](const Body& body, int stage) {
-		if (stage != D - 1 || body.borders.empty()) { return false; }
-		for (const Contact& c : body.contacts) {
-			if (c.direction == stage) { return false; }
-		}
-		return true;
-	};
 	for (int stage = 0; stage < D; stage++) {
 		for (Body& body : bodies) {
 			if (body.borderFilledByStage) {  // the previous stage's kernel has written these ghost nodes already
 				body.borderFilledByStage = false;
-				body.borderDone = true;
 				continue;
 			}
-			body.borderDone = false;
-			if (borderWithStage(body, stage)) { continue; }
-			body.borderDone = true;
+			// (for the faces across the last direction the library defers the fill to that direction's stage kernel, which
+			// mirrors the ghost nodes in its shared-memory rows -- unless a contact copy below touches the body first)
 			const std::vector<double> values = borderValues(body, stage);
 			if (!values.empty() || !body.borders.empty()) {
 				check(gcmb_cubic_border_apply(body.mesh->body, stage, (int) values.size(), values.data()));
@@ -450,10 +438,6 @@ void EngineBase::nextTimeStep() {
 				check(gcmb_cubic_stage_fill_next_border(body.mesh->body, stage, Clock::TimeStep(), D - 1,
 						(int) values.size(), values.data(), &fused));
 				body.borderFilledByStage = fused != 0;
-			} else if (!body.borderDone) {
-				const std::vector<double> values = borderValues(body, stage);
-				int fused = 0;
-				check(gcmb_cubic_stage_with_border(body.mesh->body, stage, Clock::TimeStep(), (int) values.size(), values.data(), &fused));
 			} else {
 				check(gcmb_cubic_stage(body.mesh->body, stage, Clock::TimeStep()));
 			}

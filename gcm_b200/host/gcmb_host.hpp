@@ -407,7 +407,6 @@ private:
 		std::vector<Border> borders;
 		std::vector<Odes::T> odes;
 		bool borderFilledByStage = false;  ///< the last direction's ghost nodes were written by the previous stage kernel
-		bool borderDone = false;  ///< this stage's border condition has been applied (else the stage call applies it)
 	};
 	int D;
 	gcmb_ctx* ctx = nullptr;

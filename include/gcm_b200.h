@@ -138,7 +138,15 @@ int gcmb_cubic_border_set_area(gcmb_body* body, int cond, int dir, int sides, in
                                const double* params, int n_q, const int* q_codes);
 /* apply all registered conditions of direction `dir`; values: for every registered condition of that
  * direction in order, its n_q border values b_q(t_n) evaluated by the caller (time dependencies are
- * host functors in the reference); n_values = total count, checked. */
+ * host functors in the reference); n_values = total count, checked.
+ * For the faces across the LAST direction (the contiguous axis), when the surviving condition of each face covers
+ * the whole face with plain components, no kernel runs here: the fill is deferred to gcmb_cubic_stage of that
+ * direction, whose tile kernel mirrors the ghost nodes inside the shared-memory copy of every row (no pass over the
+ * faces in HBM).  Every other call that reads or writes ghost nodes of the body (contact copy, halo exchange, transfers
+ * with ghosts, another border/stage call ...) first runs the deferred fill as a kernel, so the reference's order
+ * border conditions -> contact copies -> stage (cubic/Engine.cpp:94-111) holds in every case.  What differs from the
+ * reference: when the stage consumed the condition, these two faces' ghost nodes in HBM keep their old values (the
+ * other directions' stages read real nodes only; nothing observes them). */
 int gcmb_cubic_border_apply(gcmb_body* body, int dir, int n_values, const double* values);
 
 /* ---- contact = ghost copy from the neighbour body (engine/cubic/ContactConditions.hpp:56-68) --- */
@@ -160,13 +168,9 @@ int gcmb_cubic_stage_fill_next_border(gcmb_body* body, int dir, double tau, int 
                                       const double* values, int* fused);
 
 /* gcmb_cubic_border_apply(body, dir, n_values, values) followed by gcmb_cubic_stage(body, dir, tau) -- the reference's
- * order for one direction of one body (cubic/Engine.cpp:94-111).  When dir is the contiguous (last) axis, on each of its
- * faces the last registered condition covers the whole face with plain components, and the stage has a specialised
- * tile kernel, the ghost nodes are produced inside the stage kernel, in the shared-memory copy of every row, from that
- * row's own inner nodes (*fused = 1): no pass over the faces in HBM; the ghost nodes of these two faces in HBM are then
- * NOT refreshed (nothing reads them: the other directions' stages touch real nodes only).  Otherwise (*fused = 0) the two
- * calls are made one after the other.  The caller must have no contact of direction `dir` on this body (a contact copy
- * comes between the two in the reference and overwrites part of the ghost nodes). */
+ * order for one direction of a body without contacts across it (cubic/Engine.cpp:94-111) -- in one call;
+ * *fused = 1 when the stage kernel produced the ghost nodes itself (see gcmb_cubic_border_apply), 0 when the fill
+ * kernel ran (masked faces, pressure-trace quantities, dense kernels, rows not longer than the border size). */
 int gcmb_cubic_stage_with_border(gcmb_body* body, int dir, double tau, int n_values, const double* values, int* fused);
 
 /* ---- Maxwell viscosity (rheology/ode/Ode.hpp:28-38): sigma *= decay[table of the node];

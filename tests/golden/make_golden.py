@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/gcm_ref, built from
 /root/reference by oracle/Makefile) on every task in tests/scenarios.py.  Run in the build container
-(where /root/reference exists):   python tests/golden/make_golden.py
+(where /root/reference exists):   python tests/golden/make_golden.py [scenario ...]
 The fixtures travel to the GPU box; /root/reference does not."""
 import os
 import sys
@@ -18,7 +18,10 @@ from scenarios import SCENARIOS  # noqa: E402
 def main():
     oh.build_oracle()
     here = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]   # optional: names of the scenarios to (re)generate
     for name, text in SCENARIOS.items():
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             out = oh.run_reference(text, tmp, matrices=True)
         arrays = {"task": np.array(text)}

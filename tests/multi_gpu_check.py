@@ -66,7 +66,7 @@ def check_fixtures(lib, rank, world, local, verbose=True):
     """decomposed runs against the reference fixtures; returns {"bitwise": bool, "cases": [...]} (rank 0 decides)"""
     cases, ok = [], True
     for name in ("elastic3d_layers", "elastic3d_ortho", "acoustic3d_free", "ortho3d_contact", "maxwell3d", "ortho3d_rotated_plies",
-                 "elastic3d_layers_courant1", "ortho3d_contact_courant1"):
+                 "elastic3d_layers_courant1", "ortho3d_contact_courant1", "elastic3d_contact_z"):
         nx = int(SCENARIOS[name].split("sizes")[1].split()[0])
         bs = int(SCENARIOS[name].split("border_size")[1].split()[0])
         if nx // world < bs:  # a slab must hold at least border_size planes (CubicGrid.hpp:186-199)

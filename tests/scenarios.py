@@ -110,6 +110,28 @@ border 1 1 sphere 0.3 0.5 1.0 0.5 Vy sin 1.0 5.0
 """
 
 
+def elastic3d_contact_z(n=14, steps=5, courant=0.9, bs=2):
+    # two bodies glued across the LAST direction, both with a free-surface condition on their z faces: the reference applies
+    # the border condition to the whole face first and the contact copy then overwrites the ghost nodes of the glued face
+    # (cubic/Engine.cpp:94-107) -- the order a deferred border fill has to keep
+    h = _h(n)
+    half = n // 2
+    return f"""
+dimensionality 3
+courant {courant}
+border_size {bs}
+h {h} {h} {h}
+steps {steps}
+body 0 elastic isotropic sizes {n} {n} {half} start 0 0 0
+body 1 elastic isotropic sizes {n} {n} {half} start 0 0 {half}
+material body 0 isotropic 1 2 0.8
+material body 1 isotropic 3 5 1.5
+initial quantity PRESSURE 1 sphere 0.3 0.5 0.5 0.35
+border 0 2 infinite Sxz const 0 Syz const 0 Szz const 0
+border 1 2 infinite Sxz const 0 Syz const 0 Szz sin 1.0 4.0
+"""
+
+
 def ortho3d_rotated_plies(n=14, steps=4):
     # BASELINE config 4 with the plies turned +-45 degrees about y (the stacking axis): rotated orthotropic materials
     # in two glued bodies, one of them with a Maxwell relaxation time
@@ -298,6 +320,7 @@ SCENARIOS = {
     "elastic3d_ortho_rotated": elastic3d_ortho_rotated(),
     "ortho3d_contact": ortho3d_contact(),
     "ortho3d_rotated_plies": ortho3d_rotated_plies(),
+    "elastic3d_contact_z": elastic3d_contact_z(),
     "elastic2d_pwave": elastic2d_pwave(),
     "elastic2d_courant45": elastic2d_courant45(),
     "elastic2d_ortho": elastic2d_ortho(),
