@@ -151,6 +151,10 @@ struct Tri {
 	const uint8_t* state;   // [nLocal] 0 inner, 1 border, 2 contact, 3 multicontact
 	const int* locOff;      // [nLocal+1] the body's own cells around a local vertex, ascending cell id ...
 	const int4* locABC;     // ... as {cell, a, b, c}: the other three vertices in the order findCrossedIncidentCell takes them
+	// direction masks (k_s_dir_masks): bit k of dirMask[lv * DIR_BUCKETS + bucket] = entry locOff[lv] + k may contain a ray
+	// from the vertex whose direction falls into the bucket; every entry whose bit is clear is PROVEN not to contain it
+	const unsigned long long* dirMask = nullptr;  // or null
+	const float* dirMinShift = nullptr;  // [nLocal] shortest ray the masks hold for; < 0: no masks for this vertex (> 64 cells)
 
 	GCMB_HD V3 point(int g) const { return {xyz[3 * (long long) g], xyz[3 * (long long) g + 1], xyz[3 * (long long) g + 2]}; }
 	GCMB_HD V3 localPoint(int l) const { return point(globalOf[l]); }
@@ -211,12 +215,113 @@ GCMB_HD bool solidAngleContainsExact0(V3 a, V3 b, V3 c, V3 d, V3 q, int& err) {
 	return x0 <= 1 + 0.0 && x1 >= -0.0 && x2 >= -0.0 && l3 >= -0.0;
 }
 
+// ---- direction buckets ------------------------------------------------------------------------------------------------
+// The sphere of ray directions around a vertex is cut into 6 x DIR_N x DIR_N buckets (faces of a cube, a regular grid on
+// each).  For every (vertex, bucket) a bit mask over the vertex's incident cells says which cells' solid angles can meet
+// the bucket at all; findCrossedIncidentCell's loop -- "the first incident cell, in the table's order, whose solid angle
+// contains the ray" -- then runs its exact test only on the cells of the mask, in the same order.  A cell is left out only
+// when one face plane of its solid angle has ALL FOUR corner rays of the (padded) bucket strictly on its outer side by a
+// relative margin of DIR_MARGIN: then every ray of the bucket has a barycentric coordinate below -DIR_MARGIN * |row| * |ray|
+// in that cell, ten orders of magnitude beyond what rounding in the exact fp64 test (relative 1e-15 of |row| * (cell size +
+// |ray|)) could turn into "inside" -- for rays no shorter than dirMinShift = DIR_MIN_RAY x the largest edge around the vertex.
+// So the answer, cell for cell, is the reference's.  (The locate protocol of 428 544 queries and all engine fixtures stay
+// bit-identical; profiles/r2_simplex_dir_masks.md has the timings.)
+constexpr int DIR_N = 4;
+constexpr int DIR_BUCKETS = 6 * DIR_N * DIR_N;
+constexpr double DIR_PAD = 1e-3;      // the buckets overlap by this much (in face coordinates): rounding of dirBucket, ties
+constexpr double DIR_MARGIN = 1e-4;
+constexpr double DIR_MIN_RAY = 1e-6;
+
+GCMB_HD int dirBucket(V3 d) {
+	const double ax = fabs(d.x), ay = fabs(d.y), az = fabs(d.z);
+	const int m = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+	const double dm = m == 0 ? d.x : (m == 1 ? d.y : d.z);
+	const double da = m == 0 ? d.y : d.x;                       // the other two axes in ascending order
+	const double db = m == 2 ? d.y : d.z;
+	const double inv = 1.0 / fabs(dm);
+	int iu = (int) ((da * inv + 1.0) * (0.5 * DIR_N));
+	int iv = (int) ((db * inv + 1.0) * (0.5 * DIR_N));
+	iu = iu < 0 ? 0 : (iu > DIR_N - 1 ? DIR_N - 1 : iu);
+	iv = iv < 0 ? 0 : (iv > DIR_N - 1 ? DIR_N - 1 : iv);
+	return ((2 * m + (dm < 0 ? 1 : 0)) * DIR_N + iu) * DIR_N + iv;
+}
+
+// corner ray `c` (0..3) of a bucket, padded
+GCMB_HD V3 dirBucketCorner(int bucket, int c) {
+	const int iv = bucket % DIR_N, iu = (bucket / DIR_N) % DIR_N, face = bucket / (DIR_N * DIR_N);
+	const int m = face / 2;
+	const double sgn = (face & 1) ? -1.0 : 1.0;
+	const double u = (c & 1) ? (iu + 1) * (2.0 / DIR_N) - 1.0 + DIR_PAD : iu * (2.0 / DIR_N) - 1.0 - DIR_PAD;
+	const double v = (c & 2) ? (iv + 1) * (2.0 / DIR_N) - 1.0 + DIR_PAD : iv * (2.0 / DIR_N) - 1.0 - DIR_PAD;
+	return m == 0 ? V3{sgn, u, v} : (m == 1 ? V3{u, sgn, v} : V3{u, v, sgn});
+}
+
+// one thread per (local vertex, bucket)
+GCMB_HD void dirMaskThread(const Tri& t, int lv, int bucket, unsigned long long* masks, float* minShift) {
+	const V3 apex = t.localPoint(lv);
+	const int begin = t.locOff[lv], end = t.locOff[lv + 1];
+	if (end - begin > 64) {
+		if (bucket == 0) { minShift[lv] = -1.0f; }
+		masks[(long long) lv * DIR_BUCKETS + bucket] = ~0ull;
+		return;
+	}
+	V3 corner[4];
+	double cl[4];
+	for (int c = 0; c < 4; c++) { corner[c] = dirBucketCorner(bucket, c); cl[c] = length(corner[c]); }
+	unsigned long long mask = 0;
+	double hmax = 0;
+	for (int i = begin; i < end; i++) {
+		const int4 e = t.locABC[i];
+		const V3 pa = t.point(e.y), pb = t.point(e.z), pc = t.point(e.w);
+		const V3 e1 = pa - apex, e2 = pb - apex, e3 = pc - apex;
+		const V3 n[3] = {cross(e2, e3), cross(e3, e1), cross(e1, e2)};  // rows of the inverse of [e1 e2 e3], times det
+		const double det = dot(e1, n[0]);
+		const double edges[6] = {length(e1), length(e2), length(e3), length(pa - pb), length(pb - pc), length(pc - pa)};
+		for (int k = 0; k < 6; k++) { hmax = edges[k] > hmax ? edges[k] : hmax; }
+		bool out = false;
+		if (det != 0 && det == det && det - det == 0) {   // (finite and non-zero; a degenerate cell is always tested exactly)
+			const double sgn = det > 0 ? 1.0 : -1.0;
+			for (int r = 0; r < 3 && !out; r++) {
+				const double nl = length(n[r]);
+				bool all = true;
+				for (int c = 0; c < 4; c++) { all = all && (sgn * dot(n[r], corner[c]) < -DIR_MARGIN * nl * cl[c]); }
+				out = all;
+			}
+		}
+		if (!out) { mask |= 1ull << (i - begin); }
+	}
+	masks[(long long) lv * DIR_BUCKETS + bucket] = mask;
+	if (bucket == 0) { minShift[lv] = (float) (DIR_MIN_RAY * hmax) * 1.0001f; }
+}
+
+GCMB_HD int lowestBit(unsigned long long m) {
+#if defined(__CUDA_ARCH__)
+	return __ffsll((long long) m) - 1;
+#else
+	return __builtin_ffsll((long long) m) - 1;
+#endif
+}
+
 // Cgal3DTriangulation::findCrossedIncidentCell over the body's own cells around the vertex (table built at
 // body creation); returns the table entry {cell, a, b, c} or cell = -2.  The loop is software-pipelined: the
 // entry two cells ahead and the points of the next cell are in flight while the current cell is tested.
 GCMB_HD int4 crossedIncidentCell(const Tri& t, int lv, V3 query, double eps, int& err) {
 	const V3 apex = t.localPoint(lv);
 	const int begin = t.locOff[lv], end = t.locOff[lv + 1];
+	if (eps == 0 && t.dirMask != nullptr) {
+		const V3 ray = query - apex;
+		const double ms = (double) t.dirMinShift[lv];
+		if (ms >= 0 && dot(ray, ray) > ms * ms) {
+			// the same loop over the cells the ray can lie in at all (see "direction buckets" above)
+			unsigned long long m = t.dirMask[(long long) lv * DIR_BUCKETS + dirBucket(ray)];
+			while (m) {
+				const int4 e = t.locABC[begin + lowestBit(m)];
+				m &= m - 1;
+				if (solidAngleContainsExact0(apex, t.point(e.y), t.point(e.z), t.point(e.w), query, err)) { return e; }
+			}
+			return make_int4(-2, -1, -1, -1);
+		}
+	}
 	int4 e = t.locABC[begin];
 	int4 e1 = begin + 1 < end ? t.locABC[begin + 1] : e;
 	V3 pa = t.point(e.y), pb = t.point(e.z), pc = t.point(e.w);
