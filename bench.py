@@ -432,6 +432,11 @@ def main():
     if args.impl == "reference":
         return main_reference(args)
 
+    # the contract is ONE line on stdout: NCCL writes its banner ("NCCL version ...") and warnings there too, so its
+    # log goes to a file per process unless the user asked for a log of their own
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "WARN", "VERSION") and "NCCL_DEBUG_FILE" not in os.environ:
+        os.environ["NCCL_DEBUG_FILE"] = "/tmp/gcmb_bench_nccl.%h.%p.log"
+
     import numpy as np
     import torch
     import gcm_b200
