@@ -8,7 +8,7 @@ BASELINE.json (configs[2]: 1024^3 per GPU, border size 2, free surface on top, s
 One "step" = one full time step (all three splitting stages + border fill [+ halo exchange]) of every node.
 One JSON line is printed by rank 0; see DESIGN.md "Measurement" for how every field is obtained.  Besides the headline the
 line carries, each measured through the same engine loop: `config4` (BASELINE configs[3], at every N), and at N = 1 `config2`
-(configs[1]), `fp32`, `fma`, `courant1` / `courant09_same_size`, `simplex` (new random basis every step, the reference's
+(configs[1]), `fp32`, `fma`, `courant1` / `courant09_same_size`, `small_grids`, `simplex` (new random basis every step, the reference's
 default) / `simplex_fixed_basis`, `rotated_orthotropic`, `e2e_host_state_every_step`; at N > 1 `parity_check`: fixtures of the
 unmodified reference reproduced bit for bit by the decomposed engine in this very run.
 """
@@ -710,6 +710,17 @@ def main():
         run_section("courant09_same_size", lambda: section(
             lib, task_text(m1, m1, m1, steps=10 ** 6, detector=True), m1 ** 3, 432, 10, 3,
             what="the headline medium at %d^3, Courant 0.9 (the comparison for courant1)" % m1, **common))
+        # sizes the reference's own tasks have (its tests and launcher run 10^4 - 10^7 nodes): the launches are shaped for
+        # about four waves of blocks whatever the size (stage_inst.cu launch_march / launch_ztile)
+        def small_grids():
+            out = {}
+            for m in (64, 128, 256):
+                r = section(lib, task_text(m, m, m, steps=10 ** 6, detector=True), m ** 3, 432, 100, 10,
+                            what="the headline medium at %d^3" % m, **common)
+                out["%d^3" % m] = {"value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
+                                   "of_hbm_roofline": r["roofline"]["frac"], "e2e": r["e2e"]["value"]}
+            return out
+        run_section("small_grids", small_grids)
     if rank == 0:
         if world == 1 and not args.no_simplex and not args.no_sections:
             # secondary measurement (never the headline): the tetrahedral path of SURVEY.md §8 a13-a21

@@ -262,10 +262,20 @@ GCMB_GLOBAL void GCMB_BOUNDS(ZTILE) k_stage_ztile(const Args a, int rows) {
 // launch of the marching kernel of a pattern whose direction runs along internal axis 0 or 1
 template<class P, int BS, bool K0RT, bool ZF>
 void launch_march(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes) {
-	static const int seg_env = env_int("GCMB_MARCH_SEG", 256);
+	// planes per block along the sweep axis.  GCMB_MARCH_SEG: > 0 fixed, 0 the whole axis, unset: 256 (the best at 1024^3,
+	// profiles/r1_variants.md), shortened on small grids until the launch has about four waves of blocks -- a 128^3 body
+	// with 256-plane segments is 128 blocks for 888 slots and ran at a quarter of the roofline (profiles/r2_small_grids.md);
+	// every segment re-reads 2 * border_size planes (from L2 at these sizes), hence not below 16
+	static const int seg_env = env_int("GCMB_MARCH_SEG", -1);
 	const int len = a.axis == 0 ? a.x_end - a.x_begin : a.g.n[1];
-	const int seg = seg_env < 1 ? len : seg_env;
 	const int perp = a.axis == 0 ? a.g.n[1] : a.x_end - a.x_begin;
+	int seg = seg_env == 0 ? len : seg_env;
+	if (seg_env < 0) {
+		const long long columns = (long long) ((a.g.n[2] + ZT - 1) / ZT) * perp;   // blocks per segment
+		const long long want = 4LL * 148 * 6;
+		const long long fit = (long long) len * columns / want;                     // segment length that gives `want` blocks
+		seg = (int) (fit > 256 ? 256 : (fit < 16 ? 16 : fit));
+	}
 	const dim3 grid((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZT - 1) / ZT), (unsigned) perp);
 	constexpr int MINB = MarchBlocks<P, BS, K0RT>::value;
 #ifndef GCMB_EMUL
@@ -315,7 +325,13 @@ template<class P, int BS, bool K0RT>
 void launch_ztile(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes) {
 	static const int rows_env = env_int("GCMB_ZTILE_ROWS", 0);
 	// rows per block: 32 for the LDGSTS tiles (round 1), 16 for the bulk-copy tiles (25.0 ms against 25.9 at 32 and 27.4 at 64)
-	const int rows = rows_env > 0 ? rows_env : (impl == 3 ? 16 : 32);
+	int rows = rows_env > 0 ? rows_env : (impl == 3 ? 16 : 32);
+	if (rows_env <= 0) {
+		// small grids: fewer rows per block until the launch has about four waves of blocks (rows are independent: no re-reads)
+		const long long tiles = (long long) ((a.g.n[2] + 255) / 256) * (a.x_end - a.x_begin);
+		const long long fit = tiles * a.g.n[1] / (4LL * 148 * 3);
+		if (fit < rows) { rows = (int) (fit < 4 ? 4 : fit); }
+	}
 #ifndef GCMB_EMUL
 	if (impl == 3) {
 		// GCMB_TMA_ZTILE: 0 = a pipeline per warp; 1 = one ring per block of 8 warps
