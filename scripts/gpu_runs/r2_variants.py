@@ -33,6 +33,7 @@ VARIANTS = {
     "exp_ldgsts_regwin_idring": ({"GCMB_EXP_LIB_DIR": "regwin_idring"}, 8, False, 0.9),
     "exp_ldgsts_slot_idring": ({"GCMB_EXP_LIB_DIR": "slot_idring"}, 8, False, 0.9),
     "exp_ldgsts_slot_idring7": ({"GCMB_EXP_LIB_DIR": "slot_idring7"}, 8, False, 0.9),
+    "exp_ldgsts_cp16": ({"GCMB_EXP_LIB_DIR": "cp16"}, 8, False, 0.9),
     "exp_tma5_slot_plane": ({"GCMB_EXP_LIB_DIR": "b5", "GCMB_STAGE_IMPL": "3", "GCMB_TMA_WINDOW": "1"}, 8, False, 0.9),
     "fp32_separate_z_border_kernel": ({"GCMB_ZTILE_BORDER": "0"}, 4, False, 0.9),
     "ldgsts_separate_border": ({"GCMB_STAGE_IMPL": "2"}, 8, False, 0.9),
