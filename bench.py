@@ -432,10 +432,11 @@ def main():
     if args.impl == "reference":
         return main_reference(args)
 
-    # the contract is ONE line on stdout: NCCL writes its banner ("NCCL version ...") and warnings there too, so its
-    # log goes to a file per process unless the user asked for a log of their own
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "WARN", "VERSION") and "NCCL_DEBUG_FILE" not in os.environ:
-        os.environ["NCCL_DEBUG_FILE"] = "/tmp/gcmb_bench_nccl.%h.%p.log"
+    # the contract is ONE line on stdout, but libraries write there too (NCCL's "NCCL version ..." banner is a plain printf):
+    # file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -735,7 +736,8 @@ def main():
                 line["rotated_orthotropic"] = rotated_section(lib, local, 5, 3, not args.no_cpu_baseline)
             except Exception as e:
                 line["rotated_orthotropic"] = {"error": "%s: %s" % (type(e).__name__, e)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
