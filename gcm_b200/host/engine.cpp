@@ -512,10 +512,13 @@ void EngineBase::finishPendingSeismo() {
 	// detector value is reduced over all of them and the slab that holds the centre line writes, for any count
 	std::string dir = "snapshots";
 	if (!task.globalSettings.outputDirectory.empty()) { dir += "/" + task.globalSettings.outputDirectory; }
-	mkdir("snapshots", 0777);
-	mkdir(dir.c_str(), 0777);
-	mkdir((dir + "/zaxis").c_str(), 0777);
-	mkdir((dir + "/detector").c_str(), 0777);
+	if (!seismoDirsMade) {
+		mkdir("snapshots", 0777);
+		mkdir(dir.c_str(), 0777);
+		mkdir((dir + "/zaxis").c_str(), 0777);
+		mkdir((dir + "/detector").c_str(), 0777);
+		seismoDirsMade = true;
+	}
 	for (Body& body : bodies) {
 		const Mesh& m = *body.mesh;
 		const int last = D - 1;
@@ -538,7 +541,7 @@ void EngineBase::finishPendingSeismo() {
 			Mesh::Iterator it = {{lineNode[0], lineNode[1], lineNode[2]}};
 			for (int k = 0; k < m.sizes[last]; k++) {
 				it[(size_t) last] = k;
-				f << m.coords(it)[(size_t) last] << "\t" << line[(size_t) k] << "\t" << std::endl;
+				f << m.coords(it)[(size_t) last] << "\t" << line[(size_t) k] << "\t\n";   // (one write per file, not per line)
 			}
 		}
 		if (!isDetectorBody) { continue; }
@@ -547,7 +550,7 @@ void EngineBase::finishPendingSeismo() {
 		seismo.push_back({pendingSeismoTime, (float) value});
 		if (!writer) { continue; }
 		std::ofstream f(dir + "/detector/" + name);
-		for (const auto& s : seismo) { f << s.first << "\t" << (real) s.second << "\t" << std::endl; }
+		for (const auto& s : seismo) { f << s.first << "\t" << (real) s.second << "\t\n"; }
 	}
 }
 

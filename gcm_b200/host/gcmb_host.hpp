@@ -434,6 +434,7 @@ private:
 	void finishPendingSnapshots();
 	/// seismogram taps of a snapshot step whose read-back is in flight (gcmb_cubic_seismo_begin)
 	bool seismoPending = false;
+	bool seismoDirsMade = false;
 	int pendingSeismoStep = 0;
 	real pendingSeismoTime = 0;
 	void finishPendingSeismo();
