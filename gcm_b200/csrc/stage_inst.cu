@@ -280,21 +280,38 @@ void launch_march(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes
 	constexpr int MINB = MarchBlocks<P, BS, K0RT>::value;
 #ifndef GCMB_EMUL
 	if (impl == 3) {
-		// the bulk-copy marching kernels are compiled for at most 5 blocks per SM (96 registers, no spills): 6 or 7 blocks
-		// are no faster (29.7-30.5 ms per launch at 1024^3 at 5, 6 and 7 blocks, profiles/r2_variants.md).  (The wrong values
-		// the first 80-register builds gave came from the uninitialised register window, see tma_pipe.h; with that fixed
-		// every occupancy is bit-exact.)
-		constexpr int TMINB = MINB > 5 ? 5 : MINB;
+		// Ring depth and occupancy of the bulk-copy marching kernels (profiles/r2_variants.md, calls 12-31).  A bulk copy lands
+		// in shared memory without passing through L1, so -- unlike the cp.async rings, whose requests in flight are bounded by
+		// what is left of L1 next to the rings -- the pipeline can be made as deep as shared memory allows.  For the 9-component
+		// fp64 patterns with compile-time foot cells the best point measured is 6 slots per warp (5 planes in flight) at 3
+		// blocks = 12 warps per SM with the registers uncapped (130, no spills): 27.5 / 26.5 ms per launch at 1024^3 against
+		// 28.3 / 27.7 for the cp.async kernel at 24 warps and 29.6 / 29.6 for 3 slots at 5 blocks; 7 slots at 3 blocks and 8 at
+		// 2 are within 0.4 ms, 10-12 slots at 2 blocks fall to 30-31 ms.  The kernels with run-time foot cells stay at 3 slots
+		// and 5 blocks (deeper was slower at 512^3), the 4- and 5-component and the fp32 patterns on cp.async (launch_sparse).
+		// (The wrong values the first 80-register builds gave came from the uninitialised register window, see tma_pipe.h.)
+		constexpr bool DEEP = sizeof(Real) == 8 && P::M == 9 && !K0RT;
+#if defined(GCMB_TMA_MARCH_MAXB) && defined(GCMB_TMA_MARCH_NST)   // (experiments)
+		constexpr int TMINB = MINB > GCMB_TMA_MARCH_MAXB ? GCMB_TMA_MARCH_MAXB : MINB;
+		constexpr int NST = GCMB_TMA_MARCH_NST;
+#else
+		constexpr int TMINB = DEEP ? 3 : (MINB > 5 ? 5 : MINB);
+		constexpr int NST = DEEP ? 6 : 3;   // ring slots per warp (planes in flight + the one being consumed)
+#endif
 		// GCMB_TMA_MARCH: 0 = a pipeline per warp (256-byte copies, no coupling between warps);
 		// 1 = one ring per block, refilled by lane 0 of warp 0; 2 = one ring per block, producer warp
 		static const int mode = env_int("GCMB_TMA_MARCH", 0);
 		static unsigned long long done[3] = {0, 0, 0};
-		constexpr int NST = 3;
 		if (mode == 0) {
-			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 1, false, TMINB, ZF>;
-			const size_t smem = sizeof(MarchTmaSmem<Real, P::M, NST, 32, 4>) + tab_bytes;
+			// threads per block of the deep kernels (a pipeline per warp: the block size only sets how many warps share an SM)
+#ifndef GCMB_TMA_DEEP_ZT
+#define GCMB_TMA_DEEP_ZT 128
+#endif
+			constexpr int ZTB = DEEP ? GCMB_TMA_DEEP_ZT : MARCH_ZT;
+			const dim3 grid_t((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZTB - 1) / ZTB), (unsigned) perp);
+			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 1, false, TMINB, ZF, ZTB>;
+			const size_t smem = sizeof(MarchTmaSmem<Real, P::M, NST, 32, ZTB / 32>) + tab_bytes;
 			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024, done[0]);
-			kernel<<<grid, MARCH_ZT, smem, stream>>>(a, seg);
+			kernel<<<grid_t, ZTB, smem, stream>>>(a, seg);
 #ifdef GCMB_TMA_ALL_MODES
 		} else if (mode == 1) {
 			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 4, false, TMINB, ZF>;
@@ -388,13 +405,15 @@ template<class P, int BS, bool K0RT>
 void launch_sparse(const void* args, cudaStream_t stream) {
 	const Args& a = *static_cast<const Args*>(args);
 	// GCMB_STAGE_IMPL: 2 = cp.async (LDGSTS) rings everywhere; 3 = bulk copies (TMA) + mbarriers everywhere; default: the
-	// faster of the two per kernel as measured at 1024^3 (profiles/r2_variants.md) -- bulk copies for the fp64 tile
-	// kernel of the contiguous axis (25.0 against 26.8 ms), LDGSTS rings for the marching kernels (28.2 against 28.3 ms
-	// at equal occupancy) and for fp32 (17.6 against 18.5 ms)
+	// faster of the two per kernel as measured (profiles/r2_variants.md) -- bulk copies for the fp64 tile kernel of the
+	// contiguous axis (25.0 against 26.8 ms at 1024^3), cp.async rings for fp32 (17.6 against 18.5 ms)
 	static const int impl_env = env_int("GCMB_STAGE_IMPL", 0);
-	// ... and, for fp64, bulk copies for the marching kernels that read the foot cell from the table as well: they need
-	// 96 registers either way, and there the bulk-copy kernel has no spills (28.2 / 27.7 against 29.0 / 29.1 ms at Courant 1)
-	const int impl = impl_env ? impl_env : ((sizeof(Real) == 8 && (P::axis == 2 || K0RT)) ? 3 : 2);
+	// ... and, for fp64, bulk copies for the marching kernels that read the foot cell from the table as well (they need
+	// 96 registers either way, and there the bulk-copy kernel has no spills: 28.2 / 27.7 against 29.0 / 29.1 ms at Courant 1)
+	// and for the marching kernels of the 9-component patterns, with a deep ring at low occupancy (launch_march: 27.5 / 26.5
+	// against 28.3 / 27.7 ms).  The 4- and 5-component patterns (acoustic, 2-D) are faster on the cp.async rings
+	// (512^3 acoustic 4.53 against 4.72 ms per step, 4096^2 elastic 0.508 against 0.532)
+	const int impl = impl_env ? impl_env : ((sizeof(Real) == 8 && (P::axis == 2 || K0RT || P::M == 9)) ? 3 : 2);
 	const size_t tab_bytes = (size_t) a.n_tables * Packed<P, BS, K0RT>::SIZE * sizeof(Real);
 	if (a.axis != P::axis) { return; }  // (the caller matched the pattern by axis)
 	if constexpr (P::axis == 2) {

@@ -55,13 +55,13 @@ struct MarchTmaSmem {
 	alignas(8) unsigned long long empty[NG][NSTAGE];
 };
 
-template<int S, class R, class P, int BS, bool K0RT, int NSTAGE, int GW, bool PRODUCER, int MINB, bool ZF>
-__global__ void __launch_bounds__(MARCH_ZT + (PRODUCER ? 32 : 0), MINB) k_stage_march_tma(const StageArgsT<R> a, int seg) {
+template<int S, class R, class P, int BS, bool K0RT, int NSTAGE, int GW, bool PRODUCER, int MINB, bool ZF, int ZTB = MARCH_ZT>
+__global__ void __launch_bounds__(ZTB + (PRODUCER ? 32 : 0), MINB) k_stage_march_tma(const StageArgsT<R> a, int seg) {
 	constexpr int M = P::M;
 	constexpr int W = 2 * BS + 1;
 	constexpr unsigned IC = PatternSets<P>::interp();
 	constexpr unsigned CC = PatternSets<P>::center();
-	constexpr int NWARP = MARCH_ZT / 32;
+	constexpr int NWARP = ZTB / 32;   // ZTB = threads per block (with a pipeline per warp it only decides which warps share an SM)
 	constexpr int NG = NWARP / GW;
 	constexpr int ZW = 32 * GW;
 	static_assert(!PRODUCER || GW == NWARP, "the producer warp serves one block-wide ring");
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(MARCH_ZT + (PRODUCER ? 32 : 0), MINB) k_stage_
 	const int perp = a.axis == 0 ? (int) blockIdx.z : (int) blockIdx.z + a.x_begin;
 	const int n_it = s_end - s_begin + 2 * BS;   // iteration `it` works on s = s_begin - 2*BS + it
 	const long long sstride = g.stride(a.axis);
-	const int zb = blockIdx.y * MARCH_ZT;
+	const int zb = blockIdx.y * ZTB;
 
 	// all copies of iteration `it` of group `gi` (the caller has made sure the slot is free)
 	auto issue = [&](int gi, int it) {
@@ -121,6 +121,9 @@ __global__ void __launch_bounds__(MARCH_ZT + (PRODUCER ? 32 : 0), MINB) k_stage_
 	const int zl = tid - gi * ZW;                      // position inside the group's row segment
 	const int i2 = zb + tid;
 	const bool live = i2 < g.n[2];
+	// a warp whose 32 nodes all lie past the end of the row has nothing to copy or compute (rows shorter than the block:
+	// small grids); with a pipeline per warp nobody waits for it
+	if (GW == 1 && !PRODUCER && zb + gi * ZW >= g.n[2]) { return; }
 	const bool issuer = !PRODUCER && zl == 0;          // lane 0 of the group's first warp
 	if (issuer) {
 		for (int it = 0; it < NSTAGE - 1 && it < n_it; it++) { issue(gi, it); }
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(NWARP * 32) k_stage_ztile_tma(const StageArgsT
 	const bool issuer = zl == 0;
 	const int seg = zb + gi * ZW;  // first node of the group's part of the row
 	static_assert(GW == 1 || NG == 1, "the in-tile ghost fill synchronises a warp or the whole block");
+	if (GW == 1 && seg >= g.n[2]) { return; }   // (a warp past the end of the row: nothing to copy or compute)
 
 	auto issue = [&](int it) {
 		const int slot = it % NSTAGE;

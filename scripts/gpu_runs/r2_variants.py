@@ -34,6 +34,19 @@ VARIANTS = {
     "exp_ldgsts_slot_idring": ({"GCMB_EXP_LIB_DIR": "slot_idring"}, 8, False, 0.9),
     "exp_ldgsts_slot_idring7": ({"GCMB_EXP_LIB_DIR": "slot_idring7"}, 8, False, 0.9),
     "exp_ldgsts_cp16": ({"GCMB_EXP_LIB_DIR": "cp16"}, 8, False, 0.9),
+    "exp_tma_base": ({"GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma_nst4": ({"GCMB_EXP_LIB_DIR": "nst4", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma_nst5_4blocks": ({"GCMB_EXP_LIB_DIR": "nst5b4", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma_nst6_3blocks": ({"GCMB_EXP_LIB_DIR": "nst6b3", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma_nst7_3blocks": ({"GCMB_EXP_LIB_DIR": "nst7b3", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma_nst8_2blocks": ({"GCMB_EXP_LIB_DIR": "nst8b2", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma_nst10_2blocks": ({"GCMB_EXP_LIB_DIR": "nst10b2", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_tma_nst12_2blocks": ({"GCMB_EXP_LIB_DIR": "nst12b2", "GCMB_STAGE_IMPL": "3"}, 8, False, 0.9),
+    "exp_deep_zt160": ({"GCMB_EXP_LIB_DIR": "zt160"}, 8, False, 0.9),
+    "exp_deep_zt96_5blocks": ({"GCMB_EXP_LIB_DIR": "zt96b4"}, 8, False, 0.9),
+    "exp_deep_nst4_3blocks": ({"GCMB_EXP_LIB_DIR": "nst4b3"}, 8, False, 0.9),
+    "exp_deep_nst5_3blocks": ({"GCMB_EXP_LIB_DIR": "nst5b3"}, 8, False, 0.9),
+    "exp_deep_nst6_2blocks": ({"GCMB_EXP_LIB_DIR": "nst6b2"}, 8, False, 0.9),
     "exp_tma5_slot_plane": ({"GCMB_EXP_LIB_DIR": "b5", "GCMB_STAGE_IMPL": "3", "GCMB_TMA_WINDOW": "1"}, 8, False, 0.9),
     "fp32_separate_z_border_kernel": ({"GCMB_ZTILE_BORDER": "0"}, 4, False, 0.9),
     "ldgsts_separate_border": ({"GCMB_STAGE_IMPL": "2"}, 8, False, 0.9),
