@@ -413,7 +413,10 @@ void launch_sparse(const void* args, cudaStream_t stream) {
 	// and for the marching kernels of the 9-component patterns, with a deep ring at low occupancy (launch_march: 27.5 / 26.5
 	// against 28.3 / 27.7 ms).  The 4- and 5-component patterns (acoustic, 2-D) are faster on the cp.async rings
 	// (512^3 acoustic 4.53 against 4.72 ms per step, 4096^2 elastic 0.508 against 0.532)
-	const int impl = impl_env ? impl_env : ((sizeof(Real) == 8 && (P::axis == 2 || K0RT || P::M == 9)) ? 3 : 2);
+	int impl = impl_env ? impl_env : ((sizeof(Real) == 8 && (P::axis == 2 || K0RT || P::M == 9)) ? 3 : 2);
+	// the boundary strips of a decomposed x stage (border_size planes each, launched behind the halo exchange) are too short
+	// for a ring that is filled through 2 * border_size warm-up iterations: the cp.async kernel reads its window directly
+	if (!impl_env && P::axis == 0 && a.x_end - a.x_begin <= 2 * BS) { impl = 2; }
 	const size_t tab_bytes = (size_t) a.n_tables * Packed<P, BS, K0RT>::SIZE * sizeof(Real);
 	if (a.axis != P::axis) { return; }  // (the caller matched the pattern by axis)
 	if constexpr (P::axis == 2) {
