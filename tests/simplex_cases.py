@@ -69,6 +69,40 @@ def check_locate_protocol(lib, kind="jitter_void", n_dirs=16, lengths=9, vertice
     return hist
 
 
+def check_direction_masks(lib):
+    """the direction masks of the incident-cell search (simplex_fns.h "direction buckets") never change the answer: rays along
+    the axes, face and space diagonals of the regular mesh (they lie ON cell faces and edges: several cells pass the exact
+    test and the first in the reference's order must win), rays on the bucket boundaries, random rays, lengths from far
+    below the masks' validity limit to several cells -- with the masks against the plain loop, and against the oracle"""
+    import os
+    L = oracle()
+    rng = np.random.default_rng(5)
+    axes = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [1, 0, 1], [0, 1, 1], [1, -1, 0], [1, 0, -1], [0, 1, -1],
+                     [1, 1, 1], [1, 1, -1], [1, -1, 1], [-1, 1, 1], [1, 0.5, 0], [1, 0.5, 0.5], [0.5, 1, 0], [0, 0.5, 1], [1, 0.5, -0.5]], dtype=float)
+    dirs = np.concatenate([axes, -axes, rng.normal(size=(40, 3))])
+    lens = np.array([1e-12, 1e-7, 1e-3, 0.05, 0.3, 0.9, 2.5])
+    for kind in ("regular", "jitter_void"):
+        m = make_mesh(lib, kind)
+        vs = rng.choice(m.n_local, size=min(m.n_local, 60), replace=False).astype(np.int32)
+        v = np.repeat(vs, len(dirs) * len(lens)).astype(np.int32)
+        sh = (dirs[None, :, None, :] * lens[None, None, :, None] * 0.4).reshape(1, -1, 3)
+        sh = np.broadcast_to(sh, (len(vs), sh.shape[1], 3)).reshape(-1, 3).copy()
+        got = {}
+        for masks in ("1", "0"):
+            os.environ["GCMB_SX_DIR_MASKS"] = masks
+            try:
+                ctx = capi.Context(lib)
+                body = SimplexBody(lib, ctx, m, 0)
+                got[masks] = (body.locate(v, sh), body.errors())
+                body.close(); ctx.close()
+            finally:
+                os.environ.pop("GCMB_SX_DIR_MASKS", None)
+        assert got["1"][1] == got["0"][1]
+        assert np.array_equal(got["1"][0], got["0"][0]), "the masks changed %d of %d answers" % ((got["1"][0] != got["0"][0]).any(axis=1).sum(), len(v))
+        ref, _ = oracle_locate_all(L, m, v, sh)
+        assert np.array_equal(got["1"][0], ref)
+
+
 def check_gradient(lib, kind="jitter_void"):
     L = oracle()
     m = make_mesh(lib, kind)

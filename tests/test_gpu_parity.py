@@ -405,6 +405,11 @@ def test_simplex_cell_location_big_mesh_gpu(lib):
     simplex_cases.check_locate_protocol(lib, "big", n_dirs=8, lengths=6, vertices=vs)
 
 
+def test_simplex_direction_masks_keep_the_answer_gpu(lib):
+    import simplex_cases
+    simplex_cases.check_direction_masks(lib)
+
+
 def test_simplex_gradient_gpu(lib):
     import simplex_cases
     simplex_cases.check_gradient(lib)

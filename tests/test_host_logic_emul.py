@@ -121,6 +121,60 @@ def test_border_inside_contiguous_stage_equals_separate_fill(lib, real_bytes):
     assert tile_border_check(lib, real_bytes) == 14
 
 
+def test_deferred_border_fill_keeps_the_reference_order(lib):
+    """gcmb_cubic_border_apply defers the fill of the last direction's faces to the stage kernel; whoever looks at the ghost
+    nodes before the stage must find them filled, a second request replaces the first, and a stage of ANOTHER direction in
+    between does not lose the condition"""
+    rng = np.random.default_rng(3)
+    ctx = capi.Context(lib)
+    D, M, sizes, bs = 3, 9, (4, 5, 40), 2
+    ms = capi.host_matrices(lib, "elastic", D, ("isotropic", 2.0, 3.0, 1.0))
+    U, U1, Lm = (np.ascontiguousarray(m[None]) for m in ms)
+    h = np.array([1.0, 1.1, 0.9])
+    tau = 0.4 * h.min() / np.abs(Lm).max()
+    state = rng.normal(size=tuple(s + 2 * bs for s in sizes) + (M,))
+    table = np.zeros(sizes, dtype=np.uint8)
+
+    def body_with(values_list, between=None):
+        """border_apply(z) for every entry of values_list, then `between`, then download with ghosts"""
+        b = capi.CubicBody(ctx, D, M, sizes, [0] * D, h, bs)
+        b.set_materials(U, U1, Lm, table)
+        b.border_set_area(0, 2, ("infinite",), [5, 7, 8])
+        b.upload(state, with_ghosts=True)
+        for v in values_list:
+            b.border_apply(2, v)
+        if between:
+            between(b)
+        out = b.download(with_ghosts=True)
+        b.close()
+        return out
+
+    # what the fill kernel leaves (BorderConditions.hpp:97-114): ghost(-a) = inner(+a), the set components -inner + 2 b
+    plain_lib_env = state.copy()
+    n2 = sizes[2]
+    for a in range(1, bs + 1):
+        for ghost, inner in ((bs - a, bs + a), (bs + n2 - 1 + a, bs + n2 - 1 - a)):
+            row = state[bs:-bs, bs:-bs, inner, :].copy()
+            for c, val in zip((5, 7, 8), (0.1, 0.2, 0.3)):
+                row[..., c] = -row[..., c] + 2 * val
+            plain_lib_env[bs:-bs, bs:-bs, ghost, :] = row
+    # a reader of the ghost nodes runs the deferred fill first
+    assert np.array_equal(body_with([[0.1, 0.2, 0.3]]), plain_lib_env)
+    # the second request wins, as two fill kernels one after the other would
+    assert np.array_equal(body_with([[9.0, 9.0, 9.0], [0.1, 0.2, 0.3]]), plain_lib_env)
+    # stage x in between: the fill happens before it (the ghost nodes of the layer it leaves behind are those of the request)
+    a = body_with([[0.1, 0.2, 0.3]], between=lambda b: (b.stage(0, tau), b.stage(2, tau)))
+    b2 = capi.CubicBody(ctx, D, M, sizes, [0] * D, h, bs)
+    b2.set_materials(U, U1, Lm, table)
+    b2.border_set_area(0, 2, ("infinite",), [5, 7, 8])
+    b2.upload(plain_lib_env, with_ghosts=True)     # the state with the ghost nodes already filled
+    b2.stage(0, tau); b2.stage(2, tau)
+    real = tuple(slice(bs, bs + s) for s in sizes)
+    assert np.array_equal(a[real], b2.download(with_ghosts=True)[real])
+    b2.close()
+    ctx.close()
+
+
 def test_adhesion_contact_equals_single_body(lib):
     """test/sequence/TestEngine.cpp:27-87 through our engine: two glued bodies == one body, bitwise."""
     two = run_engine(lib, SCENARIOS["adhesion2d_two"])
@@ -214,6 +268,11 @@ def test_simplex_cell_location_protocol(lib):
     import simplex_cases
     simplex_cases.check_locate_protocol(lib, "jitter_void", n_dirs=8, lengths=5)
     simplex_cases.check_locate_protocol(lib, "regular", n_dirs=8, lengths=5)
+
+
+def test_simplex_direction_masks_keep_the_answer(lib):
+    import simplex_cases
+    simplex_cases.check_direction_masks(lib)
 
 
 def test_simplex_gradient(lib):
