@@ -952,6 +952,12 @@ int gcmb_cubic_border_set(gcmb_body* b, int cond, int dir, const uint8_t* left_m
 	for (int s = 0; s < 2; s++) {
 		if (!src[s]) { continue; }
 		c->side_on[s] = true;
+		// a mask that selects every node of the face is no mask (an infinite area turned into a mask by the caller, as the
+		// reference-side binding does for every condition): the whole-face paths -- the fill inside the stage kernel among
+		// them -- apply
+		bool all = true;
+		for (long long i = 0; i < nf && all; i++) { all = src[s][i] != 0; }
+		if (all) { continue; }
 		GCMB_CUDA(cudaMalloc(&c->mask[s], (size_t) nf));
 		GCMB_CUDA(cudaMemcpy(c->mask[s], src[s], (size_t) nf, cudaMemcpyHostToDevice));
 	}

@@ -175,6 +175,73 @@ def test_deferred_border_fill_keeps_the_reference_order(lib):
     ctx.close()
 
 
+@pytest.fixture(scope="module")
+def binding_on_the_harness(lib):
+    """oracle/_ref/gcm_ref_gpu_emul: the UNMODIFIED reference cubic::Engine<D> with integration/GpuBackend.hpp as its backend, linked
+    against the stepping harness instead of the CUDA library (built where /root/reference exists)"""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "gcm_ref_gpu_emul")
+    if os.path.isdir("/root/reference/src"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref_gpu_emul"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gcm_ref_gpu_emul is built where /root/reference exists (make -C oracle ref_gpu_emul)")
+    return exe
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_reference_engine_with_gcm_b200_backend_on_the_harness(binding_on_the_harness, name, tmp_path):
+    """The drop-in without a GPU: the reference's own engine loop drives gcm_b200 through the binding a maintainer would add
+    (GpuMesh / GpuGcm / GpuBorder / GpuContact / GpuMaxwellOde), the library's host logic and kernel bodies run on the
+    stepping harness, and the result must equal the all-CPU reference (tests/golden) bit for bit.  The binding registers every
+    border condition as face masks: whole-face masks take the fill inside the stage kernel (gcmb_cubic_border_set)."""
+    import oracle_host as oh
+    g = golden(name)
+    out = oh.run_reference(SCENARIOS[name], str(tmp_path), exe_name="gcm_ref_gpu_emul")
+    assert out["meta"]["tau"] == float(g["tau"]) and out["meta"]["time"] == float(g["time"]) and int(out["meta"]["steps"]) == int(g["steps"])
+    bid = 0
+    while "body%d" % bid in g.files:
+        assert np.array_equal(out[bid], g["body%d" % bid]), (name, bid)
+        bid += 1
+    if "detector" in g.files:
+        assert np.array_equal(out["detector"], g["detector"])
+
+
+def test_whole_face_host_masks_count_as_whole_faces(lib):
+    """the reference-side binding registers every condition as face masks (integration/GpuBackend.hpp): masks that select the
+    whole face must take the same path as an infinite area -- the fill inside the stage kernel -- and give the same bits;
+    a mask with a hole goes through the fill kernel"""
+    rng = np.random.default_rng(4)
+    ctx = capi.Context(lib)
+    D, M, sizes, bs = 3, 9, (4, 5, 40), 2
+    ms = capi.host_matrices(lib, "elastic", D, ("isotropic", 2.0, 3.0, 1.0))
+    U, U1, Lm = (np.ascontiguousarray(m[None]) for m in ms)
+    h = np.array([1.0, 1.1, 0.9])
+    tau = 0.4 * h.min() / np.abs(Lm).max()
+    state = rng.normal(size=tuple(s + 2 * bs for s in sizes) + (M,))
+    table = np.zeros(sizes, dtype=np.uint8)
+    face = sizes[0] * sizes[1]
+    out = {}
+    for kind in ("area", "full_masks", "holed_masks"):
+        b = capi.CubicBody(ctx, D, M, sizes, [0] * D, h, bs)
+        b.set_materials(U, U1, Lm, table)
+        if kind == "area":
+            b.border_set_area(0, 2, ("infinite",), [5, 7, 8])
+        else:
+            mask = np.ones(face, dtype=np.uint8)
+            if kind == "holed_masks":
+                mask[3] = 0
+            b.border_set(0, 2, mask, mask, [5, 7, 8])
+        b.upload(state, with_ghosts=True)
+        took = b.stage_with_border(2, tau, [0.1, 0.2, 0.3])
+        assert took == (kind != "holed_masks"), kind
+        out[kind] = b.download()
+        b.close()
+    assert np.array_equal(out["area"], out["full_masks"])
+    assert not np.array_equal(out["area"], out["holed_masks"])
+    ctx.close()
+
+
 def test_adhesion_contact_equals_single_body(lib):
     """test/sequence/TestEngine.cpp:27-87 through our engine: two glued bodies == one body, bitwise."""
     two = run_engine(lib, SCENARIOS["adhesion2d_two"])
