@@ -309,21 +309,21 @@ void launch_march(const Args& a, cudaStream_t stream, int impl, size_t tab_bytes
 			constexpr int ZTB = DEEP ? GCMB_TMA_DEEP_ZT : MARCH_ZT;
 			const dim3 grid_t((unsigned) ((len + seg - 1) / seg), (unsigned) ((a.g.n[2] + ZTB - 1) / ZTB), (unsigned) perp);
 			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 1, false, TMINB, ZF, ZTB>;
-			// (ring + the packed tables of all materials: up to 56 KB + 63 KB for 255 isotropic, more for orthotropic tables;
-			// the opt-in limit is the SM's 227 KB)
+			// (ring + the packed tables of all materials: 56 KB + 63 KB for 255 isotropic ones, more for orthotropic tables)
 			const size_t smem = sizeof(MarchTmaSmem<Real, P::M, NST, 32, ZTB / 32>) + tab_bytes;
-			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024, done[0]);
+			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024, done[0]);
+			if (smem > 160 * 1024) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); }  // (hundreds of orthotropic materials)
 			kernel<<<grid_t, ZTB, smem, stream>>>(a, seg);
 #ifdef GCMB_TMA_ALL_MODES
 		} else if (mode == 1) {
 			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 4, false, TMINB, ZF>;
 			const size_t smem = sizeof(MarchTmaSmem<Real, P::M, NST, 128, 1>) + tab_bytes;
-			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024, done[1]);
+			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024, done[1]);
 			kernel<<<grid, MARCH_ZT, smem, stream>>>(a, seg);
 		} else {
 			auto kernel = k_stage_march_tma<SET, Real, P, BS, K0RT, NST, 4, true, TMINB, ZF>;
 			const size_t smem = sizeof(MarchTmaSmem<Real, P::M, NST, 128, 1>) + tab_bytes;
-			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024, done[2]);
+			func_attr_once(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024, done[2]);
 			kernel<<<grid, MARCH_ZT + 32, smem, stream>>>(a, seg);
 #endif
 		}
