@@ -2,6 +2,10 @@
 variant (the kernel choice is read from the environment once), device-timed per stage class, one JSON line each.
 
   python scripts/gpu_runs/r2_variants.py [--size 1024] [--steps 5] [--only name,name]
+
+The exp_* variants load an experiment build from exp_libs/<name>/ (scripts/exp_build.py <name> -DFLAG ...; the flags of every
+build that was measured are listed with its numbers in profiles/r2_variants.md, experimental code paths that are not in the
+tree any more as patches under scripts/exp_patches/); without that directory they report an error line and go on.
 """
 import argparse
 import json
