@@ -1,7 +1,8 @@
 // gcmb_exe — command-line entry with the options of the reference's launcher (src/launcher/main.cpp:22-71,
 // src/launcher/getopt_wrapper.hpp): --task (-t) names a task, --out (-o) the output directory.  A task is a
 // plain-text task file (grammar in task_file.cpp) or the id of one shipped in gcm_b200/tasks/ (cubic2d, cubic3d,
-// acoustic: the reference launcher's cubic demo tasks; simplex_plate).
+// acoustic, ndi_empty, ndi, titan: the reference launcher's cubic demo tasks; cubeAcs, cubeEls: its simplex cube tasks;
+// simplex_plate).
 #include <chrono>
 #include <cstdio>
 #include <cstring>

@@ -105,6 +105,10 @@ Task::TimeDependency timeDependency(Words& t) {
 		const real amp = t.num(), t0 = t.num(), tau = t.num();
 		return [amp, t0, tau](real time) { time -= t0; return amp * std::exp(-time * time / (2 * tau * tau)); };
 	}
+	if (kind == "until") {  // value while t < t1, then 0: the loading pulse of the reference's cube tasks (src/launcher/main.cpp:604-618)
+		const real t1 = t.num(), value = t.num();
+		return [t1, value](real time) { return (time < t1) ? value : real(0); };
+	}
 	throw Exception(GCMB_E_INVALID_ARG, "task text: unknown time dependency " + kind);
 }
 

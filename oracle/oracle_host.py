@@ -138,6 +138,12 @@ def parse_time_dependency(tk):
     if kind == "sin":
         amp, omega = tk.num(), tk.num()
         return lambda t: amp * math.sin(omega * t)
+    if kind == "gauss":
+        amp, t0, tau = tk.num(), tk.num(), tk.num()
+        return lambda t: amp * math.exp(-(t - t0) * (t - t0) / (2 * tau * tau))
+    if kind == "until":
+        t1, value = tk.num(), tk.num()
+        return lambda t: value if t < t1 else 0.0
     raise ValueError("unknown time dependency " + kind)
 
 

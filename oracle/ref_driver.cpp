@@ -119,6 +119,10 @@ Task::TimeDependency parseTimeDependency(Tokens& tk) {
 		real amp = tk.num(), t0 = tk.num(), tau = tk.num();
 		return [amp, t0, tau](real t) { t -= t0; return amp * exp(-t * t / (2 * tau * tau)); };
 	}
+	if (kind == "until") {
+		real t1 = tk.num(), value = tk.num();
+		return [t1, value](real t) { return (t < t1) ? value : real(0); };
+	}
 	THROW_INVALID_ARG("task file: unknown time dependency " + kind);
 }
 

@@ -57,6 +57,7 @@ Task::TimeDependency parseTimeDependency(Tokens& tk) {
 	const std::string kind = tk.next();
 	if (kind == "const") { const real c = tk.num(); return [c](real) { return c; }; }
 	if (kind == "sin") { const real amp = tk.num(), omega = tk.num(); return [amp, omega](real t) { return amp * sin(omega * t); }; }
+	if (kind == "until") { const real t1 = tk.num(), value = tk.num(); return [t1, value](real t) { return (t < t1) ? value : real(0); }; }
 	THROW_INVALID_ARG("task file: unknown time dependency " + kind);
 }
 

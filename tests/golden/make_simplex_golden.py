@@ -38,6 +38,9 @@ SCENARIOS = {
     "acoustic_cavity_local_basis_pde_vectors": (1, 1, 1, "identity", 4, "border_calc_mode local"),
     "elastic_maxwell": (0, 1, 0, "identity", 4, "MAXWELL"),
     "elastic_three_bodies": (0, 3, 0, "rotated", 4),
+    # the reference launcher's cubeAcs / cubeEls tasks at reduced size (simplex_cases.cube_scenario)
+    "cube_acs": (1, 1, 0, "text", 7),
+    "cube_els": (0, 1, 0, "text", 7),
 }
 
 
@@ -48,7 +51,10 @@ def main():
         if only and name not in only:
             continue
         model, bodies, gcm, basis, steps = cfg[:5]
-        text = simplex_cases.golden_scenario(model, bodies, gcm, basis, steps) + "".join("\n" + extra for extra in cfg[5:] if extra != "MAXWELL")
+        if basis == "text":
+            text = simplex_cases.cube_scenario(model == 1, steps=steps)
+        else:
+            text = simplex_cases.golden_scenario(model, bodies, gcm, basis, steps) + "".join("\n" + extra for extra in cfg[5:] if extra != "MAXWELL")
         if "MAXWELL" in cfg[5:]:   # Maxwell viscosity ODE: the body line gets "ode maxwell", the material a relaxation time
             text = text.replace("body 0 elastic isotropic", "body 0 elastic isotropic ode maxwell")
             text = "\n".join(ln + " tau0 0.2" if ln.startswith("material body 0") else ln for ln in text.split("\n"))

@@ -526,12 +526,30 @@ def golden_scenario(model, bodies, gcm, basis, steps):
     return "\n".join(lines)
 
 
+def cube_scenario(acoustic, n=6, steps=7):
+    """The reference launcher's cubeAcs / cubeEls tasks (src/launcher/main.cpp:547-640) at reduced size: the unit cube (meshed by
+    the box mesher instead of CGAL's mesher on meshes/cube.off), Courant number 1, identity basis, zero fixed force on the
+    whole border and a loading pulse on the face x = 0 that is switched off at t = 0.25"""
+    name = "acoustic" if acoustic else "elastic"
+    zero = "const 0" if acoustic else "const 0 const 0 const 0"
+    pulse = "until 0.25 1" if acoustic else "const 0 const 0 until 0.25 -1"
+    return "\n".join([
+        "grid simplex", "dimensionality 3", "courant 1.0", "steps %d" % steps,
+        "simplex_box %d %d %d 0 0 0 %r jitter 0.3 seed 3" % (n, n, n, 1.0 / n),
+        "body 0 %s isotropic" % name,
+        "material body 0 isotropic 4 %s" % ("4 0" if acoustic else "2 1"),
+        "basis 1 0 0 0 1 0 0 0 1",
+        "border_condition infinite fixed_force " + zero,
+        "border_condition box -10 -10 -10 0.01 10 10 fixed_force " + pulse,
+        "gcm_type riemann_invariants"]) + "\n"
+
+
 GOLDEN_SIMPLEX = ["elastic_cavity", "elastic_contact", "acoustic_contact_rotated", "elastic_contact_pde_vectors", "acoustic_pde_vectors",
                   "elastic_contact_summ"]
 # BorderCalcMode::LOCAL_BASIS and the Maxwell ODE: pinned on the engine level only (the C restatement keeps to
 # GLOBAL_BASIS and has no ODE)
 GOLDEN_SIMPLEX_LOCAL = ["elastic_contact_local_basis", "acoustic_cavity_local_basis_pde_vectors", "elastic_maxwell",
-                        "elastic_three_bodies"]
+                        "elastic_three_bodies", "cube_acs", "cube_els"]
 
 
 def load_golden(name):
